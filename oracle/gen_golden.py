@@ -1,0 +1,160 @@
+"""Generate tests/golden/*.npz from the *reference itself* (shimmed import, oracle/ref_shim.py).
+
+Run in the build container only (needs /root/reference):
+
+    python -m oracle.gen_golden
+
+TEST INFRASTRUCTURE ONLY.  The reference ships no tests or golden vectors for this path, so
+these fixtures are the pin: every array under `ref_*` keys is an output of the unmodified
+reference code (plus the two-line get_opt shim), produced with numpy 2.3.5 / scipy 1.18.1 /
+scikit-learn 1.9.0 / torch 2.11.0 on CPU.  Inputs are stored next to the outputs so the tests
+need neither the reference nor scikit-learn's generator to be bit-stable.
+"""
+import os
+import time
+import warnings
+
+import numpy as np
+
+warnings.simplefilter("ignore")
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def main():
+    import torch
+    from sklearn.model_selection import train_test_split
+
+    from oracle import ref_shim
+
+    ns = ref_shim.load(fista_dtype=torch.float64)
+    os.makedirs(OUT, exist_ok=True)
+    rng = np.random.default_rng(20261018)
+
+    # ---- dataset: load_data.py:101-116 + the drivers' split (run_SRM.py:26) -------------
+    X, y = ns.load_data.get_data("synthetic", num_row=500, num_feature=40, seed=17)
+    Xtr, Xte, ytr, yte = train_test_split(X, y, test_size=0.4, random_state=17)
+    n, d = Xtr.shape
+    D = -ytr * Xtr
+    np.savez_compressed(os.path.join(OUT, "data_300x40.npz"), X=Xtr, y=ytr, X_test=Xte, y_test=yte)
+
+    # ---- spectra: objective.py:97-187 ---------------------------------------------------
+    spec = {}
+    for name, args in [("erm", None), ("extremile", [2.0]), ("superquantile", [0.8]), ("superquantile", [0.5]),
+                       ("esrm", [1.5]), ("aorr", [0.2, 0.8]), ("aorr", [0.1, 0.9]), ("aorr_dc", [60, 20]),
+                       ("ehrm", None)]:
+        for nn in (97, 300):
+            wf = ns.objective.get_weights(name, args)
+            key = f"{name}|{'' if args is None else ','.join(map(str, args))}|{nn}"
+            if isinstance(wf, tuple):
+                spec[key + "|a"] = wf[0](nn).numpy()
+                spec[key + "|b"] = wf[1](nn).numpy()
+            else:
+                spec[key] = wf(nn).numpy()
+    np.savez_compressed(os.path.join(OUT, "spectra.npz"), **spec)
+
+    # ---- z-step: algorithms.py:88-106 (margins -> sort -> PAV prox -> scatter) ----------
+    zc = {}
+    cases = [
+        ("erm", None, "binary_cross_entropy", None, 1e-3),
+        ("erm", None, "binary_cross_entropy", None, 1e-5),
+        ("superquantile", [0.8], "binary_cross_entropy", None, 1e-5),
+        ("superquantile", [0.8], "binary_cross_entropy", None, 1e-2),
+        ("extremile", [2.0], "binary_cross_entropy", None, 1e-3),
+        ("esrm", [1.5], "binary_cross_entropy", None, 1e-4),
+        ("aorr", [0.2, 0.8], "binary_cross_entropy", None, 1e-3),
+        ("aorr", [0.2, 0.8], "hinge", None, 1e-2),       # reference bisection: loose pin only
+        ("superquantile", [0.8], "hinge", None, 1.0),     # idem
+        ("ehrm", None, "binary_cross_entropy", -5, 1e-3),
+        ("ehrm", None, "binary_cross_entropy", -5, 1e-1),
+    ]
+    for ci, (wf, args, loss, B, rho) in enumerate(cases):
+        s = ns.algorithms.ADMMmethod(Xtr, ytr, wf, loss, l2_reg=0.01, B=B, args=args)
+        s.w = rng.normal(size=(d, 1)) * 0.3
+        s.lagrangian = rng.normal(size=(n, 1)) * rho
+        s.rho = rho
+        z = s.z_subproblem().reshape(-1)
+        zc[f"c{ci}_w"] = s.w.reshape(-1)
+        zc[f"c{ci}_lam"] = s.lagrangian.reshape(-1)
+        zc[f"c{ci}_ref_z"] = z
+        zc[f"c{ci}_meta"] = np.array([wf, "" if args is None else ",".join(map(str, args)), loss,
+                                      "" if B is None else str(B), repr(rho)])
+    zc["ncases"] = np.array(len(cases))
+    np.savez_compressed(os.path.join(OUT, "zstep.npz"), **zc)
+
+    # ---- element prox: individual_solver.py:112-130 -------------------------------------
+    m = np.sort(rng.normal(size=200) * 3)
+    sg = np.abs(rng.normal(size=200)) / 200
+    pr = {"m": m, "sigma": sg}
+    for rho in (1e-4, 1e-2, 1.0):
+        pr[f"ref_bce_{rho}"] = ns.individual_solver.individual_solver("binary_cross_entropy", sg, rho, m)
+        pr[f"ref_hinge_{rho}"] = ns.individual_solver.individual_solver("hinge", sg, rho, m)
+    np.savez_compressed(os.path.join(OUT, "prox.npz"), **pr)
+
+    # ---- FISTA: fast_lasso.py:22-69 as called at algorithms.py:199-201 -------------------
+    fc = {"b": rng.normal(size=n), "w0": rng.normal(size=d) * 0.01}
+    for lam in (0.5, 20.0, 300.0):
+        fc[f"ref_f64_{lam}"] = ns.FISTA(fc["w0"], D, fc["b"], lam, np.float32(17), np.float32(2.5), tol=7e-5, max_iter=5000)
+        fc[f"ref_f64_np_{lam}"] = ns.FISTA(fc["w0"], D, fc["b"], np.float64(lam), np.float32(17), np.float32(2.5), tol=7e-5, max_iter=5000)
+        fc[f"ref_f32_{lam}"] = ns._orig_fista(fc["w0"], D, fc["b"], lam, np.float32(17), np.float32(2.5), tol=7e-5,
+                                              max_iter=5000, dtype=torch.float32)
+        torch.set_default_dtype(torch.float32)
+    torch.set_default_dtype(torch.float32)
+    np.savez_compressed(os.path.join(OUT, "fista.npz"), **fc)
+
+    # ---- l2 w-step: w_LBFGS.py:31-53 -----------------------------------------------------
+    lc = {"z": rng.normal(size=n), "lam": rng.normal(size=n) * 1e-3, "w0": rng.normal(size=d) * 0.01}
+    DTD = D.T @ D
+    for rho in (1e-5, 1e-2, 1.0):
+        lc[f"ref_{rho}"] = ns.w_lbfgs.w_solver(2, lc["w0"].reshape(-1, 1), lc["z"].reshape(-1, 1),
+                                               lc["lam"].reshape(-1, 1), rho, DTD, D, 0.01).reshape(-1)
+    np.savez_compressed(os.path.join(OUT, "l2step.npz"), **lc)
+
+    # ---- objective: objective.py:71-87 ---------------------------------------------------
+    oc = {"w": rng.normal(size=d) * 0.2}
+    for wf, args, loss, B, kw in [("erm", None, "binary_cross_entropy", None, dict(l1_reg=0.01)),
+                                  ("superquantile", [0.8], "binary_cross_entropy", None, dict(l2_reg=0.01)),
+                                  ("aorr", [0.2, 0.8], "hinge", None, dict(l2_reg=1e-4)),
+                                  ("ehrm", None, "binary_cross_entropy", -5, dict(l2_reg=0.01)),
+                                  ("esrm", [1.5], "hinge", None, dict(l1_reg=0.1))]:
+        ob = ns.objective.rankbasedObjective(torch.from_numpy(Xtr.copy()), torch.from_numpy(ytr.copy()), wf, loss,
+                                             kw.get("l2_reg"), kw.get("l1_reg"), B, None, args)
+        oc[f"ref_{wf}_{loss}"] = np.array(ob.get_arrogate_loss(torch.from_numpy(oc["w"].reshape(-1, 1))))
+    np.savez_compressed(os.path.join(OUT, "objective.npz"), **oc)
+
+    # ---- trajectories: ADMMmethod.main_loop, algorithms.py:119-164,209-216 ---------------
+    tr = {}
+    runs = [
+        ("erm_l1", "erm", None, "binary_cross_entropy", None, dict(l1_reg=0.01)),
+        ("erm_l2", "erm", None, "binary_cross_entropy", None, dict(l2_reg=1e-4)),
+        ("sq_l1", "superquantile", [0.8], "binary_cross_entropy", None, dict(l1_reg=0.01)),
+        ("sq_l2", "superquantile", [0.8], "binary_cross_entropy", None, dict(l2_reg=0.01)),
+        ("extremile_l2", "extremile", [2.0], "binary_cross_entropy", None, dict(l2_reg=0.01)),
+        ("aorr_bce_l2", "aorr", [0.2, 0.8], "binary_cross_entropy", None, dict(l2_reg=1e-4)),
+        ("ehrm_l2", "ehrm", None, "binary_cross_entropy", -5, dict(l2_reg=0.01)),
+    ]
+    snaps = (1, 2, 3, 10, 40)
+    for tag, wf, args, loss, B, kw in runs:
+        s = ns.algorithms.ADMMmethod(Xtr, ytr, wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
+        t0 = time.time()
+        for i in range(40):
+            with ref_shim.quiet():
+                done = ns.algorithms.Optimizer.main_loop(s, i, t0, False)
+            if (i + 1) in snaps:
+                tr[f"{tag}_w_{i+1}"] = np.asarray(s.w, dtype=np.float64).reshape(-1)
+                tr[f"{tag}_z_{i+1}"] = s.z.reshape(-1)
+                tr[f"{tag}_lam_{i+1}"] = s.lagrangian.reshape(-1)
+                tr[f"{tag}_rho_{i+1}"] = np.array(float(s.rho))
+            if done:
+                break
+        tr[f"{tag}_obj"] = np.array(s.objective.get_arrogate_loss(torch.from_numpy(s.w).double()))
+        tr[f"{tag}_meta"] = np.array([wf, "" if args is None else ",".join(map(str, args)), loss,
+                                      "" if B is None else str(B), repr(kw)])
+        print(tag, "iters", i + 1, "obj", float(tr[f"{tag}_obj"]))
+    np.savez_compressed(os.path.join(OUT, "trajectory.npz"), **tr)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

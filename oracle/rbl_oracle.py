@@ -1,0 +1,385 @@
+"""CPU oracle: a numpy/C restatement of the reference's ADMM hot path.
+
+TEST INFRASTRUCTURE ONLY — only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s
+`cpu_baseline` / `--impl reference` legs may import this module.  The product path
+(`admm-for-rank-based-loss_b200/`) never imports anything under `oracle/`; it fails loudly
+if the CUDA library is missing.
+
+Every function cites the reference file:line (paths under the reference tree) it follows.
+The reference is pure Python (no native code), so there is no `oracle/_ref` binary; the
+restatement is pinned against outputs of the reference itself, generated in the build
+container by `oracle/gen_golden.py` (shimmed import) and committed
+under `tests/golden/`.  The reference has no tests or golden vectors of its own: parity is
+"unpinned" by the reference; the only numeric artefact it ships is the xlsx table whose
+iteration-0 objective 0.6931471805674658 reproduces bit-exactly (tests/test_oracle.py).
+
+Deliberate deviations from the shipped reference:
+  * z-step uses an exact stack PAV + bracketed Newton (machine precision) instead of the
+    sweep PAV with a global-stop damped Newton (pav.py:93-178, individual_solver.py:90-109);
+    the isotonic prox is unique, measured agreement <= ~1e-10 abs for BCE.
+  * hinge block prox is the closed form, not the early-exit bisection
+    (individual_solver.py:15-42), which is inexact at small rho (reference defect).
+  * FISTA runs in float64 (`dtype=torch.float64`, fast_lasso.py:22-26) unless fp32 is asked
+    for; scalar promotion follows numpy >= 2 (NEP 50), which is what this image runs:
+    `L_cur` and `lam/L_cur` are float32 scalars (algorithms.py:199-200 pass np.float32).
+  * sort is `kind="stable"` (reference: unstable np.argsort, algorithms.py:92; identical on
+    tie-free keys).
+"""
+import ctypes
+import math
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+LOSS_IDS = {"binary_cross_entropy": 0, "hinge": 1}
+
+
+def build_c(force=False):
+    """gcc-compile oracle/pav_oracle.c -> oracle/_build/libpav_oracle.so (git-ignored)."""
+    src = os.path.join(_HERE, "pav_oracle.c")
+    out_dir = os.path.join(_HERE, "_build")
+    out = os.path.join(out_dir, "libpav_oracle.so")
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        os.makedirs(out_dir, exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", out, src, "-lm"])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        lib = ctypes.CDLL(build_c())
+        dp = ctypes.POINTER(ctypes.c_double)
+        lib.rbl_oracle_prox.restype = ctypes.c_double
+        lib.rbl_oracle_prox.argtypes = [ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double]
+        lib.rbl_oracle_pav.restype = ctypes.c_int64
+        lib.rbl_oracle_pav.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double,
+                                       ctypes.c_int, ctypes.c_double, dp]
+        lib.rbl_oracle_prox_vec.restype = None
+        lib.rbl_oracle_prox_vec.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, dp]
+        _LIB = lib
+    return _LIB
+
+
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+# ---------------------------------------------------------------------------------------
+# spectra — src/optim/objective.py:97-187
+# ---------------------------------------------------------------------------------------
+def _distort(p, gamma):  # objective.py:148-150
+    return p ** gamma / ((p ** gamma + (1 - p) ** gamma) ** (1 / gamma))
+
+
+def spectrum(name, n, args=None):
+    """sigma in ascending-rank order (objective.py:166-187).  For 'ehrm' returns (a, b)."""
+    i = np.arange(n, dtype=np.float64)
+    if name == "erm":  # :97-98
+        return np.ones(n) / n
+    if name == "ehrm":  # :153-164 (python loop over scalars in the reference)
+        a = np.array([_distort((k + 1) / n, 0.69) - _distort(k / n, 0.69) for k in range(n)])
+        b = np.array([_distort((n - k) / n, 0.61) - _distort((n - k - 1) / n, 0.61) for k in range(n)])
+        return a, b
+    if args is None:
+        raise ValueError("args for framework is None!")
+    if name == "extremile":  # :101-105
+        r = args[0]
+        return ((i + 1) ** r - i ** r) / (n ** r)
+    if name == "superquantile":  # :108-117
+        q = args[0]
+        w = np.zeros(n)
+        idx = math.floor(n * q)
+        frac = 1 - (n - idx - 1) / (n * (1 - q))
+        if frac > 1e-12:
+            w[idx] = frac
+            w[idx + 1:] = 1 / (n * (1 - q))
+        else:
+            w[idx:] = 1 / (n - idx)
+        return w
+    if name == "esrm":  # :120-123
+        rho = args[0]
+        upper = np.exp(rho * ((i + 1) / n))
+        lower = np.exp(rho * (i / n))
+        return math.exp(-rho) * (upper - lower) / (1 - math.exp(-rho))
+    if name == "aorr":  # :126-136
+        qlow, qup = args[0], args[1]
+        w = np.zeros(n)
+        lo = math.floor(n * qlow)
+        up = math.floor(n * qup)
+        frac = 1 - (up - lo - 1) / (n * (qup - qlow))
+        if frac > 1e-12:
+            w[lo] = frac
+            w[lo + 1:up] = 1 / (n * (qup - qlow))
+        else:
+            w[lo:up] = 1 / (up - lo)
+        return w
+    if name == "aorr_dc":  # :139-145
+        k, m = args[0], args[1]
+        if k <= m:
+            raise ValueError("need args[0] > args[1]!")
+        w = np.zeros(n)
+        w[m + 1:k] = 1 / (k - m)
+        w[k + 1] = 1 - (k - m - 1) / (k - m)
+        return w
+    raise ValueError(f"Unrecognized framework '{name}'!")
+
+
+# ---------------------------------------------------------------------------------------
+# losses / objective — objective.py:11-24, 71-87
+# ---------------------------------------------------------------------------------------
+def log1pexp(u):  # individual_solver.py:52-57
+    u = np.asarray(u, dtype=np.float64)
+    return np.where(u > 0, u + np.log1p(np.exp(-np.abs(u))), np.log1p(np.exp(-np.abs(u))))
+
+
+def margin_loss(loss, u):
+    """individual loss as a function of the margin u = D w = -y * (X w)."""
+    if loss == "binary_cross_entropy":
+        return log1pexp(u)
+    if loss == "hinge":
+        return np.maximum(1.0 + u, 0.0)
+    raise ValueError(f"Unrecognized loss '{loss}'!")
+
+
+def objective(D, w, sigma, loss, l2_reg=None, l1_reg=None, lossB=None, include_reg=True):
+    """get_arrogate_loss (objective.py:71-87) in terms of D = -y*X.
+
+    Note the reference's EHRM branch uses `alphas` on both sides of lossB (:76), so the value
+    is sum(alphas * sorted losses) in every case; `lossB` is accepted and ignored on purpose.
+    """
+    w = np.asarray(w, dtype=np.float64).reshape(-1)
+    losses = np.sort(margin_loss(loss, D @ w))
+    risk = float(np.dot(sigma, losses))
+    if l2_reg and include_reg:
+        risk += 0.5 * l2_reg * float(np.sum(w ** 2))
+    if l1_reg and include_reg:
+        risk += 0.5 * l1_reg * float(np.sum(np.abs(w)))
+    return risk
+
+
+# ---------------------------------------------------------------------------------------
+# z-step — algorithms.py:88-106, pav.py:54-178, individual_solver.py:90-130, PAV_cpt.py
+# ---------------------------------------------------------------------------------------
+def prox_vec(loss, sigma, m, rho):
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    m = np.ascontiguousarray(m, dtype=np.float64)
+    out = np.empty_like(m)
+    _lib().rbl_oracle_prox_vec(LOSS_IDS[loss], m.size, _dptr(sigma), _dptr(m), float(rho), _dptr(out))
+    return out
+
+
+def pav_prox(loss, sigma, m_sorted, rho, clip=None, return_blocks=False):
+    """exact isotonic prox of sorted margins (pav.py:93-178 fixed point); clip = EHRM's B."""
+    sigma = np.ascontiguousarray(sigma, dtype=np.float64)
+    m_sorted = np.ascontiguousarray(m_sorted, dtype=np.float64)
+    out = np.empty_like(m_sorted)
+    nb = _lib().rbl_oracle_pav(LOSS_IDS[loss], m_sorted.size, _dptr(sigma), _dptr(m_sorted), float(rho),
+                               0 if clip is None else 1, 0.0 if clip is None else float(clip), _dptr(out))
+    return (out, nb) if return_blocks else out
+
+
+def pav_prox_minmax(loss, sigma, m_sorted, rho):
+    """Brute-force min-max formula z_i = max_{l<=i} min_{r>=i} v(l, r) (small n only)."""
+    n = len(m_sorted)
+    lib = _lib()
+    cs = np.concatenate([[0.0], np.cumsum(sigma)])
+    cm = np.concatenate([[0.0], np.cumsum(m_sorted)])
+    v = np.full((n, n), np.nan)
+    for l in range(n):
+        for r in range(l, n):
+            c = r - l + 1
+            v[l, r] = lib.rbl_oracle_prox(LOSS_IDS[loss], (cs[r + 1] - cs[l]) / c, (cm[r + 1] - cm[l]) / c, rho)
+    z = np.empty(n)
+    for i in range(n):
+        z[i] = max(min(v[l, r] for r in range(i, n)) for l in range(i + 1))
+    return z
+
+
+def ehrm_candidate_sums(sigma_a, sigma_b, B, m_sorted, rho):
+    """The two scalars the reference compares in PAV_solver_CPT.__init__ (PAV_cpt.py:203-226):
+    fval1 = func_value(sigma_a, min(prox_a, B)), fval2 = func_value(sigma_b, max(prox_b, B))."""
+    x1 = np.minimum(prox_vec("binary_cross_entropy", sigma_a, m_sorted, rho), B)
+    x2 = np.maximum(prox_vec("binary_cross_entropy", sigma_b, m_sorted, rho), B)
+    f1 = float(np.sum(sigma_a * log1pexp(x1)) + rho / 2 * np.dot(x1 - m_sorted, x1 - m_sorted))
+    f2 = float(np.sum(sigma_b * log1pexp(x2)) + rho / 2 * np.dot(x2 - m_sorted, x2 - m_sorted))
+    return f1, f2
+
+
+def z_step(D, w, lam, rho, sigma, loss, B=None, sigma_b=None, return_all=False):
+    """Optimizer.z_subproblem (algorithms.py:88-106)."""
+    m = (D @ w.reshape(-1) - lam.reshape(-1) / rho)
+    perm = np.argsort(m, kind="stable")
+    ms = m[perm]
+    if B is not None:  # EHRM, PAV_cpt.py:169-293 == max(B, isotonic prox with sigma=b)
+        zs = pav_prox("binary_cross_entropy", sigma_b, ms, rho, clip=B)
+    else:
+        zs = pav_prox(loss, sigma, ms, rho)
+    z = np.zeros(m.shape[0])
+    z[perm] = zs
+    if return_all:
+        return z, m, perm, zs
+    return z
+
+
+# ---------------------------------------------------------------------------------------
+# w-step, l1 — fast_lasso.py:15-69 (FISTA), algorithms.py:190-202
+# ---------------------------------------------------------------------------------------
+def soft_thr(x, alpha):  # fast_lasso.py:15-19
+    return np.maximum(np.abs(x) - alpha, 0.0) * np.sign(x)
+
+
+def fista(beta, X, y, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_iter=5000,
+          dtype=np.float64, return_info=False):
+    """FISTA for 0.5*||y - X b||^2 + lam*||b||_1 with backtracking (fast_lasso.py:22-69).
+
+    Scalar types follow the reference call (algorithms.py:199-201) under numpy >= 2:
+    L, eta are np.float32 so `L_cur = L_prev*(eta**i_k)` is a float32 product and
+    `lam/L_cur` is a float32 quotient; tensor arithmetic is in `dtype`.
+    """
+    dt = np.dtype(dtype)
+    X = np.asarray(X, dtype=dt)
+    y = np.asarray(y, dtype=dt).reshape(-1)
+    b = np.asarray(beta, dtype=dt).reshape(-1).copy()
+    b_p = b.copy()
+    b_prev = b.copy()
+    t = dt.type(1.0)
+    L_prev = L
+    n_pass = 0
+    k = 0
+    for k in range(max_iter):
+        r = y - X @ b_p
+        drbp = r @ r
+        g = X.T @ r
+        n_pass += 2
+        i_k = -1
+        while True:
+            i_k += 1
+            L_cur = L_prev * (eta ** i_k)
+            thr = lam / L_cur                      # float32 when L is float32 (NEP 50)
+            b = soft_thr(b_p + g / dt.type(L_cur), dt.type(thr)).astype(dt, copy=False)
+            diff = b - b_p
+            rhs = dt.type(L_cur) * (diff @ diff) - dt.type(2.0) * (diff @ g)
+            rr = y - X @ b
+            n_pass += 1
+            lhs = rr @ rr - drbp
+            if not (lhs > rhs):
+                break
+        L_prev = L_cur
+        tnext = (dt.type(1.0) + np.sqrt(dt.type(1.0) + dt.type(4.0) * t * t)) / dt.type(2.0)
+        diff = b - b_prev
+        t1 = (t - dt.type(1.0)) / tnext
+        b_p = b + t1 * diff
+        crit = np.sqrt(diff @ diff)
+        if crit < tol:
+            break
+        t = tnext
+        b_prev = b
+    if return_info:
+        return b, {"iters": k + 1, "passes": n_pass, "L": float(L_prev)}
+    return b
+
+
+# ---------------------------------------------------------------------------------------
+# w-step, l2 — w_LBFGS.py:31-53
+# ---------------------------------------------------------------------------------------
+def w_step_l2(w0, z, lam, rho, D, reg, DTD=None, return_info=False):
+    from scipy.optimize import minimize
+
+    b = (z.reshape(-1) + lam.reshape(-1) / rho)
+    DTb = D.T @ b
+
+    def f(w):  # wl2_fun :31-37
+        t = D @ w - b
+        return 0.5 * rho * float(t @ t) + 0.5 * reg * float(w @ w)
+
+    def g(w):  # wl2_fun_gradient :40-45
+        if DTD is not None:
+            return rho * (DTD @ w - DTb) + reg * w
+        return rho * (D.T @ (D @ w - b)) + reg * w
+
+    res = minimize(f, np.asarray(w0, dtype=np.float64).reshape(-1), jac=g, method="L-BFGS-B",
+                   options={"maxiter": 1000})
+    if return_info:
+        return res.x, {"nit": res.nit, "nfev": res.nfev}
+    return res.x
+
+
+# ---------------------------------------------------------------------------------------
+# full loop — algorithms.py:20-75 (state), :119-164 (iteration), :190-216 (ADMMmethod)
+# ---------------------------------------------------------------------------------------
+class OracleADMM:
+    def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
+                 B=None, args=None, w0=None, max_iter=200, tol=1e-4, fista_dtype=np.float64, use_gram=True):
+        X = np.asarray(X, dtype=np.float64)
+        y = np.asarray(y).reshape(-1, 1)
+        self.D = np.ascontiguousarray(-y * X)  # :23
+        self.n, self.d = X.shape
+        self.DTD = self.D.T @ self.D if (use_gram and l1_reg is None) else None  # :24 (only the l2 path reads it)
+        self.reg = l1_reg or l2_reg  # :30
+        self.l1_reg, self.l2_reg = l1_reg, l2_reg
+        self.lam = 0.1 * self.reg / self.n * np.ones(self.n)  # :32
+        self.z = 0.1 * self.reg / self.n * np.ones(self.n)  # :34
+        self.loss = loss
+        self.w = (np.asarray(w0, dtype=np.float64).reshape(-1).copy() if w0 is not None
+                  else 0.001 * self.reg / self.d / self.n * np.ones(self.d))  # :39-42
+        self.tol, self.max_iter = tol, max_iter
+        self.rho = 1e-4 if weight_function == "ehrm" else (2e-7 if weight_function in ("aorr", "aorr_dc") else 1e-5)  # :47-52
+        self.w_flag = 1 if l1_reg is not None else 2  # :55-62
+        if B is not None and weight_function != "ehrm":
+            raise ValueError(f"Unrecognized weight_function '{weight_function}'! Options: ['ehrm']")
+        self.B = B
+        sig = spectrum(weight_function, self.n, args)
+        self.sigma_a, self.sigma_b = sig if isinstance(sig, tuple) else (sig, sig)
+        self.weight_function = weight_function
+        self.fista_dtype = fista_dtype
+        self.primal = self.dual = float("inf")
+        self.iters = 0
+        self.passes = 0
+
+    def objective(self, w=None):
+        return objective(self.D, self.w if w is None else w, self.sigma_a, self.loss, self.l2_reg, self.l1_reg)
+
+    def z_step(self):
+        return z_step(self.D, self.w, self.lam, self.rho, self.sigma_a, self.loss,
+                      B=self.B if self.weight_function == "ehrm" else None, sigma_b=self.sigma_b)
+
+    def w_step(self):
+        if self.w_flag == 1:  # algorithms.py:190-202 (FISTA branch; the tiny-problem sklearn branch is out of scope)
+            b = self.z + self.lam / self.rho
+            alpha = self.reg / (2 * self.rho * self.n)
+            w, info = fista(self.w, self.D, b, alpha * self.n, np.float32(17), np.float32(2.5), tol=7e-5,
+                            max_iter=5000, dtype=self.fista_dtype, return_info=True)
+            self.passes += info["passes"]
+            return w.astype(np.float64) if self.fista_dtype == np.float64 else w
+        w, info = w_step_l2(self.w, self.z, self.lam, self.rho, self.D, self.reg, self.DTD, return_info=True)
+        self.passes += 2 * info["nfev"]
+        return w
+
+    def step(self):
+        """one Optimizer.main_loop body (:119-164); returns True on convergence."""
+        self.z = self.z_step()
+        pre_w = self.w.copy()
+        self.w = self.w_step()
+        Dw = self.D @ self.w
+        self.lam = self.lam + self.rho * (self.z - Dw)  # :132
+        self.primal = float(np.linalg.norm(self.z - Dw))  # :135
+        self.dual = float(np.linalg.norm(self.w - pre_w))  # :136
+        self.iters += 1
+        if self.primal < self.tol and self.dual < self.tol:
+            return True
+        mult = 1.02 if self.primal > 1e-2 else 1.07  # :153-157 (the :148-152 branches are dead)
+        # np.min returns np.float64: from the 2nd iteration on `lam/L_cur` in FISTA is a float64
+        # quotient, in iteration 0 (python-float rho) it is a float32 one (NEP 50) — kept as is.
+        self.rho = np.min((self.rho * mult, 217 * self.d))
+        return False
+
+    def main_loop(self):
+        for _ in range(self.max_iter):
+            if self.step():
+                break
+        return self.w

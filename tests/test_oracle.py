@@ -1,0 +1,184 @@
+"""CPU: the restated oracle (oracle/rbl_oracle.py, oracle/pav_oracle.c) against golden vectors
+produced by the reference itself (oracle/gen_golden.py) and against known-answer identities
+(SURVEY.md §4).  Tolerances are stated per test with the reason."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import rbl_oracle as O
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _args(s):
+    return None if s == "" else [float(a) if "." in a else int(a) for a in s.split(",")]
+
+
+def test_spectra_match_reference(golden_dir):
+    g = _load(golden_dir, "spectra.npz")
+    for key in g.files:
+        parts = key.split("|")
+        name, args, n = parts[0], _args(parts[1]), int(parts[2])
+        s = O.spectrum(name, n, args)
+        if name == "ehrm":
+            s = s[0] if parts[3] == "a" else s[1]
+        # same formulas on the same libm: exact up to pow/exp rounding
+        np.testing.assert_allclose(s, g[key], rtol=1e-14, atol=1e-18, err_msg=key)
+
+
+def test_spectra_sum_to_one():
+    for name, args in [("erm", None), ("extremile", [2.0]), ("superquantile", [0.8]), ("esrm", [1.5])]:
+        assert abs(O.spectrum(name, 1000, args).sum() - 1) < 1e-12
+    a, b = O.spectrum("ehrm", 500)
+    assert abs(a.sum() - 1) < 1e-12 and abs(b.sum() - 1) < 1e-12
+
+
+def test_zstep_matches_reference(golden_dir):
+    g = _load(golden_dir, "zstep.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    D = -d["y"] * d["X"]
+    n = D.shape[0]
+    for ci in range(int(g["ncases"])):
+        wf, args, loss, B, rho = g[f"c{ci}_meta"]
+        args, B, rho = _args(args), (None if B == "" else float(B)), float(rho)
+        sig = O.spectrum(wf, n, args)
+        sa, sb = sig if isinstance(sig, tuple) else (sig, sig)
+        z = O.z_step(D, g[f"c{ci}_w"], g[f"c{ci}_lam"], rho, sa, loss, B=B, sigma_b=sb)
+        ref = g[f"c{ci}_ref_z"]
+        err = np.linalg.norm(z - ref) / np.linalg.norm(ref)
+        if loss == "hinge":
+            # reference hinge prox = 50-step bisection with a global early exit
+            # (individual_solver.py:15-42): inexact by construction -> loose pin (SURVEY §8a iii)
+            assert err < 1e-4, (ci, err)
+        else:
+            # reference Newton stops at ||delta||_2 < 1e-6 (individual_solver.py:103) or 1e-4
+            # (PAV_cpt.py:72): its own z is accurate to ~1e-9 only
+            assert err < 5e-9, (ci, wf, err)
+
+
+def test_prox_matches_reference_and_stationarity(golden_dir):
+    g = _load(golden_dir, "prox.npz")
+    m, s = g["m"], g["sigma"]
+    for rho in (1e-4, 1e-2, 1.0):
+        z = O.prox_vec("binary_cross_entropy", s, m, rho)
+        np.testing.assert_allclose(z, g[f"ref_bce_{rho}"], rtol=1e-8, atol=1e-9)
+        sg = 1 / (1 + np.exp(-z))
+        step = np.abs(s * sg + rho * (z - m)) / (s * sg * (1 - sg) + rho)
+        assert step.max() < 1e-13 * max(1.0, np.abs(m).max())
+        zh = O.prox_vec("hinge", s, m, rho)
+        closed = np.where(m < -1, m, np.where(m - s / rho > -1, m - s / rho, -1.0))
+        np.testing.assert_array_equal(zh, closed)
+        np.testing.assert_allclose(zh, g[f"ref_hinge_{rho}"], atol=1e-4)
+
+
+def test_pav_known_answers():
+    rng = np.random.default_rng(3)
+    n = 500
+    m = np.sort(rng.normal(size=n))
+    # sigma = 0  =>  z = m exactly
+    np.testing.assert_array_equal(O.pav_prox("binary_cross_entropy", np.zeros(n), m, 0.1), m)
+    # ERM => zero merges (prox monotone in m for equal sigma)
+    z, nb = O.pav_prox("binary_cross_entropy", np.ones(n) / n, m, 1e-3, return_blocks=True)
+    assert nb == n and np.all(np.diff(z) >= 0)
+    # superquantile at tiny rho: one giant block around the sigma jump
+    sig = O.spectrum("superquantile", n, [0.8])
+    z, nb = O.pav_prox("binary_cross_entropy", sig, m * 1e-3, 1e-5, return_blocks=True)
+    assert nb < n and np.all(np.diff(z) >= 0)
+
+
+@pytest.mark.parametrize("loss", ["binary_cross_entropy", "hinge"])
+def test_pav_equals_minmax_formula(loss):
+    rng = np.random.default_rng(5)
+    for trial in range(30):
+        n = int(rng.integers(1, 14))
+        m = np.sort(rng.normal(size=n) * 2)
+        sig = np.abs(rng.normal(size=n)) * (rng.random(n) > 0.3)
+        rho = 10 ** rng.uniform(-2, 1)
+        z = O.pav_prox(loss, sig, m, rho)
+        zb = O.pav_prox_minmax(loss, sig, m, rho)
+        np.testing.assert_allclose(z, zb, rtol=1e-12, atol=1e-12)
+
+
+def test_fista_matches_reference(golden_dir):
+    g = _load(golden_dir, "fista.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    D = -d["y"] * d["X"]
+    for lam in (0.5, 20.0, 300.0):
+        w = O.fista(g["w0"], D, g["b"], lam)                    # python-float lam: float32 threshold
+        np.testing.assert_allclose(w, g[f"ref_f64_{lam}"], rtol=1e-11, atol=1e-14)
+        w = O.fista(g["w0"], D, g["b"], np.float64(lam))        # np.float64 lam: float64 threshold
+        np.testing.assert_allclose(w, g[f"ref_f64_np_{lam}"], rtol=1e-11, atol=1e-14)
+        # float32 FISTA as shipped (algorithms.py:201) is chaotic at its own tolerance: the
+        # line-search test sits at rounding level, L_cur overflows float32 (SURVEY §8a vii) and
+        # the answer is ~1e-2 away from the float64 one.  Loose pin only.
+        with np.errstate(all="ignore"):
+            w32 = O.fista(g["w0"], D, g["b"], lam, dtype=np.float32)
+        ref32 = g[f"ref_f32_{lam}"]
+        assert np.linalg.norm(w32 - ref32) <= 2e-2 * np.linalg.norm(ref32) + 1e-6
+
+
+def test_l2_step_matches_reference(golden_dir):
+    g = _load(golden_dir, "l2step.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    D = -d["y"] * d["X"]
+    for rho in (1e-5, 1e-2, 1.0):
+        w = O.w_step_l2(g["w0"], g["z"], g["lam"], rho, D, 0.01, D.T @ D)
+        np.testing.assert_allclose(w, g[f"ref_{rho}"], rtol=1e-10, atol=1e-13)
+
+
+def test_objective_matches_reference(golden_dir):
+    g = _load(golden_dir, "objective.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    D = -d["y"] * d["X"]
+    n = D.shape[0]
+    for wf, args, loss, kw in [("erm", None, "binary_cross_entropy", dict(l1_reg=0.01)),
+                               ("superquantile", [0.8], "binary_cross_entropy", dict(l2_reg=0.01)),
+                               ("aorr", [0.2, 0.8], "hinge", dict(l2_reg=1e-4)),
+                               ("ehrm", None, "binary_cross_entropy", dict(l2_reg=0.01)),
+                               ("esrm", [1.5], "hinge", dict(l1_reg=0.1))]:
+        sig = O.spectrum(wf, n, args)
+        sa = sig[0] if isinstance(sig, tuple) else sig
+        v = O.objective(D, g["w"], sa, loss, **kw)
+        assert abs(v - float(g[f"ref_{wf}_{loss}"])) < 1e-13 * max(1, abs(v))
+
+
+def test_trajectories_track_reference(golden_dir):
+    g = _load(golden_dir, "trajectory.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    tags = sorted({k[:-5] for k in g.files if k.endswith("_meta")})
+    assert len(tags) == 7
+    for tag in tags:
+        wf, args, loss, B, kw = g[f"{tag}_meta"]
+        args, B, kw = _args(args), (None if B == "" else float(B)), eval(kw)
+        o = O.OracleADMM(d["X"], d["y"], wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
+        for i in range(40):
+            o.step()
+            if f"{tag}_w_{i+1}" in g.files:
+                ew = np.linalg.norm(o.w - g[f"{tag}_w_{i+1}"]) / np.linalg.norm(g[f"{tag}_w_{i+1}"])
+                ez = np.linalg.norm(o.z - g[f"{tag}_z_{i+1}"]) / np.linalg.norm(g[f"{tag}_z_{i+1}"])
+                assert abs(float(o.rho) - float(g[f"{tag}_rho_{i+1}"])) <= 1e-15 * float(o.rho)
+                # the reference's inner solvers are inexact (Newton 1e-6/1e-4, FISTA 7e-5, L-BFGS
+                # pgtol 1e-5): early iterates agree to ~1e-9, later ones drift with branch flips
+                tol = 2e-8 if i + 1 <= 3 else 1e-5
+                assert ew < tol and ez < tol, (tag, i + 1, ew, ez)
+        assert abs(o.objective() - float(g[f"{tag}_obj"])) < 1e-7, tag
+
+
+def test_xlsx_iteration0_objective_pin():
+    """table/erm_synthetic_6000x1000_l1_binary_cross_entropy.xlsx row 1 col 1 (run_SRM.py:21-36):
+    the only number the reference ships for this path; reproduces bit-exactly."""
+    from sklearn import preprocessing
+    from sklearn.datasets import make_classification
+    from sklearn.model_selection import train_test_split
+
+    X, label = make_classification(n_samples=10000, n_features=1000, n_classes=2, random_state=17)
+    label[label == 0] = -1
+    X = preprocessing.scale(X)
+    Xtr, _, ytr, _ = train_test_split(X, label.reshape(-1, 1), test_size=0.4, random_state=17)
+    n, d = Xtr.shape
+    w0 = 0.001 * 0.01 / d / n * np.ones(d)
+    v = O.objective(-ytr * Xtr, w0, O.spectrum("erm", n), "binary_cross_entropy", l1_reg=0.01)
+    assert abs(v - 0.6931471805674658) < 5e-16
