@@ -133,9 +133,17 @@ def main():
         ("aorr_bce_l2", "aorr", [0.2, 0.8], "binary_cross_entropy", None, dict(l2_reg=1e-4)),
         ("ehrm_l2", "ehrm", None, "binary_cross_entropy", -5, dict(l2_reg=0.01)),
     ]
+    # l1 runs on 300x40 take the reference's sklearn-Lasso branch (n<=500 and d<=60,
+    # algorithms.py:194-197); the FISTA branch needs a bigger problem: 600x64.
+    X2, y2 = ns.load_data.get_data("synthetic", num_row=1000, num_feature=64, seed=17)
+    X2tr, _, y2tr, _ = train_test_split(X2, y2, test_size=0.4, random_state=17)
+    np.savez_compressed(os.path.join(OUT, "data_600x64.npz"), X=X2tr, y=y2tr)
+    runs += [("erm_l1_fista", "erm", None, "binary_cross_entropy", None, dict(l1_reg=0.01)),
+             ("sq_l1_fista", "superquantile", [0.8], "binary_cross_entropy", None, dict(l1_reg=0.01))]
     snaps = (1, 2, 3, 10, 40)
     for tag, wf, args, loss, B, kw in runs:
-        s = ns.algorithms.ADMMmethod(Xtr, ytr, wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
+        Xa, ya = (X2tr, y2tr) if tag.endswith("_fista") else (Xtr, ytr)
+        s = ns.algorithms.ADMMmethod(Xa, ya, wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
         t0 = time.time()
         for i in range(40):
             with ref_shim.quiet():

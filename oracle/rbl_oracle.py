@@ -314,7 +314,8 @@ def w_step_l2(w0, z, lam, rho, D, reg, DTD=None, return_info=False):
 # ---------------------------------------------------------------------------------------
 class OracleADMM:
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
-                 B=None, args=None, w0=None, max_iter=200, tol=1e-4, fista_dtype=np.float64, use_gram=True):
+                 B=None, args=None, w0=None, max_iter=200, tol=1e-4, fista_dtype=np.float64, use_gram=True,
+                 small_lasso=True):
         X = np.asarray(X, dtype=np.float64)
         y = np.asarray(y).reshape(-1, 1)
         self.D = np.ascontiguousarray(-y * X)  # :23
@@ -337,6 +338,7 @@ class OracleADMM:
         self.sigma_a, self.sigma_b = sig if isinstance(sig, tuple) else (sig, sig)
         self.weight_function = weight_function
         self.fista_dtype = fista_dtype
+        self.small_lasso = small_lasso
         self.primal = self.dual = float("inf")
         self.iters = 0
         self.passes = 0
@@ -349,9 +351,15 @@ class OracleADMM:
                       B=self.B if self.weight_function == "ehrm" else None, sigma_b=self.sigma_b)
 
     def w_step(self):
-        if self.w_flag == 1:  # algorithms.py:190-202 (FISTA branch; the tiny-problem sklearn branch is out of scope)
+        if self.w_flag == 1:  # algorithms.py:190-202
             b = self.z + self.lam / self.rho
             alpha = self.reg / (2 * self.rho * self.n)
+            if self.n <= 500 and self.d <= 60 and self.small_lasso:  # :194-197 tiny-problem branch
+                from sklearn.linear_model import Lasso
+
+                mdl = Lasso(alpha=alpha, tol=1e-8, fit_intercept=False, max_iter=50000, warm_start=True)
+                mdl.fit(X=self.D, y=b)
+                return mdl.coef_.reshape(-1).astype(np.float64)
             w, info = fista(self.w, self.D, b, alpha * self.n, np.float32(17), np.float32(2.5), tol=7e-5,
                             max_iter=5000, dtype=self.fista_dtype, return_info=True)
             self.passes += info["passes"]

@@ -149,12 +149,14 @@ def test_objective_matches_reference(golden_dir):
 
 def test_trajectories_track_reference(golden_dir):
     g = _load(golden_dir, "trajectory.npz")
-    d = _load(golden_dir, "data_300x40.npz")
+    d1 = _load(golden_dir, "data_300x40.npz")
+    d2 = _load(golden_dir, "data_600x64.npz")
     tags = sorted({k[:-5] for k in g.files if k.endswith("_meta")})
-    assert len(tags) == 7
+    assert len(tags) == 9
     for tag in tags:
         wf, args, loss, B, kw = g[f"{tag}_meta"]
         args, B, kw = _args(args), (None if B == "" else float(B)), eval(kw)
+        d = d2 if tag.endswith("_fista") else d1  # 300x40 + l1 = the reference's sklearn-Lasso branch
         o = O.OracleADMM(d["X"], d["y"], wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
         for i in range(40):
             o.step()
