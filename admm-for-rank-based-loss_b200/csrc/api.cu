@@ -1,0 +1,358 @@
+// api.cu — the C ABI declared in include/rbl_b200.h: handle, scratch, and thin launch wrappers.
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/rbl_b200.h"
+#include "common.cuh"
+
+// launchers defined in the kernel translation units
+int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, cudaStream_t s);
+int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStream_t s);
+int rbl_k_fista_update(rbl_ctx* c, cudaStream_t s);
+int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s);
+int rbl_k_margins(rbl_ctx* c, const double* Dw, const double* lam, double rho, double* m, cudaStream_t s);
+int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_clip, double clip, const double* lam,
+                  double rho, double* z, double* b, cudaStream_t s);
+int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const double* r, int from_residual,
+               double* lam, double rho, const double* w, const double* w_prev, double* out4, cudaStream_t s);
+int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
+                    cudaStream_t s);
+int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s);
+int rbl_sort_tiles(int64_t n);
+int rbl_pav_chunk_log2();
+int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double* loc_lo, double* tot_hi,
+                 double* tot_lo, double* off_hi, double* off_lo, cudaStream_t s);
+int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* z_sorted, cudaStream_t s);
+int rbl_k_prox_elementwise(rbl_ctx* c, int loss, const double* sigma, const double* m, int64_t n, double rho,
+                           double* out, cudaStream_t s);
+
+static thread_local char g_err[512] = "";
+long long g_rbl_launches = 0;
+
+void rbl_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+template <class T>
+int dev_alloc(rbl_ctx* c, T** p, size_t count) {
+    const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    RBL_CUDA(cudaMalloc((void**)p, bytes));
+    RBL_CUDA(cudaMemset(*p, 0, bytes));
+    c->bytes += bytes;
+    return RBL_OK;
+}
+
+#define RBL_TRY(x)                  \
+    do {                            \
+        int rc__ = (x);             \
+        if (rc__ != RBL_OK) return rc__; \
+    } while (0)
+
+int ctx_alloc(rbl_ctx* c) {
+    const size_t nl = (size_t)c->n_local, ng = (size_t)c->n_global, ld = (size_t)c->ld;
+    RBL_TRY(dev_alloc(c, &c->gpart, (size_t)c->pass_grid * ld));
+    RBL_TRY(dev_alloc(c, &c->sspart, (size_t)c->pass_grid));
+    RBL_TRY(dev_alloc(c, &c->vpart, (size_t)4 * c->vec_grid));
+    RBL_TRY(dev_alloc(c, &c->fista, 1));
+    RBL_CUDA(cudaMallocHost((void**)&c->fista_host, 2 * sizeof(FistaState)));
+    RBL_TRY(dev_alloc(c, &c->pow_tab, 128));
+    RBL_TRY(dev_alloc(c, &c->beta, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->beta_p, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->beta_prev, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->g_p, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->g_prev, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->rbuf[0], nl));
+    RBL_TRY(dev_alloc(c, &c->rbuf[1], nl));
+    RBL_TRY(dev_alloc(c, &c->red_own, ld + 8));
+    c->red = c->red_own;
+    RBL_TRY(dev_alloc(c, &c->c0part, (size_t)c->vec_grid));
+    c->sort_tiles = rbl_sort_tiles(c->n_global);
+    RBL_TRY(dev_alloc(c, &c->keysA, ng));
+    RBL_TRY(dev_alloc(c, &c->keysB, ng));
+    RBL_TRY(dev_alloc(c, &c->valsA, ng));
+    RBL_TRY(dev_alloc(c, &c->valsB, ng));
+    RBL_TRY(dev_alloc(c, &c->tile_hist, (size_t)256 * c->sort_tiles + 8));
+    c->chunk_log2 = rbl_pav_chunk_log2();
+    c->nchunks = (c->n_global + ((int64_t)1 << c->chunk_log2) - 1) >> c->chunk_log2;
+    const size_t nch = (size_t)c->nchunks;
+    RBL_TRY(dev_alloc(c, &c->ps_loc_hi, ng + 1));
+    RBL_TRY(dev_alloc(c, &c->ps_loc_lo, ng + 1));
+    RBL_TRY(dev_alloc(c, &c->ps_off_hi, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->ps_off_lo, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->ps_tot_hi, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->ps_tot_lo, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->pm_loc_hi, ng + 1));
+    RBL_TRY(dev_alloc(c, &c->pm_loc_lo, ng + 1));
+    RBL_TRY(dev_alloc(c, &c->pm_off_hi, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->pm_off_lo, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->ch_tot_hi, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->ch_tot_lo, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->sigma, ng));
+    RBL_TRY(dev_alloc(c, &c->obj_tmp, ng));
+    return RBL_OK;
+}
+
+void ctx_free(rbl_ctx* c) {
+    void* ptrs[] = {c->gpart,     c->sspart,    c->vpart,     c->fista,     c->pow_tab,   c->beta,      c->beta_p,
+                    c->beta_prev, c->g_p,       c->g_prev,    c->rbuf[0],   c->rbuf[1],   c->red_own,   c->c0part,
+                    c->keysA,     c->keysB,     c->valsA,     c->valsB,     c->tile_hist, c->ps_loc_hi, c->ps_loc_lo,
+                    c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
+                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+    if (c->fista_host) cudaFreeHost(c->fista_host);
+}
+
+inline cudaStream_t S(rbl_stream_t s) { return (cudaStream_t)s; }
+
+}  // namespace
+
+#define RBL_ENTER(h)                                         \
+    RBL_REQUIRE((h) != nullptr, "null handle");              \
+    RBL_CUDA(cudaSetDevice((h)->device))
+
+extern "C" {
+
+int rbl_version(void) { return RBL_ABI_VERSION; }
+
+const char* rbl_last_error(void) { return g_err; }
+
+int64_t rbl_launch_count(void) { return (int64_t)g_rbl_launches; }
+
+int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global, int64_t row_lo, int32_t d,
+               int64_t ld) {
+    RBL_REQUIRE(out != nullptr, "out is null");
+    *out = nullptr;
+    RBL_REQUIRE(n_local > 0 && n_global >= n_local && row_lo >= 0 && row_lo + n_local <= n_global,
+                "bad row partition: n_local=%lld n_global=%lld row_lo=%lld", (long long)n_local, (long long)n_global,
+                (long long)row_lo);
+    RBL_REQUIRE(n_global < ((int64_t)1 << 31), "n_global must fit int32 permutation indices");
+    RBL_REQUIRE(d > 0 && ld >= d, "bad d/ld: d=%d ld=%lld", d, (long long)ld);
+    int ndev = 0;
+    RBL_CUDA(cudaGetDeviceCount(&ndev));
+    RBL_REQUIRE(device >= 0 && device < ndev, "no CUDA device %d (found %d); this library has no CPU path", device,
+                ndev);
+    RBL_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    RBL_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        rbl_set_error("device %d is sm_%d%d; librbl_b200 is built for sm_100a (B200) only", device, prop.major,
+                      prop.minor);
+        return RBL_ERR_UNSUPPORTED;
+    }
+    rbl_ctx* c = new rbl_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->n_local = n_local;
+    c->n_global = n_global;
+    c->row_lo = row_lo;
+    c->d = d;
+    c->ld = ld;
+    c->vec_grid = c->num_sms * 4;
+    int rc = rbl_pass_configure(c);
+    if (rc == RBL_OK) rc = ctx_alloc(c);
+    if (rc != RBL_OK) {
+        ctx_free(c);
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return RBL_OK;
+}
+
+int rbl_destroy(rbl_handle_t h) {
+    if (!h) return RBL_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    ctx_free(h);
+    delete h;
+    return RBL_OK;
+}
+
+int rbl_info(rbl_handle_t h, int64_t* o) {
+    RBL_REQUIRE(h && o, "null argument");
+    o[0] = h->num_sms;
+    o[1] = h->pass_grid;
+    o[2] = h->pass_rows;
+    o[3] = h->pass_stages;
+    o[4] = (int64_t)h->pass_smem;
+    o[5] = (int64_t)h->bytes;
+    o[6] = h->vec_grid;
+    o[7] = (int64_t)1 << h->chunk_log2;
+    return RBL_OK;
+}
+
+int rbl_build_design(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(X && y && D && ldx >= h->d, "bad arguments");
+    return rbl_k_build_design(h, X, ldx, y, D, S(stream));
+}
+
+int rbl_set_spectrum(rbl_handle_t h, const double* sigma, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(sigma != nullptr, "sigma is null");
+    RBL_CUDA(cudaMemcpyAsync(h->sigma, sigma, (size_t)h->n_global * sizeof(double), cudaMemcpyDeviceToDevice,
+                             S(stream)));
+    RBL_TRY(rbl_k_prefix(h, h->sigma, h->n_global, h->ps_loc_hi, h->ps_loc_lo, h->ps_tot_hi, h->ps_tot_lo,
+                         h->ps_off_hi, h->ps_off_lo, S(stream)));
+    h->has_sigma = 1;
+    return RBL_OK;
+}
+
+int rbl_matvec(rbl_handle_t h, const double* D, const double* x, double* out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && x && out, "null argument");
+    return rbl_launch_pass(h, RBL_PASS_MATVEC, D, x, nullptr, out, nullptr, nullptr, S(stream));
+}
+
+int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho, double* m, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(Dw && lam && m, "null argument");
+    return rbl_k_margins(h, Dw, lam, rho, m, S(stream));
+}
+
+int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(m && (m_sorted || perm), "null argument");
+    return rbl_k_sort(h, m, h->n_global, m_sorted, perm, S(stream));
+}
+
+int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, double* z_sorted,
+                 rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(m_sorted && z_sorted, "null argument");
+    RBL_REQUIRE(h->has_sigma, "rbl_set_spectrum must be called before rbl_pav_prox");
+    RBL_REQUIRE(loss == RBL_LOSS_BINARY_CROSS_ENTROPY || loss == RBL_LOSS_HINGE, "unknown loss id %d", loss);
+    RBL_REQUIRE(rho > 0.0, "rho must be positive");
+    return rbl_k_pav(h, loss, m_sorted, rho, z_sorted, S(stream));
+}
+
+int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const double* m, int64_t n, double rho,
+                         double* out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(sigma && m && out && n >= 0, "bad arguments");
+    RBL_REQUIRE(loss == RBL_LOSS_BINARY_CROSS_ENTROPY || loss == RBL_LOSS_HINGE, "unknown loss id %d", loss);
+    RBL_REQUIRE(rho > 0.0, "rho must be positive");
+    return rbl_k_prox_elementwise(h, loss, sigma, m, n, rho, out, S(stream));
+}
+
+int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, int use_clip, double clip,
+                  const double* lam, double rho, double* z, double* b, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(z_sorted && perm && z && (b == nullptr || lam != nullptr), "null argument");
+    return rbl_k_scatter(h, z_sorted, perm, use_clip, clip, lam, rho, z, b, S(stream));
+}
+
+int rbl_fused_pass(rbl_handle_t h, const double* D, const double* x, const double* b, double* r, double* red,
+                   rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && x && b && r && red, "null argument");
+    RBL_TRY(rbl_launch_pass(h, RBL_PASS_FUSED, D, x, b, r, nullptr, nullptr, S(stream)));
+    RBL_TRY(rbl_k_reduce_partials(h, 0, nullptr, S(stream)));
+    RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 2) * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    return RBL_OK;
+}
+
+int rbl_fista_config(rbl_handle_t h, const float* h_pow_tab) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(h_pow_tab != nullptr, "null table");
+    RBL_CUDA(cudaMemcpy(h->pow_tab, h_pow_tab, 128 * sizeof(float), cudaMemcpyHostToDevice));
+    return RBL_OK;
+}
+
+int rbl_fista_begin(rbl_handle_t h, const double* w0, double lam, int thr_f32, float L0, double tol, int max_iter,
+                    rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(w0 != nullptr && max_iter > 0, "bad arguments");
+    FistaState* st = &h->fista_host[1];  // staging slot ([0] is the poll mirror)
+    memset(st, 0, sizeof(*st));
+    st->t = 1.0;
+    st->tol = tol;
+    st->lam = lam;
+    st->L_prev = L0;
+    st->L_cur = L0;
+    st->k = -1;
+    st->max_iter = max_iter;
+    st->thr_f32 = thr_f32;
+    RBL_CUDA(cudaMemcpyAsync(h->fista, st, sizeof(FistaState), cudaMemcpyHostToDevice, S(stream)));
+    RBL_CUDA(cudaMemcpyAsync(h->beta, w0, (size_t)h->d * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    return RBL_OK;
+}
+
+int rbl_fista_pass(rbl_handle_t h, const double* D, const double* b, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && b, "null argument");
+    RBL_TRY(rbl_launch_pass(h, RBL_PASS_FISTA, D, h->beta, b, nullptr, h->fista, h->rbuf, S(stream)));
+    return rbl_k_reduce_partials(h, 1, h->fista, S(stream));
+}
+
+int rbl_fista_bind_red(rbl_handle_t h, double* red) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    h->red = red ? red : h->red_own;
+    return RBL_OK;
+}
+
+int rbl_fista_update(rbl_handle_t h, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    return rbl_k_fista_update(h, S(stream));
+}
+
+int rbl_fista_steps(rbl_handle_t h, const double* D, const double* b, int nsteps, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && b && nsteps > 0, "bad arguments");
+    for (int i = 0; i < nsteps; ++i) {
+        RBL_TRY(rbl_launch_pass(h, RBL_PASS_FISTA, D, h->beta, b, nullptr, h->fista, h->rbuf, S(stream)));
+        RBL_TRY(rbl_k_reduce_partials(h, 1, h->fista, S(stream)));
+        RBL_TRY(rbl_k_fista_update(h, S(stream)));
+    }
+    return RBL_OK;
+}
+
+int rbl_fista_poll(rbl_handle_t h, rbl_stream_t stream, int32_t* hi, double* hd) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(hi && hd, "null argument");
+    RBL_CUDA(cudaMemcpyAsync(&h->fista_host[0], h->fista, sizeof(FistaState), cudaMemcpyDeviceToHost, S(stream)));
+    RBL_CUDA(cudaStreamSynchronize(S(stream)));
+    const FistaState& st = h->fista_host[0];
+    hi[0] = st.done;
+    hi[1] = st.k;
+    hi[2] = st.passes;
+    hi[3] = st.trials;
+    hi[4] = st.i_k;
+    hi[5] = st.cur;
+    hd[0] = st.crit;
+    hd[1] = (double)st.L_prev;
+    hd[2] = st.t;
+    hd[3] = st.ss_last;
+    return RBL_OK;
+}
+
+int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    return rbl_k_fista_result(h, w_out, r_out, S(stream));
+}
+
+int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,
+                    int from_residual, double* lam, double rho, const double* w, const double* w_prev, double* out4,
+                    rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(z && Dw && lam && out4, "null argument");
+    RBL_REQUIRE(!from_residual || (b && r), "from_residual needs b and r");
+    return rbl_k_dual(h, z, Dw, b, r, from_residual, lam, rho, w, w_prev, out4, S(stream));
+}
+
+int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double* sigma, const double* w,
+                  double* out4, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(margins && sigma && out4, "null argument");
+    RBL_TRY(rbl_k_sort(h, margins, h->n_global, h->obj_tmp, nullptr, S(stream)));
+    return rbl_k_objective(h, h->obj_tmp, sigma, loss, w, out4, S(stream));
+}
+
+}  // extern "C"

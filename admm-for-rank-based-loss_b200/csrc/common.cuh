@@ -1,0 +1,119 @@
+// common.cuh — internal declarations shared by the translation units of librbl_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "prox_core.h"
+
+#define RBL_OK 0
+#define RBL_ERR_CUDA 1
+#define RBL_ERR_ARG 2
+#define RBL_ERR_UNSUPPORTED 3
+
+void rbl_set_error(const char* fmt, ...);
+
+#define RBL_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) {                                                                   \
+            rbl_set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));    \
+            return RBL_ERR_CUDA;                                                                    \
+        }                                                                                           \
+    } while (0)
+
+extern long long g_rbl_launches;  // kernels launched by this process through the library
+#define RBL_LAUNCH_CHECK()             \
+    do {                               \
+        ++g_rbl_launches;              \
+        RBL_CUDA(cudaGetLastError());  \
+    } while (0)
+
+#define RBL_REQUIRE(cond, ...)                                                                      \
+    do {                                                                                            \
+        if (!(cond)) {                                                                              \
+            rbl_set_error(__VA_ARGS__);                                                             \
+            return RBL_ERR_ARG;                                                                     \
+        }                                                                                           \
+    } while (0)
+
+// ---- FISTA device-resident state (fast_lasso.py:22-69 control flow, kept on the device so the
+// host never has to synchronise inside the inner loop) ---------------------------------------------
+struct FistaState {
+    double t;        // momentum scalar (fast_lasso.py:39,59)
+    double c0;       // ||b - D beta_p||^2  (drbp, :42)
+    double rhs;      // L*||beta - beta_p||^2 - 2 (beta - beta_p).g_p  (:53)
+    double tol;
+    double lam;
+    double t1;       // (t-1)/tnext of the last accepted step (:61)
+    double crit;     // ||beta_k - beta_{k-1}||  (:63)
+    double ss_last;  // ||b - D beta||^2 of the last pass
+    float L_prev;    // np.float32 scalars, as the reference passes them (algorithms.py:199-200)
+    float L_cur;
+    int i_k;         // line-search index (:44-47)
+    int k;           // -1 before the initial pass, else outer iteration count
+    int max_iter;
+    int done;
+    int passes;      // D passes executed
+    int trials;      // line-search trials executed
+    int thr_f32;     // lam/L_cur evaluated in float32 (python-float lam under NEP 50) or float64
+    int accepted;    // set by the update kernel for the combine kernel: 0 none, 1 accepted, 2 init
+    int cur;         // which residual buffer the next pass writes (the other holds r at beta_prev)
+    int c0_from_red; // c0 must be taken from red[d+1] (written by the combine kernel)
+    int pad0, pad1;
+};
+
+// internal context behind rbl_handle_t
+struct rbl_ctx {
+    int device;
+    int num_sms;
+    int64_t n_local, n_global, row_lo;
+    int d;
+    int64_t ld;
+    // ---- pass kernels
+    int pass_grid;      // persistent CTAs
+    int pass_rows;      // rows per tile
+    int pass_stages;
+    size_t pass_smem;
+    double* gpart;      // [pass_grid][ld] per-CTA column partials
+    double* sspart;     // [pass_grid]
+    // ---- reductions of n-vectors
+    int vec_grid;
+    double* vpart;      // [4][vec_grid]
+    // ---- FISTA
+    FistaState* fista;      // device
+    FistaState* fista_host; // pinned mirror
+    float* pow_tab;         // device, 128 entries eta**i as float32
+    double *beta, *beta_p, *beta_prev, *g_p, *g_prev;  // d-vectors (ld padded)
+    double* rbuf[2];        // n_local residual buffers
+    double* red;            // [d + 2]: g (d), ss, c0 — internal (red_own) or bound by the host layer
+    double* red_own;
+    double* c0part;         // [vec_grid]
+    // ---- sort
+    uint64_t *keysA, *keysB;
+    uint32_t *valsA, *valsB;
+    uint32_t* tile_hist;    // [256 * ntiles] (+1)
+    int sort_tiles;
+    // ---- PAV
+    int chunk_log2;
+    int64_t nchunks;
+    double *ps_loc_hi, *ps_loc_lo, *ps_off_hi, *ps_off_lo;  // sigma prefixes (set once)
+    double *ps_tot_hi, *ps_tot_lo;                          // per-chunk totals of sigma
+    double *pm_loc_hi, *pm_loc_lo, *pm_off_hi, *pm_off_lo;  // margin prefixes (every z-step)
+    double *ch_tot_hi, *ch_tot_lo;                          // per-chunk totals scratch
+    double* sigma;          // n_global, rank order (the sigma the PAV uses: alphas, or betas for EHRM)
+    double* val;            // n_global block values
+    int has_sigma;
+    // ---- objective
+    double* obj_tmp;        // n_global
+    size_t bytes;           // total scratch allocated
+};
+
+// ---- launchers implemented in the kernel translation units --------------------------------------
+int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, const double* b, double* out,
+                    const FistaState* st, double* const* rbuf, cudaStream_t s);
+int rbl_pass_configure(rbl_ctx* c);
+
+#define RBL_PASS_MATVEC 0  // out = D x
+#define RBL_PASS_FUSED 1   // out = r = b - D x ; column partials of D^T r ; partial ||r||^2
+#define RBL_PASS_FISTA 2   // as FUSED with x = ctx->beta, out = rbuf[st->cur], skipped when st->done

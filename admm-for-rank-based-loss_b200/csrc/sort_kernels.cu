@@ -1,0 +1,192 @@
+// sort_kernels.cu — stable LSD radix sort of the fp64 margins with carried row indices.
+//
+// Replaces: np.argsort(m) + np.sort(m)  (src/optim/algorithms.py:92-93).  The reference's argsort is
+// numpy's unstable introsort; on tie-free keys it equals the stable permutation, which is the only
+// well-defined target under ties and what this sort produces (bit-exact vs np.argsort(kind="stable")).
+//
+// fp64 -> order-preserving u64 keys (-0.0 == +0.0, NaN last, prox_core.h), 8 passes of 8 bits.
+// Per pass: (1) per-tile digit histogram, (2) exclusive scan over [digit][tile] (digit-major so the
+// scan IS the global scatter base), (3) stable scatter: in-tile ranks by warp-level match_any
+// multisplit, per-warp digit counters in shared memory, no atomics, no inter-CTA spinning.
+// The first pass converts doubles on load and synthesises the index payload; the last pass writes the
+// sorted doubles and the int32 permutation directly.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kSortThreads = 256;
+constexpr int kItems = 16;
+constexpr int kTile = kSortThreads * kItems;  // 4096 keys per tile
+constexpr int kWarps = kSortThreads / 32;
+
+__device__ __forceinline__ uint64_t load_key(const void* src, int from_double, int64_t i) {
+    if (from_double) return rbl_key_from_bits(reinterpret_cast<const uint64_t*>(src)[i]);
+    return reinterpret_cast<const uint64_t*>(src)[i];
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __restrict__ keys, int from_double,
+                                                                  int64_t n, int shift, int ntiles,
+                                                                  uint32_t* __restrict__ tile_hist) {
+    __shared__ uint32_t h[256];
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const int64_t base = (int64_t)tile * kTile;
+#pragma unroll 4
+    for (int j = 0; j < kItems; ++j) {
+        const int64_t i = base + j * kSortThreads + tid;
+        if (i < n) atomicAdd(&h[(load_key(keys, from_double, i) >> shift) & 0xff], 1u);
+    }
+    __syncthreads();
+    tile_hist[(size_t)tid * ntiles + tile] = h[tid];
+}
+
+// exclusive scan of `count` uint32 in place, single CTA (count = 256 * ntiles <= ~1M at n = 16M)
+__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ a, int count) {
+    __shared__ uint32_t wsum[32];
+    __shared__ uint32_t carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < count; base += 1024 * 4) {
+        // each thread owns 4 consecutive entries
+        const int i0 = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (i0 + q < count) ? a[i0 + q] : 0u;
+        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        uint32_t x = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = wsum[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            wsum[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        uint32_t excl = carry + (warp ? wsum[warp - 1] : 0u) + (x - tsum);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (i0 + q < count) a[i0 + q] = excl;
+            excl += v[q];
+        }
+        __syncthreads();
+        if (tid == 1023) carry = carry + wsum[31];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
+    const void* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int from_double, int64_t n, int shift,
+    int ntiles, const uint32_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
+    uint32_t* __restrict__ vals_out, int last, double* __restrict__ sorted_out, int32_t* __restrict__ perm_out) {
+    __shared__ uint32_t cnt[kWarps][257];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x;
+    for (int q = tid; q < kWarps * 257; q += kSortThreads) (&cnt[0][0])[q] = 0;
+    __syncthreads();
+
+    // warp w owns the contiguous span [base + w*512, +512): round j covers 32 consecutive keys, so
+    // (warp, round, lane) order == original order inside the tile  => stable
+    const int64_t wbase = (int64_t)tile * kTile + (int64_t)warp * (kItems * 32);
+    uint64_t key[kItems];
+    uint32_t val[kItems];
+    uint16_t rank[kItems];
+    const uint32_t lt_mask = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        const bool ok = i < n;
+        key[j] = ok ? load_key(keys_in, from_double, i) : 0ull;
+        val[j] = ok ? (vals_in ? vals_in[i] : (uint32_t)i) : 0u;
+        const uint32_t dg = ok ? (uint32_t)((key[j] >> shift) & 0xff) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+        const int leader = __ffs(peers) - 1;
+        uint32_t basec = 0;
+        if (lane == leader) {
+            basec = cnt[warp][dg];
+            cnt[warp][dg] = basec + __popc(peers);
+        }
+        basec = __shfl_sync(0xffffffffu, basec, leader);
+        rank[j] = (uint16_t)(basec + __popc(peers & lt_mask));
+        __syncwarp();
+    }
+    __syncthreads();
+    // per digit: exclusive prefix over warps, seeded with this tile's global base for the digit
+    {
+        const int dg = tid;  // 256 threads == 256 digits
+        uint32_t run = tile_off[(size_t)dg * ntiles + tile];
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t c = cnt[w][dg];
+            cnt[w][dg] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kItems; ++j) {
+        const int64_t i = wbase + j * 32 + lane;
+        if (i < n) {
+            const uint32_t dg = (uint32_t)((key[j] >> shift) & 0xff);
+            const uint32_t pos = cnt[warp][dg] + rank[j];
+            if (last) {
+                if (sorted_out) reinterpret_cast<uint64_t*>(sorted_out)[pos] = rbl_bits_from_key(key[j]);
+                if (perm_out) perm_out[pos] = (int32_t)val[j];
+            } else {
+                keys_out[pos] = key[j];
+                vals_out[pos] = val[j];
+            }
+        }
+    }
+}
+
+}  // namespace
+
+int rbl_sort_tiles(int64_t n) { return (int)((n + kTile - 1) / kTile); }
+
+// sorted_out / perm_out may be null when only one of them is wanted (objective: keys only)
+int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s) {
+    if (n <= 0) return RBL_OK;
+    const int ntiles = rbl_sort_tiles(n);
+    if (ntiles > c->sort_tiles) {
+        rbl_set_error("sort of %lld keys exceeds the handle's capacity", (long long)n);
+        return RBL_ERR_ARG;
+    }
+    const void* kin = m;
+    const uint32_t* vin = nullptr;
+    uint64_t* kout = c->keysA;
+    uint32_t* vout = c->valsA;
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        const int from_double = pass == 0;
+        const int last = pass == 7;
+        radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, from_double, n, shift, ntiles, c->tile_hist);
+        RBL_LAUNCH_CHECK();
+        radix_scan_kernel<<<1, 1024, 0, s>>>(c->tile_hist, 256 * ntiles);
+        RBL_LAUNCH_CHECK();
+        radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, from_double, n, shift, ntiles, c->tile_hist,
+                                                            kout, vout, last, sorted_out, perm_out);
+        RBL_LAUNCH_CHECK();
+        kin = kout;
+        vin = vout;
+        if (kout == c->keysA) {
+            kout = c->keysB;
+            vout = c->valsB;
+        } else {
+            kout = c->keysA;
+            vout = c->valsA;
+        }
+    }
+    return RBL_OK;
+}

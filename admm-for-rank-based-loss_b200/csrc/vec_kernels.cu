@@ -1,0 +1,384 @@
+// vec_kernels.cu — n- and d-vector kernels of the ADMM loop: everything that is not a pass over D,
+// a sort or the PAV.  All reductions are two-stage with a fixed grid, so results are bit-reproducible
+// run to run and identical on every rank of a row-sharded job.
+//
+// Replaces: src/optim/algorithms.py:23 (D = -y*X), :89 (margins), :103-104 (scatter), :132-136 (dual
+// update + residual norms), src/util/fast_lasso.py:44-65 (FISTA line search / momentum / stop test —
+// here a device-resident state machine), src/optim/objective.py:71-87 (rank-weighted objective).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kVecThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// sum over the block, result valid in every thread; sh must hold >= 33 doubles
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double t = lane < nw ? sh[lane] : 0.0;
+        t = warp_sum(t);
+        if (lane == 0) sh[32] = t;
+    }
+    __syncthreads();
+    return sh[32];
+}
+
+// ---- D = -y (.) X with zero-filled padding columns (algorithms.py:23) ---------------------------
+__global__ void build_design_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y,
+                                    double* __restrict__ D, int64_t ld, int64_t n, int d) {
+    const int64_t total = n * ld;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = idx / ld;
+        const int c = (int)(idx - i * ld);
+        D[idx] = (c < d) ? -(y[i] * X[i * ldx + c]) : 0.0;
+    }
+}
+
+// ---- per-CTA partials of a pass -> red[0..d) = D^T r, red[d] = ||r||^2, red[d+1] = c0 -------------
+__global__ void reduce_partials_kernel(const double* __restrict__ gpart, const double* __restrict__ sspart,
+                                       const double* __restrict__ c0part, int nparts, int nc0, int64_t ld, int d,
+                                       double* __restrict__ red, const FistaState* st) {
+    if (st && st->done) return;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < d) {
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+        int k = 0;
+        for (; k + 3 < nparts; k += 4) {
+            a0 += gpart[(size_t)(k + 0) * ld + c];
+            a1 += gpart[(size_t)(k + 1) * ld + c];
+            a2 += gpart[(size_t)(k + 2) * ld + c];
+            a3 += gpart[(size_t)(k + 3) * ld + c];
+        }
+        for (; k < nparts; ++k) a0 += gpart[(size_t)k * ld + c];
+        red[c] = (a0 + a1) + (a2 + a3);
+    }
+    if (blockIdx.x == 0 && threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        double s = 0.0;
+        for (int k = lane; k < nparts; k += 32) s += sspart[k];
+        s = warp_sum(s);
+        double c0 = 0.0;
+        if (c0part) {
+            for (int k = lane; k < nc0; k += 32) c0 += c0part[k];
+            c0 = warp_sum(c0);
+        }
+        if (lane == 0) {
+            red[d] = s;
+            red[d + 1] = c0;
+        }
+    }
+}
+
+// ---- FISTA control flow on the device (fast_lasso.py:40-67) -------------------------------------
+// One CTA.  Consumes red = [D^T r(beta), ||r(beta)||^2, c0] of the pass that just ran at `beta`
+// and either (init) seeds the iteration, (reject) grows L and forms the next trial, or (accept)
+// applies momentum, tests convergence and forms the first trial of the next iteration.
+// The gradient and ||.||^2 at the extrapolated point beta_p are NOT recomputed with passes over D:
+// both are affine in beta, so  g(beta_p) = g(beta) + t1 (g(beta) - g(beta_prev))  and
+// r(beta_p) = r(beta) + t1 (r(beta) - r(beta_prev))  (combine kernel) — one D pass per trial instead of
+// the reference's three matvecs per iteration, same iterates up to rounding.
+__global__ void __launch_bounds__(1024) fista_update_kernel(FistaState* st, int d, const double* __restrict__ red,
+                                                            double* beta, double* beta_p, double* beta_prev,
+                                                            double* g_p, double* g_prev,
+                                                            const float* __restrict__ pow_tab) {
+    __shared__ double sh[33];
+    if (st->done) return;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const FistaState S = *st;
+    const double ss = red[d];
+    float L_prev = S.L_prev, L_cur = S.L_cur;
+    int i_k = S.i_k, k = S.k, cur = S.cur, accepted = 0, c0_from_red = 0, done = 0;
+    double t = S.t, c0 = S.c0, t1 = S.t1, crit = S.crit;
+
+    if (k < 0) {
+        // the initial pass ran at beta = w (beta_p = beta_prev = w, fast_lasso.py:37-38)
+        for (int c = tid; c < d; c += nt) {
+            const double bw = beta[c], g = red[c];
+            beta_p[c] = bw;
+            beta_prev[c] = bw;
+            g_p[c] = g;
+            g_prev[c] = g;
+        }
+        c0 = ss;
+        k = 0;
+        i_k = 0;
+        t = 1.0;
+        L_cur = __fmul_rn(L_prev, pow_tab[0]);
+        accepted = 2;
+        cur ^= 1;
+    } else {
+        if (S.c0_from_red) c0 = red[d + 1];
+        const double lhs = ss - c0;
+        if (lhs > S.rhs) {  // cond = (LHS > RHS), :56 — false for NaN, like the reference
+            ++i_k;
+            L_cur = __fmul_rn(L_prev, pow_tab[i_k < 127 ? i_k : 127]);
+        } else {
+            L_prev = L_cur;
+            const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;  // :59
+            t1 = (t - 1.0) / tnext;                                      // :61
+            double a = 0.0;
+            for (int c = tid; c < d; c += nt) {
+                const double df = beta[c] - beta_prev[c];  // :60
+                a = fma(df, df, a);
+                beta_p[c] = beta[c] + t1 * df;             // :62
+            }
+            crit = sqrt(block_sum(a, sh));                 // :63
+            ++k;
+            if (crit < S.tol || k >= S.max_iter) {
+                done = 1;  // result is beta; its residual sits in rbuf[cur]
+            } else {
+                t = tnext;
+                for (int c = tid; c < d; c += nt) {
+                    const double gb = red[c];
+                    g_p[c] = gb + t1 * (gb - g_prev[c]);
+                    g_prev[c] = gb;
+                    beta_prev[c] = beta[c];
+                }
+                i_k = 0;
+                L_cur = __fmul_rn(L_prev, pow_tab[0]);
+                accepted = 1;
+                c0_from_red = 1;
+                cur ^= 1;
+            }
+        }
+    }
+    double rhs = S.rhs;
+    if (!done) {
+        __syncthreads();
+        // trial: beta = soft(beta_p + g_p / L_cur, lam / L_cur)   (:47-49)
+        const double Ld = (double)L_cur;
+        const double thr = S.thr_f32 ? (double)__fdiv_rn((float)S.lam, L_cur) : S.lam / Ld;
+        double r1 = 0.0, r2 = 0.0;
+        for (int c = tid; c < d; c += nt) {
+            const double bp = beta_p[c], g = g_p[c];
+            const double bs = bp + g / Ld;
+            const double mag = fmax(fabs(bs) - thr, 0.0);
+            const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+            const double bn = mag * sgn;
+            beta[c] = bn;
+            const double df = bn - bp;
+            r1 = fma(df, df, r1);
+            r2 = fma(df, g, r2);
+        }
+        r1 = block_sum(r1, sh);
+        r2 = block_sum(r2, sh);
+        rhs = Ld * r1 - 2.0 * r2;  // :53
+    }
+    if (tid == 0) {
+        st->t = t;
+        st->c0 = c0;
+        st->rhs = rhs;
+        st->t1 = t1;
+        st->crit = crit;
+        st->ss_last = ss;
+        st->L_prev = L_prev;
+        st->L_cur = L_cur;
+        st->i_k = i_k;
+        st->k = k;
+        st->done = done;
+        st->passes = S.passes + 1;
+        st->trials = S.trials + (S.k < 0 ? 0 : 1);
+        st->accepted = accepted;
+        st->cur = cur;
+        st->c0_from_red = c0_from_red;
+    }
+}
+
+// after an accepted step: partial sums of || r(beta) + t1 (r(beta) - r(beta_prev)) ||^2 = ||b - D beta_p||^2
+__global__ void fista_combine_kernel(const FistaState* st, const double* r0, const double* r1, int64_t n,
+                                     double* __restrict__ c0part) {
+    __shared__ double sh[33];
+    if (st->done || st->accepted != 1) return;
+    // cur was flipped by the update kernel: the accepted residual is in rbuf[cur^1], the older in rbuf[cur]
+    const double* rn = st->cur ? r0 : r1;
+    const double* ro = st->cur ? r1 : r0;
+    const double t1 = st->t1;
+    double a = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = rn[i] + t1 * (rn[i] - ro[i]);
+        a = fma(v, v, a);
+    }
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) c0part[blockIdx.x] = a;
+}
+
+__global__ void fista_result_kernel(const FistaState* st, const double* beta, int d, double* __restrict__ w_out,
+                                    const double* r0, const double* r1, int64_t n, double* __restrict__ r_out) {
+    const double* r = st->cur ? r1 : r0;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
+    if (w_out)
+        for (int64_t c = gid; c < d; c += gs) w_out[c] = beta[c];
+    if (r_out)
+        for (int64_t i = gid; i < n; i += gs) r_out[i] = r[i];
+}
+
+// ---- margins m = D w - lambda / rho (algorithms.py:89) from a maintained Dw ----------------------
+__global__ void margins_kernel(const double* __restrict__ Dw, const double* __restrict__ lam, double rho, int64_t n,
+                               double* __restrict__ m) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        m[i] = Dw[i] - lam[i] / rho;
+}
+
+// ---- z[perm] = z_sorted (algorithms.py:103-104), only the rows this rank owns; b = z + lambda/rho
+__global__ void scatter_kernel(const double* __restrict__ zs, const int32_t* __restrict__ perm, int64_t n_global,
+                               int64_t row_lo, int64_t n_local, int use_clip, double clip,
+                               const double* __restrict__ lam, double rho, double* __restrict__ z,
+                               double* __restrict__ b) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_global;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = (int64_t)perm[i] - row_lo;
+        if (row >= 0 && row < n_local) {
+            double v = zs[i];
+            if (use_clip && v < clip) v = clip;  // EHRM: max(B, isotonic prox) (PAV_cpt.py:213,271)
+            z[row] = v;
+            if (b) b[row] = v + lam[row] / rho;
+        }
+    }
+}
+
+// ---- dual update + primal residual (algorithms.py:132,135) --------------------------------------
+// Dw is either given (from_residual = 0) or recovered from the last FISTA residual r = b - D w.
+__global__ void dual_kernel(const double* __restrict__ z, double* __restrict__ Dw, const double* __restrict__ b,
+                            const double* __restrict__ r, int from_residual, double* __restrict__ lam, double rho,
+                            int64_t n, double* __restrict__ part) {
+    __shared__ double sh[33];
+    double a = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double dw;
+        if (from_residual) {
+            dw = b[i] - r[i];
+            Dw[i] = dw;
+        } else {
+            dw = Dw[i];
+        }
+        const double res = z[i] - dw;
+        lam[i] = lam[i] + rho * res;
+        a = fma(res, res, a);
+    }
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+// out[0] = sum(part[0..np)), out[1] = ||w - w_prev||^2 (algorithms.py:136), out[2] = ||w||^2, out[3] = ||w||_1
+__global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict__ part, int np,
+                                                        const double* __restrict__ w,
+                                                        const double* __restrict__ w_prev, int d,
+                                                        double* __restrict__ out) {
+    __shared__ double sh[33];
+    double a = 0.0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) a += part[k];
+    a = block_sum(a, sh);
+    double dd = 0.0, w2 = 0.0, w1 = 0.0;
+    if (w) {
+        for (int c = threadIdx.x; c < d; c += blockDim.x) {
+            const double wc = w[c];
+            if (w_prev) {
+                const double df = wc - w_prev[c];
+                dd = fma(df, df, dd);
+            }
+            w2 = fma(wc, wc, w2);
+            w1 += fabs(wc);
+        }
+        dd = block_sum(dd, sh);
+        w2 = block_sum(w2, sh);
+        w1 = block_sum(w1, sh);
+    }
+    if (threadIdx.x == 0) {
+        out[0] = a;
+        out[1] = dd;
+        out[2] = w2;
+        out[3] = w1;
+    }
+}
+
+// ---- objective: sum_i sigma_i * loss(u_(i)) over ascending margins (objective.py:71-81) ------------
+// loss is non-decreasing in the margin u = D w, so sorting the margins sorts the losses.
+__global__ void objective_kernel(const double* __restrict__ u_sorted, const double* __restrict__ sigma, int loss,
+                                 int64_t n, double* __restrict__ part) {
+    __shared__ double sh[33];
+    double a = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        a = fma(sigma[i], rbl_margin_loss(loss, u_sorted[i]), a);
+    a = block_sum(a, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+}  // namespace
+
+// ---- host launchers ----------------------------------------------------------------------------
+int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, cudaStream_t s) {
+    build_design_kernel<<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, D, c->ld, c->n_local, c->d);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStream_t s) {
+    const int threads = 128;
+    const int blocks = (c->d + threads - 1) / threads;
+    reduce_partials_kernel<<<blocks, threads, 0, s>>>(c->gpart, c->sspart, with_c0 ? c->c0part : nullptr,
+                                                      c->pass_grid, c->vec_grid, c->ld, c->d, c->red, st);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_fista_update(rbl_ctx* c, cudaStream_t s) {
+    fista_update_kernel<<<1, 1024, 0, s>>>(c->fista, c->d, c->red, c->beta, c->beta_p, c->beta_prev, c->g_p,
+                                           c->g_prev, c->pow_tab);
+    RBL_LAUNCH_CHECK();
+    fista_combine_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(c->fista, c->rbuf[0], c->rbuf[1], c->n_local, c->c0part);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s) {
+    fista_result_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(c->fista, c->beta, c->d, w_out, c->rbuf[0], c->rbuf[1],
+                                                           c->n_local, r_out);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_margins(rbl_ctx* c, const double* Dw, const double* lam, double rho, double* m, cudaStream_t s) {
+    margins_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dw, lam, rho, c->n_local, m);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_clip, double clip, const double* lam,
+                  double rho, double* z, double* b, cudaStream_t s) {
+    scatter_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(zs, perm, c->n_global, c->row_lo, c->n_local, use_clip, clip,
+                                                      lam, rho, z, b);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const double* r, int from_residual,
+               double* lam, double rho, const double* w, const double* w_prev, double* out4, cudaStream_t s) {
+    dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(z, Dw, b, r, from_residual, lam, rho, c->n_local, c->vpart);
+    RBL_LAUNCH_CHECK();
+    finalize_kernel<<<1, 1024, 0, s>>>(c->vpart, c->vec_grid, w, w_prev, c->d, out4);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
+                    cudaStream_t s) {
+    objective_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(u_sorted, sigma, loss, c->n_global, c->vpart);
+    RBL_LAUNCH_CHECK();
+    finalize_kernel<<<1, 1024, 0, s>>>(c->vpart, c->vec_grid, w, nullptr, c->d, out4);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}

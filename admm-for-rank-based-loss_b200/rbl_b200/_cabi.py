@@ -1,0 +1,84 @@
+"""ctypes binding of librbl_b200.so (include/rbl_b200.h).  This is the only way the host layer reaches
+the GPU: there is no CPU fallback — a missing library or a non-sm_100 device raises."""
+import ctypes
+import os
+
+from . import build as _build
+
+_c = ctypes
+_dp = _c.c_void_p  # device pointers travel as integers (tensor.data_ptr())
+
+_SIGNATURES = {
+    "rbl_version": (_c.c_int, []),
+    "rbl_last_error": (_c.c_char_p, []),
+    "rbl_launch_count": (_c.c_int64, []),
+    "rbl_create": (_c.c_int, [_c.POINTER(_c.c_void_p), _c.c_int, _c.c_int64, _c.c_int64, _c.c_int64, _c.c_int32,
+                              _c.c_int64]),
+    "rbl_destroy": (_c.c_int, [_c.c_void_p]),
+    "rbl_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int64)]),
+    "rbl_build_design": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _dp, _dp, _c.c_void_p]),
+    "rbl_set_spectrum": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
+    "rbl_matvec": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p]),
+    "rbl_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_sort_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p]),
+    "rbl_pav_prox": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_prox_elementwise": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _c.c_int64, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_scatter_z": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_int, _c.c_double, _dp, _c.c_double, _dp, _dp,
+                                 _c.c_void_p]),
+    "rbl_fused_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
+    "rbl_fista_config": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_float)]),
+    "rbl_fista_begin": (_c.c_int, [_c.c_void_p, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double, _c.c_int,
+                                   _c.c_void_p]),
+    "rbl_fista_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
+    "rbl_fista_bind_red": (_c.c_int, [_c.c_void_p, _dp]),
+    "rbl_fista_update": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "rbl_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_int, _c.c_void_p]),
+    "rbl_fista_poll": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_double)]),
+    "rbl_fista_result": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
+    "rbl_dual_update": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _c.c_int, _dp, _c.c_double, _dp, _dp, _dp,
+                                   _c.c_void_p]),
+    "rbl_objective": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _dp, _dp, _c.c_void_p]),
+}
+
+_lib = None
+
+
+class RblError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """Load the shared library (building it first only if nvcc is at hand and the .so is absent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RblError(f"librbl_b200.so is missing at {path} and could not be built ({e}); "
+                           "run `python __graft_entry__.py build`. There is no CPU fallback.") from e
+    lib = ctypes.CDLL(path)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the ABI drifted
+        fn.restype = res
+        fn.argtypes = args
+    if lib.rbl_version() != 1:
+        raise RblError("librbl_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def check(rc):
+    if rc != 0:
+        msg = load().rbl_last_error()
+        raise RblError(f"librbl_b200 error {rc}: {msg.decode() if msg else ''}")

@@ -1,0 +1,336 @@
+"""Host-side engine: device buffers (torch), streams, row sharding (torch.distributed) and the calls
+into librbl_b200.so that make up one ADMM iteration.
+
+PyTorch is plumbing here (device memory, streams, NCCL); every numerical step is a hand-written
+sm_100a kernel reached through the C ABI (include/rbl_b200.h).  There is no CPU fallback: without a
+B200 and the built library, construction raises.
+
+Reference call stack this replaces: Optimizer.__init__ / z_subproblem / main_loop
+(src/optim/algorithms.py:20-164) and ADMMmethod._w_subproblem (:190-207).
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+from . import _cabi
+
+LOSS_IDS = {"binary_cross_entropy": 0, "hinge": 1}
+
+_POW_CACHE = {}
+
+
+def _pow_table(eta):
+    """float32(eta)**i for i < 128, computed by numpy exactly as fast_lasso.py:46 does (eta**i_k)."""
+    key = float(eta)
+    if key not in _POW_CACHE:
+        with np.errstate(over="ignore"):
+            _POW_CACHE[key] = np.array([np.float32(eta) ** i for i in range(128)], dtype=np.float32)
+    return _POW_CACHE[key]
+
+
+def _require_cuda(device):
+    if not torch.cuda.is_available():
+        raise _cabi.RblError("no CUDA device: rbl_b200 runs on B200 (sm_100a) only and has no CPU fallback")
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return torch.device(device)
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous row shards, sizes differing by at most one (first n % world ranks get the extra row)."""
+    base, extra = divmod(n, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class DeviceProblem:
+    """D = -y (.) X resident in HBM (row-major, padded to an even leading dimension) plus the library
+    handle that owns the scratch for passes, sort and PAV over it."""
+
+    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None):
+        self.lib = _cabi.load()
+        self.device = _require_cuda(device)
+        self.group = group
+        if row_lo is None:  # unsharded: this process holds every row
+            row_lo, n_global = 0, X.shape[0]
+            self.world, self.rank = 1, 0
+        else:               # X holds global rows [row_lo, row_lo + n_local) of an n_global-row problem
+            self.world = torch.distributed.get_world_size(group)
+            self.rank = torch.distributed.get_rank(group)
+        self.n_local, self.d = int(X.shape[0]), int(X.shape[1])
+        self.n_global, self.row_lo = int(n_global), int(row_lo)
+        self.ld = self.d + (self.d & 1)
+        with torch.cuda.device(self.device):
+            h = ctypes.c_void_p()
+            _cabi.check(self.lib.rbl_create(ctypes.byref(h), self.device.index or 0, self.n_local, self.n_global,
+                                            self.row_lo, self.d, self.ld))
+            self.h = h
+            Xd = self._to_device(X).reshape(self.n_local, self.d)
+            yd = self._to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not torch.is_tensor(y)
+                                 else y.reshape(-1).to(torch.float64))
+            self.D = torch.empty((self.n_local, self.ld), dtype=torch.float64, device=self.device)
+            _cabi.check(self.lib.rbl_build_design(self.h, Xd.data_ptr(), self.d, yd.data_ptr(), self.D.data_ptr(),
+                                                  self._stream()))
+            torch.cuda.current_stream().synchronize()
+            del Xd, yd
+            self._out4 = torch.zeros(4, dtype=torch.float64, device=self.device)
+            self._out4_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+            self._u_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+            self._u_glob = (torch.empty(self.n_global, dtype=torch.float64, device=self.device)
+                            if self.world > 1 else self._u_local)
+        info = (ctypes.c_int64 * 8)()
+        _cabi.check(self.lib.rbl_info(self.h, info))
+        self.info = dict(zip(["num_sms", "pass_grid", "rows_per_tile", "pass_stages", "pass_smem", "scratch_bytes",
+                              "vec_grid", "pav_chunk"], list(info)))
+
+    # ---- plumbing ----------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _to_device(self, a):
+        if torch.is_tensor(a):
+            return a.to(device=self.device, dtype=torch.float64).contiguous()
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        return torch.from_numpy(a).to(self.device)
+
+    def vec(self, a):
+        """d- or n-vector to a contiguous fp64 device tensor"""
+        if torch.is_tensor(a):
+            return a.to(device=self.device, dtype=torch.float64).reshape(-1).contiguous()
+        return self._to_device(np.asarray(a, dtype=np.float64).reshape(-1))
+
+    @property
+    def launches(self):
+        """kernels launched through librbl_b200 by this process (bench.py's gpu_launches)"""
+        return int(self.lib.rbl_launch_count())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            self.lib.rbl_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def gather_rows(self, local, out):
+        """all-gather of an n_local vector into the n_global vector `out` (NCCL over NVLink)."""
+        if self.world == 1:
+            if out.data_ptr() != local.data_ptr():
+                out.copy_(local)
+            return out
+        dist = torch.distributed
+        base, extra = divmod(self.n_global, self.world)
+        if extra == 0:
+            dist.all_gather_into_tensor(out, local, group=self.group)
+        else:
+            pad = base + 1
+            buf = torch.zeros(self.world * pad, dtype=local.dtype, device=self.device)
+            mine = torch.zeros(pad, dtype=local.dtype, device=self.device)
+            mine[: self.n_local] = local
+            dist.all_gather_into_tensor(buf, mine, group=self.group)
+            for r in range(self.world):
+                lo, hi = shard_bounds(self.n_global, self.world, r)
+                out[lo:hi] = buf[r * pad: r * pad + (hi - lo)]
+        return out
+
+    def all_reduce(self, t):
+        if self.world > 1:
+            torch.distributed.all_reduce(t, group=self.group)
+        return t
+
+    # ---- kernels -----------------------------------------------------------------------------
+    def matvec(self, x, out=None):
+        """out = D x  (algorithms.py:89,132,135)"""
+        if out is None:
+            out = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.rbl_matvec(self.h, self.D.data_ptr(), x.data_ptr(), out.data_ptr(), self._stream()))
+        return out
+
+    def objective_terms(self, w, sigma, loss):
+        """(sum_i sigma_i loss(u_(i)), ||w||^2, ||w||_1) for u = D w  (objective.py:71-87)"""
+        self.matvec(w, self._u_local)
+        self.gather_rows(self._u_local, self._u_glob)
+        _cabi.check(self.lib.rbl_objective(self.h, LOSS_IDS[loss], self._u_glob.data_ptr(), sigma.data_ptr(),
+                                           w.data_ptr(), self._out4.data_ptr(), self._stream()))
+        self._out4_host.copy_(self._out4, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        o = self._out4_host
+        return float(o[0]), float(o[2]), float(o[3])
+
+
+class AdmmEngine(DeviceProblem):
+    """ADMM state and the three sub-steps on the device."""
+
+    def __init__(self, X, y, loss, sigma, clip=None, **kw):
+        super().__init__(X, y, **kw)
+        if loss not in LOSS_IDS:
+            raise ValueError(f"Unrecognized loss '{loss}'! Options: ['binary_cross_entropy', 'hinge']")
+        self.loss, self.loss_id = loss, LOSS_IDS[loss]
+        self.clip = clip
+        dev, f64 = self.device, torch.float64
+        nl, ng, d = self.n_local, self.n_global, self.d
+        with torch.cuda.device(dev):
+            self.sigma = self.vec(sigma)
+            assert self.sigma.numel() == ng
+            _cabi.check(self.lib.rbl_set_spectrum(self.h, self.sigma.data_ptr(), self._stream()))
+            self.w = torch.zeros(d, dtype=f64, device=dev)
+            self.w_prev = torch.zeros(d, dtype=f64, device=dev)
+            self.z = torch.zeros(nl, dtype=f64, device=dev)
+            self.lam = torch.zeros(nl, dtype=f64, device=dev)
+            self.Dw = torch.zeros(nl, dtype=f64, device=dev)
+            self.m = torch.zeros(nl, dtype=f64, device=dev)
+            self.b = torch.zeros(nl, dtype=f64, device=dev)
+            self.r = torch.zeros(nl, dtype=f64, device=dev)
+            self.m_glob = torch.zeros(ng, dtype=f64, device=dev) if self.world > 1 else self.m
+            self.m_sorted = torch.zeros(ng, dtype=f64, device=dev)
+            self.z_sorted = torch.zeros(ng, dtype=f64, device=dev)
+            self.perm = torch.zeros(ng, dtype=torch.int32, device=dev)
+            self.red = torch.zeros(d + 2, dtype=f64, device=dev)
+            self.red_host = torch.zeros(d + 2, dtype=f64).pin_memory()
+            self.w_host = torch.zeros(d, dtype=f64).pin_memory()
+            _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red.data_ptr()))
+        self.Dw_valid = False
+        self.fista_stats = {"calls": 0, "passes": 0, "iters": 0, "polls": 0, "last_passes": 0}
+        self._fista_eta = None
+        self.fista_batch_min = int(os.environ.get("RBL_FISTA_BATCH", "4"))
+
+    # ---- state -------------------------------------------------------------------------------
+    def set_state(self, w=None, z=None, lam=None):
+        if w is not None:
+            self.w.copy_(self.vec(w))
+            self.Dw_valid = False
+        if z is not None:
+            self.z.copy_(self.vec(z))
+        if lam is not None:
+            self.lam.copy_(self.vec(lam))
+
+    def refresh_Dw(self):
+        self.matvec(self.w, self.Dw)
+        self.Dw_valid = True
+
+    # ---- z-step: margins -> sort -> PAV prox -> scatter (algorithms.py:88-106) -----------------
+    def z_step(self, rho):
+        lib, s = self.lib, self._stream()
+        if not self.Dw_valid:
+            self.refresh_Dw()
+        _cabi.check(lib.rbl_margins(self.h, self.Dw.data_ptr(), self.lam.data_ptr(), float(rho), self.m.data_ptr(), s))
+        self.gather_rows(self.m, self.m_glob)
+        _cabi.check(lib.rbl_sort_margins(self.h, self.m_glob.data_ptr(), self.m_sorted.data_ptr(),
+                                         self.perm.data_ptr(), s))
+        _cabi.check(lib.rbl_pav_prox(self.h, self.loss_id, self.m_sorted.data_ptr(), float(rho),
+                                     self.z_sorted.data_ptr(), s))
+        _cabi.check(lib.rbl_scatter_z(self.h, self.z_sorted.data_ptr(), self.perm.data_ptr(),
+                                      0 if self.clip is None else 1, 0.0 if self.clip is None else float(self.clip),
+                                      self.lam.data_ptr(), float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
+        return self.z
+
+    # ---- w-step, l1: FISTA (fast_lasso.py:22-69 via algorithms.py:190-202) ---------------------
+    def fista(self, w0, b, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_iter=5000, w_out=None,
+              r_out=None):
+        """Runs the device-resident FISTA state machine to completion; returns (w_out, info).
+
+        `lam` keeps its Python type on purpose: a python float makes `lam/L_cur` a float32 quotient
+        under numpy >= 2 (as in iteration 0 of the reference loop), np.float64 a float64 one.
+        """
+        lib, s = self.lib, self._stream()
+        if self._fista_eta != float(eta):
+            tab = _pow_table(eta)
+            _cabi.check(lib.rbl_fista_config(self.h, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
+            self._fista_eta = float(eta)
+        thr_f32 = 1 if type(lam) is float or isinstance(lam, (int, np.float32)) else 0
+        _cabi.check(lib.rbl_fista_begin(self.h, w0.data_ptr(), float(lam), thr_f32, float(np.float32(L)), float(tol),
+                                        int(max_iter), s))
+        hi = (ctypes.c_int32 * 8)()
+        hd = (ctypes.c_double * 4)()
+        # first batch: what the previous call needed (iteration counts drift slowly between ADMM
+        # iterations), then small batches; steps enqueued after convergence exit immediately
+        batch = max(self.fista_batch_min, self.fista_stats["last_passes"] - 1)
+        Dp, bp = self.D.data_ptr(), b.data_ptr()
+        while True:
+            if self.world == 1:
+                _cabi.check(lib.rbl_fista_steps(self.h, Dp, bp, batch, s))
+            else:
+                for _ in range(batch):
+                    _cabi.check(lib.rbl_fista_pass(self.h, Dp, bp, s))
+                    self.all_reduce(self.red)
+                    _cabi.check(lib.rbl_fista_update(self.h, s))
+            _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
+            self.fista_stats["polls"] += 1
+            if hi[0]:
+                break
+            batch = self.fista_batch_min
+        if w_out is None:
+            w_out = torch.empty(self.d, dtype=torch.float64, device=self.device)
+        _cabi.check(lib.rbl_fista_result(self.h, w_out.data_ptr(), 0 if r_out is None else r_out.data_ptr(), s))
+        info = {"iters": int(hi[1]), "passes": int(hi[2]), "trials": int(hi[3]), "L": float(hd[1]),
+                "crit": float(hd[0])}
+        st = self.fista_stats
+        st["calls"] += 1
+        st["passes"] += info["passes"]
+        st["iters"] += info["iters"]
+        st["last_passes"] = info["passes"]
+        return w_out, info
+
+    def w_step_fista(self, lam, tol=7e-5, max_iter=5000):
+        self.w_prev.copy_(self.w)
+        _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w, r_out=self.r)
+        self._r_matches_w = True
+        return info
+
+    # ---- w-step, l2: host L-BFGS-B over fused device f/g (w_LBFGS.py:31-53) ---------------------
+    def fg_l2(self, w_np, rho, reg):
+        """f = rho/2 ||D w - b||^2 + reg/2 ||w||^2, g = rho D^T(D w - b) + reg w — one pass over D."""
+        self._wtmp.copy_(torch.from_numpy(w_np))
+        _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
+                                            self.r.data_ptr(), self.red.data_ptr(), self._stream()))
+        self.all_reduce(self.red)
+        self.red_host.copy_(self.red, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        red = self.red_host.numpy()
+        f = 0.5 * rho * float(red[self.d]) + 0.5 * reg * float(w_np @ w_np)
+        g = -rho * red[: self.d] + reg * w_np
+        self._last_eval = w_np.copy()
+        return f, g
+
+    def w_step_lbfgs(self, rho, reg, maxiter=1000):
+        from scipy.optimize import minimize
+
+        if not hasattr(self, "_wtmp"):
+            self._wtmp = torch.zeros(self.d, dtype=torch.float64, device=self.device)
+        self.w_prev.copy_(self.w)
+        self.w_host.copy_(self.w)
+        torch.cuda.current_stream(self.device).synchronize()
+        w0 = self.w_host.numpy().copy()
+        rho, reg = float(rho), float(reg)
+        res = minimize(lambda w: self.fg_l2(w, rho, reg), w0, jac=True, method="L-BFGS-B",
+                       options={"maxiter": maxiter})
+        self.w.copy_(torch.from_numpy(res.x))
+        # L-BFGS-B normally returns the last point it evaluated; then r = b - D w is already there
+        self._r_matches_w = bool(np.array_equal(res.x, self._last_eval))
+        return {"nit": int(res.nit), "nfev": int(res.nfev)}
+
+    # ---- dual update + residuals (algorithms.py:132-136) -----------------------------------------
+    def dual_step(self, rho):
+        """lambda += rho (z - D w); returns (||z - D w||_2, ||w - w_prev||_2)."""
+        from_res = 1 if getattr(self, "_r_matches_w", False) else 0
+        if not from_res:
+            self.refresh_Dw()
+        _cabi.check(self.lib.rbl_dual_update(self.h, self.z.data_ptr(), self.Dw.data_ptr(), self.b.data_ptr(),
+                                             self.r.data_ptr(), from_res, self.lam.data_ptr(), float(rho),
+                                             self.w.data_ptr(), self.w_prev.data_ptr(), self._out4.data_ptr(),
+                                             self._stream()))
+        self.Dw_valid = True
+        self._r_matches_w = False
+        if self.world > 1:
+            # only the primal term is a partial sum over row shards
+            self.all_reduce(self._out4[:1])
+        self._out4_host.copy_(self._out4, non_blocking=True)
+        self.w_host.copy_(self.w, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        o = self._out4_host
+        return float(np.sqrt(o[0].item())), float(np.sqrt(o[1].item()))

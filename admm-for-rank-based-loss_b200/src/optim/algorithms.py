@@ -1,0 +1,258 @@
+"""Drop-in for the reference's src/optim/algorithms.py (ADMM entry point used by run_demo.py and the
+run_*.py drivers): same class names, constructor/method signatures, attributes and error behaviour —
+the numerical work runs on the B200 through librbl_b200.so (no CPU fallback).
+
+Per iteration (reference :119-164):
+    z-step  margins -> stable radix sort -> PAV/isotonic prox -> scatter        (device, :88-106)
+    w-step  l1: FISTA as a device-resident state machine, one fused pass over D per trial (:190-202)
+            l2: scipy L-BFGS-B on the host driving a fused device f/g pass        (:109-116, w_LBFGS.py)
+    dual    lambda += rho (z - D w), residual norms, stop test, rho schedule     (device + host scalars)
+
+Documented deviations from the shipped reference: exact PAV + machine-precision
+Newton in the z-step (the reference's sweep PAV / loose Newton converge to the same unique prox);
+closed-form hinge prox; stable sort; FISTA in float64 by default (`fista_dtype` is accepted for API
+compatibility; float32 is the shipped default there and is chaotic at its own tolerance); the
+tiny-problem sklearn-Lasso branch (:194-197) is served by the same FISTA kernels.
+"""
+import time
+
+import numpy as np
+import torch
+
+from rbl_b200.engine import AdmmEngine
+from src.optim.objective import rankbasedObjective
+
+
+class Optimizer:
+    def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
+                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4):
+        X = np.asarray(X)
+        y = np.asarray(y)
+        self.num_row = X.shape[0]
+        self.num_feature = X.shape[1]
+        # regularization (:30) — raises TypeError below when both are None, like the reference (:32)
+        self.reg = l1_reg or l2_reg
+        self.loss = loss
+        # objective first: it validates weight_function / loss / args exactly like the reference (:22)
+        self.objective = _LazyObjective(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args)
+        self.sigma_a = self.objective.alphas.numpy().reshape(-1)
+        self.sigma_b = self.objective.betas.numpy().reshape(-1)
+        lam0 = 0.1 * self.reg / self.num_row  # :32,34
+        if w0 is not None:
+            w_init = np.asarray(w0, dtype=np.float64).reshape(-1, 1)
+        else:
+            w_init = 0.001 * self.reg / self.num_feature / self.num_row * np.ones(shape=(self.num_feature, 1))
+        self.tol = tol
+        self.max_iter = max_iter
+        if weight_function == 'ehrm':
+            self.rho = 0.0001
+        elif weight_function == 'aorr' or weight_function == 'aorr_dc':
+            self.rho = 2e-7
+        else:
+            self.rho = 1e-5
+        if l1_reg is not None:
+            self.w_flag = 1
+        elif l2_reg is not None:
+            self.w_flag = 2
+        else:
+            raise ValueError("More arguments: l1_reg or l2_reg not l1_reg and l2_reg!")
+        self.B = B
+        if B is not None and weight_function != "ehrm":
+            raise ValueError(
+                f"Unrecognized weight_function '{weight_function}'! Options: ['ehrm']"
+            )
+        self.w_tol = 7e-5
+        self.z_maxiter = self.num_row
+        self.store = False
+        self.weight_function = weight_function
+
+        # EHRM as shipped == max(B, isotonic prox with sigma = betas) (PAV_cpt.py:203-293)
+        sigma_for_prox = self.sigma_b if weight_function == 'ehrm' else self.sigma_a
+        self.engine = AdmmEngine(X, y, loss, sigma_for_prox, clip=B if weight_function == 'ehrm' else None)
+        self.objective._attach(self.engine)
+        self.engine.set_state(w=w_init, z=np.full(self.num_row, lam0), lam=np.full(self.num_row, lam0))
+        self._w = w_init.astype(np.float64)
+        self.fista_max_iter = 5000
+        self.last_info = {}
+
+    # ---- state views (numpy, like the reference's attributes) -----------------------------------
+    @property
+    def w(self):
+        return self._w
+
+    @w.setter
+    def w(self, value):
+        self._w = np.asarray(value, dtype=np.float64).reshape(-1, 1)
+        self.engine.set_state(w=self._w)
+
+    @property
+    def z(self):
+        return self.engine.z.cpu().numpy().reshape(-1, 1)
+
+    @z.setter
+    def z(self, value):
+        self.engine.set_state(z=value)
+
+    @property
+    def lagrangian(self):
+        return self.engine.lam.cpu().numpy().reshape(-1, 1)
+
+    @lagrangian.setter
+    def lagrangian(self, value):
+        self.engine.set_state(lam=value)
+
+    @property
+    def D(self):
+        return self.engine.D[:, : self.num_feature].cpu().numpy()
+
+    @property
+    def DTD(self):
+        D = self.D
+        return D.T @ D
+
+    def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
+                    B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):
+        # X, y both are test set.
+        self.test_objective = rankbasedObjective(torch.from_numpy(np.asarray(X)), torch.from_numpy(np.asarray(y)),
+                                                 weight_function, loss, l2_reg, l1_reg, B, n_class, args)
+        self.w_time = [0]
+        self.z_time = [0]
+        self.train_losses = [self.objective.get_arrogate_loss(torch.from_numpy(self.w).double())]
+        self.test_losses = [self.test_objective.get_arrogate_loss(torch.from_numpy(self.w).double())]
+        self.time_array = [0]
+        self.store = True
+
+    def z_subproblem(self):
+        self.engine.z_step(self.rho)
+        return self.z
+
+    def w_subproblem(self):
+        if self.w_flag == 2:
+            self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg)
+        else:
+            raise ValueError("w_flag can only be 0, 1 or 2.")
+        return self.engine.w.cpu().numpy().reshape(-1, 1)
+
+    def _sync_timer(self):
+        if self.store:
+            torch.cuda.synchronize(self.engine.device)
+        return time.time()
+
+    def main_loop(self, i, t_start, verbose):
+        t1 = self._sync_timer()
+        self.engine.z_step(self.rho)
+        t2 = self._sync_timer()
+        if self.store:
+            self.z_time.append(t2 - t1 + self.z_time[i])
+
+        self._w_subproblem_device()
+        if self.store:
+            self.w_time.append(self._sync_timer() - t2 + self.w_time[i])
+
+        # Lagrange multiplier update + stopping criterion (:132-136), fused on the device
+        primal_feasibility, dual_feasibility = self.engine.dual_step(self.rho)
+        self._w = self.engine.w_host.numpy().reshape(-1, 1).copy()
+        self.primal_feasibility, self.dual_feasibility = primal_feasibility, dual_feasibility
+        if primal_feasibility < self.tol and dual_feasibility < self.tol:
+            print('algorithm converges within tolerance')
+            print('iter_num=', i, 'primal_feasibility: ', primal_feasibility, 'dual_feasibility: ', dual_feasibility)
+            print('loss=', self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+            return True
+        if verbose:
+            if i % 10 == 0:
+                print('iter_num=', i, 'primal_feasibility: ', primal_feasibility, 'dual_feasibility: ', dual_feasibility)
+                print('loss=', self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+
+        # ALM penalty update (:147-157; the 'ehrm'/'aorr'/'aorr_dc' branches compare self.loss — a loss
+        # name — against weight-function names and never fire; reproduced as is)
+        if self.loss == 'ehrm' or self.loss == 'aorr':
+            self.rho = np.min((self.rho * 1.2, 17 * self.num_feature))
+        elif self.loss == 'aorr_dc':
+            if i >= 7 and i % 3 == 0:
+                self.rho = np.min((self.rho * 5, 17 * self.num_feature))
+        else:
+            if primal_feasibility > 1e-2:
+                self.rho = np.min((self.rho * 1.02, 217 * self.num_feature))
+            else:
+                self.rho = np.min((self.rho * 1.07, 217 * self.num_feature))
+
+        if self.store:
+            self.train_losses.append(self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+            self.test_losses.append(self.test_objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+            self.time_array.append(time.time() - t_start)
+
+        return False
+
+    def _w_subproblem_device(self):
+        """w-step leaving the result on the device (the numpy view is refreshed by the dual step)."""
+        if self.w_flag == 2:
+            self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg)
+        else:
+            raise ValueError("w_flag can only be 0, 1 or 2.")
+
+    def final_res(self):
+        if self.store:
+            return self.w, self.time_array, self.train_losses, self.test_losses
+        else:
+            raise ValueError("Data was not saved.")
+
+
+class _LazyObjective(rankbasedObjective):
+    """rankbasedObjective that shares the ADMM engine's device-resident D instead of building its own."""
+
+    def __init__(self, X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args):
+        super().__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args, _problem=_Deferred())
+
+    def _attach(self, engine):
+        self.problem = engine
+        self._alphas_dev = engine.vec(self.alphas)
+
+
+class _Deferred:
+    def vec(self, a):
+        return None
+
+
+class ADMMmethod(Optimizer):
+    def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
+                 l2_reg=None, l1_reg=None, B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4):
+        super(ADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
+                                         args, w0, max_iter, tol)
+
+    def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
+                    B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):
+        super(ADMMmethod, self).start_store(X, y, weight_function, loss, B,
+                                            l2_reg, l1_reg, n_class, args)
+
+    def _z_subproblem(self):
+        return super(ADMMmethod, self).z_subproblem()
+
+    def _w_subproblem_device(self):
+        if self.w_flag == 1:
+            # const_y = z + lambda/rho was written by the scatter kernel; lam = alpha*n = reg/(2 rho) (:192-193,200)
+            alpha = self.reg / (2 * self.rho * self.num_row)
+            self.last_info = self.engine.w_step_fista(alpha * self.num_row, tol=self.w_tol,
+                                                      max_iter=self.fista_max_iter)
+        elif self.w_flag == 0 or self.w_flag == 2:
+            super(ADMMmethod, self)._w_subproblem_device()
+        else:
+            raise ValueError("w_flag can only be 0, 1 or 2.")
+
+    def _w_subproblem(self):
+        """reference :190-207 — standalone w-step on the current (z, lambda, rho); returns numpy d x 1"""
+        e = self.engine
+        e.b.copy_(e.z + e.lam / float(self.rho))
+        self._w_subproblem_device()
+        return e.w.cpu().numpy().reshape(-1, 1)
+
+    def main_loop(self, verbose=True):
+        t_start = time.time()
+
+        for i in range(self.max_iter):
+            if super(ADMMmethod, self).main_loop(i, t_start, verbose):
+                break
+
+        return self.w
+
+    def final_res(self):
+        return super(ADMMmethod, self).final_res()

@@ -1,0 +1,119 @@
+/*
+ * rbl_b200.h — C ABI of librbl_b200.so: the B200 (sm_100a) kernels behind the ADMM inner loop of the
+ * rank-based-loss framework (SRM / EHRM / AoRR).
+ *
+ * The reference (RufengXiao/ADMM-for-rank-based-loss) is pure Python and has no FFI; its plug point
+ * for this path is the Python class `ADMMmethod` (src/optim/algorithms.py:173-220).  This header is the
+ * boundary a native replacement of that class's numerical steps exposes: plain C, opaque handle,
+ * `int` status (0 = OK, message via rbl_last_error()), no torch types.  Every entry point cites the
+ * reference lines it replaces.  The host layer in admm-for-rank-based-loss_b200/ binds it with ctypes
+ * (INTEGRATION.md shows the binding a maintainer of the reference would add).
+ *
+ * Conventions
+ *   - every `const double*` / `double*` / `int32_t*` argument is a DEVICE pointer unless its name starts
+ *     with `h_`; the caller (PyTorch) owns all of them; the library owns only handle-internal scratch.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), except rbl_create,
+ *     rbl_destroy and rbl_fista_poll (which synchronises the stream to read the device state).
+ *   - one handle per (device, problem shape); a handle is not thread-safe, distinct handles are.
+ *   - D is row-major n_local x d with leading dimension ld (even, >= d; padding columns must be 0 —
+ *     rbl_build_design produces this layout).  Row sharding: this rank holds global rows
+ *     [row_lo, row_lo + n_local) of an n_global-row problem; sort and PAV always run on n_global.
+ */
+#ifndef RBL_B200_H
+#define RBL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rbl_ctx* rbl_handle_t;
+typedef void* rbl_stream_t; /* cudaStream_t */
+
+#define RBL_ABI_VERSION 1
+
+/* loss ids (src/optim/objective.py:26-37 get_loss) */
+#define RBL_LOSS_BINARY_CROSS_ENTROPY 0
+#define RBL_LOSS_HINGE 1
+
+int rbl_version(void);
+const char* rbl_last_error(void);
+/* kernels launched through the library by this process (instrumentation for bench.py) */
+int64_t rbl_launch_count(void);
+
+/* handle + scratch.  Replaces the state set up in Optimizer.__init__ (algorithms.py:20-75). */
+int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global, int64_t row_lo, int32_t d,
+               int64_t ld);
+int rbl_destroy(rbl_handle_t h);
+/* h_out[0..8) = num_sms, pass_grid, rows_per_tile, pass_stages, pass_smem_bytes, scratch_bytes, vec_grid,
+ * pav_chunk */
+int rbl_info(rbl_handle_t h, int64_t* h_out);
+
+/* D = -y (.) X, zero padding up to ld.  algorithms.py:23 */
+int rbl_build_design(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, rbl_stream_t stream);
+
+/* rank-order spectrum sigma (n_global) used by the PAV: alphas, or betas for EHRM.  algorithms.py:74-75 */
+int rbl_set_spectrum(rbl_handle_t h, const double* sigma, rbl_stream_t stream);
+
+/* out = D x  (one pass over D).  algorithms.py:89,132,135 */
+int rbl_matvec(rbl_handle_t h, const double* D, const double* x, double* out, rbl_stream_t stream);
+
+/* m = Dw - lambda / rho from a maintained Dw.  algorithms.py:89 */
+int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho, double* m, rbl_stream_t stream);
+
+/* stable ascending key-index sort of n_global margins.  algorithms.py:92-93 */
+int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream);
+
+/* z_sorted = argmin_{z1<=..<=zn} sum sigma_i loss(z_i) + rho/2 (z_i - m_i)^2.  pav.py:54-178,
+ * individual_solver.py:90-130, PAV_cpt.py:169-293 (with sigma = betas; clip in rbl_scatter_z) */
+int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, double* z_sorted, rbl_stream_t stream);
+
+/* out[i] = argmin_z sigma_i loss(z) + rho/2 (z - m_i)^2, no pooling.  individual_solver.py:112-130 */
+int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const double* m, int64_t n, double rho,
+                         double* out, rbl_stream_t stream);
+
+/* z[perm] = max(clip, z_sorted) on the rows this rank owns; b = z + lambda/rho (may be NULL).
+ * algorithms.py:103-104,192 */
+int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, int use_clip, double clip,
+                  const double* lam, double rho, double* z, double* b, rbl_stream_t stream);
+
+/* r = b - D x ; red[0..d) = D^T r ; red[d] = ||r||^2  (one pass over D).  w_LBFGS.py:31-45,
+ * fast_lasso.py:41-43.  red must hold d + 2 doubles. */
+int rbl_fused_pass(rbl_handle_t h, const double* D, const double* x, const double* b, double* r, double* red,
+                   rbl_stream_t stream);
+
+/* FISTA for 0.5||b - D beta||^2 + lam ||beta||_1 as a device-resident state machine.
+ * fast_lasso.py:22-69 as called from algorithms.py:199-201.
+ *   h_pow_tab[i] = float32(eta)**i, i < 128 (host pointer), L0 = float32(17) in the reference. */
+int rbl_fista_config(rbl_handle_t h, const float* h_pow_tab);
+int rbl_fista_begin(rbl_handle_t h, const double* w0, double lam, int thr_f32, float L0, double tol, int max_iter,
+                    rbl_stream_t stream);
+/* caller-owned reduce buffer (d + 2 doubles) the passes leave [D^T r, ||r||^2, c0] in, so a row-sharded
+ * host layer can all-reduce it in place between rbl_fista_pass and rbl_fista_update (NULL: internal) */
+int rbl_fista_bind_red(rbl_handle_t h, double* red);
+/* one pass at the current trial point + fixed-order reduction of the per-CTA partials into red */
+int rbl_fista_pass(rbl_handle_t h, const double* D, const double* b, rbl_stream_t stream);
+int rbl_fista_update(rbl_handle_t h, rbl_stream_t stream);
+/* single-GPU convenience: enqueue nsteps x (pass, update) without host round trips */
+int rbl_fista_steps(rbl_handle_t h, const double* D, const double* b, int nsteps, rbl_stream_t stream);
+/* synchronises `stream`; h_int[0..6) = done, k, passes, trials, i_k, cur; h_dbl[0..4) = crit, L, t, ss */
+int rbl_fista_poll(rbl_handle_t h, rbl_stream_t stream, int32_t* h_int, double* h_dbl);
+/* w_out (d) = beta, r_out (n_local) = b - D beta of the accepted iterate; either may be NULL */
+int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t stream);
+
+/* lambda += rho (z - Dw); out4 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1].
+ * from_residual != 0: Dw := b - r first (r from rbl_fista_result), saving the pass.  algorithms.py:132-136 */
+int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,
+                    int from_residual, double* lam, double rho, const double* w, const double* w_prev, double* out4,
+                    rbl_stream_t stream);
+
+/* out4[0] = sum_i sigma_i loss(u_(i)) over the ascending margins u = D w (n_global, unsorted input),
+ * out4[2] = ||w||^2, out4[3] = ||w||_1.  objective.py:71-87 */
+int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double* sigma, const double* w,
+                  double* out4, rbl_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBL_B200_H */

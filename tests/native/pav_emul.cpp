@@ -1,0 +1,66 @@
+// Host emulation of the device PAV pipeline (chunk stage + tree levels), built from the SAME
+// header the CUDA kernels include (csrc/pav_core.h).  Test infrastructure: lets the CPU test-suite
+// check the merge logic against the oracle's sequential stack PAV without a GPU.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "pav_core.h"
+
+static void fill(double* val, int64_t lo, int64_t hi, double v) {
+    for (int64_t i = lo; i < hi; ++i) val[i] = v;
+}
+
+extern "C" int emul_pav(int loss, int64_t n, const double* sigma, const double* m, double rho, int chunk_log2,
+                        double* val, int64_t* n_merges) {
+    const int64_t CH = int64_t(1) << chunk_log2;
+    const int64_t nch = (n + CH - 1) / CH;
+    int64_t merges = 0;
+    for (int64_t i = 0; i < n; ++i) val[i] = rbl_block_prox(loss, sigma[i], m[i], rho);
+    // chunk-local exclusive prefixes (n entries) + chunk totals
+    std::vector<double> lsh(n + 1), lsl(n + 1), lmh(n + 1), lml(n + 1);  // entry n: end of a partial last chunk
+    std::vector<double> osh(nch + 1), osl(nch + 1), omh(nch + 1), oml(nch + 1);
+    dd_t ts = dd_make(0.0), tm = dd_make(0.0);
+    for (int64_t ch = 0; ch < nch; ++ch) {
+        osh[ch] = ts.hi; osl[ch] = ts.lo; omh[ch] = tm.hi; oml[ch] = tm.lo;
+        int64_t base = ch * CH, len = (n - base < CH) ? n - base : CH;
+        // flat local prefix with len+1 entries for the in-chunk levels
+        std::vector<double> psh(len + 1), psl(len + 1), pmh(len + 1), pml(len + 1);
+        dd_t as = dd_make(0.0), am = dd_make(0.0);
+        for (int64_t i = 0; i < len; ++i) {
+            psh[i] = as.hi; psl[i] = as.lo; pmh[i] = am.hi; pml[i] = am.lo;
+            lsh[base + i] = as.hi; lsl[base + i] = as.lo; lmh[base + i] = am.hi; lml[base + i] = am.lo;
+            as = dd_add_d(as, sigma[base + i]);
+            am = dd_add_d(am, m[base + i]);
+        }
+        psh[len] = as.hi; psl[len] = as.lo; pmh[len] = am.hi; pml[len] = am.lo;
+        if (len < CH) { lsh[base + len] = as.hi; lsl[base + len] = as.lo; lmh[base + len] = am.hi; lml[base + len] = am.lo; }
+        ts = dd_add(ts, as);
+        tm = dd_add(tm, am);
+        PrefixFlat ps{psh.data(), psl.data()}, pm{pmh.data(), pml.data()};
+        double* v = val + base;
+        for (int64_t w = 1; w < len; w <<= 1) {
+            for (int64_t a = 0; a + w < len; a += 2 * w) {
+                int64_t b = a + w, c = (a + 2 * w < len) ? a + 2 * w : len;
+                int64_t lo, hi; double vv;
+                if (pav_merge_search(loss, rho, v, ps, pm, a, b, c, &lo, &hi, &vv)) { fill(v, lo, hi, vv); ++merges; }
+            }
+        }
+    }
+    osh[nch] = ts.hi; osl[nch] = ts.lo; omh[nch] = tm.hi; oml[nch] = tm.lo;
+    PrefixChunked ps{lsh.data(), lsl.data(), osh.data(), osl.data(), chunk_log2};
+    PrefixChunked pm{lmh.data(), lml.data(), omh.data(), oml.data(), chunk_log2};
+    for (int64_t w = CH; w < n; w <<= 1) {
+        for (int64_t a = 0; a + w < n; a += 2 * w) {
+            int64_t b = a + w, c = (a + 2 * w < n) ? a + 2 * w : n;
+            int64_t lo, hi; double vv;
+            if (pav_merge_search(loss, rho, val, ps, pm, a, b, c, &lo, &hi, &vv)) { fill(val, lo, hi, vv); ++merges; }
+        }
+    }
+    if (n_merges) *n_merges = merges;
+    return 0;
+}
+
+extern "C" uint64_t emul_key(double x) { uint64_t b; memcpy(&b, &x, 8); return rbl_key_from_bits(b); }
+extern "C" double emul_unkey(uint64_t k) { uint64_t b = rbl_bits_from_key(k); double x; memcpy(&x, &b, 8); return x; }
+extern "C" double emul_prox(int loss, double s, double m, double rho) { return rbl_block_prox(loss, s, m, rho); }

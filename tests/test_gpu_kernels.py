@@ -1,0 +1,153 @@
+"""GPU parity tests, kernel by kernel, through the C ABI (ctypes) — each compares the sm_100a path with
+the CPU oracle (oracle/rbl_oracle.py) or numpy on the same seeded inputs.  Tolerances are stated at
+each assert.  Run on the B200 box:  python -m pytest tests -m gpu -x -q"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import rbl_oracle as O  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def E():
+    from rbl_b200 import _cabi, engine
+
+    assert torch.cuda.is_available(), "gpu tests need a CUDA device"
+    return engine, _cabi
+
+
+def _mk(E, X, y=None, loss="binary_cross_entropy", sigma=None, clip=None):
+    engine, _ = E
+    n = X.shape[0]
+    if y is None:
+        y = -np.ones(n)  # D = X
+    if sigma is None:
+        sigma = np.ones(n) / n
+    return engine.AdmmEngine(X, y, loss, sigma, clip=clip)
+
+
+SHAPES = [(1000, 200), (777, 201), (6000, 1000), (300, 40), (50, 7), (3000, 1500), (1500, 3000), (257, 5000),
+          (64, 8192), (100003, 64)]
+
+
+@pytest.mark.parametrize("n,d", SHAPES)
+def test_matvec_and_fused_pass(E, n, d):
+    rng = np.random.default_rng(n * 31 + d)
+    X = rng.normal(size=(n, d))
+    y = np.where(rng.random(n) > 0.5, 1.0, -1.0)
+    e = _mk(E, X, y)
+    D = -y[:, None] * X
+    # D itself is bit-exact (one multiply and a sign flip)
+    np.testing.assert_array_equal(e.D[:, :d].cpu().numpy(), D)
+    assert float(e.D[:, d:].abs().sum()) == 0.0
+    x = rng.normal(size=d)
+    b = rng.normal(size=n)
+    xd, bd = e.vec(x), e.vec(b)
+    out = e.matvec(xd).cpu().numpy()
+    ref = D @ x
+    scale = np.abs(D) @ np.abs(x)
+    # fp64 dot products in a different summation order: error <= ~d*eps*sum|terms|
+    assert np.max(np.abs(out - ref) / scale) < 1e-14
+    _, cabi = E
+    cabi.check(e.lib.rbl_fused_pass(e.h, e.D.data_ptr(), xd.data_ptr(), bd.data_ptr(), e.r.data_ptr(),
+                                    e.red.data_ptr(), e._stream()))
+    r = e.r.cpu().numpy()
+    red = e.red.cpu().numpy()
+    rref = b - ref
+    assert np.max(np.abs(r - rref) / (np.abs(b) + scale)) < 1e-14
+    gref = D.T @ rref
+    gscale = np.abs(D).T @ np.abs(rref)
+    assert np.max(np.abs(red[:d] - gref) / gscale) < 1e-13
+    assert abs(red[d] - rref @ rref) < 1e-13 * (rref @ rref)
+    e.close()
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100003, 1 << 20])
+def test_sort_bit_exact_vs_stable_argsort(E, n):
+    rng = np.random.default_rng(n)
+    e = _mk(E, np.zeros((n, 2)))
+    cases = {"normal": rng.normal(size=n), "ties": np.round(rng.normal(size=n), 1),
+             "mixed": np.concatenate([rng.normal(size=n - n // 2) * 1e-300, rng.normal(size=n // 2) * 1e300])}
+    sp = rng.normal(size=n)
+    if n >= 31:
+        sp[:8] = [0.0, -0.0, np.inf, -np.inf, 5e-324, -5e-324, 1.0, -1.0]
+        sp[8:16] = sp[:8]
+    cases["special"] = sp
+    for name, m in cases.items():
+        md = e.vec(m)
+        E[1].check(e.lib.rbl_sort_margins(e.h, md.data_ptr(), e.m_sorted.data_ptr(), e.perm.data_ptr(), e._stream()))
+        perm = e.perm.cpu().numpy()
+        ms = e.m_sorted.cpu().numpy()
+        ref = np.argsort(m, kind="stable")
+        np.testing.assert_array_equal(perm, ref, err_msg=name)          # bit-exact permutation
+        np.testing.assert_array_equal(ms, m[ref] + 0.0, err_msg=name)   # -0.0 is canonicalised to +0.0
+    e.close()
+
+
+SPECTRA = [("erm", None), ("superquantile", [0.8]), ("aorr", [0.2, 0.8]), ("extremile", [2.5]), ("esrm", [1.5]),
+           ("ehrm", None)]
+
+
+@pytest.mark.parametrize("loss", ["binary_cross_entropy", "hinge"])
+@pytest.mark.parametrize("n", [1, 2, 3, 1023, 1024, 1025, 5000, 200000])
+def test_pav_matches_oracle(E, loss, n):
+    rng = np.random.default_rng(n + (7 if loss == "hinge" else 0))
+    for wf, args in SPECTRA:
+        if wf == "aorr" and n < 5:
+            continue
+        sig = O.spectrum(wf, n, args)
+        sig = sig[1] if isinstance(sig, tuple) else sig
+        for rho, scale in [(1e-5, 1e-3), (1e-3, 1.0), (1.0, 3.0)]:
+            m = np.sort(rng.normal(size=n) * scale)
+            if rho == 1e-3 and loss == "hinge":
+                m = np.round(m, 2)  # ties, many blocks on the kink
+            e = _mk(E, np.zeros((n, 2)), loss=loss, sigma=sig)
+            e.m_sorted.copy_(e.vec(m))
+            E[1].check(e.lib.rbl_pav_prox(e.h, O.LOSS_IDS[loss], e.m_sorted.data_ptr(), rho, e.z_sorted.data_ptr(),
+                                          e._stream()))
+            z = e.z_sorted.cpu().numpy()
+            zo = O.pav_prox(loss, sig, m, rho)
+            # same unique minimiser, both solved to machine precision; block sums in double-double
+            assert np.max(np.abs(z - zo)) <= 1e-12 * max(1.0, np.max(np.abs(zo))), (wf, rho, n)
+            assert np.all(np.diff(z) >= 0)
+            e.close()
+
+
+def test_prox_elementwise(E):
+    rng = np.random.default_rng(3)
+    n = 10000
+    m = rng.normal(size=n) * 10 ** rng.uniform(-2, 2, size=n)
+    s = 10 ** rng.uniform(-8, 0, size=n) * (rng.random(n) > 0.1)
+    from src.util.individual_solver import individual_solver
+
+    for rho in (1e-6, 1e-2, 10.0):
+        for loss in ("binary_cross_entropy", "hinge"):
+            z = individual_solver(loss, s, rho, m)
+            zo = O.prox_vec(loss, s, m, rho)
+            assert np.max(np.abs(z - zo) / np.maximum(1.0, np.abs(m))) < 1e-13, (loss, rho)
+
+
+def test_objective_matches_oracle(E):
+    rng = np.random.default_rng(5)
+    n, d = 5000, 33
+    X = rng.normal(size=(n, d))
+    y = np.where(rng.random(n) > 0.5, 1.0, -1.0).reshape(-1, 1)
+    w = rng.normal(size=d) * 0.3
+    from src.optim.objective import rankbasedObjective
+
+    for wf, args, loss, kw in [("erm", None, "binary_cross_entropy", dict(l1_reg=0.01)),
+                               ("superquantile", [0.8], "binary_cross_entropy", dict(l2_reg=0.01)),
+                               ("aorr", [0.2, 0.8], "hinge", dict(l2_reg=1e-4)),
+                               ("ehrm", None, "binary_cross_entropy", dict(l2_reg=0.01))]:
+        ob = rankbasedObjective(torch.from_numpy(X), torch.from_numpy(y), wf, loss, kw.get("l2_reg"),
+                                kw.get("l1_reg"), -5 if wf == "ehrm" else None, None, args)
+        v = ob.get_arrogate_loss(torch.from_numpy(w.reshape(-1, 1)))
+        sig = O.spectrum(wf, n, args)
+        sig = sig[0] if isinstance(sig, tuple) else sig
+        vo = O.objective(-y * X, w, sig, loss, **kw)
+        assert abs(v - vo) < 1e-12 * abs(vo), (wf, v, vo)  # fp64 sums in a different order
+        ob.problem.close()

@@ -1,0 +1,139 @@
+"""CPU: host-side logic — C-ABI surface, shard arithmetic, the CPU emulation of the device PAV (same
+header as the kernels), loud failure without a GPU, and the N>1 collective plumbing on gloo."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import rbl_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "admm-for-rank-based-loss_b200")
+
+
+def test_cabi_library_loads_and_exports_every_declared_symbol():
+    from rbl_b200 import _cabi, build
+
+    build.build()
+    hdr = open(os.path.join(ROOT, "include", "rbl_b200.h")).read()
+    declared = sorted(set(re.findall(r"\b(rbl_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(build.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/rbl_b200.h but not exported"
+    assert sorted(_cabi.exported_symbols()) == declared      # the ctypes binding covers the whole header
+    assert _cabi.load().rbl_version() == 1
+
+
+def test_product_fails_loudly_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from rbl_b200 import RblError
+    from src.optim.algorithms import ADMMmethod
+
+    with pytest.raises(RblError):
+        ADMMmethod(np.zeros((8, 2)), np.ones((8, 1)), l1_reg=0.1)
+
+
+def test_product_never_imports_the_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f"{f} imports the oracle"
+                assert "libpav_oracle" not in src and "rbl_oracle" not in src, f"{f} links the oracle"
+
+
+def test_shard_bounds_cover_rows_exactly():
+    from rbl_b200.engine import shard_bounds
+
+    for n in (1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _emul_lib():
+    path = os.path.join(ROOT, "tests", "native", "libpav_emul.so")
+    src = os.path.join(ROOT, "tests", "native", "pav_emul.cpp")
+    hdrs = [os.path.join(PKG, "csrc", h) for h in ("pav_core.h", "prox_core.h")]
+    if not os.path.exists(path) or any(os.path.getmtime(p) > os.path.getmtime(path) for p in [src] + hdrs):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-I", os.path.join(PKG, "csrc"),
+                               "-o", path, src])
+    lib = ctypes.CDLL(path)
+    dp = ctypes.POINTER(ctypes.c_double)
+    lib.emul_pav.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_int, dp,
+                             ctypes.POINTER(ctypes.c_int64)]
+    lib.emul_key.restype = ctypes.c_uint64
+    lib.emul_key.argtypes = [ctypes.c_double]
+    lib.emul_unkey.restype = ctypes.c_double
+    lib.emul_unkey.argtypes = [ctypes.c_uint64]
+    return lib
+
+
+def test_device_pav_logic_matches_stack_pav_on_cpu():
+    """csrc/pav_core.h (the code the kernels run) emulated on the host vs the oracle's stack PAV."""
+    lib = _emul_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(11)
+    for trial in range(1500):
+        n = int(rng.integers(1, 400))
+        loss = ["binary_cross_entropy", "hinge"][trial % 2]
+        kind = trial % 5
+        m = np.sort(rng.normal(size=n) * 10 ** rng.uniform(-3, 1.5))
+        if kind == 0:
+            sig = np.abs(rng.normal(size=n)) * (rng.random(n) > 0.3)
+        elif kind == 1:
+            sig = O.spectrum("superquantile", n, [rng.uniform(0.1, 0.95)])
+        elif kind == 2:
+            sig = O.spectrum("aorr", n, [0.2, 0.8]) if n >= 5 else np.ones(n) / n
+        elif kind == 3:
+            sig = O.spectrum("extremile", n, [rng.uniform(1, 4)])
+        else:
+            sig = O.spectrum("ehrm", n)[1]
+        if trial % 7 == 0:
+            m = np.round(m, 1)
+        rho = 10 ** rng.uniform(-6, 1)
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        zo = O.pav_prox(loss, sig, m, rho)
+        z = np.empty_like(m)
+        lib.emul_pav(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m.ctypes.data_as(dp), rho, int(rng.integers(1, 8)),
+                     z.ctypes.data_as(dp), None)
+        assert np.max(np.abs(z - zo)) <= 1e-13 * max(1.0, np.max(np.abs(zo))), (trial, n, loss, kind)
+        assert np.all(np.diff(z) >= 0)
+
+
+def test_radix_key_transform_is_order_preserving():
+    lib = _emul_lib()
+    rng = np.random.default_rng(2)
+    x = np.concatenate([rng.normal(size=2000) * 10 ** rng.uniform(-300, 300, size=2000),
+                        [0.0, -0.0, np.inf, -np.inf, 5e-324, -5e-324, np.nan]])
+    keys = np.array([lib.emul_key(float(v)) for v in x], dtype=np.uint64)
+    order = np.argsort(keys, kind="stable")
+    ref = np.argsort(x, kind="stable")          # numpy: NaN last, -0.0 == +0.0
+    np.testing.assert_array_equal(order, ref)
+    back = np.array([lib.emul_unkey(int(k)) for k in keys])
+    np.testing.assert_array_equal(back[:-1], x[:-1] + 0.0)
+    assert np.isnan(back[-1])
+
+
+def test_row_sharded_collectives_on_gloo():
+    """world_size = 2 on CPU/gloo: the sharded data flow of engine.py (all-gather of margins, all-reduce
+    of [D^T r, ||r||^2] partials, replicated sort+PAV, local scatter) reproduces the unsharded oracle."""
+    script = os.path.join(ROOT, "tests", "_gloo_worker.py")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29611", PYTHONPATH=ROOT + os.pathsep + PKG)
+    procs = [subprocess.Popen([sys.executable, script, str(r), "2"], env=env, stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0].decode() for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert all("OK" in o for o in outs), outs
