@@ -248,11 +248,11 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
 
 template <int XJ, int WPR, int CJ>
 int launch_t(rbl_ctx* c, const PassParams& p, cudaStream_t s) {
-    static bool attr_set = false;  // per instantiation; one device per process (one rank per GPU)
-    if (!attr_set) {
+    static size_t attr_smem = 0;  // per instantiation; one device per process (one rank per GPU)
+    if (c->pass_smem > attr_smem) {
         RBL_CUDA(cudaFuncSetAttribute(rbl_pass_kernel<XJ, WPR, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)c->pass_smem));
-        attr_set = true;
+        attr_smem = c->pass_smem;
     }
     rbl_pass_kernel<XJ, WPR, CJ><<<c->pass_grid, kThreads, c->pass_smem, s>>>(p);
     RBL_LAUNCH_CHECK();

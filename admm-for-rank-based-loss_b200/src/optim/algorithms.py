@@ -25,16 +25,20 @@ from src.optim.objective import rankbasedObjective
 
 class Optimizer:
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
-                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4):
+                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None):
+        # _shard (extension, not in the reference): dict(row_lo=, n_global=[, group=]) when X, y are this
+        # rank's contiguous rows of a row-sharded problem (one process per GPU, torch.distributed/NCCL)
         X = np.asarray(X)
         y = np.asarray(y)
-        self.num_row = X.shape[0]
+        _shard = _shard or {}
+        self.num_row = int(_shard.get("n_global", X.shape[0]))
         self.num_feature = X.shape[1]
         # regularization (:30) — raises TypeError below when both are None, like the reference (:32)
         self.reg = l1_reg or l2_reg
         self.loss = loss
         # objective first: it validates weight_function / loss / args exactly like the reference (:22)
-        self.objective = _LazyObjective(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args)
+        self.objective = _LazyObjective(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args,
+                                        self.num_row)
         self.sigma_a = self.objective.alphas.numpy().reshape(-1)
         self.sigma_b = self.objective.betas.numpy().reshape(-1)
         lam0 = 0.1 * self.reg / self.num_row  # :32,34
@@ -68,9 +72,10 @@ class Optimizer:
 
         # EHRM as shipped == max(B, isotonic prox with sigma = betas) (PAV_cpt.py:203-293)
         sigma_for_prox = self.sigma_b if weight_function == 'ehrm' else self.sigma_a
-        self.engine = AdmmEngine(X, y, loss, sigma_for_prox, clip=B if weight_function == 'ehrm' else None)
+        self.engine = AdmmEngine(X, y, loss, sigma_for_prox, clip=B if weight_function == 'ehrm' else None, **_shard)
         self.objective._attach(self.engine)
-        self.engine.set_state(w=w_init, z=np.full(self.num_row, lam0), lam=np.full(self.num_row, lam0))
+        nl = self.engine.n_local
+        self.engine.set_state(w=w_init, z=np.full(nl, lam0), lam=np.full(nl, lam0))
         self._w = w_init.astype(np.float64)
         self.fista_max_iter = 5000
         self.last_info = {}
@@ -200,8 +205,9 @@ class Optimizer:
 class _LazyObjective(rankbasedObjective):
     """rankbasedObjective that shares the ADMM engine's device-resident D instead of building its own."""
 
-    def __init__(self, X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args):
-        super().__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args, _problem=_Deferred())
+    def __init__(self, X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args, n_global):
+        super().__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class, args, _problem=_Deferred(),
+                         _n=n_global)
 
     def _attach(self, engine):
         self.problem = engine
@@ -215,9 +221,10 @@ class _Deferred:
 
 class ADMMmethod(Optimizer):
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
-                 l2_reg=None, l1_reg=None, B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4):
+                 l2_reg=None, l1_reg=None, B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4,
+                 _shard=None):
         super(ADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
-                                         args, w0, max_iter, tol)
+                                         args, w0, max_iter, tol, _shard)
 
     def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                     B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):

@@ -48,8 +48,10 @@ class rankbasedObjective:
     device once and kept there (`self.problem`)."""
 
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None, B=None,
-                 n_class=None, args=None, _problem=None):
+                 n_class=None, args=None, _problem=None, _n=None):
         self.n, self.d = X.shape
+        if _n is not None:
+            self.n = _n  # global row count of a row-sharded problem
         wf = get_weights(weight_function, args)
         if isinstance(wf, tuple):
             self.weight_function, self.weight_function2 = wf

@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — ADMM iterations/sec for SRM (superquantile q=0.8, BCE, l1_reg=0.01) on synthetic
+n = 1M x d = 1000 fp64, the configuration BASELINE.json's metric is quoted on (configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   (N > 1: rows sharded)
+
+A "step" is one ADMM iteration (z-step: margins, radix sort, PAV prox, scatter; w-step: FISTA to its
+tolerance; dual update + stop test) of one solve started from the reference's initial state; W
+warm-up iterations are iterations 0..W-1 of that solve, the K timed ones are W..W+K-1.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "admm-for-rank-based-loss_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "admm_iters_per_sec"
+UNIT = "iterations/s"
+Q, L1_REG, TOL = 0.8, 0.01, 1e-6
+BLOCK_ROWS = 125_000  # data is generated in fixed 125k-row blocks so every --gpus N solves the SAME problem
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--d", type=int, default=1000)
+    ap.add_argument("--no-solve", action="store_true", help="skip the run-to-tolerance tail")
+    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
+    return ap.parse_args()
+
+
+def planted_wstar(d):
+    rng = np.random.default_rng(17)
+    w = np.zeros(d)
+    w[:10] = rng.normal(size=min(10, d))
+    return w
+
+
+def gen_rows_numpy(lo, hi, d):
+    """CPU twin of the device generator for the reference arm / cpu_baseline sample (same recipe:
+    X ~ N(0,1), y = sign(X w* + 0.1 eps); not the same random stream as the device blocks)."""
+    rng = np.random.default_rng(1000 + lo)
+    X = rng.standard_normal(size=(hi - lo, d))
+    y = np.sign(X @ planted_wstar(d) + 0.1 * rng.standard_normal(hi - lo))
+    y[y == 0] = 1.0
+    return X, y.reshape(-1, 1)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback"
+
+
+def cpu_iters_per_sec(n_full, d, rows, iters, threads=None):
+    """The oracle port (numpy/BLAS + C stack PAV + numpy FISTA) timed on `rows` rows of the same recipe;
+    ADMM cost is linear in rows (matvec-bound), so the figure is scaled by rows / n_full."""
+    import torch
+
+    from oracle import rbl_oracle as O
+
+    if threads:
+        torch.set_num_threads(threads)
+    X, y = gen_rows_numpy(0, rows, d)
+    o = O.OracleADMM(X, y, "superquantile", "binary_cross_entropy", l1_reg=L1_REG, args=[Q], max_iter=10_000,
+                     tol=TOL)
+    o.step()  # iteration 0 (warm-up: BLAS thread pools, page faults)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        o.step()
+    dt = time.perf_counter() - t0
+    return (iters / dt) * (rows / n_full), dt, o.passes
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    rows = args.cpu_rows or 40_000
+    vals = []
+    for _ in range(max(1, min(args.steps, 3))):
+        v, dt, passes = cpu_iters_per_sec(args.n, args.d, rows, iters=max(2, args.warmup))
+        vals.append(v)
+    v = float(np.median(vals))
+    sample = (f"oracle port (numpy/BLAS matvecs, C stack-PAV, numpy FISTA fp64) on {rows} rows x {args.d} of the "
+              f"same planted recipe, {max(2, args.warmup)} ADMM iterations after 1 warm-up, repeated "
+              f"{len(vals)}x; iterations/s scaled by rows/n = {rows}/{args.n} (cost is linear in rows)")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SRM superquantile(q={Q}) BCE l1_reg={L1_REG} ADMM, n={args.n} d={args.d} fp64",
+                   "note": "reference is pure Python and O(n^2) in its PAV; it cannot run this n — the restated "
+                           "oracle (exact stack PAV) is timed instead"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rbl_b200 import _cabi
+    from rbl_b200.engine import shard_bounds
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n, d, K, W = args.n, args.d, args.steps, args.warmup
+    lo, hi = shard_bounds(n, world, rank)
+
+    # ---- synthetic planted data, generated on the device in fixed blocks -----------
+    wstar = torch.from_numpy(planted_wstar(d)).to(dev)
+    Xs, ys = [], []
+    for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
+        b_lo, b_hi = blk * BLOCK_ROWS, min(n, (blk + 1) * BLOCK_ROWS)
+        g = torch.Generator(device=dev)
+        g.manual_seed(17 + blk)
+        Xb = torch.randn(b_hi - b_lo, d, generator=g, dtype=torch.float64, device=dev)
+        eb = torch.randn(b_hi - b_lo, generator=g, dtype=torch.float64, device=dev)
+        yb = torch.sign(Xb @ wstar + 0.1 * eb)
+        yb[yb == 0] = 1.0
+        s_lo, s_hi = max(lo, b_lo) - b_lo, min(hi, b_hi) - b_lo
+        Xs.append(Xb[s_lo:s_hi])
+        ys.append(yb[s_lo:s_hi])
+    X_dev = torch.cat(Xs) if len(Xs) > 1 else Xs[0].contiguous()
+    y_dev = torch.cat(ys) if len(ys) > 1 else ys[0].contiguous()
+    del Xs, ys
+    # host copies in pinned memory: the e2e leg uploads from these inside its timed region
+    X_host = torch.empty(X_dev.shape, dtype=torch.float64, pin_memory=True)
+    y_host = torch.empty(y_dev.shape, dtype=torch.float64, pin_memory=True)
+    X_host.copy_(X_dev)
+    y_host.copy_(y_dev)
+    del X_dev, y_dev
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=L1_REG, args=[Q],
+              max_iter=100_000, tol=TOL)
+    shard = dict(row_lo=lo, n_global=n) if world > 1 else {}
+
+    # ---- upload + build (e2e part 1): pinned host -> HBM, D = -y (.) X -------------------------------
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    solver = ADMMmethod(X_host.numpy(), y_host.numpy().reshape(-1, 1), _shard=shard, **kw)
+    ev[1].record()
+    barrier()
+    t_upload = ev[0].elapsed_time(ev[1]) / 1e3
+    h2d_bytes = X_host.numel() * 8 + y_host.numel() * 8
+    launches0 = solver.engine.launches
+
+    quiet = contextlib.redirect_stdout(io.StringIO())
+    done = False
+    w0_ev, w1_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0_ev.record()
+    with quiet:
+        for it in range(W):
+            done = Optimizer.main_loop(solver, it, 0.0, False) or done
+    w1_ev.record()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches1 = solver.engine.launches
+    passes1 = solver.engine.fista_stats["passes"]
+    ev[2].record()
+    with quiet:
+        for it in range(W, W + K):
+            done = Optimizer.main_loop(solver, it, 0.0, False) or done
+    ev[3].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    t_steps = ev[2].elapsed_time(ev[3]) / 1e3
+    t_warm = w0_ev.elapsed_time(w1_ev) / 1e3
+    launches_timed = solver.engine.launches - launches1
+    passes_timed = solver.engine.fista_stats["passes"] - passes1
+    if world > 1:
+        t = torch.tensor([t_steps, t_upload], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_steps, t_upload = float(t[0]), float(t[1])
+    value = K / t_steps
+    e2e_value = K / (t_steps + t_upload)
+
+    # ---- roofline of the dominant kernel: the fused D pass, timed alone on its stream -----------------
+    eng = solver.engine
+    reps = 20
+    xd = eng.w.clone()
+    for _ in range(3):
+        _cabi.check(eng.lib.rbl_fused_pass(eng.h, eng.D.data_ptr(), xd.data_ptr(), eng.b.data_ptr(), eng.r.data_ptr(),
+                                           eng.red.data_ptr(), eng._stream()))
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for _ in range(reps):
+        _cabi.check(eng.lib.rbl_fused_pass(eng.h, eng.D.data_ptr(), xd.data_ptr(), eng.b.data_ptr(), eng.r.data_ptr(),
+                                           eng.red.data_ptr(), eng._stream()))
+    p1.record()
+    torch.cuda.synchronize()
+    t_pass = p0.elapsed_time(p1) / 1e3 / reps
+    nl = hi - lo
+    alg_bytes = nl * d * 8 + (2 * nl + 2 * d) * 8  # D once; b in, r out; x in, g out  
+    peak, peak_kind = measured_peak_gbs()
+    achieved = alg_bytes / t_pass / 1e9
+    # z-step alone (sort + PAV + scatter): 68 n bytes algorithmic
+    torch.cuda.synchronize()
+    z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    z0.record()
+    for _ in range(5):
+        eng.z_step(solver.rho)
+    z1.record()
+    torch.cuda.synchronize()
+    t_z = z0.elapsed_time(z1) / 1e3 / 5
+
+    # ---- optional tail: keep iterating the same solve to the 1e-6 stop test ---------------------------
+    solve = None
+    if not args.no_solve:
+        eng._r_matches_w = False
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        it2 = W + K
+        with quiet:
+            while not done and it2 < 1000:
+                done = Optimizer.main_loop(solver, it2, 0.0, False)
+                it2 += 1
+        s1.record()
+        barrier()
+        t_tail = s0.elapsed_time(s1) / 1e3
+        with quiet:
+            obj = solver.objective.get_arrogate_loss(torch.from_numpy(solver.w).double())
+        solve = {"iterations": it2, "converged": bool(done),
+                 "time_to_1e-6_s": round(t_warm + t_steps + t_tail, 3),
+                 "time_to_1e-6_s_incl_upload": round(t_upload + t_warm + t_steps + t_tail, 3), "objective": obj, "nnz_w": int(np.count_nonzero(solver.w)),
+                 "primal": solver.primal_feasibility, "dual": solver.dual_feasibility,
+                 "fista_passes_total": eng.fista_stats["passes"], "fista_calls": eng.fista_stats["calls"]}
+        # degenerate-benchmark guard: the solve must do real work
+        solve["non_degenerate"] = bool(obj < np.log(2.0) and solve["nnz_w"] > 0)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    cpu = None
+    if world == 1:
+        rows = args.cpu_rows or 20_000
+        v, dt, _ = cpu_iters_per_sec(n, d, rows, iters=3)
+        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"oracle port on {rows} rows x {d} of the same recipe, 3 ADMM iterations after 1 warm-up "
+                         f"({dt:.1f} s of CPU work), iterations/s scaled by {rows}/{n}"}
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": 1e3 * t_steps / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"SRM superquantile(q={Q}) BCE l1_reg={L1_REG} ADMM, n={n} d={d} fp64 "
+                               f"(BASELINE configs[1])",
+                   "rows_per_gpu": hi - lo, "parallelism": f"rows sharded x{world}" if world > 1 else "single GPU",
+                   "timed_iterations": f"{W}..{W + K - 1} of one solve from the reference's initial state",
+                   "l2_flush": "none needed: every D pass streams %.1f GB per GPU, far above the 126 MB L2"
+                               % ((hi - lo) * d * 8 / 1e9),
+                   "fista_passes_in_timed_region": passes_timed,
+                   "pass_tiles": {k: solver.engine.info[k] for k in ("pass_grid", "rows_per_tile", "pass_stages")}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / K,
+                "d2h_bytes_per_step": (d + 4) * 8,
+                "note": "K iterations through ADMMmethod (host numpy in, numpy w out each iteration) plus the "
+                        "whole pinned-host -> HBM upload of X, y and the D build charged to the K steps",
+                "upload_s": t_upload},
+        "gpu_launches": launches_timed,
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "rbl_pass_kernel (fused r = b - D x, ||r||^2, D^T r)",
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
+                     "launch_ms": 1e3 * t_pass,
+                     "pass_share_of_step": passes_timed * t_pass / t_steps},
+        "zstep": {"ms": 1e3 * t_z, "keys_per_s": n / t_z, "algorithmic_bytes": 68 * n,
+                  "frac_of_hbm_peak": 68 * n / t_z / 1e9 / peak},
+        "cpu_baseline": cpu,
+        "solve": solve,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
