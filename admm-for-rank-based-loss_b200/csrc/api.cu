@@ -76,7 +76,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->keysB, ng));
     RBL_TRY(dev_alloc(c, &c->valsA, ng));
     RBL_TRY(dev_alloc(c, &c->valsB, ng));
-    RBL_TRY(dev_alloc(c, &c->tile_hist, (size_t)256 * c->sort_tiles + 8));
+    RBL_TRY(dev_alloc(c, &c->tile_hist, (size_t)256 * c->sort_tiles + 256 + 8));
     c->chunk_log2 = rbl_pav_chunk_log2();
     c->nchunks = (c->n_global + ((int64_t)1 << c->chunk_log2) - 1) >> c->chunk_log2;
     const size_t nch = (size_t)c->nchunks;
@@ -92,6 +92,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->pm_off_lo, nch + 1));
     RBL_TRY(dev_alloc(c, &c->ch_tot_hi, nch + 1));
     RBL_TRY(dev_alloc(c, &c->ch_tot_lo, nch + 1));
+    RBL_TRY(dev_alloc(c, &c->node_cnt, nch + 64));
     RBL_TRY(dev_alloc(c, &c->sigma, ng));
     RBL_TRY(dev_alloc(c, &c->obj_tmp, ng));
     return RBL_OK;
@@ -102,7 +103,7 @@ void ctx_free(rbl_ctx* c) {
                     c->beta_prev, c->g_p,       c->g_prev,    c->rbuf[0],   c->rbuf[1],   c->red_own,   c->c0part,
                     c->keysA,     c->keysB,     c->valsA,     c->valsB,     c->tile_hist, c->ps_loc_hi, c->ps_loc_lo,
                     c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
-                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp};
+                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);

@@ -92,7 +92,7 @@ struct rbl_ctx {
     // ---- sort
     uint64_t *keysA, *keysB;
     uint32_t *valsA, *valsB;
-    uint32_t* tile_hist;    // [256 * ntiles] (+1)
+    uint32_t* tile_hist;    // [256 * ntiles] per-digit tile counts, then [256] digit totals
     int sort_tiles;
     // ---- PAV
     int chunk_log2;
@@ -101,6 +101,7 @@ struct rbl_ctx {
     double *ps_tot_hi, *ps_tot_lo;                          // per-chunk totals of sigma
     double *pm_loc_hi, *pm_loc_lo, *pm_off_hi, *pm_off_lo;  // margin prefixes (every z-step)
     double *ch_tot_hi, *ch_tot_lo;                          // per-chunk totals scratch
+    unsigned int* node_cnt;  // merge-tree arrival counters (self-cleaning)
     double* sigma;          // n_global, rank order (the sigma the PAV uses: alphas, or betas for EHRM)
     double* val;            // n_global block values
     int has_sigma;

@@ -6,9 +6,9 @@
 // because the pooled block swallows one sigma=0 neighbour per pass.  Here the same fixed point
 // (the unique isotonic prox) is reached by a balanced tree of merges of depth log2(n):
 //
-//   level 0 : every element is a solved range, val[i] = prox(sigma_i, m_i)
+//   level 0 : every element is a solved range, val(i) = prox(sigma_i, m_i)
 //   level l : adjacent solved ranges L=[a,b), R=[b,c) are merged.  Inside a solved range val is
-//             non-decreasing.  If val[b-1] <= val[b] nothing changes.  Otherwise exactly one new
+//             non-decreasing.  If val(b-1) <= val(b) nothing changes.  Otherwise exactly one new
 //             pooled block [lo*, hi*) appears across the boundary; everything else is unchanged
 //             ("clipping" property of isotonic merges):  z_i = min(z^L_i, t*) on L and
 //             max(z^R_i, t*) on R, where t* minimises
@@ -66,22 +66,63 @@ struct PrefixChunked {
     }
 };
 
-// first i in [lo,hi) with val[i] >= u  (hi if none)
-RBL_HD int64_t pav_lower_bound(const double* val, int64_t lo, int64_t hi, double u) {
+// read accessors for the block-value array: plain (host emulation, shared memory) or L1-bypassing
+// (device global memory that other CTAs of the same launch have written)
+struct ValPlain {
+    const double* p;
+    RBL_HDM double operator()(int64_t i) const { return p[i]; }
+};
+#if defined(__CUDACC__)
+struct ValCG {
+    const double* p;
+    __device__ __forceinline__ double operator()(int64_t i) const { return __ldcg(p + i); }
+};
+#endif
+
+// first i in [lo,hi) with val(i) >= u  (hi if none)
+template <class V>
+RBL_HD int64_t pav_lower_bound(const V& val, int64_t lo, int64_t hi, double u) {
     while (lo < hi) {
         int64_t mid = lo + ((hi - lo) >> 1);
-        if (val[mid] < u) lo = mid + 1; else hi = mid;
+        if (val(mid) < u) lo = mid + 1; else hi = mid;
     }
     return lo;
 }
 
-// first i in [lo,hi) with val[i] > u  (hi if none)
-RBL_HD int64_t pav_upper_bound(const double* val, int64_t lo, int64_t hi, double u) {
+// first i in [lo,hi) with val(i) > u  (hi if none)
+template <class V>
+RBL_HD int64_t pav_upper_bound(const V& val, int64_t lo, int64_t hi, double u) {
     while (lo < hi) {
         int64_t mid = lo + ((hi - lo) >> 1);
-        if (val[mid] <= u) lo = mid + 1; else hi = mid;
+        if (val(mid) <= u) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// upper_bound over [lo,hi) galloping up from lo (cheap when the answer is near lo)
+template <class V>
+RBL_HD int64_t pav_gallop_upper_from_lo(const V& val, int64_t lo, int64_t hi, double u) {
+    int64_t step = 1, prev = lo, probe = lo;  // invariant: everything before prev is <= u
+    while (probe < hi && val(probe) <= u) {
+        prev = probe + 1;
+        probe = lo + step;
+        step <<= 1;
+    }
+    if (probe > hi) probe = hi;
+    return pav_upper_bound(val, prev, probe, u);
+}
+
+// lower_bound over [lo,hi) galloping down from hi (cheap when the answer is near hi)
+template <class V>
+RBL_HD int64_t pav_gallop_lower_from_hi(const V& val, int64_t lo, int64_t hi, double u) {
+    int64_t step = 1, prev = hi, probe = hi - 1;  // invariant: everything from prev on is >= u
+    while (probe >= lo && val(probe) >= u) {
+        prev = probe;
+        probe = hi - 1 - step;
+        step <<= 1;
+    }
+    if (probe < lo - 1) probe = lo - 1;
+    return pav_lower_bound(val, probe + 1, prev, u);
 }
 
 // sum_{i in [l,r)} f_i'(u) with the one-sided loss derivative
@@ -101,11 +142,12 @@ RBL_HD double pav_block_value(int loss, double rho, const PS& ps, const PM& pm, 
     return rbl_block_prox(loss, ssig / cnt, sm / cnt, rho);
 }
 
-// end of the run of values <= u that contains position p (val[p] <= u): first i in (p, limit) with
-// val[i] > u, found by galloping so that the usual short run costs one or two reads
-RBL_HD int64_t pav_run_end(const double* val, int64_t p, int64_t limit, double u) {
+// end of the run of values <= u that contains position p (val(p) <= u): first i in (p, limit) with
+// val(i) > u, found by galloping so that the usual short run costs one or two reads
+template <class V>
+RBL_HD int64_t pav_run_end(const V& val, int64_t p, int64_t limit, double u) {
     int64_t prev = p, step = 1, probe = p + 1;
-    while (probe < limit && val[probe] <= u) {
+    while (probe < limit && val(probe) <= u) {
         prev = probe;
         step <<= 1;
         probe = prev + step;
@@ -114,11 +156,12 @@ RBL_HD int64_t pav_run_end(const double* val, int64_t p, int64_t limit, double u
     return pav_upper_bound(val, prev + 1, probe, u);
 }
 
-// start of the run of values >= u that contains position p (val[p] >= u): first i in [limit, p] with
-// val[i] >= u, galloping backwards
-RBL_HD int64_t pav_run_start(const double* val, int64_t p, int64_t limit, double u) {
+// start of the run of values >= u that contains position p (val(p) >= u): first i in [limit, p] with
+// val(i) >= u, galloping backwards
+template <class V>
+RBL_HD int64_t pav_run_start(const V& val, int64_t p, int64_t limit, double u) {
     int64_t prev = p, step = 1, probe = p - 1;
-    while (probe >= limit && val[probe] >= u) {
+    while (probe >= limit && val(probe) >= u) {
         prev = probe;
         step <<= 1;
         probe = prev - step;
@@ -133,57 +176,233 @@ RBL_HD int64_t pav_run_start(const double* val, int64_t p, int64_t limit, double
 // Cost: the bound searches on the probe's own side gallop from the probe (runs are short), and the
 // searches on the opposite side are monotone in the probe position, so their window [xlo, xhi]
 // shrinks together with the outer binary search: O(log n) dependent reads per side in total.
-template <class PS, class PM>
-RBL_HD bool pav_merge_search(int loss, double rho, const double* val, const PS& ps, const PM& pm, int64_t a,
+template <class V, class PS, class PM>
+RBL_HD bool pav_merge_search(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
                              int64_t b, int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
-    if (!(val[b - 1] > val[b])) return false;
-    // ---- left side: first p in [a,b) with Phi(val[p]+) >= 0; val[b-1] always qualifies
+    if (!(val(b - 1) > val(b))) return false;
+    // ---- left side: first p in [a,b) with Phi(val(p)+) >= 0; val(b-1) always qualifies.
+    // Probes gallop outward from the boundary (most pooled blocks are short), then bisect.  A probe
+    // decides for the whole run of equal values around it (an earlier pooled block, possibly huge),
+    // so the interval jumps to the run's start / end instead of stepping through it.
     int64_t lo = a, hi = b - 1;
-    int64_t xlo = b, xhi = c;  // window of upper_bound(val[b..c), val[p]) for the remaining probes
+    int64_t xlo = b, xhi = c;  // window of upper_bound(val(b..c), val(p)) for the remaining probes
+    bool gallop = true;
+    int64_t step = 1;
     while (lo < hi) {
-        int64_t mid = lo + ((hi - lo) >> 1);
-        double u = val[mid];
-        int64_t l = pav_run_end(val, mid, b, u);          // {L: val > u} = [l, b)
-        int64_t r = pav_upper_bound(val, xlo, xhi, u);    // {R: val <= u} = [b, r)
-        if (pav_phi(loss, rho, ps, pm, l, r, u, +1) >= 0.0) {
-            hi = mid;
-            xhi = r;
+        int64_t mid;
+        if (gallop) {
+            mid = hi - step;
+            if (mid < lo) mid = lo;
         } else {
-            lo = mid + 1;
+            mid = lo + ((hi - lo) >> 1);
+        }
+        const double u = val(mid);
+        const int64_t l = pav_run_end(val, mid, b, u);  // {L: val > u} = [l, b)
+        const int64_t r = gallop ? pav_gallop_upper_from_lo(val, xlo, xhi, u)
+                                 : pav_upper_bound(val, xlo, xhi, u);  // {R: val <= u} = [b, r)
+        if (pav_phi(loss, rho, ps, pm, l, r, u, +1) >= 0.0) {
+            hi = pav_run_start(val, mid, lo, u);
+            xhi = r;
+            step <<= 1;
+        } else {
+            lo = l;
             xlo = r;
+            gallop = false;
         }
     }
     int64_t lo_star = lo;
-    // ---- right side: first p in (b,c) with Phi(val[p]-) > 0; val[b] never qualifies
+    // ---- right side: first p in (b,c) with Phi(val(p)-) > 0; val(b) never qualifies
     lo = b + 1;
     hi = c;
     xlo = a;
-    xhi = b;  // window of lower_bound(val[a..b), val[p])
+    xhi = b;  // window of lower_bound(val(a..b), val(p))
+    gallop = true;
+    step = 1;
     while (lo < hi) {
-        int64_t mid = lo + ((hi - lo) >> 1);
-        double u = val[mid];
-        int64_t l = pav_lower_bound(val, xlo, xhi, u);    // {L: val >= u} = [l, b)
-        int64_t r = pav_run_start(val, mid, b, u);        // {R: val < u} = [b, r)
-        if (pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0) {
-            hi = mid;
-            xhi = l;
+        int64_t mid;
+        if (gallop) {
+            mid = lo + step - 1;
+            if (mid > hi - 1) mid = hi - 1;
         } else {
-            lo = mid + 1;
+            mid = lo + ((hi - lo) >> 1);
+        }
+        const double u = val(mid);
+        const int64_t l = gallop ? pav_gallop_lower_from_hi(val, xlo, xhi, u)
+                                 : pav_lower_bound(val, xlo, xhi, u);  // {L: val >= u} = [l, b)
+        const int64_t r = pav_run_start(val, mid, b, u);               // {R: val < u} = [b, r)
+        if (pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0) {
+            hi = r;
+            xhi = l;
+            gallop = false;
+        } else {
+            lo = pav_run_end(val, mid, hi, u);
             xlo = l;
+            step <<= 1;
         }
     }
     int64_t hi_star = lo;
     // snap to whole runs of equal values (probes inside a run give the same answer, but rounding
     // in Phi near a tie may split one; equal values pool for free)
-    lo_star = pav_run_start(val, lo_star, a, val[lo_star]);
-    hi_star = pav_run_end(val, hi_star - 1, c, val[hi_star - 1]);
+    lo_star = pav_run_start(val, lo_star, a, val(lo_star));
+    hi_star = pav_run_end(val, hi_star - 1, c, val(hi_star - 1));
     double v = pav_block_value(loss, rho, ps, pm, lo_star, hi_star);
-    // exact arithmetic guarantees val[lo*-1] <= v <= val[hi*]; clamp so rounding can never break the
+    // exact arithmetic guarantees val(lo*-1) <= v <= val(hi*); clamp so rounding can never break the
     // "non-decreasing inside a solved range" invariant the bound searches rely on
-    if (lo_star > a && v < val[lo_star - 1]) v = val[lo_star - 1];
-    if (hi_star < c && v > val[hi_star]) v = val[hi_star];
+    if (lo_star > a && v < val(lo_star - 1)) v = val(lo_star - 1);
+    if (hi_star < c && v > val(hi_star)) v = val(hi_star);
     *lo_out = lo_star;
     *hi_out = hi_star;
     *v_out = v;
+    return true;
+}
+
+// =================================================================================================
+// Global levels (ranges wider than one chunk, values in global memory): the same merge as
+// pav_merge_search, but with 32-ary searches — the 32 lanes of a warp probe 32 positions per round,
+// each lane running its own opposite-side bound search, so the dependent-load chain of a merge is
+// ~3 rounds instead of ~20 bisection steps.  Round 0 probes exponentially growing distances from the
+// boundary (most pooled blocks are short), later rounds subdivide the bracket evenly.
+// The per-lane probes and the round bookkeeping below are shared between the CUDA kernel (one lane
+// per probe, ballot/shuffle) and the host emulation in tests/native (loops over lanes).
+// =================================================================================================
+
+// left-side probe at p in [a,b): the whole run of equal values around p joins the pooled block iff
+// Phi(val(p)+) >= 0.  [xlo,xhi] bounds upper_bound(val[b..c), val(p)); outputs: that bound, and the run.
+template <class V, class PS, class PM>
+RBL_HD bool pav_probe_left(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
+                           int64_t p, int64_t xlo, int64_t xhi, bool gallop, int64_t* r_out, int64_t* rs_out,
+                           int64_t* re_out) {
+    const double u = val(p);
+    const int64_t l = pav_run_end(val, p, b, u);                                // {L: val > u} = [l, b)
+    const int64_t r = gallop ? pav_gallop_upper_from_lo(val, xlo, xhi, u)
+                             : pav_upper_bound(val, xlo, xhi, u);                // {R: val <= u} = [b, r)
+    *r_out = r;
+    *re_out = l;
+    *rs_out = pav_run_start(val, p, a, u);
+    return pav_phi(loss, rho, ps, pm, l, r, u, +1) >= 0.0;
+}
+
+// right-side probe at p in (b,c): the run around p stays out of the pooled block iff Phi(val(p)-) > 0
+template <class V, class PS, class PM>
+RBL_HD bool pav_probe_right(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t b, int64_t c,
+                            int64_t p, int64_t xlo, int64_t xhi, bool gallop, int64_t* l_out, int64_t* rs_out,
+                            int64_t* re_out) {
+    const double u = val(p);
+    const int64_t l = gallop ? pav_gallop_lower_from_hi(val, xlo, xhi, u)
+                             : pav_lower_bound(val, xlo, xhi, u);                // {L: val >= u} = [l, b)
+    const int64_t r = pav_run_start(val, p, b, u);                               // {R: val < u} = [b, r)
+    *l_out = l;
+    *rs_out = r;
+    *re_out = pav_run_end(val, p, c, u);
+    return pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0;
+}
+
+// probe position of lane j when the unknown candidates are [lo, lo+width); lanes j >= width idle if width <= 32
+RBL_HD int64_t pav_kary_pos(int64_t lo, int64_t width, int j) {
+    if (width <= 32) return lo + j;
+    return lo + (int64_t)(((long long)(j + 1) * (long long)width) / 33);
+}
+
+template <class V, class PS, class PM>
+RBL_HD void pav_kary_finish(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t c,
+                            int64_t lo_star, int64_t hi_star, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+    lo_star = pav_run_start(val, lo_star, a, val(lo_star));
+    hi_star = pav_run_end(val, hi_star - 1, c, val(hi_star - 1));
+    double v = pav_block_value(loss, rho, ps, pm, lo_star, hi_star);
+    if (lo_star > a) {
+        const double vl = val(lo_star - 1);
+        if (v < vl) v = vl;
+    }
+    if (hi_star < c) {
+        const double vr = val(hi_star);
+        if (v > vr) v = vr;
+    }
+    *lo_out = lo_star;
+    *hi_out = hi_star;
+    *v_out = v;
+}
+
+// lane-loop version (host emulation); the CUDA kernel mirrors it with one lane per probe
+template <class V, class PS, class PM>
+RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
+                                  int64_t b, int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+    if (!(val(b - 1) > val(b))) return false;
+    // ---- left: first p in [a, b-1] whose probe is true (b-1 is): pattern over p is F..F T..T
+    int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
+    bool first = true;
+    while (lo < hi) {
+        const int64_t width = hi - lo;
+        int active;
+        int64_t pos[32], rr[32], rs[32], re[32];
+        bool pr[32];
+        if (first) {  // exponential distances hi - 2^j: lanes see T..T F..F
+            active = 0;
+            while (active < 32 && ((int64_t)1 << active) <= width) ++active;
+            for (int j = 0; j < active; ++j) pos[j] = hi - ((int64_t)1 << j);
+        } else {
+            active = width <= 32 ? (int)width : 32;
+            for (int j = 0; j < active; ++j) pos[j] = pav_kary_pos(lo, width, j);
+        }
+        for (int j = 0; j < active; ++j)
+            pr[j] = pav_probe_left(loss, rho, val, ps, pm, a, b, pos[j], xlo, xhi, first, &rr[j], &rs[j], &re[j]);
+        if (first) {
+            int f = active;  // first false lane
+            for (int j = 0; j < active; ++j)
+                if (!pr[j]) { f = j; break; }
+            if (f < active) { lo = re[f] > lo ? re[f] : lo; xlo = rr[f]; }
+            if (f > 0) { hi = rs[f - 1] < hi ? rs[f - 1] : hi; xhi = rr[f - 1]; }
+            first = false;
+        } else {
+            int f = -1;  // first true lane
+            for (int j = 0; j < active; ++j)
+                if (pr[j]) { f = j; break; }
+            if (f >= 0) {
+                hi = rs[f] < hi ? rs[f] : hi;
+                xhi = rr[f];
+                if (f > 0) { lo = re[f - 1] > lo ? re[f - 1] : lo; xlo = rr[f - 1]; }
+            } else {
+                lo = re[active - 1] > lo ? re[active - 1] : lo;
+                xlo = rr[active - 1];
+            }
+        }
+        if (hi < lo) hi = lo;
+    }
+    const int64_t lo_star = lo;
+    // ---- right: first p in [b+1, c) whose probe is true, else c: pattern over p is F..F T..T
+    lo = b + 1;
+    hi = c;
+    xlo = a;
+    xhi = b;
+    first = true;
+    while (lo < hi) {
+        const int64_t width = hi - lo;
+        int active;
+        int64_t pos[32], ll[32], rs[32], re[32];
+        bool pr[32];
+        if (first) {  // exponential distances lo + 2^j - 1
+            active = 0;
+            while (active < 32 && ((int64_t)1 << active) <= width) ++active;
+            for (int j = 0; j < active; ++j) pos[j] = lo + ((int64_t)1 << j) - 1;
+        } else {
+            active = width <= 32 ? (int)width : 32;
+            for (int j = 0; j < active; ++j) pos[j] = pav_kary_pos(lo, width, j);
+        }
+        for (int j = 0; j < active; ++j)
+            pr[j] = pav_probe_right(loss, rho, val, ps, pm, b, c, pos[j], xlo, xhi, first, &ll[j], &rs[j], &re[j]);
+        int f = -1;  // first true lane
+        for (int j = 0; j < active; ++j)
+            if (pr[j]) { f = j; break; }
+        if (f >= 0) {
+            hi = rs[f] < hi ? rs[f] : hi;
+            xhi = ll[f];
+            if (f > 0) { lo = re[f - 1] > lo ? re[f - 1] : lo; xlo = ll[f - 1]; }
+        } else {
+            lo = re[active - 1] > lo ? re[active - 1] : lo;
+            xlo = ll[active - 1];
+        }
+        first = false;
+        if (hi < lo) hi = lo;
+    }
+    pav_kary_finish(loss, rho, val, ps, pm, a, c, lo_star, lo, lo_out, hi_out, v_out);
     return true;
 }

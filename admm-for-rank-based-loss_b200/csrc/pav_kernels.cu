@@ -9,10 +9,10 @@
 // Kernels
 //   chunk_prefix   : chunk-local exclusive prefix sums in double-double (sigma once, margins per call)
 //   chunk_offsets  : exclusive scan of the chunk totals (one small CTA)
-//   pav_chunk      : one CTA per 1024-element chunk; prox per element, local prefix of m, then the
-//                    10 in-chunk merge levels entirely in shared memory
-//   pav_level      : one CTA per pair of solved ranges for the remaining log2(n/1024) levels; one
-//                    thread runs the O(log n) merge search, the whole CTA fills the pooled block
+//   pav_chunk      : one CTA per 1024-element chunk: element prox + the 10 in-chunk merge levels in
+//                    shared memory
+//   pav_tree       : the remaining log2(n/1024) levels in ONE launch: one CTA per pair of chunks climbs
+//                    the merge tree ("last arriver continues": no CTA ever waits for another)
 #include "common.cuh"
 #include "pav_core.h"
 
@@ -135,107 +135,258 @@ struct ChunkSmem {
     double val[kChunk];
     double psh[kChunk + 1], psl[kChunk + 1];
     double pmh[kChunk + 1], pml[kChunk + 1];
-    double sh[16];
     int64_t rec_lo[16], rec_hi[16];
     double rec_v[16];
 };
 
-__global__ void __launch_bounds__(kPavThreads) pav_chunk_kernel(
-    int loss, double rho, const double* __restrict__ sigma, const double* __restrict__ m, int64_t n,
-    const double* __restrict__ ps_loc_hi, const double* __restrict__ ps_loc_lo, const double* __restrict__ ps_tot_hi,
-    const double* __restrict__ ps_tot_lo, double* __restrict__ pm_loc_hi, double* __restrict__ pm_loc_lo,
-    double* __restrict__ pm_tot_hi, double* __restrict__ pm_tot_lo, double* __restrict__ val_out) {
+struct TreeParams {
+    int loss;
+    double rho;
+    const double* sigma;
+    const double* m;
+    int64_t n;
+    const double *ps_loc_hi, *ps_loc_lo, *ps_tot_hi, *ps_tot_lo, *ps_off_hi, *ps_off_lo;
+    const double *pm_loc_hi, *pm_loc_lo, *pm_tot_hi, *pm_tot_lo, *pm_off_hi, *pm_off_lo;
+    double* val;
+    unsigned int* node_cnt;
+    int64_t nchunks;
+};
+
+// one merge of two solved ranges by a full warp (shared- or global-memory values): the rounds of pav_merge_search_kary (pav_core.h, which the CPU
+// tests run with a loop over lanes) with one lane per probe — keep the two in sync
+template <class V, class PS, class PM>
+__device__ bool merge_kary_warp(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
+                                int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    if (!(val(b - 1) > val(b))) return false;
+    // ---- left
+    int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
+    bool first = true;
+    while (lo < hi) {
+        const int64_t width = hi - lo;
+        int active;
+        int64_t pos;
+        if (first) {
+            active = 0;
+            while (active < 32 && ((int64_t)1 << active) <= width) ++active;
+            pos = hi - ((int64_t)1 << lane);
+        } else {
+            active = width <= 32 ? (int)width : 32;
+            pos = pav_kary_pos(lo, width, lane);
+        }
+        int64_t rr = 0, rs = 0, re = 0;
+        bool pr = first;  // idle lanes must not look like the searched-for transition
+        if (lane < active) pr = pav_probe_left(loss, rho, val, ps, pm, a, b, pos, xlo, xhi, first, &rr, &rs, &re);
+        const unsigned ball = __ballot_sync(FULL, pr);
+        if (first) {
+            const unsigned nb = ~ball;  // first false lane (idle lanes vote true)
+            const int f = nb ? (__ffs(nb) - 1) : active;
+            const int fs = f < 32 ? f : 31, fm = f > 0 ? f - 1 : 0;
+            const int64_t re_f = __shfl_sync(FULL, re, fs), rr_f = __shfl_sync(FULL, rr, fs);
+            const int64_t rs_m = __shfl_sync(FULL, rs, fm), rr_m = __shfl_sync(FULL, rr, fm);
+            if (f < active) {
+                lo = re_f > lo ? re_f : lo;
+                xlo = rr_f;
+            }
+            if (f > 0) {
+                hi = rs_m < hi ? rs_m : hi;
+                xhi = rr_m;
+            }
+            first = false;
+        } else {
+            const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
+            const int fs = f >= 0 ? f : active - 1, fm = f > 0 ? f - 1 : 0;
+            const int64_t rs_f = __shfl_sync(FULL, rs, fs), rr_f = __shfl_sync(FULL, rr, fs), re_f = __shfl_sync(FULL, re, fs);
+            const int64_t re_m = __shfl_sync(FULL, re, fm), rr_m = __shfl_sync(FULL, rr, fm);
+            if (f >= 0) {
+                hi = rs_f < hi ? rs_f : hi;
+                xhi = rr_f;
+                if (f > 0) {
+                    lo = re_m > lo ? re_m : lo;
+                    xlo = rr_m;
+                }
+            } else {
+                lo = re_f > lo ? re_f : lo;
+                xlo = rr_f;
+            }
+        }
+        if (hi < lo) hi = lo;
+    }
+    const int64_t lo_star = lo;
+    // ---- right
+    lo = b + 1;
+    hi = c;
+    xlo = a;
+    xhi = b;
+    first = true;
+    while (lo < hi) {
+        const int64_t width = hi - lo;
+        int active;
+        int64_t pos;
+        if (first) {
+            active = 0;
+            while (active < 32 && ((int64_t)1 << active) <= width) ++active;
+            pos = lo + ((int64_t)1 << lane) - 1;
+        } else {
+            active = width <= 32 ? (int)width : 32;
+            pos = pav_kary_pos(lo, width, lane);
+        }
+        int64_t ll = 0, rs = 0, re = 0;
+        bool pr = false;
+        if (lane < active) pr = pav_probe_right(loss, rho, val, ps, pm, b, c, pos, xlo, xhi, first, &ll, &rs, &re);
+        const unsigned ball = __ballot_sync(FULL, pr);
+        const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
+        const int fs = f >= 0 ? f : active - 1, fm = f > 0 ? f - 1 : 0;
+        const int64_t rs_f = __shfl_sync(FULL, rs, fs), ll_f = __shfl_sync(FULL, ll, fs), re_f = __shfl_sync(FULL, re, fs);
+        const int64_t re_m = __shfl_sync(FULL, re, fm), ll_m = __shfl_sync(FULL, ll, fm);
+        if (f >= 0) {
+            hi = rs_f < hi ? rs_f : hi;
+            xhi = ll_f;
+            if (f > 0) {
+                lo = re_m > lo ? re_m : lo;
+                xlo = ll_m;
+            }
+        } else {
+            lo = re_f > lo ? re_f : lo;
+            xlo = ll_f;
+        }
+        first = false;
+        if (hi < lo) hi = lo;
+    }
+    pav_kary_finish(loss, rho, val, ps, pm, a, c, lo_star, lo, lo_out, hi_out, v_out);
+    return true;
+}
+
+// Chunk stage: each CTA solves its 1024-element chunk in shared memory (element prox + the 10
+// in-chunk merge levels) and writes the chunk-stage block values.
+__global__ void __launch_bounds__(kPavThreads, 3) pav_chunk_kernel(const TreeParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
     const int tid = threadIdx.x;
+    const int loss = P.loss;
+    const double rho = P.rho;
+    const int64_t n = P.n;
     const int64_t base = (int64_t)blockIdx.x * kChunk;
     const int len = (int)((n - base < kChunk) ? (n - base) : kChunk);
-    const int l0 = tid * kPer;
 
-    // element prox + local prefix of m (exclusive, dd) ; sigma's local prefix was built once at setup
-    double mv[kPer];
-    dd_t run = dd_make(0.0);
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int li = l0 + q;
-        if (li < len) {
-            const double sg = sigma[base + li];
-            mv[q] = m[base + li];
-            S.val[li] = rbl_block_prox(loss, sg, mv[q], rho);
-            S.psh[li] = ps_loc_hi[base + li];
-            S.psl[li] = ps_loc_lo[base + li];
-        } else {
-            mv[q] = 0.0;
-        }
-        run = dd_add_d(run, mv[q]);
+    // ---- stage 1: this chunk, in shared memory
+    for (int li = tid; li < len; li += kPavThreads) {
+        S.val[li] = rbl_block_prox(loss, P.sigma[base + li], P.m[base + li], rho);
+        S.psh[li] = P.ps_loc_hi[base + li];
+        S.psl[li] = P.ps_loc_lo[base + li];
+        S.pmh[li] = P.pm_loc_hi[base + li];
+        S.pml[li] = P.pm_loc_lo[base + li];
     }
-    dd_t total;
-    dd_t ex = block_excl_scan_dd(run, &total, S.sh);
-#pragma unroll
-    for (int q = 0; q < kPer; ++q) {
-        const int li = l0 + q;
-        if (li < len) {
-            S.pmh[li] = ex.hi;
-            S.pml[li] = ex.lo;
-            pm_loc_hi[base + li] = ex.hi;
-            pm_loc_lo[base + li] = ex.lo;
-        }
-        ex = dd_add_d(ex, mv[q]);
-    }
-    if (tid == 0) {
-        pm_tot_hi[blockIdx.x] = total.hi;
-        pm_tot_lo[blockIdx.x] = total.lo;
-        // closing entries of the exclusive prefixes
-        S.pmh[len] = total.hi;
-        S.pml[len] = total.lo;
-        if (len < kChunk) {
-            pm_loc_hi[base + len] = total.hi;
-            pm_loc_lo[base + len] = total.lo;
-        }
-        S.psh[len] = (len == kChunk) ? ps_tot_hi[blockIdx.x] : ps_loc_hi[base + len];
-        S.psl[len] = (len == kChunk) ? ps_tot_lo[blockIdx.x] : ps_loc_lo[base + len];
+    if (tid == 0) {  // closing entries of the chunk-local exclusive prefixes
+        const bool full = (len == kChunk);
+        S.psh[len] = full ? P.ps_tot_hi[blockIdx.x] : P.ps_loc_hi[base + len];
+        S.psl[len] = full ? P.ps_tot_lo[blockIdx.x] : P.ps_loc_lo[base + len];
+        S.pmh[len] = full ? P.pm_tot_hi[blockIdx.x] : P.pm_loc_hi[base + len];
+        S.pml[len] = full ? P.pm_tot_lo[blockIdx.x] : P.pm_loc_lo[base + len];
     }
     __syncthreads();
-
-    PrefixFlat ps{S.psh, S.psl}, pm{S.pmh, S.pml};
-    for (int w = 1; w < len; w <<= 1) {
-        const int npairs = (len + 2 * w - 1) / (2 * w);
-        if (2 * w <= 32) {
-            // many small pairs: the searching thread fills its own pooled block
-            for (int pr = tid; pr < npairs; pr += kPavThreads) {
-                const int a = pr * 2 * w, b = a + w;
-                if (b < len) {
-                    const int c = (a + 2 * w < len) ? a + 2 * w : len;
-                    int64_t lo, hi;
-                    double v;
-                    if (pav_merge_search(loss, rho, S.val, ps, pm, a, b, c, &lo, &hi, &v))
-                        for (int64_t i = lo; i < hi; ++i) S.val[i] = v;
+    {
+        PrefixFlat ps{S.psh, S.psl}, pm{S.pmh, S.pml};
+        ValPlain sval{S.val};
+        for (int w = 1; w < len; w <<= 1) {
+            const int npairs = (len + 2 * w - 1) / (2 * w);
+            if (2 * w <= 32) {
+                // many small pairs: the searching thread fills its own pooled block
+                for (int pr = tid; pr < npairs; pr += kPavThreads) {
+                    const int a = pr * 2 * w, b = a + w;
+                    if (b < len) {
+                        const int c = (a + 2 * w < len) ? a + 2 * w : len;
+                        int64_t lo, hi;
+                        double v;
+                        if (pav_merge_search(loss, rho, sval, ps, pm, a, b, c, &lo, &hi, &v))
+                            for (int64_t i = lo; i < hi; ++i) S.val[i] = v;
+                    }
                 }
-            }
-            __syncthreads();
-        } else {
-            // few large pairs (<= 16): search by one thread each, fill by the whole CTA
-            if (tid < npairs) {
-                const int a = tid * 2 * w, b = a + w;
-                int64_t lo = 0, hi = 0;
-                double v = 0.0;
-                if (b < len) {
-                    const int c = (a + 2 * w < len) ? a + 2 * w : len;
-                    if (!pav_merge_search(loss, rho, S.val, ps, pm, a, b, c, &lo, &hi, &v)) lo = hi = 0;
+                __syncthreads();
+            } else {
+                // few large pairs (<= 16): one warp per pair runs the 32-ary search, the CTA fills
+                const int wid = tid >> 5;
+                for (int pr = wid; pr < npairs; pr += kPavThreads / 32) {
+                    const int a = pr * 2 * w, b = a + w;
+                    int64_t lo = 0, hi = 0;
+                    double v = 0.0;
+                    if (b < len) {
+                        const int c = (a + 2 * w < len) ? a + 2 * w : len;
+                        if (!merge_kary_warp(loss, rho, sval, ps, pm, a, b, c, &lo, &hi, &v)) lo = hi = 0;
+                    }
+                    if ((tid & 31) == 0) {
+                        S.rec_lo[pr] = lo;
+                        S.rec_hi[pr] = hi;
+                        S.rec_v[pr] = v;
+                    }
                 }
-                S.rec_lo[tid] = lo;
-                S.rec_hi[tid] = hi;
-                S.rec_v[tid] = v;
+                __syncthreads();
+                for (int i = tid; i < len; i += kPavThreads) {
+                    const int pr = i / (2 * w);
+                    if (i >= S.rec_lo[pr] && i < S.rec_hi[pr]) S.val[i] = S.rec_v[pr];
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            for (int i = tid; i < len; i += kPavThreads) {
-                const int pr = i / (2 * w);
-                if (i >= S.rec_lo[pr] && i < S.rec_hi[pr]) S.val[i] = S.rec_v[pr];
-            }
-            __syncthreads();
         }
     }
-    for (int i = tid; i < len; i += kPavThreads) val_out[base + i] = S.val[i];
+    for (int i = tid; i < len; i += kPavThreads) P.val[base + i] = S.val[i];
+}
+
+// Tree stage: one CTA per pair of chunks merges them and then climbs the merge tree: at every node
+// the first child to arrive leaves, the second one performs the merge ("last arriver continues" —
+// nobody ever waits, so there is no inter-CTA spinning and no co-residency requirement).  Warp 0
+// runs the merge search (32-ary, galloping outward from the boundary), the whole CTA fills the
+// pooled block.
+__global__ void __launch_bounds__(kPavThreads) pav_tree_kernel(const TreeParams P) {
+    __shared__ unsigned int s_arrive;
+    __shared__ int64_t s_lo, s_hi;
+    __shared__ double s_v;
+    const int tid = threadIdx.x;
+    const int loss = P.loss;
+    const double rho = P.rho;
+    const int64_t n = P.n;
+    PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
+    PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
+    ValCG gval{P.val};
+    int64_t parent = blockIdx.x;  // this CTA starts as the only arriver of level-0 node blockIdx.x
+    long long cnt_base = 0, level_nodes = (P.nchunks + 1) / 2;
+    bool need_arrive = false;
+    for (int64_t w = kChunk; w < n; w <<= 1) {
+        const int64_t a = parent * 2 * w, b = a + w;
+        if (b < n) {  // the node has two children
+            if (need_arrive) {
+                __threadfence();  // publish this CTA's fills
+                __syncthreads();
+                if (tid == 0) s_arrive = atomicAdd(&P.node_cnt[cnt_base + parent], 1u);
+                __syncthreads();
+                if (s_arrive == 0) return;  // first to arrive: the sibling's CTA merges
+            }
+            if (tid < 32) {
+                if (need_arrive) {
+                    if (tid == 0) P.node_cnt[cnt_base + parent] = 0;  // self-cleaning for the next call
+                    __threadfence();                                   // acquire the sibling's writes
+                }
+                const int64_t c = (a + 2 * w < n) ? a + 2 * w : n;
+                int64_t lo = 0, hi = 0;
+                double v = 0.0;
+                if (!merge_kary_warp(loss, rho, gval, gps, gpm, a, b, c, &lo, &hi, &v)) lo = hi = 0;
+                if (tid == 0) {
+                    s_lo = lo;
+                    s_hi = hi;
+                    s_v = v;
+                }
+            }
+            __syncthreads();
+            const int64_t lo = s_lo, hi = s_hi;
+            const double v = s_v;
+            for (int64_t i = lo + tid; i < hi; i += kPavThreads) P.val[i] = v;
+        }
+        cnt_base += level_nodes;
+        level_nodes = (level_nodes + 1) / 2;
+        parent >>= 1;
+        need_arrive = true;
+    }
 }
 
 // element-wise prox without pooling (PAV level 0 as a standalone op; individual_solver.py:112-130)
@@ -243,29 +394,6 @@ __global__ void prox_elementwise_kernel(int loss, double rho, const double* __re
                                         const double* __restrict__ m, int64_t n, double* __restrict__ out) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         out[i] = rbl_block_prox(loss, sigma[i], m[i], rho);
-}
-
-// one CTA per pair of solved ranges of width w (w >= chunk)
-__global__ void __launch_bounds__(kPavThreads) pav_level_kernel(int loss, double rho, double* __restrict__ val,
-                                                                int64_t n, int64_t w, PrefixChunked ps,
-                                                                PrefixChunked pm) {
-    __shared__ int64_t s_lo, s_hi;
-    __shared__ double s_v;
-    const int64_t a = (int64_t)blockIdx.x * 2 * w, b = a + w;
-    if (b >= n) return;
-    const int64_t c = (a + 2 * w < n) ? a + 2 * w : n;
-    if (threadIdx.x == 0) {
-        int64_t lo = 0, hi = 0;
-        double v = 0.0;
-        if (!pav_merge_search(loss, rho, val, ps, pm, a, b, c, &lo, &hi, &v)) lo = hi = 0;
-        s_lo = lo;
-        s_hi = hi;
-        s_v = v;
-    }
-    __syncthreads();
-    const int64_t lo = s_lo, hi = s_hi;
-    const double v = s_v;
-    for (int64_t i = lo + threadIdx.x; i < hi; i += kPavThreads) val[i] = v;
 }
 
 }  // namespace
@@ -290,7 +418,7 @@ int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double*
     return RBL_OK;
 }
 
-// sigma: rank-order weights; ps_tot = per-chunk totals of sigma kept from setup
+// z_sorted = isotonic prox of the sorted margins: 2 prefix kernels + 1 tree kernel
 int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* z_sorted, cudaStream_t s) {
     const int64_t n = c->n_global;
     const int64_t nch = c->nchunks;
@@ -300,20 +428,31 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
                                       (int)sizeof(ChunkSmem)));
         attr_set = true;
     }
-    pav_chunk_kernel<<<(unsigned)nch, kPavThreads, sizeof(ChunkSmem), s>>>(
-        loss, rho, c->sigma, m_sorted, n, c->ps_loc_hi, c->ps_loc_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi,
-        c->pm_loc_lo, c->ch_tot_hi, c->ch_tot_lo, z_sorted);
+    chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(m_sorted, n, c->pm_loc_hi, c->pm_loc_lo, c->ch_tot_hi,
+                                                             c->ch_tot_lo);
+    RBL_LAUNCH_CHECK();
+    chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
+    RBL_LAUNCH_CHECK();
+    TreeParams P;
+    P.loss = loss;
+    P.rho = rho;
+    P.sigma = c->sigma;
+    P.m = m_sorted;
+    P.n = n;
+    P.ps_loc_hi = c->ps_loc_hi; P.ps_loc_lo = c->ps_loc_lo;
+    P.ps_tot_hi = c->ps_tot_hi; P.ps_tot_lo = c->ps_tot_lo;
+    P.ps_off_hi = c->ps_off_hi; P.ps_off_lo = c->ps_off_lo;
+    P.pm_loc_hi = c->pm_loc_hi; P.pm_loc_lo = c->pm_loc_lo;
+    P.pm_tot_hi = c->ch_tot_hi; P.pm_tot_lo = c->ch_tot_lo;
+    P.pm_off_hi = c->pm_off_hi; P.pm_off_lo = c->pm_off_lo;
+    P.val = z_sorted;
+    P.node_cnt = c->node_cnt;
+    P.nchunks = nch;
+    pav_chunk_kernel<<<(unsigned)nch, kPavThreads, sizeof(ChunkSmem), s>>>(P);
     RBL_LAUNCH_CHECK();
     if (nch > 1) {
-        chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
+        pav_tree_kernel<<<(unsigned)((nch + 1) / 2), kPavThreads, 0, s>>>(P);
         RBL_LAUNCH_CHECK();
-        PrefixChunked ps{c->ps_loc_hi, c->ps_loc_lo, c->ps_off_hi, c->ps_off_lo, kChunkLog2};
-        PrefixChunked pm{c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi, c->pm_off_lo, kChunkLog2};
-        for (int64_t w = kChunk; w < n; w <<= 1) {
-            const int64_t npairs = (n + 2 * w - 1) / (2 * w);
-            pav_level_kernel<<<(unsigned)npairs, kPavThreads, 0, s>>>(loss, rho, z_sorted, n, w, ps, pm);
-            RBL_LAUNCH_CHECK();
-        }
     }
     return RBL_OK;
 }

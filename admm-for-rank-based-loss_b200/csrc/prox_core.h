@@ -130,7 +130,11 @@ RBL_HD double rbl_block_prox(int loss, double sbar, double mbar, double rho) {
         z = lo > 0.0 ? lo : 0.0;
         if (lo < 0.0) lo = 0.0;
     }
-    for (int it = 0; it < 100; ++it) {
+    // g is evaluated as sbar*sigmoid(z) + rho*(z - mbar): its rounding error is ~eps*max(|z|,|mbar|)*rho,
+    // so the root is only defined to ~eps*max(|z|,|mbar|).  Stopping on that (not on eps*|z|) matters:
+    // roots near zero would otherwise jitter for the full iteration budget and stall their warp.
+    const double floor_abs = 2.3e-16 * fabs(mbar);
+    for (int it = 0; it < 64; ++it) {
         double s = rbl_sigmoid(z);
         double g = sbar * s + rho * (z - mbar);
         if (g == 0.0) break;
@@ -141,7 +145,7 @@ RBL_HD double rbl_block_prox(int loss, double sbar, double mbar, double rho) {
         if (zn == z) break;
         double dz = fabs(zn - z);
         z = zn;
-        if (dz <= 2.3e-16 * fabs(z)) break;
+        if (dz <= fmax(2.3e-16 * fabs(z), floor_abs)) break;
     }
     return z;
 }

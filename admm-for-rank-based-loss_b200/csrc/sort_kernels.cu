@@ -5,9 +5,12 @@
 // well-defined target under ties and what this sort produces (bit-exact vs np.argsort(kind="stable")).
 //
 // fp64 -> order-preserving u64 keys (-0.0 == +0.0, NaN last, prox_core.h), 8 passes of 8 bits.
-// Per pass: (1) per-tile digit histogram, (2) exclusive scan over [digit][tile] (digit-major so the
-// scan IS the global scatter base), (3) stable scatter: in-tile ranks by warp-level match_any
-// multisplit, per-warp digit counters in shared memory, no atomics, no inter-CTA spinning.
+// Per pass, three short kernels, none of which spins on another CTA:
+//   hist    : per-tile digit histogram (2048 keys per tile; warp-aggregated with match.any so a pass
+//             whose keys all share one digit does not serialise on shared-memory atomics)
+//   scan    : one CTA per digit: exclusive scan of that digit's counts over the tiles + digit total
+//   scatter : digit bases (256-wide scan of the totals, in-CTA) + tile offsets + stable in-tile ranks by
+//             warp-level match.any multisplit with per-warp digit counters in shared memory
 // The first pass converts doubles on load and synthesises the index payload; the last pass writes the
 // sorted doubles and the int32 permutation directly.
 #include "common.cuh"
@@ -15,8 +18,8 @@
 namespace {
 
 constexpr int kSortThreads = 256;
-constexpr int kItems = 16;
-constexpr int kTile = kSortThreads * kItems;  // 4096 keys per tile
+constexpr int kItems = 8;
+constexpr int kTile = kSortThreads * kItems;  // 2048 keys per tile
 constexpr int kWarps = kSortThreads / 32;
 
 __device__ __forceinline__ uint64_t load_key(const void* src, int from_double, int64_t i) {
@@ -27,36 +30,40 @@ __device__ __forceinline__ uint64_t load_key(const void* src, int from_double, i
 __global__ void __launch_bounds__(kSortThreads) radix_hist_kernel(const void* __restrict__ keys, int from_double,
                                                                   int64_t n, int shift, int ntiles,
                                                                   uint32_t* __restrict__ tile_hist) {
-    __shared__ uint32_t h[256];
-    const int tid = threadIdx.x;
+    __shared__ uint32_t h[kWarps][257];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
-    h[tid] = 0;
+    for (int q = tid; q < kWarps * 257; q += kSortThreads) (&h[0][0])[q] = 0;
     __syncthreads();
-    const int64_t base = (int64_t)tile * kTile;
-#pragma unroll 4
+    const int64_t wbase = (int64_t)tile * kTile + (int64_t)warp * (kItems * 32);
+#pragma unroll
     for (int j = 0; j < kItems; ++j) {
-        const int64_t i = base + j * kSortThreads + tid;
-        if (i < n) atomicAdd(&h[(load_key(keys, from_double, i) >> shift) & 0xff], 1u);
+        const int64_t i = wbase + j * 32 + lane;
+        const uint32_t dg = (i < n) ? (uint32_t)((load_key(keys, from_double, i) >> shift) & 0xff) : 256u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+        if (lane == __ffs(peers) - 1) h[warp][dg] += __popc(peers);
+        __syncwarp();
     }
     __syncthreads();
-    tile_hist[(size_t)tid * ntiles + tile] = h[tid];
+    uint32_t s = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += h[w][tid];
+    tile_hist[(size_t)tid * ntiles + tile] = s;
 }
 
-// exclusive scan of `count` uint32 in place, single CTA (count = 256 * ntiles <= ~1M at n = 16M)
-__global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__ a, int count) {
-    __shared__ uint32_t wsum[32];
+// one CTA per digit: in-place exclusive scan of tile_hist[digit][0..ntiles), total -> digit_tot[digit]
+__global__ void __launch_bounds__(kSortThreads) radix_scan_kernel(uint32_t* __restrict__ tile_hist, int ntiles,
+                                                                  uint32_t* __restrict__ digit_tot) {
+    __shared__ uint32_t wsum[kWarps];
     __shared__ uint32_t carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t* a = tile_hist + (size_t)blockIdx.x * ntiles;
     if (tid == 0) carry = 0;
     __syncthreads();
-    for (int base = 0; base < count; base += 1024 * 4) {
-        // each thread owns 4 consecutive entries
-        const int i0 = base + tid * 4;
-        uint32_t v[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (i0 + q < count) ? a[i0 + q] : 0u;
-        const uint32_t tsum = v[0] + v[1] + v[2] + v[3];
-        uint32_t x = tsum;
+    for (int base = 0; base < ntiles; base += kSortThreads) {
+        const int i = base + tid;
+        const uint32_t v = (i < ntiles) ? a[i] : 0u;
+        uint32_t x = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -64,39 +71,34 @@ __global__ void __launch_bounds__(1024) radix_scan_kernel(uint32_t* __restrict__
         }
         if (lane == 31) wsum[warp] = x;
         __syncthreads();
-        if (warp == 0) {
-            uint32_t w = wsum[lane];
+        uint32_t woff = 0, tot = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= o) w += y;
-            }
-            wsum[lane] = w;  // inclusive over warps
+        for (int w = 0; w < kWarps; ++w) {
+            const uint32_t t = wsum[w];
+            if (w < warp) woff += t;
+            tot += t;
         }
+        if (i < ntiles) a[i] = carry + woff + (x - v);
         __syncthreads();
-        uint32_t excl = carry + (warp ? wsum[warp - 1] : 0u) + (x - tsum);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (i0 + q < count) a[i0 + q] = excl;
-            excl += v[q];
-        }
-        __syncthreads();
-        if (tid == 1023) carry = carry + wsum[31];
+        if (tid == 0) carry += tot;
         __syncthreads();
     }
+    if (tid == 0) digit_tot[blockIdx.x] = carry;
 }
 
 __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
     const void* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, int from_double, int64_t n, int shift,
-    int ntiles, const uint32_t* __restrict__ tile_off, uint64_t* __restrict__ keys_out,
-    uint32_t* __restrict__ vals_out, int last, double* __restrict__ sorted_out, int32_t* __restrict__ perm_out) {
+    int ntiles, const uint32_t* __restrict__ tile_off, const uint32_t* __restrict__ digit_tot,
+    uint64_t* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int last, double* __restrict__ sorted_out,
+    int32_t* __restrict__ perm_out) {
     __shared__ uint32_t cnt[kWarps][257];
+    __shared__ uint32_t wtot[kWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x;
     for (int q = tid; q < kWarps * 257; q += kSortThreads) (&cnt[0][0])[q] = 0;
     __syncthreads();
 
-    // warp w owns the contiguous span [base + w*512, +512): round j covers 32 consecutive keys, so
+    // warp w owns the contiguous span [base + w*256, +256): round j covers 32 consecutive keys, so
     // (warp, round, lane) order == original order inside the tile  => stable
     const int64_t wbase = (int64_t)tile * kTile + (int64_t)warp * (kItems * 32);
     uint64_t key[kItems];
@@ -121,11 +123,23 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
         rank[j] = (uint16_t)(basec + __popc(peers & lt_mask));
         __syncwarp();
     }
-    __syncthreads();
-    // per digit: exclusive prefix over warps, seeded with this tile's global base for the digit
+    // digit base = exclusive scan of the 256 digit totals (thread t <-> digit t)
+    uint32_t dtot = digit_tot[tid];
+    uint32_t x = dtot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) wtot[warp] = x;
+    __syncthreads();  // also orders the per-warp counters
+    uint32_t woff = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w)
+        if (w < warp) woff += wtot[w];
     {
-        const int dg = tid;  // 256 threads == 256 digits
-        uint32_t run = tile_off[(size_t)dg * ntiles + tile];
+        const int dg = tid;
+        uint32_t run = woff + (x - dtot) + tile_off[(size_t)dg * ntiles + tile];
 #pragma unroll
         for (int w = 0; w < kWarps; ++w) {
             const uint32_t c = cnt[w][dg];
@@ -167,16 +181,17 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
     const uint32_t* vin = nullptr;
     uint64_t* kout = c->keysA;
     uint32_t* vout = c->valsA;
+    uint32_t* digit_tot = c->tile_hist + (size_t)256 * c->sort_tiles;
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
         const int from_double = pass == 0;
         const int last = pass == 7;
         radix_hist_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, from_double, n, shift, ntiles, c->tile_hist);
         RBL_LAUNCH_CHECK();
-        radix_scan_kernel<<<1, 1024, 0, s>>>(c->tile_hist, 256 * ntiles);
+        radix_scan_kernel<<<256, kSortThreads, 0, s>>>(c->tile_hist, ntiles, digit_tot);
         RBL_LAUNCH_CHECK();
         radix_scatter_kernel<<<ntiles, kSortThreads, 0, s>>>(kin, vin, from_double, n, shift, ntiles, c->tile_hist,
-                                                            kout, vout, last, sorted_out, perm_out);
+                                                            digit_tot, kout, vout, last, sorted_out, perm_out);
         RBL_LAUNCH_CHECK();
         kin = kout;
         vin = vout;

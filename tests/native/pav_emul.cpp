@@ -43,7 +43,9 @@ extern "C" int emul_pav(int loss, int64_t n, const double* sigma, const double* 
             for (int64_t a = 0; a + w < len; a += 2 * w) {
                 int64_t b = a + w, c = (a + 2 * w < len) ? a + 2 * w : len;
                 int64_t lo, hi; double vv;
-                if (pav_merge_search(loss, rho, v, ps, pm, a, b, c, &lo, &hi, &vv)) { fill(v, lo, hi, vv); ++merges; }
+                bool hit = (2 * w <= 32) ? pav_merge_search(loss, rho, ValPlain{v}, ps, pm, a, b, c, &lo, &hi, &vv)
+                                          : pav_merge_search_kary(loss, rho, ValPlain{v}, ps, pm, a, b, c, &lo, &hi, &vv);
+                if (hit) { fill(v, lo, hi, vv); ++merges; }
             }
         }
     }
@@ -54,7 +56,7 @@ extern "C" int emul_pav(int loss, int64_t n, const double* sigma, const double* 
         for (int64_t a = 0; a + w < n; a += 2 * w) {
             int64_t b = a + w, c = (a + 2 * w < n) ? a + 2 * w : n;
             int64_t lo, hi; double vv;
-            if (pav_merge_search(loss, rho, val, ps, pm, a, b, c, &lo, &hi, &vv)) { fill(val, lo, hi, vv); ++merges; }
+            if (pav_merge_search_kary(loss, rho, ValPlain{val}, ps, pm, a, b, c, &lo, &hi, &vv)) { fill(val, lo, hi, vv); ++merges; }
         }
     }
     if (n_merges) *n_merges = merges;
