@@ -23,6 +23,13 @@ int rbl_pav_chunk_log2();
 int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double* loc_lo, double* tot_hi,
                  double* tot_lo, double* off_hi, double* off_lo, cudaStream_t s);
 int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* z_sorted, cudaStream_t s);
+int rbl_k_pass_multi(rbl_ctx* c, const double* D, const double* x, int64_t xstride, const double* b, double* r0,
+                     double* r1, const FistaState* st, int ninst, double* red, int64_t red_stride, const double* c0part,
+                     cudaStream_t s);
+int rbl_k_fista_update_batch(rbl_ctx* c, int g0, int ng, cudaStream_t s);
+int rbl_k_fista_result_batch(rbl_ctx* c, int B, double* w_out, double* r_out, cudaStream_t s);
+size_t rbl_batch_smem(int64_t ld, int stages);
+int rbl_batch_group();
 int rbl_k_prox_elementwise(rbl_ctx* c, int loss, const double* sigma, const double* m, int64_t n, double rho,
                            double* out, cudaStream_t s);
 
@@ -107,6 +114,7 @@ void ctx_free(rbl_ctx* c) {
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);
+    if (c->bfista_host) cudaFreeHost(c->bfista_host);
 }
 
 inline cudaStream_t S(rbl_stream_t s) { return (cudaStream_t)s; }
@@ -337,6 +345,99 @@ int rbl_fista_poll(rbl_handle_t h, rbl_stream_t stream, int32_t* hi, double* hd)
 int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t stream) {
     RBL_ENTER(h);
     return rbl_k_fista_result(h, w_out, r_out, S(stream));
+}
+
+// ---- batched mode (K10) ---------------------------------------------------------------------------
+int rbl_batch_create(rbl_handle_t h, int B) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(B > 0 && B <= 4096, "bad batch size %d", B);
+    RBL_REQUIRE(h->batch_cap == 0, "batched buffers already created for this handle");
+    RBL_REQUIRE(h->ld <= 1024, "batched mode supports d <= 1024 (got %d)", h->d);
+    int dev_max = 0;
+    RBL_CUDA(cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    int stages = 3;
+    while (stages > 1 && rbl_batch_smem(h->ld, stages) > (size_t)dev_max) --stages;
+    RBL_REQUIRE(rbl_batch_smem(h->ld, stages) <= (size_t)dev_max, "row tiles do not fit in shared memory");
+    h->batch_stages = stages;
+    const size_t vs = (size_t)h->ld + 8, nl = (size_t)h->n_local;
+    RBL_TRY(dev_alloc(h, &h->bfista, (size_t)B));
+    RBL_CUDA(cudaMallocHost((void**)&h->bfista_host, 2 * (size_t)B * sizeof(FistaState)));
+    RBL_TRY(dev_alloc(h, &h->bbeta, B * vs));
+    RBL_TRY(dev_alloc(h, &h->bbeta_p, B * vs));
+    RBL_TRY(dev_alloc(h, &h->bbeta_prev, B * vs));
+    RBL_TRY(dev_alloc(h, &h->bg_p, B * vs));
+    RBL_TRY(dev_alloc(h, &h->bg_prev, B * vs));
+    RBL_TRY(dev_alloc(h, &h->brbuf[0], B * nl));
+    RBL_TRY(dev_alloc(h, &h->brbuf[1], B * nl));
+    RBL_TRY(dev_alloc(h, &h->bred, B * vs));
+    RBL_TRY(dev_alloc(h, &h->bgpart, (size_t)h->pass_grid * rbl_batch_group() * h->ld));
+    RBL_TRY(dev_alloc(h, &h->bsspart, (size_t)h->pass_grid * rbl_batch_group()));
+    RBL_TRY(dev_alloc(h, &h->bc0part, (size_t)B * h->vec_grid));
+    h->batch_cap = B;
+    return RBL_OK;
+}
+
+int rbl_fista_batch_begin(rbl_handle_t h, int B, const double* w0s, const double* h_lams, const int32_t* h_thr_f32,
+                          float L0, double tol, int max_iter, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(B > 0 && B <= h->batch_cap, "batch of %d exceeds rbl_batch_create capacity %d", B, h->batch_cap);
+    RBL_REQUIRE(w0s && h_lams && h_thr_f32 && max_iter > 0, "bad arguments");
+    FistaState* st = h->bfista_host + h->batch_cap;  // staging half
+    for (int g = 0; g < B; ++g) {
+        memset(&st[g], 0, sizeof(FistaState));
+        st[g].t = 1.0;
+        st[g].tol = tol;
+        st[g].lam = h_lams[g];
+        st[g].L_prev = L0;
+        st[g].L_cur = L0;
+        st[g].k = -1;
+        st[g].max_iter = max_iter;
+        st[g].thr_f32 = h_thr_f32[g];
+    }
+    RBL_CUDA(cudaMemcpyAsync(h->bfista, st, (size_t)B * sizeof(FistaState), cudaMemcpyHostToDevice, S(stream)));
+    RBL_CUDA(cudaMemcpy2DAsync(h->bbeta, ((size_t)h->ld + 8) * sizeof(double), w0s, (size_t)h->d * sizeof(double),
+                               (size_t)h->d * sizeof(double), (size_t)B, cudaMemcpyDeviceToDevice, S(stream)));
+    return RBL_OK;
+}
+
+int rbl_fista_batch_steps(rbl_handle_t h, int B, const double* D, const double* bs, int nsteps,
+                          rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(B > 0 && B <= h->batch_cap && D && bs && nsteps > 0, "bad arguments");
+    const int G = rbl_batch_group();
+    const size_t vs = (size_t)h->ld + 8, nl = (size_t)h->n_local;
+    for (int i = 0; i < nsteps; ++i) {
+        for (int g0 = 0; g0 < B; g0 += G) {
+            const int ng = (B - g0 < G) ? (B - g0) : G;
+            RBL_TRY(rbl_k_pass_multi(h, D, h->bbeta + g0 * vs, (int64_t)vs, bs + g0 * nl, h->brbuf[0] + g0 * nl,
+                                     h->brbuf[1] + g0 * nl, h->bfista + g0, ng, h->bred + g0 * vs, (int64_t)vs,
+                                     h->bc0part + (size_t)g0 * h->vec_grid, S(stream)));
+            RBL_TRY(rbl_k_fista_update_batch(h, g0, ng, S(stream)));
+        }
+    }
+    return RBL_OK;
+}
+
+int rbl_fista_batch_poll(rbl_handle_t h, int B, rbl_stream_t stream, int32_t* h_done, int32_t* h_iters,
+                         int32_t* h_passes, double* h_L) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(B > 0 && B <= h->batch_cap && h_done && h_iters && h_passes, "bad arguments");
+    RBL_CUDA(cudaMemcpyAsync(h->bfista_host, h->bfista, (size_t)B * sizeof(FistaState), cudaMemcpyDeviceToHost,
+                             S(stream)));
+    RBL_CUDA(cudaStreamSynchronize(S(stream)));
+    for (int g = 0; g < B; ++g) {
+        h_done[g] = h->bfista_host[g].done;
+        h_iters[g] = h->bfista_host[g].k;
+        h_passes[g] = h->bfista_host[g].passes;
+        if (h_L) h_L[g] = (double)h->bfista_host[g].L_prev;
+    }
+    return RBL_OK;
+}
+
+int rbl_fista_batch_result(rbl_handle_t h, int B, double* w_out, double* r_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(B > 0 && B <= h->batch_cap, "bad arguments");
+    return rbl_k_fista_result_batch(h, B, w_out, r_out, S(stream));
 }
 
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,

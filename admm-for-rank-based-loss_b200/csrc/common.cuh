@@ -105,6 +105,15 @@ struct rbl_ctx {
     double* sigma;          // n_global, rank order (the sigma the PAV uses: alphas, or betas for EHRM)
     double* val;            // n_global block values
     int has_sigma;
+    // ---- batched mode (K10): B instances sharing D
+    int batch_cap;          // instances the batched buffers were sized for (0: not created)
+    int batch_stages;
+    FistaState* bfista;     // [B] device
+    FistaState* bfista_host;  // [2B] pinned: poll mirror, begin staging
+    double *bbeta, *bbeta_p, *bbeta_prev, *bg_p, *bg_prev;  // [B][ld+8]
+    double* brbuf[2];       // [B][n_local]
+    double* bred;           // [B][ld+8]
+    double *bgpart, *bsspart, *bc0part;  // [grid][8][ld], [grid][8], [B][vec_grid]
     // ---- objective
     double* obj_tmp;        // n_global
     size_t bytes;           // total scratch allocated

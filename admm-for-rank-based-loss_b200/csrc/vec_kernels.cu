@@ -49,22 +49,27 @@ __global__ void build_design_kernel(const double* __restrict__ X, int64_t ldx, c
 }
 
 // ---- per-CTA partials of a pass -> red[0..d) = D^T r, red[d] = ||r||^2, red[d+1] = c0 -------------
-__global__ void reduce_partials_kernel(const double* __restrict__ gpart, const double* __restrict__ sspart,
-                                       const double* __restrict__ c0part, int nparts, int nc0, int64_t ld, int d,
-                                       double* __restrict__ red, const FistaState* st) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __restrict__ gpart,
+                                                              const double* __restrict__ sspart,
+                                                              const double* __restrict__ c0part, int nparts, int nc0,
+                                                              int64_t ld, int d, double* __restrict__ red,
+                                                              const FistaState* st) {
+    // 32 columns x 8 row-slices per CTA: coalesced 256-byte row segments, 8 independent partial sums per
+    // column combined in a fixed order (slice 0..7) => deterministic
+    __shared__ double sh[8][33];
     if (st && st->done) return;
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c < d) {
-        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-        int k = 0;
-        for (; k + 3 < nparts; k += 4) {
-            a0 += gpart[(size_t)(k + 0) * ld + c];
-            a1 += gpart[(size_t)(k + 1) * ld + c];
-            a2 += gpart[(size_t)(k + 2) * ld + c];
-            a3 += gpart[(size_t)(k + 3) * ld + c];
-        }
-        for (; k < nparts; ++k) a0 += gpart[(size_t)k * ld + c];
-        red[c] = (a0 + a1) + (a2 + a3);
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cx;
+    double a = 0.0;
+    if (c < d)
+        for (int k = ry; k < nparts; k += 8) a += gpart[(size_t)k * ld + c];
+    sh[ry][cx] = a;
+    __syncthreads();
+    if (ry == 0 && c < d) {
+        double t = sh[0][cx];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += sh[q][cx];
+        red[c] = t;
     }
     if (blockIdx.x == 0 && threadIdx.x < 32) {
         const int lane = threadIdx.x;
@@ -92,10 +97,20 @@ __global__ void reduce_partials_kernel(const double* __restrict__ gpart, const d
 // r(beta_p) = r(beta) + t1 (r(beta) - r(beta_prev))  (combine kernel) — one D pass per trial instead of
 // the reference's three matvecs per iteration, same iterates up to rounding.
 __global__ void __launch_bounds__(1024) fista_update_kernel(FistaState* st, int d, const double* __restrict__ red,
-                                                            double* beta, double* beta_p, double* beta_prev,
-                                                            double* g_p, double* g_prev,
-                                                            const float* __restrict__ pow_tab) {
+                                                            int64_t red_stride, double* beta, double* beta_p,
+                                                            double* beta_prev, double* g_p, double* g_prev,
+                                                            int64_t vstride, const float* __restrict__ pow_tab) {
     __shared__ double sh[33];
+    {   // batched mode: one CTA per instance
+        const int64_t g = blockIdx.x;
+        st += g;
+        red += g * red_stride;
+        beta += g * vstride;
+        beta_p += g * vstride;
+        beta_prev += g * vstride;
+        g_p += g * vstride;
+        g_prev += g * vstride;
+    }
     if (st->done) return;
     const int tid = threadIdx.x, nt = blockDim.x;
     const FistaState S = *st;
@@ -202,6 +217,13 @@ __global__ void __launch_bounds__(1024) fista_update_kernel(FistaState* st, int 
 __global__ void fista_combine_kernel(const FistaState* st, const double* r0, const double* r1, int64_t n,
                                      double* __restrict__ c0part) {
     __shared__ double sh[33];
+    {   // batched mode: blockIdx.y = instance
+        const int64_t g = blockIdx.y;
+        st += g;
+        r0 += g * n;
+        r1 += g * n;
+        c0part += g * gridDim.x;
+    }
     if (st->done || st->accepted != 1) return;
     // cur was flipped by the update kernel: the accepted residual is in rbuf[cur^1], the older in rbuf[cur]
     const double* rn = st->cur ? r0 : r1;
@@ -216,8 +238,18 @@ __global__ void fista_combine_kernel(const FistaState* st, const double* r0, con
     if (threadIdx.x == 0) c0part[blockIdx.x] = a;
 }
 
-__global__ void fista_result_kernel(const FistaState* st, const double* beta, int d, double* __restrict__ w_out,
-                                    const double* r0, const double* r1, int64_t n, double* __restrict__ r_out) {
+__global__ void fista_result_kernel(const FistaState* st, const double* beta, int64_t vstride, int d,
+                                    double* __restrict__ w_out, const double* r0, const double* r1, int64_t n,
+                                    double* __restrict__ r_out) {
+    {   // batched mode: blockIdx.y = instance; outputs are [B][d] and [B][n]
+        const int64_t g = blockIdx.y;
+        st += g;
+        beta += g * vstride;
+        r0 += g * n;
+        r1 += g * n;
+        if (w_out) w_out += g * d;
+        if (r_out) r_out += g * n;
+    }
     const double* r = st->cur ? r1 : r0;
     const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gs = (int64_t)gridDim.x * blockDim.x;
     if (w_out)
@@ -327,8 +359,8 @@ int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y
 }
 
 int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStream_t s) {
-    const int threads = 128;
-    const int blocks = (c->d + threads - 1) / threads;
+    const int threads = 256;
+    const int blocks = (c->d + 31) / 32;
     reduce_partials_kernel<<<blocks, threads, 0, s>>>(c->gpart, c->sspart, with_c0 ? c->c0part : nullptr,
                                                       c->pass_grid, c->vec_grid, c->ld, c->d, c->red, st);
     RBL_LAUNCH_CHECK();
@@ -336,8 +368,8 @@ int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStr
 }
 
 int rbl_k_fista_update(rbl_ctx* c, cudaStream_t s) {
-    fista_update_kernel<<<1, 1024, 0, s>>>(c->fista, c->d, c->red, c->beta, c->beta_p, c->beta_prev, c->g_p,
-                                           c->g_prev, c->pow_tab);
+    fista_update_kernel<<<1, 1024, 0, s>>>(c->fista, c->d, c->red, 0, c->beta, c->beta_p, c->beta_prev, c->g_p,
+                                           c->g_prev, 0, c->pow_tab);
     RBL_LAUNCH_CHECK();
     fista_combine_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(c->fista, c->rbuf[0], c->rbuf[1], c->n_local, c->c0part);
     RBL_LAUNCH_CHECK();
@@ -345,8 +377,8 @@ int rbl_k_fista_update(rbl_ctx* c, cudaStream_t s) {
 }
 
 int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s) {
-    fista_result_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(c->fista, c->beta, c->d, w_out, c->rbuf[0], c->rbuf[1],
-                                                           c->n_local, r_out);
+    fista_result_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(c->fista, c->beta, 0, c->d, w_out, c->rbuf[0],
+                                                           c->rbuf[1], c->n_local, r_out);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -379,6 +411,30 @@ int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int
     objective_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(u_sorted, sigma, loss, c->n_global, c->vpart);
     RBL_LAUNCH_CHECK();
     finalize_kernel<<<1, 1024, 0, s>>>(c->vpart, c->vec_grid, w, nullptr, c->d, out4);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+// ---- batched (K10) launchers: B instances, buffers laid out [B][...] --------------------------------
+int rbl_k_fista_update_batch(rbl_ctx* c, int g0, int ng, cudaStream_t s) {
+    const int64_t vs = c->ld + 8;
+    fista_update_kernel<<<ng, 1024, 0, s>>>(c->bfista + g0, c->d, c->bred + (size_t)g0 * vs, vs,
+                                            c->bbeta + (size_t)g0 * vs, c->bbeta_p + (size_t)g0 * vs,
+                                            c->bbeta_prev + (size_t)g0 * vs, c->bg_p + (size_t)g0 * vs,
+                                            c->bg_prev + (size_t)g0 * vs, vs, c->pow_tab);
+    RBL_LAUNCH_CHECK();
+    dim3 grid(c->vec_grid, ng);
+    fista_combine_kernel<<<grid, kVecThreads, 0, s>>>(c->bfista + g0, c->brbuf[0] + (size_t)g0 * c->n_local,
+                                                     c->brbuf[1] + (size_t)g0 * c->n_local, c->n_local,
+                                                     c->bc0part + (size_t)g0 * c->vec_grid);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_fista_result_batch(rbl_ctx* c, int B, double* w_out, double* r_out, cudaStream_t s) {
+    dim3 grid(c->vec_grid, B);
+    fista_result_kernel<<<grid, kVecThreads, 0, s>>>(c->bfista, c->bbeta, c->ld + 8, c->d, w_out, c->brbuf[0],
+                                                    c->brbuf[1], c->n_local, r_out);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

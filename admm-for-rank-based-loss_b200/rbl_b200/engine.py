@@ -283,8 +283,9 @@ class AdmmEngine(DeviceProblem):
         return info
 
     # ---- w-step, l2: host L-BFGS-B over fused device f/g (w_LBFGS.py:31-53) ---------------------
-    def fg_l2(self, w_np, rho, reg):
-        """f = rho/2 ||D w - b||^2 + reg/2 ||w||^2, g = rho D^T(D w - b) + reg w — one pass over D."""
+    def fg_smooth(self, w_np, rho, reg_fg):
+        """f = rho/2 ||D w - b||^2 + R(w), g = rho D^T(D w - b) + R'(w) — the n x d part is ONE fused pass
+        over D on the device; `reg_fg(w) -> (R, R')` is a d-vector formula evaluated on the host."""
         self._wtmp.copy_(torch.from_numpy(w_np))
         _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
                                             self.r.data_ptr(), self.red.data_ptr(), self._stream()))
@@ -292,22 +293,30 @@ class AdmmEngine(DeviceProblem):
         self.red_host.copy_(self.red, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         red = self.red_host.numpy()
-        f = 0.5 * rho * float(red[self.d]) + 0.5 * reg * float(w_np @ w_np)
-        g = -rho * red[: self.d] + reg * w_np
+        R, dR = reg_fg(w_np)
+        f = 0.5 * rho * float(red[self.d]) + R
+        g = -rho * red[: self.d] + dR
         self._last_eval = w_np.copy()
+        self.lbfgs_evals += 1
         return f, g
 
-    def w_step_lbfgs(self, rho, reg, maxiter=1000):
+    def w_step_lbfgs(self, rho, reg, maxiter=1000, reg_fg=None):
+        """scipy L-BFGS-B (host, d-vector control logic) over the fused device pass.
+        reg_fg=None: the l2 problem of w_LBFGS.py:31-53; otherwise a smooth regulariser (sADMM)."""
         from scipy.optimize import minimize
 
         if not hasattr(self, "_wtmp"):
             self._wtmp = torch.zeros(self.d, dtype=torch.float64, device=self.device)
+            self.lbfgs_evals = 0
         self.w_prev.copy_(self.w)
         self.w_host.copy_(self.w)
         torch.cuda.current_stream(self.device).synchronize()
         w0 = self.w_host.numpy().copy()
         rho, reg = float(rho), float(reg)
-        res = minimize(lambda w: self.fg_l2(w, rho, reg), w0, jac=True, method="L-BFGS-B",
+        if reg_fg is None:
+            def reg_fg(w):  # wl2_fun / wl2_fun_gradient regulariser, w_LBFGS.py:36,44
+                return 0.5 * reg * float(w @ w), reg * w
+        res = minimize(lambda w: self.fg_smooth(w, rho, reg_fg), w0, jac=True, method="L-BFGS-B",
                        options={"maxiter": maxiter})
         self.w.copy_(torch.from_numpy(res.x))
         # L-BFGS-B normally returns the last point it evaluated; then r = b - D w is already there

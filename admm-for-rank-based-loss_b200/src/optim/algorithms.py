@@ -263,3 +263,58 @@ class ADMMmethod(Optimizer):
 
     def final_res(self):
         return super(ADMMmethod, self).final_res()
+
+
+class smoothADMMmethod(Optimizer):
+    """reference :223-263 — ADMM with the l1 term replaced by its Huber-type smoothing
+    reg/2 * (w^2/(2t) if |w| <= t else |w| - t/2) (w_LBFGS.py:11-28), minimised by L-BFGS-B; t follows the
+    reference's schedule (:255) and the final iterate is soft-thresholded at t (:258)."""
+
+    def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
+                 B=None, l2_reg=None, l1_reg=None, n_class=None, args=None, w0=None, t=1, max_iter=200, tol=1e-4,
+                 _shard=None):
+        super(smoothADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
+                                               args, w0, max_iter, tol, _shard)
+        self.t = t
+
+    def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
+                    B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):
+        super(smoothADMMmethod, self).start_store(X, y, weight_function, loss, B,
+                                                  l2_reg, l1_reg, n_class, args)
+
+    def _z_subproblem(self):
+        return super(smoothADMMmethod, self).z_subproblem()
+
+    def _w_subproblem_device(self):
+        if self.w_flag == 1:
+            reg, t = float(self.reg), float(self.t)
+
+            def huber(w):  # wl1_fun_smooth / wl1_fun_smooth_gradient, w_LBFGS.py:11-28
+                small = np.abs(w) <= t
+                R = 0.5 * 0.5 * reg * float(np.sum(np.square(w[small]))) / t
+                R += 0.5 * reg * float(np.sum(np.abs(w[~small]) - 0.5 * t))
+                g = np.where(small, 0.5 * reg * w / t, 0.5 * reg * np.sign(w))
+                return R, g
+
+            self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg, reg_fg=huber)
+        elif self.w_flag == 0 or self.w_flag == 2:
+            super(smoothADMMmethod, self)._w_subproblem_device()
+        else:
+            raise ValueError("w_flag can only be 0, 1 or 2.")
+
+    def main_loop(self, verbose=True):
+        t_start = time.time()
+
+        for i in range(self.max_iter):
+            if super(smoothADMMmethod, self).main_loop(i, t_start, verbose):
+                break
+            if i >= 17:
+                self.t = max(self.t * 0.9, 1e-9) % np.power(self.rho, -0.1) * np.power(i, -0.1)
+
+        if self.w_flag == 1:
+            self.w = np.sign(self.w) * np.where((np.abs(self.w) - self.t) > 0, np.abs(self.w) - self.t, 0)
+            print('final true loss=', self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+        return self.w
+
+    def final_res(self):
+        return super(smoothADMMmethod, self).final_res()

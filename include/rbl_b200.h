@@ -102,6 +102,21 @@ int rbl_fista_poll(rbl_handle_t h, rbl_stream_t stream, int32_t* h_int, double* 
 /* w_out (d) = beta, r_out (n_local) = b - D beta of the accepted iterate; either may be NULL */
 int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t stream);
 
+/* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
+ * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].
+ * One pass over D serves 8 instances at a time (multi-RHS fused pass on the FP64 tensor-core path). */
+int rbl_batch_create(rbl_handle_t h, int B);
+int rbl_fista_batch_begin(rbl_handle_t h, int B, const double* w0s /* [B][d] */, const double* h_lams /* host [B] */,
+                          const int32_t* h_thr_f32 /* host [B] */, float L0, double tol, int max_iter,
+                          rbl_stream_t stream);
+int rbl_fista_batch_steps(rbl_handle_t h, int B, const double* D, const double* bs /* [B][n_local] */, int nsteps,
+                          rbl_stream_t stream);
+/* synchronises `stream`; per instance: done flag, outer iterations, passes, final L (h_L may be NULL) */
+int rbl_fista_batch_poll(rbl_handle_t h, int B, rbl_stream_t stream, int32_t* h_done, int32_t* h_iters,
+                         int32_t* h_passes, double* h_L);
+int rbl_fista_batch_result(rbl_handle_t h, int B, double* w_out /* [B][d] */, double* r_out /* [B][n_local] */,
+                           rbl_stream_t stream);
+
 /* lambda += rho (z - Dw); out4 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1].
  * from_residual != 0: Dw := b - r first (r from rbl_fista_result), saving the pass.  algorithms.py:132-136 */
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,

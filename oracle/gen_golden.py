@@ -159,6 +159,14 @@ def main():
         tr[f"{tag}_meta"] = np.array([wf, "" if args is None else ",".join(map(str, args)), loss,
                                       "" if B is None else str(B), repr(kw)])
         print(tag, "iters", i + 1, "obj", float(tr[f"{tag}_obj"]))
+    # ---- smoothADMMmethod (algorithms.py:223-263): full run incl. t schedule and final soft-threshold
+    sm = ns.algorithms.smoothADMMmethod(Xtr, ytr, "erm", "binary_cross_entropy", l1_reg=0.01, max_iter=40, tol=1e-6)
+    with ref_shim.quiet():
+        w_s = sm.main_loop(verbose=False)
+    tr["sadmm_erm_l1_w_final"] = np.asarray(w_s, dtype=np.float64).reshape(-1)
+    tr["sadmm_erm_l1_t_final"] = np.array(float(sm.t))
+    tr["sadmm_erm_l1_obj"] = np.array(sm.objective.get_arrogate_loss(torch.from_numpy(sm.w).double()))
+    print("sadmm", float(tr["sadmm_erm_l1_obj"]), float(sm.t))
     np.savez_compressed(os.path.join(OUT, "trajectory.npz"), **tr)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))

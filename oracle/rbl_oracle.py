@@ -309,6 +309,33 @@ def w_step_l2(w0, z, lam, rho, D, reg, DTD=None, return_info=False):
     return res.x
 
 
+def w_step_smooth_l1(w0, z, lam, rho, D, reg, t, DTD=None, return_info=False):
+    """smoothed-l1 w-step of smoothADMMmethod: w_LBFGS.py:11-28,54-62 (Huber-type smoothing of reg/2*|w|)."""
+    from scipy.optimize import minimize
+
+    b = (z.reshape(-1) + lam.reshape(-1) / rho)
+    DTb = D.T @ b
+
+    def f(w):  # wl1_fun_smooth :11-19
+        tmp = D @ w - b
+        res1 = 0.5 * rho * float(np.sum(np.square(tmp)))
+        small = np.abs(w) <= t
+        res2 = 0.5 * 0.5 * reg * float(np.sum(np.square(w[small]))) / t
+        res2 += 0.5 * reg * float(np.sum(np.abs(w[~small]) - 0.5 * t))
+        return res1 + res2
+
+    def g(w):  # wl1_fun_smooth_gradient :22-28
+        g1 = rho * ((DTD @ w - DTb) if DTD is not None else D.T @ (D @ w - b))
+        small = np.abs(w) <= t
+        return g1 + np.where(small, 0.5 * reg * w / t, 0.5 * reg * np.sign(w))
+
+    res = minimize(f, np.asarray(w0, dtype=np.float64).reshape(-1), jac=g, method="L-BFGS-B",
+                   options={"maxiter": 1000})
+    if return_info:
+        return res.x, {"nit": res.nit, "nfev": res.nfev}
+    return res.x
+
+
 # ---------------------------------------------------------------------------------------
 # full loop — algorithms.py:20-75 (state), :119-164 (iteration), :190-216 (ADMMmethod)
 # ---------------------------------------------------------------------------------------
@@ -363,6 +390,8 @@ class OracleADMM:
             w, info = fista(self.w, self.D, b, alpha * self.n, np.float32(17), np.float32(2.5), tol=7e-5,
                             max_iter=5000, dtype=self.fista_dtype, return_info=True)
             self.passes += info["passes"]
+            self.last_fista_iters = info["iters"]
+            self.last_fista_info = (info["iters"], info["passes"] - 2 * info["iters"], info["L"])  # (iters, trials, L)
             return w.astype(np.float64) if self.fista_dtype == np.float64 else w
         w, info = w_step_l2(self.w, self.z, self.lam, self.rho, self.D, self.reg, self.DTD, return_info=True)
         self.passes += 2 * info["nfev"]
@@ -390,4 +419,33 @@ class OracleADMM:
         for _ in range(self.max_iter):
             if self.step():
                 break
+        return self.w
+
+
+class OracleSmoothADMM(OracleADMM):
+    """smoothADMMmethod (algorithms.py:223-263): Huber-smoothed l1 w-step, t schedule, final soft-threshold."""
+
+    def __init__(self, *a, t=1, **kw):
+        kw.setdefault("use_gram", True)
+        super().__init__(*a, **kw)
+        if self.DTD is None:
+            self.DTD = self.D.T @ self.D
+        self.t = t
+
+    def w_step(self):
+        if self.w_flag == 1:
+            w, info = w_step_smooth_l1(self.w, self.z, self.lam, self.rho, self.D, self.reg, self.t, self.DTD,
+                                       return_info=True)
+            self.passes += 2 * info["nfev"]
+            return w
+        return super().w_step()
+
+    def main_loop(self):
+        for i in range(self.max_iter):
+            if self.step():
+                break
+            if i >= 17:  # :254-255
+                self.t = max(self.t * 0.9, 1e-9) % np.power(self.rho, -0.1) * np.power(i, -0.1)
+        if self.w_flag == 1:  # :257-258
+            self.w = np.sign(self.w) * np.where((np.abs(self.w) - self.t) > 0, np.abs(self.w) - self.t, 0)
         return self.w

@@ -185,3 +185,32 @@ def test_full_size_properties():
         assert np.max(np.abs(z - zo)) < 1e-12 * max(1.0, np.max(np.abs(zo)))
         # idempotence of the projection part: with sigma = 0 the prox of an isotonic vector is itself
     e.close()
+
+
+def test_smooth_admm_vs_oracle_and_reference(golden_dir):
+    """smoothADMMmethod on the device path vs the oracle (first 30 iterations, before
+    the t -> 0 schedule makes the trajectory chaotic) and the reference's end state (loose, see test_oracle)."""
+    from src.optim.algorithms import Optimizer, smoothADMMmethod
+
+    g = _load(golden_dir, "trajectory.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    s = smoothADMMmethod(d["X"], d["y"], "erm", "binary_cross_entropy", l1_reg=0.01, max_iter=40, tol=1e-6)
+    o = O.OracleSmoothADMM(d["X"], d["y"], "erm", "binary_cross_entropy", l1_reg=0.01, max_iter=40, tol=1e-6)
+    for i in range(30):
+        with contextlib.redirect_stdout(io.StringIO()):
+            Optimizer.main_loop(s, i, 0.0, False)
+        o.step()
+        if i >= 17:
+            s.t = max(s.t * 0.9, 1e-9) % np.power(s.rho, -0.1) * np.power(i, -0.1)
+            o.t = max(o.t * 0.9, 1e-9) % np.power(o.rho, -0.1) * np.power(i, -0.1)
+        assert _rel(s.w, o.w) < 1e-8 and _rel(s.z, o.z) < 1e-8, (i, _rel(s.w, o.w))
+    s.engine.close()
+    s2 = smoothADMMmethod(d["X"], d["y"], "erm", "binary_cross_entropy", l1_reg=0.01, max_iter=40, tol=1e-6)
+    with contextlib.redirect_stdout(io.StringIO()):
+        w = s2.main_loop(verbose=False)
+    ref = g["sadmm_erm_l1_w_final"]
+    assert abs(float(s2.t) - float(g["sadmm_erm_l1_t_final"])) < 1e-12 * float(s2.t)
+    assert _rel(w, ref) < 2e-3
+    obj = s2.objective.get_arrogate_loss(torch.from_numpy(s2.w).double())
+    assert abs(obj - float(g["sadmm_erm_l1_obj"])) < 5e-5
+    s2.engine.close()
