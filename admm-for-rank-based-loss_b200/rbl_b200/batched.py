@@ -19,6 +19,42 @@ from . import spectra as _sp
 from .engine import AdmmEngine, LOSS_IDS, _pow_table
 
 
+class ZWorker:
+    """Scratch + CUDA stream for the z-step (margins, radix sort, PAV prox, scatter) of one instance at a
+    time.  The z-step never touches D, so several workers run the z-steps of different instances
+    concurrently on their own streams while sharing nothing but read-only inputs."""
+
+    def __init__(self, n, sigma, loss_id, clip, device):
+        self.lib = _cabi.load()
+        self.n, self.loss_id, self.clip, self.device = n, loss_id, clip, device
+        h = ctypes.c_void_p()
+        _cabi.check(self.lib.rbl_create(ctypes.byref(h), device.index or 0, n, n, 0, 2, 2))
+        self.h = h
+        self.stream = torch.cuda.Stream(device=device)
+        f64 = torch.float64
+        self.m = torch.empty(n, dtype=f64, device=device)
+        self.m_sorted = torch.empty(n, dtype=f64, device=device)
+        self.z_sorted = torch.empty(n, dtype=f64, device=device)
+        self.perm = torch.empty(n, dtype=torch.int32, device=device)
+        with torch.cuda.stream(self.stream):
+            _cabi.check(self.lib.rbl_set_spectrum(self.h, sigma.data_ptr(), ctypes.c_void_p(self.stream.cuda_stream)))
+        self.stream.synchronize()
+
+    def z_step(self, Dw, lam, rho, z_out, b_out):
+        lib, h, s = self.lib, self.h, ctypes.c_void_p(self.stream.cuda_stream)
+        _cabi.check(lib.rbl_margins(h, Dw.data_ptr(), lam.data_ptr(), rho, self.m.data_ptr(), s))
+        _cabi.check(lib.rbl_sort_margins(h, self.m.data_ptr(), self.m_sorted.data_ptr(), self.perm.data_ptr(), s))
+        _cabi.check(lib.rbl_pav_prox(h, self.loss_id, self.m_sorted.data_ptr(), rho, self.z_sorted.data_ptr(), s))
+        _cabi.check(lib.rbl_scatter_z(h, self.z_sorted.data_ptr(), self.perm.data_ptr(), 0 if self.clip is None else 1,
+                                      0.0 if self.clip is None else float(self.clip), lam.data_ptr(), rho,
+                                      z_out.data_ptr(), b_out.data_ptr(), s))
+
+    def close(self):
+        if self.h is not None and self.h.value:
+            self.lib.rbl_destroy(self.h)
+            self.h = None
+
+
 def instance_shard(B, world, rank):
     """contiguous block of instances for this rank (sizes differ by at most one)"""
     base, extra = divmod(B, world)
@@ -35,7 +71,7 @@ class BatchedADMM:
     """
 
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l1_regs=None, B_clip=None, args=None,
-                 w0s=None, max_iter=200, tol=1e-4, device=None, group=None, shard=True):
+                 w0s=None, max_iter=200, tol=1e-4, device=None, group=None, shard=True, z_streams=8):
         if l1_regs is None or len(l1_regs) == 0:
             raise ValueError("l1_regs: one l1 regulariser per instance is required (batched mode is the l1/FISTA path)")
         if B_clip is not None and weight_function != "ehrm":
@@ -94,6 +130,8 @@ class BatchedADMM:
             _cabi.check(e.lib.rbl_fista_config(e.h, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
             for j in range(self.B):  # D w0 per instance
                 e.matvec(self.W[j], self.DW[j])
+            torch.cuda.current_stream(e.device).synchronize()
+            self.zworkers = [ZWorker(n, e.sigma, e.loss_id, e.clip, e.device) for _ in range(min(z_streams, self.B))]
 
     # ------------------------------------------------------------------------------------------
     def _swap_slots(self, a, b):
@@ -113,15 +151,19 @@ class BatchedADMM:
         if Ba == 0:
             return 0
         s = e._stream
-        # ---- z-steps, per instance (algorithms.py:88-106)
+        # ---- z-steps, per instance (algorithms.py:88-106), round-robin over the z-workers' streams
+        main = torch.cuda.current_stream(e.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for zw in self.zworkers:
+            zw.stream.wait_event(ready)
         for a in range(Ba):
-            rho = float(self.rho[a])
-            _cabi.check(lib.rbl_margins(e.h, self.DW[a].data_ptr(), self.LAM[a].data_ptr(), rho, e.m.data_ptr(), s()))
-            _cabi.check(lib.rbl_sort_margins(e.h, e.m.data_ptr(), e.m_sorted.data_ptr(), e.perm.data_ptr(), s()))
-            _cabi.check(lib.rbl_pav_prox(e.h, e.loss_id, e.m_sorted.data_ptr(), rho, e.z_sorted.data_ptr(), s()))
-            _cabi.check(lib.rbl_scatter_z(e.h, e.z_sorted.data_ptr(), e.perm.data_ptr(), 0 if e.clip is None else 1,
-                                          0.0 if e.clip is None else float(e.clip), self.LAM[a].data_ptr(), rho,
-                                          self.Z[a].data_ptr(), self.Bv[a].data_ptr(), s()))
+            zw = self.zworkers[a % len(self.zworkers)]
+            zw.z_step(self.DW[a], self.LAM[a], float(self.rho[a]), self.Z[a], self.Bv[a])
+        for zw in self.zworkers:
+            done_ev = torch.cuda.Event()
+            done_ev.record(zw.stream)
+            main.wait_event(done_ev)
         # ---- w-steps, all active instances together (algorithms.py:190-202, fast_lasso.py:22-69)
         self.W_prev[:Ba].copy_(self.W[:Ba])
         lams = (ctypes.c_double * Ba)()
@@ -185,6 +227,11 @@ class BatchedADMM:
             if left == 0:
                 break
         return self.result()
+
+    def close(self):
+        for zw in getattr(self, "zworkers", []):
+            zw.close()
+        self.eng.close()
 
     def result(self, gather=True):
         """d x B matrix of solutions, columns in the order of `l1_regs` (all ranks' instances if gathered)"""

@@ -93,7 +93,7 @@ def test_batched_admm_matches_independent_solves(golden_dir):
         for j, o in enumerate(orc):
             o.w = b.state(j)[0].copy()
             assert abs(b.objective(j) - o.objective()) < 1e-11 * abs(o.objective())
-        b.eng.close()
+        b.close()
 
 
 def test_batched_admm_ragged_convergence():
@@ -119,4 +119,4 @@ def test_batched_admm_ragged_convergence():
         assert abs(int(o.iters) - int(b.iters[j])) <= 2, (j, o.iters, b.iters[j])
         assert _rel(W[:, j], wo) < 1e-4, (j, _rel(W[:, j], wo))
         assert abs(b.objective(j) - o.objective()) < 1e-7 * abs(o.objective())
-    b.eng.close()
+    b.close()
