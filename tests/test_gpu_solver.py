@@ -214,3 +214,44 @@ def test_smooth_admm_vs_oracle_and_reference(golden_dir):
     obj = s2.objective.get_arrogate_loss(torch.from_numpy(s2.w).double())
     assert abs(obj - float(g["sadmm_erm_l1_obj"])) < 5e-5
     s2.engine.close()
+
+
+@pytest.mark.parametrize("tag,n,d,wf,args,loss,B,kw,intercept", [
+    ("C2 twin", 6000, 100, "superquantile", [0.8], "binary_cross_entropy", None, dict(l1_reg=0.01), False),
+    ("C2 twin l2", 6000, 100, "superquantile", [0.8], "binary_cross_entropy", None, dict(l2_reg=0.01), False),
+    ("C3 twin", 6000, 50, "ehrm", None, "binary_cross_entropy", -5, dict(l2_reg=0.01), False),
+    ("C4 twin hinge", 2400, 200, "aorr", [0.2, 0.8], "hinge", None, dict(l2_reg=1e-4), True),
+    ("C4 twin bce", 2400, 200, "aorr", [0.2, 0.8], "binary_cross_entropy", None, dict(l2_reg=1e-4), True),
+    ("extremile", 3000, 40, "extremile", [2.0], "hinge", None, dict(l1_reg=0.05), False),
+])
+def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw, intercept):
+    """Reduced-n twins of BASELINE configs 2-4 on planted data, 30 ADMM iterations in lockstep
+    with the oracle: every iteration starts from the device state and must land within 1e-9 (w, z) unless
+    the inner solver took a different branch on a rounding-level near-tie (then ~ the inner tolerance)."""
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    rng = np.random.default_rng(len(tag) * 1000 + n)
+    X = rng.normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:6] = rng.normal(size=6)
+    y = np.sign(X @ ws + 0.1 * rng.normal(size=n)).reshape(-1, 1)
+    if intercept:  # run_AoRR_ratio.py:40-41 appends a column of ones (odd d: padded leading dimension)
+        X = np.hstack([X, np.ones((n, 1))])
+    s = ADMMmethod(X, y, wf, loss, B=B, args=args, max_iter=30, tol=1e-9, **kw)
+    o = O.OracleADMM(X, y, wf, loss, B=B, args=args, max_iter=30, tol=1e-9, small_lasso=False, **kw)
+    flips = 0
+    for i in range(30):
+        o.w, o.z, o.lam, o.rho = s.w.reshape(-1).copy(), s.z.reshape(-1).copy(), s.lagrangian.reshape(-1).copy(), s.rho
+        with contextlib.redirect_stdout(io.StringIO()):
+            Optimizer.main_loop(s, i, 0.0, False)
+        o.step()
+        ew, ez = _rel(s.w, o.w), _rel(s.z, o.z)
+        assert ez < 1e-9, (tag, i, ez)
+        if ew >= 1e-9:
+            flips += 1
+            assert ew < 5e-3, (tag, i, ew)
+    assert flips <= 2, (tag, flips)
+    obj = s.objective.get_arrogate_loss(torch.from_numpy(s.w).double())
+    o.w = s.w.reshape(-1).copy()
+    assert abs(obj - o.objective()) < 1e-11 * abs(obj)
+    s.engine.close()
