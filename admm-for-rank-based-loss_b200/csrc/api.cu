@@ -33,6 +33,16 @@ int rbl_batch_group();
 int rbl_k_prox_elementwise(rbl_ctx* c, int loss, const double* sigma, const double* m, int64_t n, double rho,
                            double* out, cudaStream_t s);
 
+int rbl_k_gram_fista_init(rbl_ctx* c, const double* G, const double* w0, const double* red0, cudaStream_t s);
+int rbl_k_gram_fista_steps(rbl_ctx* c, const double* G, int nsteps, cudaStream_t s);
+int rbl_k_gram_result(rbl_ctx* c, double* w_out, cudaStream_t s);
+int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double* red0, const double* w,
+                    double* red_out, cudaStream_t s);
+size_t rbl_gram_scratch_doubles(rbl_ctx* c);
+int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s);
+int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, const double* w_prev, double* out4,
+                   cudaStream_t s);
+
 static thread_local char g_err[512] = "";
 long long g_rbl_launches = 0;
 
@@ -78,6 +88,10 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->red_own, ld + 8));
     c->red = c->red_own;
     RBL_TRY(dev_alloc(c, &c->c0part, (size_t)c->vec_grid));
+    RBL_TRY(dev_alloc(c, &c->gq_prev, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->gxs, 2 * ld + 8));
+    RBL_TRY(dev_alloc(c, &c->gvu, 2 * ld + 8));
+    RBL_TRY(dev_alloc(c, &c->gticket, 64));
     c->sort_tiles = rbl_sort_tiles(c->n_global);
     RBL_TRY(dev_alloc(c, &c->keysA, ng));
     RBL_TRY(dev_alloc(c, &c->keysB, ng));
@@ -110,7 +124,8 @@ void ctx_free(rbl_ctx* c) {
                     c->beta_prev, c->g_p,       c->g_prev,    c->rbuf[0],   c->rbuf[1],   c->red_own,   c->c0part,
                     c->keysA,     c->keysB,     c->valsA,     c->valsB,     c->tile_hist, c->ps_loc_hi, c->ps_loc_lo,
                     c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
-                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt};
+                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt,  c->gq_prev,   c->gxs,       c->gvu,
+                    c->gticket};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);
@@ -438,6 +453,64 @@ int rbl_fista_batch_result(rbl_handle_t h, int B, double* w_out, double* r_out, 
     RBL_ENTER(h);
     RBL_REQUIRE(B > 0 && B <= h->batch_cap, "bad arguments");
     return rbl_k_fista_result_batch(h, B, w_out, r_out, S(stream));
+}
+
+// ---- Gram mode (gram_kernels.cu) ------------------------------------------------------------------
+int rbl_gram_build(rbl_handle_t h, const double* D, double* G, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && G, "null argument");
+    double* scratch = nullptr;
+    const size_t bytes = rbl_gram_scratch_doubles(h) * sizeof(double);
+    RBL_CUDA(cudaMallocAsync((void**)&scratch, bytes, S(stream)));
+    int rc = rbl_k_gram_build(h, D, G, scratch, S(stream));
+    RBL_CUDA(cudaFreeAsync(scratch, S(stream)));
+    return rc;
+}
+
+int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam,
+                         int thr_f32, float L0, double tol, int max_iter, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w0 && red0 && max_iter > 0, "bad arguments");
+    FistaState* st = &h->fista_host[1];
+    memset(st, 0, sizeof(*st));
+    st->t = 1.0;
+    st->tol = tol;
+    st->lam = lam;
+    st->L_prev = L0;
+    st->L_cur = L0;
+    st->k = -1;
+    st->max_iter = max_iter;
+    st->thr_f32 = thr_f32;
+    RBL_CUDA(cudaMemcpyAsync(h->fista, st, sizeof(FistaState), cudaMemcpyHostToDevice, S(stream)));
+    return rbl_k_gram_fista_init(h, G, w0, red0, S(stream));
+}
+
+int rbl_gram_fista_steps(rbl_handle_t h, const double* G, int nsteps, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && nsteps > 0 && h->gram_w0, "bad arguments (rbl_gram_fista_begin first)");
+    return rbl_k_gram_fista_steps(h, G, nsteps, S(stream));
+}
+
+int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(w_out != nullptr, "null argument");
+    return rbl_k_gram_result(h, w_out, S(stream));
+}
+
+int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const double* red0, const double* w,
+                  double* red_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w0 && red0 && w && red_out, "null argument");
+    return rbl_k_gram_eval(h, G, w0, red0, w, red_out, S(stream));
+}
+
+int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
+                  double* Dw, double* lam, double rho, int gate_on_fista, double* out4, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && w && z && Dw && lam && out4, "null argument");
+    RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho,
+                            gate_on_fista ? h->fista : nullptr));
+    return rbl_k_finalize(h, h->sspart, h->pass_grid, w, w_prev, out4, S(stream));
 }
 
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,

@@ -89,6 +89,10 @@ struct rbl_ctx {
     double* red;            // [d + 2]: g (d), ss, c0 — internal (red_own) or bound by the host layer
     double* red_own;
     double* c0part;         // [vec_grid]
+    // ---- Gram-mode w-step (gram_kernels.cu): q(beta_prev), right-hand sides, products, last-CTA ticket
+    double *gq_prev, *gxs, *gvu;
+    unsigned int* gticket;
+    const double *gram_w0, *gram_red0;  // caller-owned warm start and [g0, ss0] of the running FISTA call
     // ---- sort
     uint64_t *keysA, *keysB;
     uint32_t *valsA, *valsB;
@@ -121,9 +125,11 @@ struct rbl_ctx {
 
 // ---- launchers implemented in the kernel translation units --------------------------------------
 int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, const double* b, double* out,
-                    const FistaState* st, double* const* rbuf, cudaStream_t s);
+                    const FistaState* st, double* const* rbuf, cudaStream_t s, double* lam = nullptr,
+                    double rho = 0.0, const FistaState* gate = nullptr);
 int rbl_pass_configure(rbl_ctx* c);
 
 #define RBL_PASS_MATVEC 0  // out = D x
 #define RBL_PASS_FUSED 1   // out = r = b - D x ; column partials of D^T r ; partial ||r||^2
 #define RBL_PASS_FISTA 2   // as FUSED with x = ctx->beta, out = rbuf[st->cur], skipped when st->done
+#define RBL_PASS_DUAL 3    // out = D x ; lam += rho (b - D x) with b = z ; partial ||z - D x||^2

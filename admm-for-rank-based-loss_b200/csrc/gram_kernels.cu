@@ -1,0 +1,523 @@
+// gram_kernels.cu — the w-step on the Gram matrix G = D^T D (d x d) instead of on D (n x d).
+//
+// The reference precomputes DTD = D.T @ D in Optimizer.__init__ (src/optim/algorithms.py:24) and uses it
+// in the l2 gradient (src/util/w_LBFGS.py:39-45).  Here it carries the WHOLE inner loop of the w-step:
+// the LASSO / ridge sub-problem  min_w 1/2 ||b - D w||^2 + g(w)  is a quadratic in w, so with
+//     w0  = the warm start (the previous ADMM iterate),
+//     g0  = D^T (b - D w0),  ss0 = ||b - D w0||^2         (ONE fused pass over D per ADMM iteration)
+// every quantity FISTA (src/util/fast_lasso.py:40-67) or L-BFGS-B (w_LBFGS.py:31-45) asks for follows from
+// d x d products with G:
+//     D^T (b - D beta)            = g0 - G (beta - w0)
+//     ||b - D beta||^2            = ss0 - 2 (beta - w0).g0 + (beta - w0).G (beta - w0)
+//     LHS - RHS of the line search (fast_lasso.py:50-56)
+//        = [ ||b - D beta||^2 - ||b - D beta_p||^2 ] - [ L ||D||^2 - 2 D.g_p ]       (D := beta - beta_p)
+//        = D.G D - L ||D||^2                          (exactly: the -2 D.g_p terms cancel)
+// so a line-search trial costs one read of G (8 MB at d = 1000, L2-resident on B200: 126 MB L2) instead of
+// one read of D (8 GB at n = 1M): an ADMM iteration needs exactly TWO passes over D (D^T b here, D w for the
+// dual update) however many trials FISTA takes.  Working in the displacement beta - w0 keeps the
+// cancellation in g0 - G(.) at the level of the step, not of ||G|| ||w||.
+//
+// Kernels
+//   gram_step_kernel<2> : v = G (beta - w0), u = G (beta - beta_p) in one sweep over G (a warp per row,
+//                         128-bit loads, both right-hand sides staged in shared memory), then the LAST CTA
+//                         to finish (ticket) runs the FISTA control flow for that trial — accept/reject,
+//                         momentum, stop test, next trial point — so a trial is ONE launch and the host
+//                         never synchronises inside the inner loop.
+//   gram_step_kernel<1> : q = G (w - w0) and, in the last CTA, red = [g0 - q, ss0 - 2 dw.g0 + dw.q]: the
+//                         f/g evaluation L-BFGS-B asks for (w_LBFGS.py:31-45), same layout as rbl_fused_pass.
+//   gram_syrk_kernel    : G = D^T D over this rank's rows on the FP64 tensor-core path (DMMA m8n8k4);
+//                         algorithms.py:24.  Row-sharded jobs all-reduce G once at construction.
+// All reductions run in a fixed order: results are bit-reproducible and identical on every rank.
+#include "common.cuh"
+
+namespace {
+
+constexpr int kGThreads = 256;
+constexpr int kGWarps = kGThreads / 32;
+
+__device__ __forceinline__ double warp_sum(double v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 16);
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+}
+
+// sum over the block (kGThreads threads), valid in every thread; sh holds >= kGWarps + 1 doubles
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kGWarps; ++w) t += sh[w];
+        sh[kGWarps] = t;
+    }
+    __syncthreads();
+    return sh[kGWarps];
+}
+
+struct GramParams {
+    const double* G;
+    int64_t ldg;
+    int d;
+    FistaState* st;
+    const double* w0;     // warm start (beta0)
+    const double* red0;   // [g0 (d), ss0]
+    double *beta, *beta_p, *beta_prev, *q_p, *q_prev, *g_p;
+    double* xs;           // [2][ldg] right-hand sides: beta - w0, beta - beta_p
+    double* vu;           // [2][ldg] products
+    unsigned int* ticket;
+    const float* pow_tab;
+    // eval mode (NRHS = 1)
+    const double* w;      // evaluation point
+    double* red_out;      // [d + 2]
+};
+
+// ---- FISTA control flow for one trial (fast_lasso.py:44-65), run by one CTA of kGThreads threads ------
+// init: seeds the iteration at beta_p = beta_prev = w0 (fast_lasso.py:32-39) and forms the first trial.
+__device__ void gram_fista_update(const GramParams& p, bool init, double* sh) {
+    FistaState* st = p.st;
+    const int tid = threadIdx.x, nt = kGThreads, d = p.d;
+    const FistaState S = *st;
+    __syncthreads();  // everyone holds S before thread 0 rewrites *st
+    const double* g0 = p.red0;
+    double* xs0 = p.xs;
+    double* xs1 = p.xs + p.ldg;
+    float L_prev = S.L_prev, L_cur = S.L_cur;
+    int i_k = S.i_k, k = S.k, done = 0;
+    double t = S.t, t1 = S.t1, crit = S.crit, lhs = 0.0;
+
+    if (init) {
+        for (int c = tid; c < d; c += nt) {
+            const double bw = p.w0[c];
+            p.beta_p[c] = bw;
+            p.beta_prev[c] = bw;
+            p.q_p[c] = 0.0;
+            p.q_prev[c] = 0.0;
+            p.g_p[c] = g0[c];
+        }
+        k = 0;
+        i_k = 0;
+        t = 1.0;
+        L_cur = __fmul_rn(L_prev, p.pow_tab[0]);
+    } else {
+        // LHS > RHS  <=>  D.G D > L ||D||^2 with D = beta - beta_p (header); false for NaN like the reference
+        double a = 0.0;
+        for (int c = tid; c < d; c += nt) a = fma(xs1[c], __ldcg(&p.vu[p.ldg + c]), a);
+        lhs = block_sum(a, sh);
+        if (lhs > S.rhs) {
+            ++i_k;  // :45-46
+            L_cur = __fmul_rn(L_prev, p.pow_tab[i_k < 127 ? i_k : 127]);
+        } else {
+            L_prev = L_cur;                                              // :58
+            const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;  // :59
+            t1 = (t - 1.0) / tnext;                                      // :61
+            double a2 = 0.0;
+            for (int c = tid; c < d; c += nt) {
+                const double df = p.beta[c] - p.beta_prev[c];  // :60
+                a2 = fma(df, df, a2);
+            }
+            crit = sqrt(block_sum(a2, sh));  // :63
+            ++k;
+            if (crit < S.tol || k >= S.max_iter) {
+                done = 1;  // result is beta
+            } else {
+                t = tnext;
+                for (int c = tid; c < d; c += nt) {
+                    const double bc = p.beta[c];
+                    const double v = __ldcg(&p.vu[c]);         // G (beta - w0)
+                    const double df = bc - p.beta_prev[c];
+                    p.beta_p[c] = bc + t1 * df;                // :62
+                    const double qp = v + t1 * (v - p.q_prev[c]);  // G (beta_p - w0): affine in beta
+                    p.q_p[c] = qp;
+                    p.q_prev[c] = v;
+                    p.g_p[c] = g0[c] - qp;                     // D^T (b - D beta_p), :41-43
+                    p.beta_prev[c] = bc;
+                }
+                i_k = 0;
+                L_cur = __fmul_rn(L_prev, p.pow_tab[0]);
+            }
+        }
+    }
+    double rhs = S.rhs;
+    if (!done) {
+        __syncthreads();
+        // trial: beta = soft(beta_p + g_p / L_cur, lam / L_cur)   (:47-49)
+        const double Ld = (double)L_cur;
+        const double thr = S.thr_f32 ? (double)__fdiv_rn((float)S.lam, L_cur) : S.lam / Ld;
+        double r1 = 0.0;
+        for (int c = tid; c < d; c += nt) {
+            const double bp = p.beta_p[c], g = p.g_p[c];
+            const double bs = bp + g / Ld;
+            const double mag = fmax(fabs(bs) - thr, 0.0);
+            const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+            const double bn = mag * sgn;
+            p.beta[c] = bn;
+            const double df = bn - bp;
+            xs0[c] = bn - p.w0[c];
+            xs1[c] = df;
+            r1 = fma(df, df, r1);
+        }
+        r1 = block_sum(r1, sh);
+        rhs = Ld * r1;  // L ||D||^2 (:51-53 without the common -2 D.g_p term)
+    }
+    if (tid == 0) {
+        st->t = t;
+        st->rhs = rhs;
+        st->t1 = t1;
+        st->crit = crit;
+        st->ss_last = lhs;
+        st->L_prev = L_prev;
+        st->L_cur = L_cur;
+        st->i_k = i_k;
+        st->k = k;
+        st->done = done;
+        st->passes = S.passes + (init ? 0 : 1);  // sweeps over G
+        st->trials = S.trials + (init ? 0 : 1);
+    }
+}
+
+__global__ void __launch_bounds__(kGThreads) gram_fista_init_kernel(const GramParams p) {
+    __shared__ double sh[kGWarps + 1];
+    gram_fista_update(p, true, sh);
+}
+
+// NRHS = 2: FISTA trial; NRHS = 1: f/g evaluation at p.w
+template <int NRHS>
+__global__ void __launch_bounds__(kGThreads) gram_step_kernel(const GramParams p) {
+    extern __shared__ __align__(16) double xsm[];  // [NRHS][ldg]
+    __shared__ double sh[kGWarps + 1];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int d = p.d;
+    const int64_t ldg = p.ldg;
+    if (NRHS == 2 && p.st->done) return;  // converged earlier in this batch of enqueued steps
+    if (NRHS == 2) {
+        for (int c = tid; c < ldg; c += kGThreads) {
+            xsm[c] = (c < d) ? p.xs[c] : 0.0;
+            xsm[ldg + c] = (c < d) ? p.xs[ldg + c] : 0.0;
+        }
+    } else {
+        for (int c = tid; c < ldg; c += kGThreads) xsm[c] = (c < d) ? p.w[c] - p.w0[c] : 0.0;
+    }
+    __syncthreads();
+    const int row = blockIdx.x * kGWarps + warp;
+    if (row < d) {
+        const double2* g2 = reinterpret_cast<const double2*>(p.G + (size_t)row * ldg);
+        const double2* x0 = reinterpret_cast<const double2*>(xsm);
+        const double2* x1 = reinterpret_cast<const double2*>(xsm + ldg);
+        const int ld2 = (int)(ldg >> 1);
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 4
+        for (int c2 = lane; c2 < ld2; c2 += 32) {
+            const double2 g = __ldg(&g2[c2]);
+            const double2 xa = x0[c2];
+            a0 = fma(g.x, xa.x, a0);
+            a1 = fma(g.y, xa.y, a1);
+            if (NRHS == 2) {
+                const double2 xb = x1[c2];
+                b0 = fma(g.x, xb.x, b0);
+                b1 = fma(g.y, xb.y, b1);
+            }
+        }
+        const double a = warp_sum(a0 + a1);
+        if (NRHS == 2) {
+            const double b = warp_sum(b0 + b1);
+            if (lane == 0) {
+                p.vu[row] = a;
+                p.vu[ldg + row] = b;
+            }
+        } else if (lane == 0) {
+            p.vu[row] = a;
+        }
+    }
+    // ---- last CTA to arrive consumes the products
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int t = atomicAdd(p.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (tid == 0) *p.ticket = 0u;  // self-cleaning for the next launch
+    __threadfence();
+    if (NRHS == 2) {
+        gram_fista_update(p, false, sh);
+    } else {
+        // red_out = [D^T (b - D w) (d), ||b - D w||^2]  (header identities)
+        const double* g0 = p.red0;
+        double a = 0.0, bq = 0.0;
+        for (int c = tid; c < d; c += kGThreads) {
+            const double q = __ldcg(&p.vu[c]);
+            const double dw = xsm[c];
+            p.red_out[c] = g0[c] - q;
+            a = fma(dw, g0[c], a);
+            bq = fma(dw, q, bq);
+        }
+        a = block_sum(a, sh);
+        bq = block_sum(bq, sh);
+        if (tid == 0) {
+            p.red_out[d] = g0[d] - 2.0 * a + bq;
+            p.red_out[d + 1] = 0.0;
+        }
+    }
+}
+
+__global__ void gram_result_kernel(const double* __restrict__ beta, int d, double* __restrict__ w_out) {
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d; c += gridDim.x * blockDim.x) w_out[c] = beta[c];
+}
+
+// ---- G = D^T D over the local rows (algorithms.py:24) on the FP64 tensor cores --------------------------
+// CTA tile: 64 x 64 of G, K-chunks of 32 rows of D staged (transposed access is free: A = D^T is read
+// "row.col" straight from the row-major tile).  Split-K over row slabs; partials are summed in a fixed
+// order by gram_syrk_reduce_kernel.  Only tiles with tj <= ti are computed, the reduce mirrors them.
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int kST = 64;    // tile edge of G
+constexpr int kSK = 16;    // rows of D per stage
+constexpr int kSLd = 68;   // padded smem leading dimension (doubles): 4 mod 16 -> conflict-free fragment loads
+
+struct SyrkParams {
+    const double* D;
+    int64_t ld;
+    int64_t n;
+    int d;
+    int ntile;       // tiles per edge
+    int nslab;       // split-K factor
+    double* part;    // [nslab][npairs][64*64]
+};
+
+__device__ __forceinline__ void pair_to_tiles(int pair, int* ti, int* tj) {
+    int t = 0;
+    while (pair > t) {  // pair index -> (ti, tj) with tj <= ti
+        pair -= t + 1;
+        ++t;
+    }
+    *ti = t;
+    *tj = pair;
+}
+
+__global__ void __launch_bounds__(256) gram_syrk_kernel(const SyrkParams p) {
+    __shared__ __align__(16) double As[2][kSK][kSLd];  // rows k, columns of tile ti
+    __shared__ __align__(16) double Bs[2][kSK][kSLd];  // rows k, columns of tile tj
+    int ti, tj;
+    pair_to_tiles(blockIdx.x, &ti, &tj);
+    const int slab = blockIdx.y;
+    const int64_t rows_per_slab = ((p.n + p.nslab - 1) / p.nslab + kSK - 1) / kSK * kSK;
+    const int64_t r_begin = (int64_t)slab * rows_per_slab;
+    const int64_t r_end = (r_begin + rows_per_slab < p.n) ? r_begin + rows_per_slab : p.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    // warp tile: 32 (i) x 16 (j): wi = (warp & 1) * 32, wj = (warp >> 1) * 16
+    const int wi = (warp & 1) * 32, wj = (warp >> 1) * 16;
+    double acc[4][2][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    const int ci0 = ti * kST, cj0 = tj * kST;
+    // stage = 16 rows x 64 columns per operand = 1024 doubles / 256 threads = 4 each
+    double ra[4], rb[4];
+    auto fetch = [&](int64_t r0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 256;
+            const int r = e >> 6, c = e & 63;
+            const int64_t gr = r0 + r;
+            const bool ok = gr < r_end;
+            ra[q] = (ok && ci0 + c < p.d) ? __ldg(&p.D[gr * p.ld + ci0 + c]) : 0.0;
+            rb[q] = (ok && cj0 + c < p.d) ? __ldg(&p.D[gr * p.ld + cj0 + c]) : 0.0;
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int e = tid + q * 256;
+            As[buf][e >> 6][e & 63] = ra[q];
+            Bs[buf][e >> 6][e & 63] = rb[q];
+        }
+    };
+    int buf = 0;
+    if (r_begin < r_end) {
+        fetch(r_begin);
+        stash(0);
+    }
+    __syncthreads();
+    for (int64_t r0 = r_begin; r0 < r_end; r0 += kSK) {
+        const bool more = r0 + kSK < r_end;
+        if (more) fetch(r0 + kSK);  // global loads in flight during the MMAs
+#pragma unroll
+        for (int kk = 0; kk < kSK; kk += 4) {
+            double af[4], bf[2];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) af[a] = As[buf][kk + fk][wi + a * 8 + fr];  // A[m = i][k] = D[k][i]
+#pragma unroll
+            for (int b = 0; b < 2; ++b) bf[b] = Bs[buf][kk + fk][wj + b * 8 + fr];  // B[k][n = j] = D[k][j]
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 2; ++b) dmma(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        if (more) stash(buf ^ 1);
+        __syncthreads();
+        buf ^= 1;
+    }
+    double* out = p.part + ((size_t)slab * gridDim.x + blockIdx.x) * (kST * kST);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+            const int i = wi + a * 8 + fr, j = wj + b * 8 + 2 * fk;  // C[m = fr][n = 2 fk, 2 fk + 1]
+            out[i * kST + j] = acc[a][b][0];
+            out[i * kST + j + 1] = acc[a][b][1];
+        }
+}
+
+// fixed-order sum of the split-K partials; the lower triangle is mirrored so G is exactly symmetric
+__global__ void gram_syrk_reduce_kernel(const double* __restrict__ part, int nslab, int npairs, int d, int64_t ldg,
+                                        double* __restrict__ G) {
+    int ti, tj;
+    pair_to_tiles(blockIdx.x, &ti, &tj);
+    for (int e = threadIdx.x; e < kST * kST; e += blockDim.x) {
+        const int li = e >> 6, lj = e & 63;
+        if (ti == tj && lj > li) continue;
+        double s = 0.0;
+        for (int k = 0; k < nslab; ++k) s += part[((size_t)k * npairs + blockIdx.x) * (kST * kST) + e];
+        const int i = ti * kST + li, j = tj * kST + lj;
+        if (i < d && j < d) {
+            G[(size_t)i * ldg + j] = s;
+            G[(size_t)j * ldg + i] = s;
+        }
+    }
+}
+
+}  // namespace
+
+// ---- host launchers ------------------------------------------------------------------------------------
+static GramParams gram_params(rbl_ctx* c, const double* G, const double* w0, const double* red0) {
+    GramParams p;
+    p.G = G;
+    p.ldg = c->ld;
+    p.d = c->d;
+    p.st = c->fista;
+    p.w0 = w0;
+    p.red0 = red0;
+    p.beta = c->beta;
+    p.beta_p = c->beta_p;
+    p.beta_prev = c->beta_prev;
+    p.q_p = c->g_prev;  // the stream-mode g_prev slot is free in Gram mode
+    p.q_prev = c->gq_prev;
+    p.g_p = c->g_p;
+    p.xs = c->gxs;
+    p.vu = c->gvu;
+    p.ticket = c->gticket;
+    p.pow_tab = c->pow_tab;
+    p.w = nullptr;
+    p.red_out = nullptr;
+    return p;
+}
+
+static int gram_set_smem(size_t smem) {
+    static size_t attr2 = 0, attr1 = 0;
+    if (smem > 48 * 1024) {
+        if (smem > attr2) {
+            RBL_CUDA(cudaFuncSetAttribute(gram_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr2 = smem;
+        }
+        if (smem > attr1) {
+            RBL_CUDA(cudaFuncSetAttribute(gram_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr1 = smem;
+        }
+    }
+    return RBL_OK;
+}
+
+int rbl_k_gram_fista_init(rbl_ctx* c, const double* G, const double* w0, const double* red0, cudaStream_t s) {
+    c->gram_w0 = w0;
+    c->gram_red0 = red0;
+    const GramParams p = gram_params(c, G, w0, red0);
+    gram_fista_init_kernel<<<1, kGThreads, 0, s>>>(p);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_gram_fista_steps(rbl_ctx* c, const double* G, int nsteps, cudaStream_t s) {
+    const GramParams p = gram_params(c, G, c->gram_w0, c->gram_red0);
+    const size_t smem = 2 * (size_t)c->ld * sizeof(double);
+    int rc = gram_set_smem(smem);
+    if (rc != RBL_OK) return rc;
+    const int grid = (c->d + kGWarps - 1) / kGWarps;
+    for (int i = 0; i < nsteps; ++i) {
+        gram_step_kernel<2><<<grid, kGThreads, smem, s>>>(p);
+        RBL_LAUNCH_CHECK();
+    }
+    return RBL_OK;
+}
+
+int rbl_k_gram_result(rbl_ctx* c, double* w_out, cudaStream_t s) {
+    gram_result_kernel<<<(c->d + 255) / 256, 256, 0, s>>>(c->beta, c->d, w_out);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double* red0, const double* w,
+                    double* red_out, cudaStream_t s) {
+    GramParams p = gram_params(c, G, w0, red0);
+    p.w = w;
+    p.red_out = red_out;
+    const size_t smem = (size_t)c->ld * sizeof(double);
+    int rc = gram_set_smem(2 * smem);
+    if (rc != RBL_OK) return rc;
+    const int grid = (c->d + kGWarps - 1) / kGWarps;
+    gram_step_kernel<1><<<grid, kGThreads, smem, s>>>(p);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+// scratch doubles rbl_k_gram_build needs for its split-K partials
+static void syrk_shape(rbl_ctx* c, int* ntile, int* npairs, int* nslab) {
+    *ntile = (c->d + kST - 1) / kST;
+    *npairs = *ntile * (*ntile + 1) / 2;
+    // enough CTAs to fill the machine ~4x over, at least 256 rows per slab
+    int64_t want = ((int64_t)c->num_sms * 4 + *npairs - 1) / *npairs;
+    const int64_t max_slabs = (c->n_local + 255) / 256;
+    if (want > max_slabs) want = max_slabs;
+    if (want < 1) want = 1;
+    if (want > 64) want = 64;
+    *nslab = (int)want;
+}
+
+size_t rbl_gram_scratch_doubles(rbl_ctx* c) {
+    int ntile, npairs, nslab;
+    syrk_shape(c, &ntile, &npairs, &nslab);
+    return (size_t)nslab * npairs * kST * kST;
+}
+
+int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s) {
+    SyrkParams p;
+    int npairs;
+    syrk_shape(c, &p.ntile, &npairs, &p.nslab);
+    p.D = D;
+    p.ld = c->ld;
+    p.n = c->n_local;
+    p.d = c->d;
+    p.part = scratch;
+    RBL_CUDA(cudaMemsetAsync(G, 0, (size_t)c->d * c->ld * sizeof(double), s));
+    dim3 grid(npairs, p.nslab);
+    gram_syrk_kernel<<<grid, 256, 0, s>>>(p);
+    RBL_LAUNCH_CHECK();
+    gram_syrk_reduce_kernel<<<npairs, 256, 0, s>>>(scratch, p.nslab, npairs, c->d, c->ld, G);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}

@@ -83,6 +83,9 @@ struct PassParams {
     int mode;
     int evict_first;
     uint32_t stage_stride;  // bytes, multiple of 128
+    double* lam;            // RBL_PASS_DUAL: multiplier updated in place, b = z
+    double rho;
+    const FistaState* gate; // RBL_PASS_DUAL: run only if gate->done (the w-step converged); may be null
 };
 
 constexpr int kThreads = 256;
@@ -101,7 +104,9 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
         if (p.st->done) return;  // converged earlier in this batch of enqueued steps
         out = p.st->cur ? p.r1 : p.r0;
     }
-    const bool fused = (mode != RBL_PASS_MATVEC);
+    if (mode == RBL_PASS_DUAL && p.gate && !p.gate->done) return;  // w-step still running: host re-enqueues
+    const bool fused = (mode == RBL_PASS_FUSED || mode == RBL_PASS_FISTA);
+    const bool dual = (mode == RBL_PASS_DUAL);
     const int R = p.R, S = p.stages;
     const int64_t ld = p.ld;
     const int ld2 = (int)(ld >> 1);
@@ -161,7 +166,9 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
         const int rows = (int)((p.n - row0 < R) ? (p.n - row0) : R);
         // issue the b load now; it is consumed after phase A
         double bv = 0.0;
-        if (fused && tid < rows) bv = p.b[row0 + tid];
+        double lv = 0.0;
+        if ((fused || dual) && tid < rows) bv = p.b[row0 + tid];
+        if (dual && tid < rows) lv = p.lam[row0 + tid];
         while (!mbar_try_wait(&bars[s], parity)) {
         }
         const double2* T2 = reinterpret_cast<const double2*>(stage_base + (size_t)s * p.stage_stride);
@@ -197,6 +204,12 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
                 out[row0 + tid] = r;
                 rt[tid] = r;
                 ss = fma(r, r, ss);
+            } else if (dual) {
+                // lambda += rho (z - D w), partial ||z - D w||^2 (algorithms.py:132,135) in the matvec epilogue
+                const double res = bv - dot;
+                out[row0 + tid] = dot;
+                p.lam[row0 + tid] = lv + p.rho * res;
+                ss = fma(res, res, ss);
             } else {
                 out[row0 + tid] = dot;
             }
@@ -229,6 +242,8 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
             const int c2 = tid + kThreads * j;
             if (c2 < ld2) gp[c2] = acc[j];
         }
+    }
+    if (fused || dual) {
         // block-reduce ss (only threads < R hold non-zero values); fixed order
         ss += __shfl_xor_sync(0xffffffffu, ss, 16);
         ss += __shfl_xor_sync(0xffffffffu, ss, 8);
@@ -298,8 +313,12 @@ int rbl_pass_configure(rbl_ctx* c) {
 }
 
 int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, const double* b, double* out,
-                    const FistaState* st, double* const* rbuf, cudaStream_t s) {
+                    const FistaState* st, double* const* rbuf, cudaStream_t s, double* lam, double rho,
+                    const FistaState* gate) {
     PassParams p;
+    p.lam = lam;
+    p.rho = rho;
+    p.gate = gate;
     p.D = D;
     p.ld = c->ld;
     p.n = c->n_local;

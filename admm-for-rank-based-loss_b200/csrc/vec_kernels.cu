@@ -406,6 +406,13 @@ int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const d
     return RBL_OK;
 }
 
+int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, const double* w_prev, double* out4,
+                   cudaStream_t s) {
+    finalize_kernel<<<1, 1024, 0, s>>>(part, np, w, w_prev, c->d, out4);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
 int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
                     cudaStream_t s) {
     objective_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(u_sorted, sigma, loss, c->n_global, c->vpart);

@@ -195,7 +195,19 @@ class AdmmEngine(DeviceProblem):
             self.w_host = torch.zeros(d, dtype=f64).pin_memory()
             _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red.data_ptr()))
         self.Dw_valid = False
-        self.fista_stats = {"calls": 0, "passes": 0, "iters": 0, "polls": 0, "last_passes": 0}
+        self.fista_stats = {"calls": 0, "passes": 0, "iters": 0, "polls": 0, "last_passes": 0, "d_passes": 0}
+        # w-step formulation: "gram" runs FISTA / L-BFGS f-g on G = D^T D (two passes over D per ADMM
+        # iteration), "stream" runs every trial as a pass over D.  auto: gram whenever G is the smaller object.
+        mode = os.environ.get("RBL_W_MODE", "auto").lower()
+        if mode not in ("auto", "gram", "stream"):
+            raise ValueError(f"RBL_W_MODE must be auto, gram or stream (got {mode!r})")
+        if mode == "auto":
+            mode = "gram" if (d <= 4096 and ng >= 2 * d) else "stream"
+        self.w_mode = mode
+        self.G = None
+        self.gram_build_s = 0.0
+        if mode == "gram":
+            self.gram()  # like the reference, which forms DTD in Optimizer.__init__ (algorithms.py:24)
         self._fista_eta = None
         self.fista_batch_min = int(os.environ.get("RBL_FISTA_BATCH", "4"))
 
@@ -212,6 +224,30 @@ class AdmmEngine(DeviceProblem):
     def refresh_Dw(self):
         self.matvec(self.w, self.Dw)
         self.Dw_valid = True
+
+    # ---- Gram matrix (algorithms.py:24), built on first use ------------------------------------------
+    def gram(self):
+        if self.G is None:
+            t0 = torch.cuda.Event(enable_timing=True)
+            t1 = torch.cuda.Event(enable_timing=True)
+            with torch.cuda.device(self.device):
+                self.G = torch.empty((self.d, self.ld), dtype=torch.float64, device=self.device)
+                self.red0 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
+                self.red1 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
+                t0.record()
+                _cabi.check(self.lib.rbl_gram_build(self.h, self.D.data_ptr(), self.G.data_ptr(), self._stream()))
+                self.all_reduce(self.G)
+                t1.record()
+                t1.synchronize()
+            self.gram_build_s = t0.elapsed_time(t1) * 1e-3
+        return self.G
+
+    def _pass_at(self, w0, b):
+        """red0 = [D^T (b - D w0), ||b - D w0||^2] — the one pass over D a Gram-mode w-step makes."""
+        _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), w0.data_ptr(), b.data_ptr(),
+                                            self.r.data_ptr(), self.red0.data_ptr(), self._stream()))
+        self.all_reduce(self.red0)
+        self.fista_stats["d_passes"] += 1
 
     # ---- z-step: margins -> sort -> PAV prox -> scatter (algorithms.py:88-106) -----------------
     def z_step(self, rho):
@@ -243,10 +279,13 @@ class AdmmEngine(DeviceProblem):
             _cabi.check(lib.rbl_fista_config(self.h, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_float))))
             self._fista_eta = float(eta)
         thr_f32 = 1 if type(lam) is float or isinstance(lam, (int, np.float32)) else 0
-        _cabi.check(lib.rbl_fista_begin(self.h, w0.data_ptr(), float(lam), thr_f32, float(np.float32(L)), float(tol),
-                                        int(max_iter), s))
+        if self.w_mode != "gram":
+            _cabi.check(lib.rbl_fista_begin(self.h, w0.data_ptr(), float(lam), thr_f32, float(np.float32(L)),
+                                            float(tol), int(max_iter), s))
         hi = (ctypes.c_int32 * 8)()
         hd = (ctypes.c_double * 4)()
+        if self.w_mode == "gram":
+            return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd)
         # first batch: what the previous call needed (iteration counts drift slowly between ADMM
         # iterations), then small batches; steps enqueued after convergence exit immediately
         batch = max(self.fista_batch_min, self.fista_stats["last_passes"] - 1)
@@ -274,9 +313,47 @@ class AdmmEngine(DeviceProblem):
         st["passes"] += info["passes"]
         st["iters"] += info["iters"]
         st["last_passes"] = info["passes"]
+        st["d_passes"] += info["passes"]
+        return w_out, info
+
+    def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd):
+        """FISTA on G = D^T D: one fused pass over D at the warm start, then one sweep over G per trial."""
+        lib, s = self.lib, self._stream()
+        G = self.gram()
+        if w0.data_ptr() == (w_out.data_ptr() if w_out is not None else 0):
+            raise ValueError("w0 and w_out must not alias in Gram mode")
+        self._pass_at(w0, b)
+        _cabi.check(lib.rbl_gram_fista_begin(self.h, G.data_ptr(), w0.data_ptr(), self.red0.data_ptr(), float(lam),
+                                             thr_f32, float(np.float32(L)), float(tol), int(max_iter), s))
+        batch = max(self.fista_batch_min, self.fista_stats["last_passes"] + 2)
+        while True:
+            _cabi.check(lib.rbl_gram_fista_steps(self.h, G.data_ptr(), batch, s))
+            _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
+            self.fista_stats["polls"] += 1
+            if hi[0]:
+                break
+            batch = 2 * self.fista_batch_min
+        if w_out is None:
+            w_out = torch.empty(self.d, dtype=torch.float64, device=self.device)
+        _cabi.check(lib.rbl_gram_fista_result(self.h, w_out.data_ptr(), s))
+        if r_out is not None:  # seam users that want r = b - D beta: one more pass
+            self.matvec(w_out, r_out)
+            torch.sub(b, r_out, out=r_out)
+        info = {"iters": int(hi[1]), "passes": int(hi[2]), "trials": int(hi[3]), "L": float(hd[1]),
+                "crit": float(hd[0]), "mode": "gram"}
+        st = self.fista_stats
+        st["calls"] += 1
+        st["passes"] += info["passes"]
+        st["iters"] += info["iters"]
+        st["last_passes"] = info["passes"]
         return w_out, info
 
     def w_step_fista(self, lam, tol=7e-5, max_iter=5000):
+        if self.w_mode == "gram":
+            self.w_prev.copy_(self.w)
+            _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w)
+            self._r_matches_w = False
+            return info
         self.w_prev.copy_(self.w)
         _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w, r_out=self.r)
         self._r_matches_w = True
@@ -287,10 +364,18 @@ class AdmmEngine(DeviceProblem):
         """f = rho/2 ||D w - b||^2 + R(w), g = rho D^T(D w - b) + R'(w) — the n x d part is ONE fused pass
         over D on the device; `reg_fg(w) -> (R, R')` is a d-vector formula evaluated on the host."""
         self._wtmp.copy_(torch.from_numpy(w_np))
-        _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
-                                            self.r.data_ptr(), self.red.data_ptr(), self._stream()))
-        self.all_reduce(self.red)
-        self.red_host.copy_(self.red, non_blocking=True)
+        if self.w_mode == "gram":
+            # one sweep over G: [D^T (b - D w), ||b - D w||^2] from the pass made at the warm start
+            _cabi.check(self.lib.rbl_gram_eval(self.h, self.G.data_ptr(), self.w_prev.data_ptr(),
+                                               self.red0.data_ptr(), self._wtmp.data_ptr(), self.red1.data_ptr(),
+                                               self._stream()))
+            self.red_host.copy_(self.red1, non_blocking=True)
+        else:
+            _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
+                                                self.r.data_ptr(), self.red.data_ptr(), self._stream()))
+            self.all_reduce(self.red)
+            self.fista_stats["d_passes"] += 1
+            self.red_host.copy_(self.red, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         red = self.red_host.numpy()
         R, dR = reg_fg(w_np)
@@ -310,6 +395,9 @@ class AdmmEngine(DeviceProblem):
             self.lbfgs_evals = 0
         self.w_prev.copy_(self.w)
         self.w_host.copy_(self.w)
+        if self.w_mode == "gram":
+            self.gram()
+            self._pass_at(self.w_prev, self.b)
         torch.cuda.current_stream(self.device).synchronize()
         w0 = self.w_host.numpy().copy()
         rho, reg = float(rho), float(reg)
@@ -320,7 +408,7 @@ class AdmmEngine(DeviceProblem):
                        options={"maxiter": maxiter})
         self.w.copy_(torch.from_numpy(res.x))
         # L-BFGS-B normally returns the last point it evaluated; then r = b - D w is already there
-        self._r_matches_w = bool(np.array_equal(res.x, self._last_eval))
+        self._r_matches_w = self.w_mode != "gram" and bool(np.array_equal(res.x, self._last_eval))
         return {"nit": int(res.nit), "nfev": int(res.nfev)}
 
     # ---- dual update + residuals (algorithms.py:132-136) -----------------------------------------
@@ -328,11 +416,16 @@ class AdmmEngine(DeviceProblem):
         """lambda += rho (z - D w); returns (||z - D w||_2, ||w - w_prev||_2)."""
         from_res = 1 if getattr(self, "_r_matches_w", False) else 0
         if not from_res:
-            self.refresh_Dw()
-        _cabi.check(self.lib.rbl_dual_update(self.h, self.z.data_ptr(), self.Dw.data_ptr(), self.b.data_ptr(),
-                                             self.r.data_ptr(), from_res, self.lam.data_ptr(), float(rho),
-                                             self.w.data_ptr(), self.w_prev.data_ptr(), self._out4.data_ptr(),
-                                             self._stream()))
+            # Dw = D w with the multiplier update and ||z - Dw||^2 in the pass epilogue
+            _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(), self.w.data_ptr(), self.w_prev.data_ptr(),
+                                               self.z.data_ptr(), self.Dw.data_ptr(), self.lam.data_ptr(),
+                                               float(rho), 0, self._out4.data_ptr(), self._stream()))
+            self.fista_stats["d_passes"] += 1
+        else:
+            _cabi.check(self.lib.rbl_dual_update(self.h, self.z.data_ptr(), self.Dw.data_ptr(), self.b.data_ptr(),
+                                                 self.r.data_ptr(), from_res, self.lam.data_ptr(), float(rho),
+                                                 self.w.data_ptr(), self.w_prev.data_ptr(), self._out4.data_ptr(),
+                                                 self._stream()))
         self.Dw_valid = True
         self._r_matches_w = False
         if self.world > 1:

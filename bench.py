@@ -233,6 +233,7 @@ def main():
         sampler.start()
     launches1 = solver.engine.launches
     passes1 = solver.engine.fista_stats["passes"]
+    dpasses1 = solver.engine.fista_stats["d_passes"]
     ev[2].record()
     with quiet:
         for it in range(W, W + K):
@@ -244,6 +245,7 @@ def main():
     t_warm = w0_ev.elapsed_time(w1_ev) / 1e3
     launches_timed = solver.engine.launches - launches1
     passes_timed = solver.engine.fista_stats["passes"] - passes1
+    dpasses_timed = solver.engine.fista_stats["d_passes"] - dpasses1
     if world > 1:
         t = torch.tensor([t_steps, t_upload], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -330,7 +332,13 @@ def main():
                    "timed_iterations": f"{W}..{W + K - 1} of one solve from the reference's initial state",
                    "l2_flush": "none needed: every D pass streams %.1f GB per GPU, far above the 126 MB L2"
                                % ((hi - lo) * d * 8 / 1e9),
-                   "fista_passes_in_timed_region": passes_timed,
+                   "w_mode": solver.engine.w_mode,
+                   "w_mode_note": "gram: FISTA trials sweep G = D^T D (d x d, L2-resident), D is read twice per "
+                                  "ADMM iteration (D^T b, D w); stream: every FISTA trial is a pass over D "
+                                  "(RBL_W_MODE=stream)",
+                   "fista_trials_in_timed_region": passes_timed,
+                   "d_passes_in_timed_region": dpasses_timed,
+                   "gram_build_s": solver.engine.gram_build_s,
                    "pass_tiles": {k: solver.engine.info[k] for k in ("pass_grid", "rows_per_tile", "pass_stages")}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / K,
                 "d2h_bytes_per_step": (d + 4) * 8,
@@ -343,7 +351,7 @@ def main():
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
                      "launch_ms": 1e3 * t_pass,
-                     "pass_share_of_step": passes_timed * t_pass / t_steps},
+                     "pass_share_of_step": dpasses_timed * t_pass / t_steps},
         "zstep": {"ms": 1e3 * t_z, "keys_per_s": n / t_z, "algorithmic_bytes": 68 * n,
                   "frac_of_hbm_peak": 68 * n / t_z / 1e9 / peak},
         "cpu_baseline": cpu,

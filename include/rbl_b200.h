@@ -102,6 +102,32 @@ int rbl_fista_poll(rbl_handle_t h, rbl_stream_t stream, int32_t* h_int, double* 
 /* w_out (d) = beta, r_out (n_local) = b - D beta of the accepted iterate; either may be NULL */
 int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t stream);
 
+/* ---- Gram mode: the w-step on G = D^T D (d x d) instead of on D.  algorithms.py:24 builds DTD; w_LBFGS.py:39-45
+ * uses it for the l2 gradient.  With w0 the warm start and red0 = [g0 = D^T(b - D w0) (d), ss0 = ||b - D w0||^2]
+ * from ONE rbl_fused_pass at w0, every FISTA trial / L-BFGS evaluation is a sweep over G (L2-resident) instead
+ * of a pass over D, so an ADMM iteration reads D exactly twice (here and in rbl_dual_pass).
+ * G is row-major d x ld (same leading dimension as D), exactly symmetric. */
+/* G = D^T D over this rank's rows (FP64 tensor cores); a row-sharded host layer all-reduces it once */
+int rbl_gram_build(rbl_handle_t h, const double* D, double* G, rbl_stream_t stream);
+/* FISTA (fast_lasso.py:22-69) on G: same trial points, same accept/reject rule (LHS - RHS = D.G D - L||D||^2),
+ * same float32 L schedule; state polled with rbl_fista_poll (passes = sweeps over G).  w0 and red0 are
+ * caller-owned and must stay valid until the call converges. */
+int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam,
+                         int thr_f32, float L0, double tol, int max_iter, rbl_stream_t stream);
+int rbl_gram_fista_steps(rbl_handle_t h, const double* G, int nsteps, rbl_stream_t stream);
+int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream);
+/* red_out = [D^T (b - D w) (d), ||b - D w||^2, 0] at any w, from G, w0, red0 (same layout as rbl_fused_pass):
+ * the f/g evaluation of w_LBFGS.py:31-45 */
+int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const double* red0, const double* w,
+                  double* red_out, rbl_stream_t stream);
+
+/* Dw = D w with the dual update in the epilogue: lambda += rho (z - Dw);
+ * out4 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1].  One pass over D.  algorithms.py:132-136.
+ * gate_on_fista != 0: the whole call is a no-op on the device unless the FISTA state says `done` (lets the host
+ * enqueue it behind rbl_gram_fista_steps without synchronising; check rbl_fista_poll afterwards). */
+int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
+                  double* Dw, double* lam, double rho, int gate_on_fista, double* out4, rbl_stream_t stream);
+
 /* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
  * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].
  * One pass over D serves 8 instances at a time (multi-RHS fused pass on the FP64 tensor-core path). */

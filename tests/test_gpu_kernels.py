@@ -151,3 +151,45 @@ def test_objective_matches_oracle(E):
         vo = O.objective(-y * X, w, sig, loss, **kw)
         assert abs(v - vo) < 1e-12 * abs(vo), (wf, v, vo)  # fp64 sums in a different order
         ob.problem.close()
+
+
+@pytest.mark.parametrize("n,d", [(3000, 40), (2400, 201), (5000, 1000), (70000, 130), (900, 64), (4097, 513)])
+def test_gram_build_eval_and_dual_pass(E, n, d):
+    """G = D^T D on the FP64 tensor cores vs numpy; the Gram identities behind the w-step
+    (D^T(b - D w) = g0 - G (w - w0), ||b - D w||^2 = ss0 - 2 dw.g0 + dw.G dw); the dual update fused into
+    the D w pass (algorithms.py:132-136)."""
+    _, cabi = E
+    rng = np.random.default_rng(n + 7 * d)
+    X = rng.normal(size=(n, d))
+    e = _mk(E, X)
+    G = e.gram()[:, :d].cpu().numpy()
+    ref = X.T @ X
+    # fp64 dot products of length n in a different order: |err| <= ~ n eps sum|terms|; observed ~1e-15 relative
+    assert np.max(np.abs(G - ref)) < 1e-13 * np.max(np.abs(ref))
+    np.testing.assert_array_equal(G, G.T)                      # exactly symmetric
+    assert float(e.G[:, d:].abs().sum()) == 0.0                # padding column stays zero
+    w0, w, b = rng.normal(size=d), rng.normal(size=d), rng.normal(size=n)
+    w0d, wd, bd = e.vec(w0), e.vec(w0 + 1e-3 * w), e.vec(b)
+    e._pass_at(w0d, bd)
+    cabi.check(e.lib.rbl_gram_eval(e.h, e.G.data_ptr(), w0d.data_ptr(), e.red0.data_ptr(), wd.data_ptr(),
+                                   e.red1.data_ptr(), e._stream()))
+    red = e.red1.cpu().numpy()
+    r = b - X @ (w0 + 1e-3 * w)
+    gref = X.T @ r
+    assert np.max(np.abs(red[:d] - gref)) < 1e-12 * np.max(np.abs(np.abs(X).T @ np.abs(r)))
+    assert abs(red[d] - r @ r) < 1e-13 * (r @ r)
+    # dual pass
+    z, lam = rng.normal(size=n), rng.normal(size=n)
+    zd, lamd, Dw = e.vec(z), e.vec(lam), torch.empty(n, dtype=torch.float64, device=e.device)
+    cabi.check(e.lib.rbl_dual_pass(e.h, e.D.data_ptr(), wd.data_ptr(), w0d.data_ptr(), zd.data_ptr(), Dw.data_ptr(),
+                                   lamd.data_ptr(), 0.37, 0, e._out4.data_ptr(), e._stream()))
+    wv = w0 + 1e-3 * w
+    dw = X @ wv
+    scale = np.abs(X) @ np.abs(wv)
+    assert np.max(np.abs(Dw.cpu().numpy() - dw) / scale) < 1e-14
+    assert np.max(np.abs(lamd.cpu().numpy() - (lam + 0.37 * (z - dw)))) < 1e-13 * np.max(scale)
+    o = e._out4.cpu().numpy()
+    assert abs(o[0] - np.sum((z - dw) ** 2)) < 1e-13 * o[0]
+    assert abs(o[1] - np.sum((wv - w0) ** 2)) < 1e-13 * o[1]
+    assert abs(o[2] - wv @ wv) < 1e-13 * o[2] and abs(o[3] - np.abs(wv).sum()) < 1e-13 * o[3]
+    e.close()
