@@ -39,7 +39,13 @@ int rbl_k_gram_result(rbl_ctx* c, double* w_out, cudaStream_t s);
 int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double* red0, const double* w,
                     double* red_out, cudaStream_t s);
 size_t rbl_gram_scratch_doubles(rbl_ctx* c);
+int rbl_gram_persist_config(rbl_ctx* c);
+int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
+                         float L0, double tol, int max_iter, double* w_out, cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s);
+int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* w, const double* z, double* Dw, double* lam,
+                      double rho, int cap, cudaStream_t s);
+int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s);
 int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, const double* w_prev, double* out4,
                    cudaStream_t s);
 
@@ -92,6 +98,10 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->gxs, 2 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->gvu, 2 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->gticket, 64));
+    RBL_TRY(dev_alloc(c, &c->gvu2, 4 * ld + 8));
+    RBL_TRY(dev_alloc(c, &c->sup_idx, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->sup_val, ld + 8));
+    RBL_TRY(dev_alloc(c, &c->sup_nnz, 64));
     c->sort_tiles = rbl_sort_tiles(c->n_global);
     RBL_TRY(dev_alloc(c, &c->keysA, ng));
     RBL_TRY(dev_alloc(c, &c->keysB, ng));
@@ -125,7 +135,8 @@ void ctx_free(rbl_ctx* c) {
                     c->keysA,     c->keysB,     c->valsA,     c->valsB,     c->tile_hist, c->ps_loc_hi, c->ps_loc_lo,
                     c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
                     c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt,  c->gq_prev,   c->gxs,       c->gvu,
-                    c->gticket};
+                    c->gticket,   c->sup_idx,   c->sup_val,   c->sup_nnz,
+                    c->gvu2};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);
@@ -485,6 +496,25 @@ int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, cons
     return rbl_k_gram_fista_init(h, G, w0, red0, S(stream));
 }
 
+int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
+                       float L0, double tol, int max_iter, double* w_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w0 && red0 && max_iter > 0, "bad arguments");
+    RBL_REQUIRE(w0 != w_out, "w0 and w_out must not alias");
+    if (!rbl_gram_persist_config(h)) {
+        rbl_set_error("persistent FISTA kernel unavailable for d = %d (state does not fit in shared memory or no "
+                      "cooperative launch); use rbl_gram_fista_begin/steps", h->d);
+        return RBL_ERR_UNSUPPORTED;
+    }
+    return rbl_k_gram_fista_run(h, G, w0, red0, lam, thr_f32, L0, tol, max_iter, w_out, S(stream));
+}
+
+int rbl_gram_fista_persistent_ok(rbl_handle_t h) {
+    if (!h) return 0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return 0;
+    return rbl_gram_persist_config(h);
+}
+
 int rbl_gram_fista_steps(rbl_handle_t h, const double* G, int nsteps, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(G && nsteps > 0 && h->gram_w0, "bad arguments (rbl_gram_fista_begin first)");
@@ -505,12 +535,14 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
 }
 
 int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
-                  double* Dw, double* lam, double rho, int gate_on_fista, double* out4, rbl_stream_t stream) {
+                  double* Dw, double* lam, double rho, int sparse_cap, double* out8, rbl_stream_t stream) {
     RBL_ENTER(h);
-    RBL_REQUIRE(D && w && z && Dw && lam && out4, "null argument");
-    RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho,
-                            gate_on_fista ? h->fista : nullptr));
-    return rbl_k_finalize(h, h->sspart, h->pass_grid, w, w_prev, out4, S(stream));
+    RBL_REQUIRE(D && w && z && Dw && lam && out8, "null argument");
+    const int cap = sparse_cap < 0 ? 0 : sparse_cap;
+    // exactly one of the two kernels does the work, chosen on the device from nnz(w): no host round trip
+    RBL_TRY(rbl_k_dual_sparse(h, D, w, z, Dw, lam, rho, cap, S(stream)));
+    RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho, h->sup_nnz, cap));
+    return rbl_k_dual_finalize(h, cap, w, w_prev, out8, S(stream));
 }
 
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,

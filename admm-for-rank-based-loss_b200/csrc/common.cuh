@@ -92,7 +92,14 @@ struct rbl_ctx {
     // ---- Gram-mode w-step (gram_kernels.cu): q(beta_prev), right-hand sides, products, last-CTA ticket
     double *gq_prev, *gxs, *gvu;
     unsigned int* gticket;
+    double* gvu2;                       // [2][2][ld] parity-double-buffered products of the persistent kernel
+    int gp_checked, gp_grid, gp_rpc, gp_g_in_smem;  // persistent FISTA kernel shape (gp_grid = 0: unavailable)
+    size_t gp_smem;
     const double *gram_w0, *gram_red0;  // caller-owned warm start and [g0, ss0] of the running FISTA call
+    // ---- support of w (sparse D w in the dual pass): ascending column indices, values, count
+    int32_t* sup_idx;
+    double* sup_val;
+    int* sup_nnz;
     // ---- sort
     uint64_t *keysA, *keysB;
     uint32_t *valsA, *valsB;
@@ -126,7 +133,7 @@ struct rbl_ctx {
 // ---- launchers implemented in the kernel translation units --------------------------------------
 int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, const double* b, double* out,
                     const FistaState* st, double* const* rbuf, cudaStream_t s, double* lam = nullptr,
-                    double rho = 0.0, const FistaState* gate = nullptr);
+                    double rho = 0.0, const int* gate_nnz = nullptr, int gate_cap = 0);
 int rbl_pass_configure(rbl_ctx* c);
 
 #define RBL_PASS_MATVEC 0  // out = D x

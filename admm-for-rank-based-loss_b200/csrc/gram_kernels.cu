@@ -269,6 +269,210 @@ __global__ void __launch_bounds__(kGThreads) gram_step_kernel(const GramParams p
     }
 }
 
+// ---- the whole FISTA call as ONE persistent cooperative kernel ------------------------------------------
+// CTA c owns rows [c rpc, (c+1) rpc) of G (kept in shared memory when they fit: 8 MB of G spread over 148 SMs is
+// 56 KB each at d = 1000) and a private copy of the d-vector state in shared memory.  Per trial: every CTA
+// multiplies its rows by the two right-hand sides, publishes the 2 rpc products, ONE grid barrier, then every
+// CTA redundantly runs the same control flow on the same numbers (bit-identical by construction), so no
+// second barrier and no host round trip is needed until the call has converged.
+struct GramPersist {
+    const double* G;
+    int64_t ldg;
+    int d;
+    FistaState* st;       // final state for the host (k, sweeps, L, crit)
+    const double* w0;
+    const double* red0;
+    double* vu;           // [2 (parity)][2][ldg]
+    double* beta_out;     // global copy of the final iterate (handle-internal)
+    double* w_out;        // caller's w (may be null)
+    unsigned int* bar;    // zeroed before the launch
+    const float* pow_tab;
+    int rpc;
+    int g_in_smem;
+    double lam, tol;
+    float L0;
+    int thr_f32, max_iter;
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(const GramPersist p) {
+    extern __shared__ __align__(16) double psm[];
+    __shared__ double sh[kGWarps + 1];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = kGThreads;
+    const int d = p.d;
+    const int64_t ld = p.ldg;
+    double* W0 = psm;
+    double* G0 = W0 + ld;
+    double* BETA = G0 + ld;
+    double* BETA_P = BETA + ld;
+    double* BETA_PREV = BETA_P + ld;
+    double* Q_P = BETA_PREV + ld;
+    double* Q_PREV = Q_P + ld;
+    double* G_P = Q_PREV + ld;
+    double* X0 = G_P + ld;
+    double* X1 = X0 + ld;
+    double* Gs = X1 + ld;  // [rpc][ld] when g_in_smem
+    const int row0 = blockIdx.x * p.rpc;
+    const int row1 = (row0 + p.rpc < d) ? row0 + p.rpc : d;
+
+    for (int c = tid; c < ld; c += nt) {
+        const double bw = (c < d) ? p.w0[c] : 0.0, g = (c < d) ? p.red0[c] : 0.0;
+        W0[c] = bw;
+        G0[c] = g;
+        BETA[c] = bw;
+        BETA_P[c] = bw;
+        BETA_PREV[c] = bw;
+        Q_P[c] = 0.0;
+        Q_PREV[c] = 0.0;
+        G_P[c] = g;
+        X0[c] = 0.0;
+        X1[c] = 0.0;
+    }
+    if (p.g_in_smem) {
+        const int ld2 = (int)(ld >> 1);
+        const double2* src = reinterpret_cast<const double2*>(p.G + (size_t)row0 * ld);
+        double2* dst = reinterpret_cast<double2*>(Gs);
+        const int total = (row1 - row0) * ld2;
+        for (int e = tid; e < total; e += nt) dst[e] = __ldg(&src[e]);
+    }
+    float L_prev = p.L0, L_cur = __fmul_rn(p.L0, p.pow_tab[0]);
+    int i_k = 0, k = 0, done = 0, sweeps = 0, par = 0;
+    double t = 1.0, t1 = 0.0, crit = 0.0, rhs = 0.0, lhs = 0.0;
+    unsigned int target = 0;
+    __syncthreads();
+
+    while (true) {
+        // ---- trial: beta = soft(beta_p + g_p / L_cur, lam / L_cur)   (fast_lasso.py:47-49)
+        {
+            const double Ld = (double)L_cur;
+            const double thr = p.thr_f32 ? (double)__fdiv_rn((float)p.lam, L_cur) : p.lam / Ld;
+            double r1 = 0.0;
+            for (int c = tid; c < d; c += nt) {
+                const double bp = BETA_P[c], g = G_P[c];
+                const double bs = bp + g / Ld;
+                const double mag = fmax(fabs(bs) - thr, 0.0);
+                const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+                const double bn = mag * sgn;
+                BETA[c] = bn;
+                const double df = bn - bp;
+                X0[c] = bn - W0[c];
+                X1[c] = df;
+                r1 = fma(df, df, r1);
+            }
+            r1 = block_sum(r1, sh);  // ends with a __syncthreads: X0, X1 complete
+            rhs = Ld * r1;
+        }
+        // ---- products of my rows with both right-hand sides
+        double* vu = p.vu + (size_t)par * 2 * ld;
+        for (int row = row0 + warp; row < row1; row += kGWarps) {
+            const double2* g2 = p.g_in_smem ? reinterpret_cast<const double2*>(Gs + (size_t)(row - row0) * ld)
+                                            : reinterpret_cast<const double2*>(p.G + (size_t)row * ld);
+            const double2* x0 = reinterpret_cast<const double2*>(X0);
+            const double2* x1 = reinterpret_cast<const double2*>(X1);
+            const int ld2 = (int)(ld >> 1);
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+#pragma unroll 4
+            for (int c2 = lane; c2 < ld2; c2 += 32) {
+                const double2 g = p.g_in_smem ? g2[c2] : __ldg(&g2[c2]);
+                const double2 xa = x0[c2], xb = x1[c2];
+                a0 = fma(g.x, xa.x, a0);
+                a1 = fma(g.y, xa.y, a1);
+                b0 = fma(g.x, xb.x, b0);
+                b1 = fma(g.y, xb.y, b1);
+            }
+            const double a = warp_sum(a0 + a1), b = warp_sum(b0 + b1);
+            if (lane == 0) {
+                __stcg(&vu[row], a);
+                __stcg(&vu[ld + row], b);
+            }
+        }
+        ++sweeps;
+        target += gridDim.x;
+        grid_barrier(p.bar, target);
+        // ---- control flow, identical in every CTA (fast_lasso.py:50-65)
+        {
+            double a = 0.0;
+            for (int c = tid; c < d; c += nt) a = fma(X1[c], __ldcg(&vu[ld + c]), a);
+            lhs = block_sum(a, sh);
+        }
+        if (lhs > rhs) {  // LHS > RHS  <=>  D.G D > L ||D||^2; false for NaN like the reference
+            ++i_k;
+            L_cur = __fmul_rn(L_prev, p.pow_tab[i_k < 127 ? i_k : 127]);
+        } else {
+            L_prev = L_cur;
+            const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
+            t1 = (t - 1.0) / tnext;
+            double a2 = 0.0;
+            for (int c = tid; c < d; c += nt) {
+                const double df = BETA[c] - BETA_PREV[c];
+                a2 = fma(df, df, a2);
+            }
+            crit = sqrt(block_sum(a2, sh));
+            ++k;
+            if (crit < p.tol || k >= p.max_iter) {
+                done = 1;
+            } else {
+                t = tnext;
+                for (int c = tid; c < d; c += nt) {
+                    const double bc = BETA[c];
+                    const double v = __ldcg(&vu[c]);
+                    const double df = bc - BETA_PREV[c];
+                    BETA_P[c] = bc + t1 * df;
+                    const double qp = v + t1 * (v - Q_PREV[c]);
+                    Q_P[c] = qp;
+                    Q_PREV[c] = v;
+                    G_P[c] = G0[c] - qp;
+                    BETA_PREV[c] = bc;
+                }
+                i_k = 0;
+                L_cur = __fmul_rn(L_prev, p.pow_tab[0]);
+            }
+        }
+        if (done) break;
+        par ^= 1;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0) {
+        for (int c = tid; c < d; c += nt) {
+            const double b = BETA[c];
+            p.beta_out[c] = b;
+            if (p.w_out) p.w_out[c] = b;
+        }
+        if (tid == 0) {
+            FistaState* st = p.st;
+            st->t = t;
+            st->rhs = rhs;
+            st->t1 = t1;
+            st->crit = crit;
+            st->ss_last = lhs;
+            st->tol = p.tol;
+            st->lam = p.lam;
+            st->L_prev = L_prev;
+            st->L_cur = L_cur;
+            st->i_k = i_k;
+            st->k = k;
+            st->max_iter = p.max_iter;
+            st->done = 1;
+            st->passes = sweeps;
+            st->trials = sweeps;
+            st->thr_f32 = p.thr_f32;
+        }
+    }
+}
+
 __global__ void gram_result_kernel(const double* __restrict__ beta, int d, double* __restrict__ w_out) {
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < d; c += gridDim.x * blockDim.x) w_out[c] = beta[c];
 }
@@ -518,6 +722,69 @@ int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cu
     gram_syrk_kernel<<<grid, 256, 0, s>>>(p);
     RBL_LAUNCH_CHECK();
     gram_syrk_reduce_kernel<<<npairs, 256, 0, s>>>(scratch, p.nslab, npairs, c->d, c->ld, G);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+// ---- persistent FISTA: shape + launch ----------------------------------------------------------------------
+// returns 0 if the persistent kernel cannot hold its state in shared memory (caller uses the per-trial launches)
+int rbl_gram_persist_config(rbl_ctx* c) {
+    if (c->gp_checked) return c->gp_grid > 0;
+    c->gp_checked = 1;
+    c->gp_grid = 0;
+    int dev_max = 0, coop = 0;
+    if (cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop) return 0;
+    const size_t vec_bytes = 10 * (size_t)c->ld * sizeof(double);
+    if (vec_bytes + 1024 > (size_t)dev_max) return 0;
+    int grid = c->num_sms;
+    if (grid > c->d) grid = c->d;
+    const int rpc = (c->d + grid - 1) / grid;
+    grid = (c->d + rpc - 1) / rpc;
+    const size_t g_bytes = (size_t)rpc * c->ld * sizeof(double);
+    c->gp_g_in_smem = (vec_bytes + g_bytes + 1024 <= (size_t)dev_max) ? 1 : 0;
+    c->gp_smem = vec_bytes + (c->gp_g_in_smem ? g_bytes : 0);
+    if (cudaFuncSetAttribute(gram_fista_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)c->gp_smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_fista_persistent_kernel, kGThreads, c->gp_smem) !=
+            cudaSuccess || per_sm * c->num_sms < grid) {
+        cudaGetLastError();
+        return 0;
+    }
+    c->gp_rpc = rpc;
+    c->gp_grid = grid;
+    return 1;
+}
+
+int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
+                         float L0, double tol, int max_iter, double* w_out, cudaStream_t s) {
+    GramPersist p;
+    p.G = G;
+    p.ldg = c->ld;
+    p.d = c->d;
+    p.st = c->fista;
+    p.w0 = w0;
+    p.red0 = red0;
+    p.vu = c->gvu2;
+    p.beta_out = c->beta;
+    p.w_out = w_out;
+    p.bar = c->gticket + 8;
+    p.pow_tab = c->pow_tab;
+    p.rpc = c->gp_rpc;
+    p.g_in_smem = c->gp_g_in_smem;
+    p.lam = lam;
+    p.tol = tol;
+    p.L0 = L0;
+    p.thr_f32 = thr_f32;
+    p.max_iter = max_iter;
+    RBL_CUDA(cudaMemsetAsync(c->gticket + 8, 0, sizeof(unsigned int), s));
+    void* args[] = {(void*)&p};
+    RBL_CUDA(cudaLaunchCooperativeKernel((const void*)gram_fista_persistent_kernel, dim3(c->gp_grid), dim3(kGThreads),
+                                         args, c->gp_smem, s));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

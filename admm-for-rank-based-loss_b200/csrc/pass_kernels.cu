@@ -85,7 +85,8 @@ struct PassParams {
     uint32_t stage_stride;  // bytes, multiple of 128
     double* lam;            // RBL_PASS_DUAL: multiplier updated in place, b = z
     double rho;
-    const FistaState* gate; // RBL_PASS_DUAL: run only if gate->done (the w-step converged); may be null
+    const int* gate_nnz;    // RBL_PASS_DUAL: run only if *gate_nnz > gate_cap (w too dense for the sparse path)
+    int gate_cap;
 };
 
 constexpr int kThreads = 256;
@@ -104,7 +105,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
         if (p.st->done) return;  // converged earlier in this batch of enqueued steps
         out = p.st->cur ? p.r1 : p.r0;
     }
-    if (mode == RBL_PASS_DUAL && p.gate && !p.gate->done) return;  // w-step still running: host re-enqueues
+    if (mode == RBL_PASS_DUAL && p.gate_nnz && *p.gate_nnz <= p.gate_cap) return;  // sparse kernel took it
     const bool fused = (mode == RBL_PASS_FUSED || mode == RBL_PASS_FISTA);
     const bool dual = (mode == RBL_PASS_DUAL);
     const int R = p.R, S = p.stages;
@@ -314,11 +315,12 @@ int rbl_pass_configure(rbl_ctx* c) {
 
 int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, const double* b, double* out,
                     const FistaState* st, double* const* rbuf, cudaStream_t s, double* lam, double rho,
-                    const FistaState* gate) {
+                    const int* gate_nnz, int gate_cap) {
     PassParams p;
     p.lam = lam;
     p.rho = rho;
-    p.gate = gate;
+    p.gate_nnz = gate_nnz;
+    p.gate_cap = gate_cap;
     p.D = D;
     p.ld = c->ld;
     p.n = c->n_local;

@@ -337,6 +337,142 @@ __global__ void __launch_bounds__(1024) finalize_kernel(const double* __restrict
     }
 }
 
+// ---- support of w: ascending indices of the non-zero coordinates, compacted by a block scan (1 CTA) ------
+__global__ void __launch_bounds__(1024) support_kernel(const double* __restrict__ w, int d, int32_t* __restrict__ idx,
+                                                       double* __restrict__ val, int* __restrict__ nnz) {
+    __shared__ int wsum[32];
+    __shared__ int base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int c0 = 0; c0 < d; c0 += 1024) {
+        const int c = c0 + tid;
+        const double v = (c < d) ? w[c] : 0.0;
+        const bool nz = (v != 0.0);
+        const unsigned m = __ballot_sync(0xffffffffu, nz);
+        if (lane == 0) wsum[warp] = __popc(m);
+        __syncthreads();
+        int off = base;
+        for (int q = 0; q < warp; ++q) off += wsum[q];
+        if (nz) {
+            const int k = off + __popc(m & ((1u << lane) - 1u));
+            idx[k] = c;
+            val[k] = v;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int t = base;
+            for (int q = 0; q < 32; ++q) t += wsum[q];
+            base = t;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) *nnz = base;
+}
+
+// ---- dual update with a SPARSE w (algorithms.py:132,135): Dw_i = sum_{k in supp} D[i][j_k] w_k ------------
+// The l1 w-step leaves exact zeros in w; skipping them reads nnz 32-byte sectors per row instead of the
+// whole 8 d-byte row (HBM traffic down by d / (4 nnz)).  A group of GS lanes owns a row (GS = 8, 16 or 32,
+// the smallest that covers nnz), 4 rows in flight per group.  Runs only when nnz <= cap; the dense
+// pass (RBL_PASS_DUAL) is gated the other way.
+template <int GS>
+__device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, int64_t ld, int64_t n,
+                                                 const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                                 int nnz, const double* __restrict__ z, double* __restrict__ Dw,
+                                                 double* __restrict__ lam, double rho, double& acc) {
+    const int lane = threadIdx.x & 31;
+    const int sub = lane % GS, grp = lane / GS;
+    constexpr int GPW = 32 / GS;
+    // warp-uniform loop bounds (the shuffles below need every lane of the warp): a warp owns GPW consecutive
+    // rows per step, 4 steps in flight
+    const int64_t wbase = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW;
+    const int64_t gstride = (int64_t)gridDim.x * (blockDim.x >> 5) * GPW;
+    for (int64_t b0 = wbase; b0 < n; b0 += 4 * gstride) {
+        const int64_t i0 = b0 + grp;
+        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int k = sub; k < nnz; k += GS) {
+            const int j = idx[k];
+            const double wv = val[k];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int64_t i = i0 + u * gstride;
+                if (i < n) a[u] = fma(__ldg(&D[i * ld + j]), wv, a[u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int o = GS / 2; o; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+            const int64_t i = i0 + u * gstride;
+            if (sub == 0 && i < n) {
+                const double res = z[i] - a[u];
+                Dw[i] = a[u];
+                lam[i] = lam[i] + rho * res;
+                acc = fma(res, res, acc);
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restrict__ D, int64_t ld, int64_t n,
+                                                          const int32_t* __restrict__ idx,
+                                                          const double* __restrict__ val,
+                                                          const int* __restrict__ nnz_ptr, int cap,
+                                                          const double* __restrict__ z, double* __restrict__ Dw,
+                                                          double* __restrict__ lam, double rho,
+                                                          double* __restrict__ part) {
+    __shared__ double sh[33];
+    const int nnz = *nnz_ptr;
+    if (nnz > cap) return;  // the dense pass handles it
+    double acc = 0.0;
+    if (nnz <= 8) sparse_dual_rows<8>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
+    else if (nnz <= 16) sparse_dual_rows<16>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
+    else sparse_dual_rows<32>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// out8 = [||z - Dw||^2, ||w - w_prev||^2, ||w||^2, ||w||_1, nnz(w), 1 if the sparse kernel ran, k, sweeps]
+__global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __restrict__ part_dense, int np_dense,
+                                                             const double* __restrict__ part_sparse, int np_sparse,
+                                                             const int* __restrict__ nnz_ptr, int cap,
+                                                             const double* __restrict__ w,
+                                                             const double* __restrict__ w_prev, int d,
+                                                             const FistaState* __restrict__ st,
+                                                             double* __restrict__ out) {
+    __shared__ double sh[33];
+    const int nnz = *nnz_ptr;
+    const bool sparse = nnz <= cap;
+    const double* part = sparse ? part_sparse : part_dense;
+    const int np = sparse ? np_sparse : np_dense;
+    double a = 0.0;
+    for (int k = threadIdx.x; k < np; k += blockDim.x) a += part[k];
+    a = block_sum(a, sh);
+    double dd = 0.0, w2 = 0.0, w1 = 0.0;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+        const double wc = w[c];
+        if (w_prev) {
+            const double df = wc - w_prev[c];
+            dd = fma(df, df, dd);
+        }
+        w2 = fma(wc, wc, w2);
+        w1 += fabs(wc);
+    }
+    dd = block_sum(dd, sh);
+    w2 = block_sum(w2, sh);
+    w1 = block_sum(w1, sh);
+    if (threadIdx.x == 0) {
+        out[0] = a;
+        out[1] = dd;
+        out[2] = w2;
+        out[3] = w1;
+        out[4] = (double)nnz;
+        out[5] = sparse ? 1.0 : 0.0;
+        out[6] = (double)st->k;       // last w-step: FISTA iterations, sweeps/passes (saves the host a poll)
+        out[7] = (double)st->passes;
+    }
+}
+
 // ---- objective: sum_i sigma_i * loss(u_(i)) over ascending margins (objective.py:71-81) ------------
 // loss is non-decreasing in the margin u = D w, so sorting the margins sorts the losses.
 __global__ void objective_kernel(const double* __restrict__ u_sorted, const double* __restrict__ sigma, int loss,
@@ -402,6 +538,24 @@ int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const d
     dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(z, Dw, b, r, from_residual, lam, rho, c->n_local, c->vpart);
     RBL_LAUNCH_CHECK();
     finalize_kernel<<<1, 1024, 0, s>>>(c->vpart, c->vec_grid, w, w_prev, c->d, out4);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+// support list, sparse kernel (gated nnz <= cap), then the caller launches the dense pass (gated nnz > cap)
+int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* w, const double* z, double* Dw, double* lam,
+                      double rho, int cap, cudaStream_t s) {
+    support_kernel<<<1, 1024, 0, s>>>(w, c->d, c->sup_idx, c->sup_val, c->sup_nnz);
+    RBL_LAUNCH_CHECK();
+    sparse_dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(D, c->ld, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
+                                                          cap, z, Dw, lam, rho, c->vpart);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s) {
+    dual_finalize_kernel<<<1, 1024, 0, s>>>(c->sspart, c->pass_grid, c->vpart, c->vec_grid, c->sup_nnz, cap, w,
+                                            w_prev, c->d, c->fista, out8);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

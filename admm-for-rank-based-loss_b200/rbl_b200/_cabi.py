@@ -38,6 +38,9 @@ _SIGNATURES = {
     "rbl_gram_build": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
     "rbl_gram_fista_begin": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double,
                                         _c.c_int, _c.c_void_p]),
+    "rbl_gram_fista_persistent_ok": (_c.c_int, [_c.c_void_p]),
+    "rbl_gram_fista_run": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double,
+                                      _c.c_int, _dp, _c.c_void_p]),
     "rbl_gram_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_result": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),

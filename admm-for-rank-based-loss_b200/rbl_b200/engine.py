@@ -75,8 +75,8 @@ class DeviceProblem:
                                                   self._stream()))
             torch.cuda.current_stream().synchronize()
             del Xd, yd
-            self._out4 = torch.zeros(4, dtype=torch.float64, device=self.device)
-            self._out4_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+            self._out4 = torch.zeros(8, dtype=torch.float64, device=self.device)
+            self._out4_host = torch.zeros(8, dtype=torch.float64).pin_memory()
             self._u_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
             self._u_glob = (torch.empty(self.n_global, dtype=torch.float64, device=self.device)
                             if self.world > 1 else self._u_local)
@@ -206,6 +206,11 @@ class AdmmEngine(DeviceProblem):
         self.w_mode = mode
         self.G = None
         self.gram_build_s = 0.0
+        self._persistent = None
+        self._fista_info_pending = False
+        # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
+        self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
+        self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
         if mode == "gram":
             self.gram()  # like the reference, which forms DTD in Optimizer.__init__ (algorithms.py:24)
         self._fista_eta = None
@@ -267,7 +272,7 @@ class AdmmEngine(DeviceProblem):
 
     # ---- w-step, l1: FISTA (fast_lasso.py:22-69 via algorithms.py:190-202) ---------------------
     def fista(self, w0, b, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_iter=5000, w_out=None,
-              r_out=None):
+              r_out=None, want_info=True):
         """Runs the device-resident FISTA state machine to completion; returns (w_out, info).
 
         `lam` keeps its Python type on purpose: a python float makes `lam/L_cur` a float32 quotient
@@ -285,7 +290,7 @@ class AdmmEngine(DeviceProblem):
         hi = (ctypes.c_int32 * 8)()
         hd = (ctypes.c_double * 4)()
         if self.w_mode == "gram":
-            return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd)
+            return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info)
         # first batch: what the previous call needed (iteration counts drift slowly between ADMM
         # iterations), then small batches; steps enqueued after convergence exit immediately
         batch = max(self.fista_batch_min, self.fista_stats["last_passes"] - 1)
@@ -316,33 +321,49 @@ class AdmmEngine(DeviceProblem):
         st["d_passes"] += info["passes"]
         return w_out, info
 
-    def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd):
-        """FISTA on G = D^T D: one fused pass over D at the warm start, then one sweep over G per trial."""
+    def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info=True):
+        """FISTA on G = D^T D: one fused pass over D at the warm start, then one sweep over G per trial —
+        the whole call is one persistent cooperative kernel when its state fits in shared memory."""
         lib, s = self.lib, self._stream()
         G = self.gram()
-        if w0.data_ptr() == (w_out.data_ptr() if w_out is not None else 0):
-            raise ValueError("w0 and w_out must not alias in Gram mode")
-        self._pass_at(w0, b)
-        _cabi.check(lib.rbl_gram_fista_begin(self.h, G.data_ptr(), w0.data_ptr(), self.red0.data_ptr(), float(lam),
-                                             thr_f32, float(np.float32(L)), float(tol), int(max_iter), s))
-        batch = max(self.fista_batch_min, self.fista_stats["last_passes"] + 2)
-        while True:
-            _cabi.check(lib.rbl_gram_fista_steps(self.h, G.data_ptr(), batch, s))
-            _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
-            self.fista_stats["polls"] += 1
-            if hi[0]:
-                break
-            batch = 2 * self.fista_batch_min
         if w_out is None:
             w_out = torch.empty(self.d, dtype=torch.float64, device=self.device)
-        _cabi.check(lib.rbl_gram_fista_result(self.h, w_out.data_ptr(), s))
+        if w0.data_ptr() == w_out.data_ptr():
+            raise ValueError("w0 and w_out must not alias in Gram mode")
+        self._pass_at(w0, b)
+        if self._persistent is None:
+            self._persistent = bool(lib.rbl_gram_fista_persistent_ok(self.h)) and \
+                os.environ.get("RBL_GRAM_PERSISTENT", "1") != "0"
+        if self._persistent:
+            _cabi.check(lib.rbl_gram_fista_run(self.h, G.data_ptr(), w0.data_ptr(), self.red0.data_ptr(), float(lam),
+                                               thr_f32, float(np.float32(L)), float(tol), int(max_iter),
+                                               w_out.data_ptr(), s))
+            if want_info:
+                _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
+        else:
+            _cabi.check(lib.rbl_gram_fista_begin(self.h, G.data_ptr(), w0.data_ptr(), self.red0.data_ptr(),
+                                                 float(lam), thr_f32, float(np.float32(L)), float(tol),
+                                                 int(max_iter), s))
+            batch = max(self.fista_batch_min, self.fista_stats["last_passes"] + 2)
+            while True:
+                _cabi.check(lib.rbl_gram_fista_steps(self.h, G.data_ptr(), batch, s))
+                _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
+                self.fista_stats["polls"] += 1
+                if hi[0]:
+                    break
+                batch = 2 * self.fista_batch_min
+            _cabi.check(lib.rbl_gram_fista_result(self.h, w_out.data_ptr(), s))
+            want_info = True
         if r_out is not None:  # seam users that want r = b - D beta: one more pass
             self.matvec(w_out, r_out)
             torch.sub(b, r_out, out=r_out)
-        info = {"iters": int(hi[1]), "passes": int(hi[2]), "trials": int(hi[3]), "L": float(hd[1]),
-                "crit": float(hd[0]), "mode": "gram"}
         st = self.fista_stats
         st["calls"] += 1
+        if not want_info:
+            self._fista_info_pending = True  # k and sweeps arrive with the dual step's read-back
+            return w_out, {"mode": "gram"}
+        info = {"iters": int(hi[1]), "passes": int(hi[2]), "trials": int(hi[3]), "L": float(hd[1]),
+                "crit": float(hd[0]), "mode": "gram"}
         st["passes"] += info["passes"]
         st["iters"] += info["iters"]
         st["last_passes"] = info["passes"]
@@ -351,7 +372,8 @@ class AdmmEngine(DeviceProblem):
     def w_step_fista(self, lam, tol=7e-5, max_iter=5000):
         if self.w_mode == "gram":
             self.w_prev.copy_(self.w)
-            _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w)
+            _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w,
+                                 want_info=False)
             self._r_matches_w = False
             return info
         self.w_prev.copy_(self.w)
@@ -419,8 +441,8 @@ class AdmmEngine(DeviceProblem):
             # Dw = D w with the multiplier update and ||z - Dw||^2 in the pass epilogue
             _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(), self.w.data_ptr(), self.w_prev.data_ptr(),
                                                self.z.data_ptr(), self.Dw.data_ptr(), self.lam.data_ptr(),
-                                               float(rho), 0, self._out4.data_ptr(), self._stream()))
-            self.fista_stats["d_passes"] += 1
+                                               float(rho), self.sparse_cap, self._out4.data_ptr(),
+                                               self._stream()))
         else:
             _cabi.check(self.lib.rbl_dual_update(self.h, self.z.data_ptr(), self.Dw.data_ptr(), self.b.data_ptr(),
                                                  self.r.data_ptr(), from_res, self.lam.data_ptr(), float(rho),
@@ -435,4 +457,15 @@ class AdmmEngine(DeviceProblem):
         self.w_host.copy_(self.w, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         o = self._out4_host
+        if not from_res:
+            took_sparse = bool(o[5].item())
+            self.dual_stats["sparse" if took_sparse else "dense"] += 1
+            self.dual_stats["nnz_last"] = int(o[4].item())
+            if self._fista_info_pending:
+                self._fista_info_pending = False
+                st = self.fista_stats
+                st["iters"] += int(o[6].item())
+                st["passes"] += int(o[7].item())
+                st["last_passes"] = int(o[7].item())
+            self.fista_stats["d_passes"] += 0 if took_sparse else 1
         return float(np.sqrt(o[0].item())), float(np.sqrt(o[1].item()))

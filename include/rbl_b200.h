@@ -115,6 +115,12 @@ int rbl_gram_build(rbl_handle_t h, const double* D, double* G, rbl_stream_t stre
 int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam,
                          int thr_f32, float L0, double tol, int max_iter, rbl_stream_t stream);
 int rbl_gram_fista_steps(rbl_handle_t h, const double* G, int nsteps, rbl_stream_t stream);
+/* the whole call as ONE persistent cooperative kernel (G rows and the d-vector state live in shared memory,
+ * one grid barrier per trial, no host round trip): runs to convergence, leaves w_out (may be NULL) and the
+ * final state for rbl_fista_poll.  rbl_gram_fista_persistent_ok() == 0 (large d): use begin/steps instead. */
+int rbl_gram_fista_persistent_ok(rbl_handle_t h);
+int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
+                       float L0, double tol, int max_iter, double* w_out, rbl_stream_t stream);
 int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream);
 /* red_out = [D^T (b - D w) (d), ||b - D w||^2, 0] at any w, from G, w0, red0 (same layout as rbl_fused_pass):
  * the f/g evaluation of w_LBFGS.py:31-45 */
@@ -122,11 +128,13 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
                   double* red_out, rbl_stream_t stream);
 
 /* Dw = D w with the dual update in the epilogue: lambda += rho (z - Dw);
- * out4 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1].  One pass over D.  algorithms.py:132-136.
- * gate_on_fista != 0: the whole call is a no-op on the device unless the FISTA state says `done` (lets the host
- * enqueue it behind rbl_gram_fista_steps without synchronising; check rbl_fista_poll afterwards). */
+ * out8 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1, nnz(w), sparse path taken (0/1),
+ * FISTA iterations and sweeps of the last w-step].
+ * algorithms.py:132-136.  The l1 w-step leaves exact zeros in w: when nnz(w) <= sparse_cap the product reads only
+ * the nnz(w) touched 32-byte sectors of each row of D (chosen on the device, no host round trip), otherwise one
+ * streaming pass over D.  sparse_cap = 0 forces the dense pass. */
 int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
-                  double* Dw, double* lam, double rho, int gate_on_fista, double* out4, rbl_stream_t stream);
+                  double* Dw, double* lam, double rho, int sparse_cap, double* out8, rbl_stream_t stream);
 
 /* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
  * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].

@@ -178,18 +178,25 @@ def test_gram_build_eval_and_dual_pass(E, n, d):
     gref = X.T @ r
     assert np.max(np.abs(red[:d] - gref)) < 1e-12 * np.max(np.abs(np.abs(X).T @ np.abs(r)))
     assert abs(red[d] - r @ r) < 1e-13 * (r @ r)
-    # dual pass
-    z, lam = rng.normal(size=n), rng.normal(size=n)
-    zd, lamd, Dw = e.vec(z), e.vec(lam), torch.empty(n, dtype=torch.float64, device=e.device)
-    cabi.check(e.lib.rbl_dual_pass(e.h, e.D.data_ptr(), wd.data_ptr(), w0d.data_ptr(), zd.data_ptr(), Dw.data_ptr(),
-                                   lamd.data_ptr(), 0.37, 0, e._out4.data_ptr(), e._stream()))
-    wv = w0 + 1e-3 * w
-    dw = X @ wv
-    scale = np.abs(X) @ np.abs(wv)
-    assert np.max(np.abs(Dw.cpu().numpy() - dw) / scale) < 1e-14
-    assert np.max(np.abs(lamd.cpu().numpy() - (lam + 0.37 * (z - dw)))) < 1e-13 * np.max(scale)
-    o = e._out4.cpu().numpy()
-    assert abs(o[0] - np.sum((z - dw) ** 2)) < 1e-13 * o[0]
-    assert abs(o[1] - np.sum((wv - w0) ** 2)) < 1e-13 * o[1]
-    assert abs(o[2] - wv @ wv) < 1e-13 * o[2] and abs(o[3] - np.abs(wv).sum()) < 1e-13 * o[3]
+    # dual pass: dense w takes the streaming pass; a sparse w (exact zeros, as the l1 w-step leaves them) takes
+    # the sector-gather kernel — both chosen on the device from nnz(w) vs the cap
+    for nnz, cap in ((d, max(1, d // 16)), (min(d, 5), max(5, d // 16)), (min(d, 13), 16), (min(d, 29), 32), (0, 4),
+                     (min(d, 40), 64)):
+        wv = np.zeros(d)
+        sup = rng.choice(d, size=nnz, replace=False)
+        wv[sup] = rng.normal(size=nnz)
+        z, lam = rng.normal(size=n), rng.normal(size=n)
+        wd2, zd, lamd = e.vec(wv), e.vec(z), e.vec(lam)
+        Dw = torch.empty(n, dtype=torch.float64, device=e.device)
+        cabi.check(e.lib.rbl_dual_pass(e.h, e.D.data_ptr(), wd2.data_ptr(), w0d.data_ptr(), zd.data_ptr(),
+                                       Dw.data_ptr(), lamd.data_ptr(), 0.37, cap, e._out4.data_ptr(), e._stream()))
+        dw = X @ wv
+        scale = np.abs(X) @ np.abs(wv) + 1e-300
+        assert np.max(np.abs(Dw.cpu().numpy() - dw) / scale) < 1e-14, (nnz, cap)
+        assert np.max(np.abs(lamd.cpu().numpy() - (lam + 0.37 * (z - dw)))) < 1e-13 * max(1.0, np.max(scale))
+        o = e._out4.cpu().numpy()
+        assert abs(o[0] - np.sum((z - dw) ** 2)) < 1e-13 * o[0]
+        assert abs(o[1] - np.sum((wv - w0) ** 2)) < 1e-13 * o[1]
+        assert abs(o[2] - wv @ wv) <= 1e-13 * o[2] and abs(o[3] - np.abs(wv).sum()) <= 1e-13 * o[3]
+        assert int(o[4]) == nnz and bool(o[5]) == (nnz <= cap), (nnz, cap, o[4:6])
     e.close()
