@@ -22,6 +22,9 @@ int rbl_sort_tiles(int64_t n);
 int rbl_pav_chunk_log2();
 int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double* loc_lo, double* tot_hi,
                  double* tot_lo, double* off_hi, double* off_lo, cudaStream_t s);
+int rbl_k_segments(rbl_ctx* c, cudaStream_t s);
+int rbl_pav_max_seg();
+size_t rbl_pav_segblocks_bytes();
 int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* z_sorted, cudaStream_t s);
 int rbl_k_pass_multi(rbl_ctx* c, const double* D, const double* x, int64_t xstride, const double* b, double* r0,
                      double* r1, const FistaState* st, int ninst, double* red, int64_t red_stride, const double* c0part,
@@ -108,6 +111,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->valsA, ng));
     RBL_TRY(dev_alloc(c, &c->valsB, ng));
     RBL_TRY(dev_alloc(c, &c->tile_hist, (size_t)256 * c->sort_tiles + 256 + 8));
+    RBL_TRY(dev_alloc(c, &c->sort_counts, (size_t)256 * c->num_sms));
     c->chunk_log2 = rbl_pav_chunk_log2();
     c->nchunks = (c->n_global + ((int64_t)1 << c->chunk_log2) - 1) >> c->chunk_log2;
     const size_t nch = (size_t)c->nchunks;
@@ -125,6 +129,9 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->ch_tot_lo, nch + 1));
     RBL_TRY(dev_alloc(c, &c->node_cnt, nch + 64));
     RBL_TRY(dev_alloc(c, &c->sigma, ng));
+    RBL_TRY(dev_alloc(c, &c->seg_count, 16));
+    RBL_TRY(dev_alloc(c, &c->seg_bounds, (size_t)rbl_pav_max_seg() + 8));
+    RBL_TRY(dev_alloc(c, (unsigned char**)&c->seg_blocks, rbl_pav_segblocks_bytes()));
     RBL_TRY(dev_alloc(c, &c->obj_tmp, ng));
     return RBL_OK;
 }
@@ -136,7 +143,8 @@ void ctx_free(rbl_ctx* c) {
                     c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
                     c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt,  c->gq_prev,   c->gxs,       c->gvu,
                     c->gticket,   c->sup_idx,   c->sup_val,   c->sup_nnz,
-                    c->gvu2};
+                    c->gvu2,      c->seg_count, c->seg_bounds, c->seg_blocks,
+                    c->sort_counts};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);
@@ -236,6 +244,7 @@ int rbl_set_spectrum(rbl_handle_t h, const double* sigma, rbl_stream_t stream) {
                              S(stream)));
     RBL_TRY(rbl_k_prefix(h, h->sigma, h->n_global, h->ps_loc_hi, h->ps_loc_lo, h->ps_tot_hi, h->ps_tot_lo,
                          h->ps_off_hi, h->ps_off_lo, S(stream)));
+    RBL_TRY(rbl_k_segments(h, S(stream)));
     h->has_sigma = 1;
     return RBL_OK;
 }
@@ -266,6 +275,19 @@ int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, d
     RBL_REQUIRE(loss == RBL_LOSS_BINARY_CROSS_ENTROPY || loss == RBL_LOSS_HINGE, "unknown loss id %d", loss);
     RBL_REQUIRE(rho > 0.0, "rho must be positive");
     return rbl_k_pav(h, loss, m_sorted, rho, z_sorted, S(stream));
+}
+
+int rbl_sort_config(rbl_handle_t h, int legacy) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    h->sort_legacy = legacy ? 1 : 0;
+    return RBL_OK;
+}
+
+int rbl_pav_config(rbl_handle_t h, int force_tree, int32_t* h_nseg) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    h->force_tree = force_tree ? 1 : 0;
+    if (h_nseg) *h_nseg = h->nseg;
+    return RBL_OK;
 }
 
 int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const double* m, int64_t n, double rho,

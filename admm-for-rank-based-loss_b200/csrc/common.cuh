@@ -105,6 +105,8 @@ struct rbl_ctx {
     uint32_t *valsA, *valsB;
     uint32_t* tile_hist;    // [256 * ntiles] per-digit tile counts, then [256] digit totals
     int sort_tiles;
+    uint32_t* sort_counts;  // [num_sms][256] per-CTA digit counts of the persistent sort
+    int psort_checked, psort_ok, sort_legacy;
     // ---- PAV
     int chunk_log2;
     int64_t nchunks;
@@ -116,6 +118,11 @@ struct rbl_ctx {
     double* sigma;          // n_global, rank order (the sigma the PAV uses: alphas, or betas for EHRM)
     double* val;            // n_global block values
     int has_sigma;
+    int nseg;               // runs of non-increasing sigma (0: too many, use the merge tree)
+    int force_tree;         // testing: always take the merge tree
+    int* seg_count;
+    int64_t* seg_bounds;    // [nseg + 1] device
+    void* seg_blocks;       // SegBlocks (pooled blocks of the last few-segment call)
     // ---- batched mode (K10): B instances sharing D
     int batch_cap;          // instances the batched buffers were sized for (0: not created)
     int batch_stages;

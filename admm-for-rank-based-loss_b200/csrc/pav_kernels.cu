@@ -13,6 +13,14 @@
 //                    shared memory
 //   pav_tree       : the remaining log2(n/1024) levels in ONE launch: one CTA per pair of chunks climbs
 //                    the merge tree ("last arriver continues": no CTA ever waits for another)
+//
+// Few-segment path.  The element prox z(sigma, m) is non-decreasing in m and non-increasing in sigma, so on
+// sorted margins it is ALREADY isotonic over every maximal run of ranks where sigma does not increase:
+// violations can only start where the spectrum steps UP.  ERM has no such step (no pooling ever),
+// superquantile has two (0 -> fractional weight -> 1/(n(1-q))), AoRR at most two.  When the spectrum has
+// <= kMaxSeg such runs (found once in rbl_set_spectrum) the level-0 solved ranges are those runs, and the
+// whole tree collapses to (#runs - 1) merges done by one warp over a lazily-overlaid value array, followed by
+// a grid-wide fill of the (few) pooled blocks: ~0.1 ms at n = 1M however large the pooled block is.
 #include "common.cuh"
 #include "pav_core.h"
 
@@ -69,7 +77,9 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
                                                                    double* __restrict__ loc_hi,
                                                                    double* __restrict__ loc_lo,
                                                                    double* __restrict__ tot_hi,
-                                                                   double* __restrict__ tot_lo) {
+                                                                   double* __restrict__ tot_lo,
+                                                                   const double* __restrict__ sigma, int loss,
+                                                                   double rho, double* __restrict__ prox_out) {
     __shared__ double sh[16];
     const int64_t base = (int64_t)blockIdx.x * kChunk;
     const int64_t i0 = base + (int64_t)threadIdx.x * kPer;
@@ -79,6 +89,11 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
     for (int q = 0; q < kPer; ++q) {
         v[q] = (i0 + q < n) ? x[i0 + q] : 0.0;
         run = dd_add_d(run, v[q]);
+    }
+    if (prox_out) {  // few-segment path: the element prox rides along with the prefix of the margins
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+            if (i0 + q < n) prox_out[i0 + q] = rbl_block_prox(loss, sigma[i0 + q], v[q], rho);
     }
     dd_t total;
     dd_t ex = block_excl_scan_dd(run, &total, sh);
@@ -389,6 +404,99 @@ __global__ void __launch_bounds__(kPavThreads) pav_tree_kernel(const TreeParams 
     }
 }
 
+// ---- few-segment path ------------------------------------------------------------------------------------
+constexpr int kMaxSeg = 8;
+
+// value array with a short list of pending pooled blocks laid over it (disjoint, at most kMaxSeg)
+struct ValOverlay {
+    const double* p;
+    const int* nblk;
+    const int64_t* lo;
+    const int64_t* hi;
+    const double* v;
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        const int nb = *nblk;
+        for (int k = 0; k < nb; ++k)
+            if (i >= lo[k] && i < hi[k]) return v[k];
+        return __ldg(p + i);
+    }
+};
+
+struct SegBlocks {
+    int nblk;
+    int pad;
+    int64_t lo[kMaxSeg], hi[kMaxSeg];
+    double v[kMaxSeg];
+};
+
+// positions i (1 <= i < n) where sigma steps up; count may exceed cap (then the list is truncated)
+__global__ void sigma_ascents_kernel(const double* __restrict__ sigma, int64_t n, int cap, int* __restrict__ count,
+                                     int64_t* __restrict__ pos) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        if (sigma[i] > sigma[i - 1]) {
+            const int k = atomicAdd(count, 1);
+            if (k < cap) pos[k] = i;
+        }
+    }
+}
+
+// one warp: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1
+__global__ void __launch_bounds__(32) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
+                                                           int nseg, SegBlocks* __restrict__ out) {
+    __shared__ int s_nblk;
+    __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
+    __shared__ double s_v[kMaxSeg];
+    const int lane = threadIdx.x;
+    if (lane == 0) s_nblk = 0;
+    __syncwarp();
+    PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
+    PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
+    ValOverlay val{P.val, &s_nblk, s_lo, s_hi, s_v};
+    for (int j = 1; j < nseg; ++j) {
+        const int64_t b = bounds[j], c = bounds[j + 1];
+        int64_t lo = 0, hi = 0;
+        double v = 0.0;
+        const bool merged = merge_kary_warp(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c, &lo, &hi, &v);
+        __syncwarp();
+        if (merged && lane == 0) {
+            // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
+            int k2 = 0;
+            const int nb = s_nblk;
+            for (int k = 0; k < nb; ++k) {
+                if (s_lo[k] >= lo && s_hi[k] <= hi) continue;
+                s_lo[k2] = s_lo[k];
+                s_hi[k2] = s_hi[k];
+                s_v[k2] = s_v[k];
+                ++k2;
+            }
+            s_lo[k2] = lo;
+            s_hi[k2] = hi;
+            s_v[k2] = v;
+            s_nblk = k2 + 1;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        out->nblk = s_nblk;
+        for (int k = 0; k < s_nblk; ++k) {
+            out->lo[k] = s_lo[k];
+            out->hi[k] = s_hi[k];
+            out->v[k] = s_v[k];
+        }
+    }
+}
+
+__global__ void pav_seg_fill_kernel(const SegBlocks* __restrict__ blk, double* __restrict__ val) {
+    const int nb = blk->nblk;
+    for (int k = 0; k < nb; ++k) {
+        const int64_t lo = blk->lo[k], hi = blk->hi[k];
+        const double v = blk->v[k];
+        for (int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < hi;
+             i += (int64_t)gridDim.x * blockDim.x)
+            val[i] = v;
+    }
+}
+
 // element-wise prox without pooling (PAV level 0 as a standalone op; individual_solver.py:112-130)
 __global__ void prox_elementwise_kernel(int loss, double rho, const double* __restrict__ sigma,
                                         const double* __restrict__ m, int64_t n, double* __restrict__ out) {
@@ -411,10 +519,43 @@ int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double*
                  double* tot_lo, double* off_hi, double* off_lo, cudaStream_t s) {
     const int64_t nch = (n + kChunk - 1) / kChunk;
     (void)c;
-    chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(x, n, loc_hi, loc_lo, tot_hi, tot_lo);
+    chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(x, n, loc_hi, loc_lo, tot_hi, tot_lo, nullptr, 0, 0.0,
+                                                             nullptr);
     RBL_LAUNCH_CHECK();
     chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(tot_hi, tot_lo, nch, off_hi, off_lo);
     RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_pav_max_seg() { return kMaxSeg; }
+size_t rbl_pav_segblocks_bytes() { return sizeof(SegBlocks); }
+
+// runs of non-increasing sigma: writes the ascending run boundaries [0, ..., n] to c->seg_bounds (device) and
+// sets c->nseg (0: more than kMaxSeg runs, use the merge tree).  Synchronises `s` (set-up time only).
+int rbl_k_segments(rbl_ctx* c, cudaStream_t s) {
+    const int cap = kMaxSeg;
+    int count = 0;
+    int64_t pos[kMaxSeg + 2];
+    RBL_CUDA(cudaMemsetAsync(c->seg_count, 0, sizeof(int), s));
+    sigma_ascents_kernel<<<c->vec_grid, 256, 0, s>>>(c->sigma, c->n_global, cap, c->seg_count, c->seg_bounds + 1);
+    RBL_LAUNCH_CHECK();
+    RBL_CUDA(cudaMemcpyAsync(&count, c->seg_count, sizeof(int), cudaMemcpyDeviceToHost, s));
+    RBL_CUDA(cudaStreamSynchronize(s));
+    if (count + 1 > kMaxSeg) {
+        c->nseg = 0;
+        return RBL_OK;
+    }
+    RBL_CUDA(cudaMemcpy(pos + 1, c->seg_bounds + 1, (size_t)count * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    for (int i = 1; i <= count; ++i)  // insertion sort (atomics filled the list in arbitrary order)
+        for (int j = i; j > 1 && pos[j] < pos[j - 1]; --j) {
+            const int64_t t = pos[j];
+            pos[j] = pos[j - 1];
+            pos[j - 1] = t;
+        }
+    pos[0] = 0;
+    pos[count + 1] = c->n_global;
+    RBL_CUDA(cudaMemcpy(c->seg_bounds, pos, (size_t)(count + 2) * sizeof(int64_t), cudaMemcpyHostToDevice));
+    c->nseg = count + 1;
     return RBL_OK;
 }
 
@@ -428,9 +569,12 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
                                       (int)sizeof(ChunkSmem)));
         attr_set = true;
     }
+    const bool few = c->nseg > 0 && !c->force_tree;
     chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(m_sorted, n, c->pm_loc_hi, c->pm_loc_lo, c->ch_tot_hi,
-                                                             c->ch_tot_lo);
+                                                             c->ch_tot_lo, c->sigma, loss, rho,
+                                                             few ? z_sorted : nullptr);
     RBL_LAUNCH_CHECK();
+    if (few && c->nseg == 1) return RBL_OK;  // sigma never steps up (ERM): the element prox is the answer
     chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
     RBL_LAUNCH_CHECK();
     TreeParams P;
@@ -448,6 +592,14 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.val = z_sorted;
     P.node_cnt = c->node_cnt;
     P.nchunks = nch;
+    if (few) {
+        SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
+        pav_seg_merge_kernel<<<1, 32, 0, s>>>(P, c->seg_bounds, c->nseg, blk);
+        RBL_LAUNCH_CHECK();
+        pav_seg_fill_kernel<<<c->vec_grid, 256, 0, s>>>(blk, z_sorted);
+        RBL_LAUNCH_CHECK();
+        return RBL_OK;
+    }
     pav_chunk_kernel<<<(unsigned)nch, kPavThreads, sizeof(ChunkSmem), s>>>(P);
     RBL_LAUNCH_CHECK();
     if (nch > 1) {

@@ -165,13 +165,238 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
     }
 }
 
+// ---- the whole 8-pass sort as ONE persistent cooperative kernel ---------------------------------------------
+// CTA c owns the contiguous key range [c chunk, (c+1) chunk) in every pass (chunk = ceil(n / grid), one CTA
+// per SM).  Per pass: (1) rank the range's keys by digit in shared memory (warp multisplit, as above) and
+// publish the CTA's 256 digit counts; grid barrier; (2) every CTA sums the published counts (digit totals and
+// the counts of the CTAs before it: G coalesced 1 KB rows), scans the totals, and scatters — keys, payload and
+// ranks stay in registers across the barrier when the range is a single 8192-key tile (n <= 1.2M on 148 SMs);
+// grid barrier.  16 barriers instead of 24 launches: the sort of 1M (key, index) pairs is latency-bound, not
+// bandwidth-bound (12 MB per pass lives in L2).
+constexpr int kPT = 1024;
+constexpr int kPWarps = kPT / 32;
+constexpr int kPTile = kPT * kItems;  // 8192 keys
+
+struct PSortParams {
+    const double* m;
+    int64_t n;
+    uint64_t *kA, *kB;
+    uint32_t *vA, *vB;
+    uint32_t* counts;    // [grid][256]
+    unsigned int* bar;   // zeroed before the launch
+    double* sorted_out;
+    int32_t* perm_out;
+    int64_t chunk;
+};
+
+__device__ __forceinline__ void sort_grid_barrier(unsigned int* ctr, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSortParams p) {
+    __shared__ uint32_t cnt[kPWarps][257];
+    __shared__ uint32_t base[256];
+    __shared__ uint32_t tot[256];
+    __shared__ uint32_t part_tot[4][256], part_pre[4][256];
+    __shared__ uint32_t wtot[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, me = blockIdx.x;
+    const int64_t r0 = (int64_t)me * p.chunk;
+    const int64_t r1 = (r0 + p.chunk < p.n) ? r0 + p.chunk : p.n;
+    const int ntile = r0 < r1 ? (int)((r1 - r0 + kPTile - 1) / kPTile) : 0;
+    const bool single = p.chunk <= kPTile;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    unsigned int target = 0;
+
+    uint64_t key[kItems];
+    uint32_t val[kItems];
+    uint16_t rank[kItems];
+
+    for (int pass = 0; pass < 8; ++pass) {
+        const int shift = pass * 8;
+        const bool from_double = pass == 0, last = pass == 7;
+        const void* kin = from_double ? (const void*)p.m : (const void*)((pass & 1) ? p.kA : p.kB);
+        const uint32_t* vin = from_double ? nullptr : ((pass & 1) ? p.vA : p.vB);
+        uint64_t* kout = (pass & 1) ? p.kB : p.kA;
+        uint32_t* vout = (pass & 1) ? p.vB : p.vA;
+
+        auto rank_tile = [&](int k) {
+            for (int q = tid; q < kPWarps * 257; q += kPT) (&cnt[0][0])[q] = 0;
+            __syncthreads();
+            const int64_t wbase = r0 + (int64_t)k * kPTile + (int64_t)warp * (kItems * 32);
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = wbase + j * 32 + lane;
+                const bool ok = i < r1;
+                // L1-bypassing loads: other CTAs rewrote these buffers earlier in this launch
+                key[j] = ok ? (from_double ? rbl_key_from_bits(reinterpret_cast<const uint64_t*>(kin)[i])
+                                           : __ldcg(reinterpret_cast<const unsigned long long*>(kin) + i))
+                            : 0ull;
+                val[j] = ok ? (vin ? __ldcg(vin + i) : (uint32_t)i) : 0u;
+                const uint32_t dg = ok ? (uint32_t)((key[j] >> shift) & 0xff) : 256u;
+                const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+                const int leader = __ffs(peers) - 1;
+                uint32_t basec = 0;
+                if (lane == leader) {
+                    basec = cnt[warp][dg];
+                    cnt[warp][dg] = basec + __popc(peers);
+                }
+                basec = __shfl_sync(0xffffffffu, basec, leader);
+                rank[j] = (uint16_t)(basec + __popc(peers & lt_mask));
+                __syncwarp();
+            }
+            __syncthreads();
+        };
+
+        // ---- phase 1: digit counts of my range
+        if (tid < 256) tot[tid] = 0;
+        for (int k = 0; k < ntile; ++k) {
+            rank_tile(k);
+            if (tid < 256) {
+                uint32_t t = 0;
+#pragma unroll 8
+                for (int w = 0; w < kPWarps; ++w) t += cnt[w][tid];
+                tot[tid] += t;
+            }
+            if (!single) __syncthreads();
+        }
+        __syncthreads();
+        if (tid < 256) __stcg(&p.counts[(size_t)me * 256 + tid], tot[tid]);
+        target += G;
+        sort_grid_barrier(p.bar, target);
+
+        // ---- phase 2: digit totals, counts of the CTAs before me, digit bases
+        {
+            const int q = tid >> 8, dg = tid & 255;
+            const int c0 = (G * q) / 4, c1 = (G * (q + 1)) / 4;
+            uint32_t t = 0, pre = 0;
+            for (int c = c0; c < c1; ++c) {
+                const uint32_t v = __ldcg(&p.counts[(size_t)c * 256 + dg]);
+                t += v;
+                if (c < me) pre += v;
+            }
+            part_tot[q][dg] = t;
+            part_pre[q][dg] = pre;
+        }
+        __syncthreads();
+        uint32_t dtot = 0, dpre = 0, x = 0;
+        if (tid < 256) {
+            dtot = part_tot[0][tid] + part_tot[1][tid] + part_tot[2][tid] + part_tot[3][tid];
+            dpre = part_pre[0][tid] + part_pre[1][tid] + part_pre[2][tid] + part_pre[3][tid];
+            x = dtot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) wtot[warp] = x;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w)
+                if (w < warp) woff += wtot[w];
+            base[tid] = woff + (x - dtot) + dpre;
+        }
+        __syncthreads();
+        for (int k = 0; k < ntile; ++k) {
+            if (!single) rank_tile(k);
+            if (tid < 256) {
+                uint32_t run = base[tid];
+#pragma unroll 8
+                for (int w = 0; w < kPWarps; ++w) {
+                    const uint32_t c = cnt[w][tid];
+                    cnt[w][tid] = run;
+                    run += c;
+                }
+                base[tid] = run;
+            }
+            __syncthreads();
+            const int64_t wbase = r0 + (int64_t)k * kPTile + (int64_t)warp * (kItems * 32);
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = wbase + j * 32 + lane;
+                if (i < r1) {
+                    const uint32_t dg = (uint32_t)((key[j] >> shift) & 0xff);
+                    const uint32_t pos = cnt[warp][dg] + rank[j];
+                    if (last) {
+                        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[pos] = rbl_bits_from_key(key[j]);
+                        if (p.perm_out) p.perm_out[pos] = (int32_t)val[j];
+                    } else {
+                        kout[pos] = key[j];
+                        vout[pos] = val[j];
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (!last) {
+            target += G;
+            sort_grid_barrier(p.bar, target);
+        }
+    }
+}
+
 }  // namespace
+
+// 1 if the persistent sort can run on this device (cooperative launch, one CTA per SM)
+int rbl_sort_persistent_ok(rbl_ctx* c) {
+    if (c->psort_checked) return c->psort_ok;
+    c->psort_checked = 1;
+    c->psort_ok = 0;
+    int coop = 0, per_sm = 0;
+    if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_persistent_kernel, kPT, 0) != cudaSuccess ||
+        per_sm < 1) {
+        cudaGetLastError();
+        return 0;
+    }
+    c->psort_ok = 1;
+    return 1;
+}
+
+int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out,
+                          cudaStream_t s) {
+    PSortParams p;
+    int G = c->num_sms;
+    const int64_t min_chunk = 2048;  // do not spread tiny sorts over the whole machine
+    if ((int64_t)G * min_chunk > n) G = (int)((n + min_chunk - 1) / min_chunk);
+    if (G < 1) G = 1;
+    p.m = m;
+    p.n = n;
+    p.kA = c->keysA;
+    p.kB = c->keysB;
+    p.vA = c->valsA;
+    p.vB = c->valsB;
+    p.counts = c->sort_counts;
+    p.bar = c->gticket + 16;
+    p.sorted_out = sorted_out;
+    p.perm_out = perm_out;
+    p.chunk = (n + G - 1) / G;
+    RBL_CUDA(cudaMemsetAsync(c->gticket + 16, 0, sizeof(unsigned int), s));
+    void* args[] = {(void*)&p};
+    RBL_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_persistent_kernel, dim3(G), dim3(kPT), args, 0, s));
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
 
 int rbl_sort_tiles(int64_t n) { return (int)((n + kTile - 1) / kTile); }
 
 // sorted_out / perm_out may be null when only one of them is wanted (objective: keys only)
 int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s) {
     if (n <= 0) return RBL_OK;
+    if (!c->sort_legacy && rbl_sort_persistent_ok(c)) return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s);
     const int ntiles = rbl_sort_tiles(n);
     if (ntiles > c->sort_tiles) {
         rbl_set_error("sort of %lld keys exceeds the handle's capacity", (long long)n);

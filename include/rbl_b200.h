@@ -64,10 +64,18 @@ int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho,
 
 /* stable ascending key-index sort of n_global margins.  algorithms.py:92-93 */
 int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream);
+/* legacy != 0: three launches per radix pass instead of the single persistent cooperative kernel (testing) */
+int rbl_sort_config(rbl_handle_t h, int legacy);
 
 /* z_sorted = argmin_{z1<=..<=zn} sum sigma_i loss(z_i) + rho/2 (z_i - m_i)^2.  pav.py:54-178,
  * individual_solver.py:90-130, PAV_cpt.py:169-293 (with sigma = betas; clip in rbl_scatter_z) */
 int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, double* z_sorted, rbl_stream_t stream);
+
+/* The element prox is already isotonic over every run of ranks where sigma does not increase, so a spectrum with
+ * few such runs (ERM 1, superquantile / AoRR <= 3) needs (#runs - 1) merges instead of the merge tree; rbl_set_spectrum
+ * finds the runs.  force_tree != 0 makes rbl_pav_prox take the general tree anyway (testing);
+ * *h_nseg (may be NULL) = number of runs, 0 if there are too many for the few-segment path. */
+int rbl_pav_config(rbl_handle_t h, int force_tree, int32_t* h_nseg);
 
 /* out[i] = argmin_z sigma_i loss(z) + rho/2 (z - m_i)^2, no pooling.  individual_solver.py:112-130 */
 int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const double* m, int64_t n, double rho,

@@ -107,13 +107,21 @@ def test_pav_matches_oracle(E, loss, n):
                 m = np.round(m, 2)  # ties, many blocks on the kink
             e = _mk(E, np.zeros((n, 2)), loss=loss, sigma=sig)
             e.m_sorted.copy_(e.vec(m))
-            E[1].check(e.lib.rbl_pav_prox(e.h, O.LOSS_IDS[loss], e.m_sorted.data_ptr(), rho, e.z_sorted.data_ptr(),
-                                          e._stream()))
-            z = e.z_sorted.cpu().numpy()
             zo = O.pav_prox(loss, sig, m, rho)
-            # same unique minimiser, both solved to machine precision; block sums in double-double
-            assert np.max(np.abs(z - zo)) <= 1e-12 * max(1.0, np.max(np.abs(zo))), (wf, rho, n)
-            assert np.all(np.diff(z) >= 0)
+            nseg = ctypes.c_int32(-1)
+            # both routes to the same unique minimiser: the general merge tree, and (when the spectrum has few
+            # runs of non-increasing sigma: erm, superquantile, aorr) the few-segment path
+            for force_tree in (1, 0):
+                E[1].check(e.lib.rbl_pav_config(e.h, force_tree, ctypes.byref(nseg)))
+                e.z_sorted.zero_()
+                E[1].check(e.lib.rbl_pav_prox(e.h, O.LOSS_IDS[loss], e.m_sorted.data_ptr(), rho,
+                                              e.z_sorted.data_ptr(), e._stream()))
+                z = e.z_sorted.cpu().numpy()
+                # both solved to machine precision; block sums in double-double
+                assert np.max(np.abs(z - zo)) <= 1e-12 * max(1.0, np.max(np.abs(zo))), (wf, rho, n, force_tree)
+                assert np.all(np.diff(z) >= 0)
+            if wf in ("erm", "superquantile", "aorr") and n >= 5:
+                assert 1 <= nseg.value <= 3, (wf, nseg.value)
             e.close()
 
 
