@@ -15,6 +15,8 @@ int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_cli
                   double rho, double* z, double* b, cudaStream_t s);
 int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const double* r, int from_residual,
                double* lam, double rho, const double* w, const double* w_prev, double* out4, cudaStream_t s);
+int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const int32_t* perm, int use_clip,
+                         double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s);
 int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
                     cudaStream_t s);
 int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s);
@@ -102,6 +104,10 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->gvu, 2 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->gticket, 64));
     RBL_TRY(dev_alloc(c, &c->gvu2, 4 * ld + 8));
+    RBL_TRY(dev_alloc(c, &c->act_cta_count, (size_t)c->vec_grid + 8));
+    RBL_TRY(dev_alloc(c, &c->act_row, nl + 8));
+    RBL_TRY(dev_alloc(c, &c->act_delta, nl + 8));
+    RBL_TRY(dev_alloc(c, &c->act_total, 16));
     RBL_TRY(dev_alloc(c, &c->sup_idx, ld + 8));
     RBL_TRY(dev_alloc(c, &c->sup_val, ld + 8));
     RBL_TRY(dev_alloc(c, &c->sup_nnz, 64));
@@ -144,7 +150,7 @@ void ctx_free(rbl_ctx* c) {
                     c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt,  c->gq_prev,   c->gxs,       c->gvu,
                     c->gticket,   c->sup_idx,   c->sup_val,   c->sup_nnz,
                     c->gvu2,      c->seg_count, c->seg_bounds, c->seg_blocks,
-                    c->sort_counts};
+                    c->sort_counts, c->act_cta_count, c->act_row, c->act_delta, c->act_total};
     for (void* p : ptrs)
         if (p) cudaFree(p);
     if (c->fista_host) cudaFreeHost(c->fista_host);
@@ -304,6 +310,42 @@ int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, i
     RBL_ENTER(h);
     RBL_REQUIRE(z_sorted && perm && z && (b == nullptr || lam != nullptr), "null argument");
     return rbl_k_scatter(h, z_sorted, perm, use_clip, clip, lam, rho, z, b, S(stream));
+}
+
+int rbl_scatter_active(rbl_handle_t h, const double* z_sorted, const double* m_sorted, const int32_t* perm,
+                       int use_clip, double clip, const double* lam, double rho, double* z, double* b,
+                       rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(z_sorted && m_sorted && perm && z && (b == nullptr || lam != nullptr), "null argument");
+    return rbl_k_scatter_active(h, z_sorted, m_sorted, perm, use_clip, clip, lam, rho, z, b, S(stream));
+}
+
+int rbl_grad_pass(rbl_handle_t h, const double* D, const double* w0, const double* b, double* r, int64_t dense_above,
+                  double* red, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && w0 && b && r && red, "null argument");
+    const int cap = (int)(dense_above < 0 ? 0 : (dense_above > h->n_local ? h->n_local : dense_above));
+    // exactly one of the two does the work, chosen on the device from the active-row count
+    RBL_TRY(rbl_launch_gather(h, D, h->act_row, h->act_delta, h->act_total, cap, S(stream)));
+    RBL_TRY(rbl_launch_pass(h, RBL_PASS_FUSED, D, w0, b, r, nullptr, nullptr, S(stream), nullptr, 0.0, h->act_total,
+                            cap));
+    RBL_TRY(rbl_k_reduce_partials(h, 0, nullptr, S(stream)));
+    RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 1) * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    return RBL_OK;
+}
+
+int rbl_gather_only(rbl_handle_t h, const double* D, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D != nullptr, "null argument");
+    return rbl_launch_gather(h, D, h->act_row, h->act_delta, h->act_total, (int)h->n_local, S(stream));
+}
+
+int rbl_active_count(rbl_handle_t h, int32_t* h_count, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(h_count != nullptr, "null argument");
+    RBL_CUDA(cudaMemcpyAsync(h_count, h->act_total, sizeof(int), cudaMemcpyDeviceToHost, S(stream)));
+    RBL_CUDA(cudaStreamSynchronize(S(stream)));
+    return RBL_OK;
 }
 
 int rbl_fused_pass(rbl_handle_t h, const double* D, const double* x, const double* b, double* r, double* red,

@@ -100,6 +100,11 @@ struct rbl_ctx {
     int32_t* sup_idx;
     double* sup_val;
     int* sup_nnz;
+    // ---- active rows of the last rbl_scatter_active: rows whose z differs from the margin (rank order)
+    int* act_cta_count;   // [vec_grid]
+    int32_t* act_row;     // [n_local] local row indices
+    double* act_delta;    // [n_local] z - m
+    int* act_total;
     // ---- sort
     uint64_t *keysA, *keysB;
     uint32_t *valsA, *valsB;
@@ -142,6 +147,9 @@ int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, cons
                     const FistaState* st, double* const* rbuf, cudaStream_t s, double* lam = nullptr,
                     double rho = 0.0, const int* gate_nnz = nullptr, int gate_cap = 0);
 int rbl_pass_configure(rbl_ctx* c);
+// column partials of sum_k delta_k D[row_k] over the active-row list (runs iff *count <= cap)
+int rbl_launch_gather(rbl_ctx* c, const double* D, const int32_t* rows, const double* delta, const int* count,
+                      int cap, cudaStream_t s);
 
 #define RBL_PASS_MATVEC 0  // out = D x
 #define RBL_PASS_FUSED 1   // out = r = b - D x ; column partials of D^T r ; partial ||r||^2

@@ -282,6 +282,104 @@ __global__ void scatter_kernel(const double* __restrict__ zs, const int32_t* __r
     }
 }
 
+// ---- scatter + the ACTIVE-ROW list -------------------------------------------------------------------------
+// r0 = b - D w = z + lambda/rho - D w = z - m  is exactly zero wherever the prox is the identity: every rank
+// with sigma_i = 0 outside the pooled blocks (80% of the rows for superquantile q = 0.8), and for the hinge
+// every margin below the kink.  The gradient pass D^T r0 therefore only has to read the ACTIVE rows.  Two
+// kernels: (1) scatter as before, with a blocked rank assignment, also counting the owned active ranks per
+// CTA; (2) stable compaction in rank order (deterministic: every CTA re-derives its base from the counts).
+constexpr int kActThreads = 256;
+
+__device__ __forceinline__ bool active_item(const double* __restrict__ zs, const double* __restrict__ ms,
+                                            const int32_t* __restrict__ perm, int64_t i, int64_t row_lo,
+                                            int64_t n_local, int use_clip, double clip, int64_t* row_out,
+                                            double* v_out, double* delta_out) {
+    const int64_t row = (int64_t)perm[i] - row_lo;
+    double v = zs[i];
+    if (use_clip && v < clip) v = clip;  // EHRM: max(B, isotonic prox) (PAV_cpt.py:213,271)
+    *row_out = row;
+    *v_out = v;
+    const double dl = v - ms[i];
+    *delta_out = dl;
+    return row >= 0 && row < n_local && dl != 0.0;
+}
+
+__global__ void __launch_bounds__(kActThreads) scatter_active_kernel(
+    const double* __restrict__ zs, const double* __restrict__ ms, const int32_t* __restrict__ perm, int64_t n_global,
+    int64_t row_lo, int64_t n_local, int use_clip, double clip, const double* __restrict__ lam, double rho,
+    double* __restrict__ z, double* __restrict__ b, int64_t chunk, int* __restrict__ cta_count) {
+    __shared__ int wcount[kActThreads / 32];
+    const int64_t r0 = (int64_t)blockIdx.x * chunk;
+    const int64_t r1 = (r0 + chunk < n_global) ? r0 + chunk : n_global;
+    int cnt = 0;
+    for (int64_t i = r0 + threadIdx.x; i < r1; i += kActThreads) {
+        int64_t row;
+        double v, dl;
+        const bool act = active_item(zs, ms, perm, i, row_lo, n_local, use_clip, clip, &row, &v, &dl);
+        if (row >= 0 && row < n_local) {
+            z[row] = v;
+            if (b) b[row] = v + lam[row] / rho;
+        }
+        cnt += act ? 1 : 0;
+    }
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) wcount[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kActThreads / 32; ++w) t += wcount[w];
+        cta_count[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kActThreads) compact_active_kernel(
+    const double* __restrict__ zs, const double* __restrict__ ms, const int32_t* __restrict__ perm, int64_t n_global,
+    int64_t row_lo, int64_t n_local, int use_clip, double clip, int64_t chunk, const int* __restrict__ cta_count,
+    int32_t* __restrict__ act_row, double* __restrict__ act_delta, int* __restrict__ act_total) {
+    __shared__ int sh[kActThreads / 32 + 1];
+    __shared__ int s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // base = sum of the counts of the CTAs before me (and the grand total, written by the last CTA)
+    int part = 0;
+    for (int c = tid; c < (int)blockIdx.x; c += kActThreads) part += cta_count[c];
+    for (int o = 16; o; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) sh[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kActThreads / 32; ++w) t += sh[w];
+        s_base = t;
+        if (blockIdx.x == gridDim.x - 1) *act_total = t + cta_count[blockIdx.x];
+    }
+    __syncthreads();
+    int base = s_base;
+    const int64_t r0 = (int64_t)blockIdx.x * chunk;
+    const int64_t r1 = (r0 + chunk < n_global) ? r0 + chunk : n_global;
+    for (int64_t i0 = r0; i0 < r1; i0 += kActThreads) {  // block-uniform trip count
+        const int64_t i = i0 + tid;
+        int64_t row = 0;
+        double v, dl = 0.0;
+        const bool act = (i < r1) && active_item(zs, ms, perm, i, row_lo, n_local, use_clip, clip, &row, &v, &dl);
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        __syncthreads();
+        if (lane == 0) sh[warp] = __popc(m);
+        __syncthreads();
+        int off = base, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kActThreads / 32; ++w) {
+            const int t = sh[w];
+            if (w < warp) off += t;
+            tot += t;
+        }
+        if (act) {
+            const int k = off + __popc(m & ((1u << lane) - 1u));
+            act_row[k] = (int32_t)row;
+            act_delta[k] = dl;
+        }
+        base += tot;
+    }
+}
+
 // ---- dual update + primal residual (algorithms.py:132,135) --------------------------------------
 // Dw is either given (from_residual = 0) or recovered from the last FISTA residual r = b - D w.
 __global__ void dual_kernel(const double* __restrict__ z, double* __restrict__ Dw, const double* __restrict__ b,
@@ -439,6 +537,7 @@ __global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __res
                                                              const double* __restrict__ w,
                                                              const double* __restrict__ w_prev, int d,
                                                              const FistaState* __restrict__ st,
+                                                             const int* __restrict__ act_total,
                                                              double* __restrict__ out) {
     __shared__ double sh[33];
     const int nnz = *nnz_ptr;
@@ -470,6 +569,7 @@ __global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __res
         out[5] = sparse ? 1.0 : 0.0;
         out[6] = (double)st->k;       // last w-step: FISTA iterations, sweeps/passes (saves the host a poll)
         out[7] = (double)st->passes;
+        out[8] = (double)*act_total;  // active rows of the last rbl_scatter_active
     }
 }
 
@@ -533,6 +633,20 @@ int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_cli
     return RBL_OK;
 }
 
+int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const int32_t* perm, int use_clip,
+                         double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s) {
+    const int grid = c->vec_grid;
+    const int64_t chunk = (c->n_global + grid - 1) / grid;
+    scatter_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
+                                                      clip, lam, rho, z, b, chunk, c->act_cta_count);
+    RBL_LAUNCH_CHECK();
+    compact_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
+                                                      clip, chunk, c->act_cta_count, c->act_row, c->act_delta,
+                                                      c->act_total);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
 int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const double* r, int from_residual,
                double* lam, double rho, const double* w, const double* w_prev, double* out4, cudaStream_t s) {
     dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(z, Dw, b, r, from_residual, lam, rho, c->n_local, c->vpart);
@@ -555,7 +669,7 @@ int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* w, const double
 
 int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s) {
     dual_finalize_kernel<<<1, 1024, 0, s>>>(c->sspart, c->pass_grid, c->vpart, c->vec_grid, c->sup_nnz, cap, w,
-                                            w_prev, c->d, c->fista, out8);
+                                            w_prev, c->d, c->fista, c->act_total, out8);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

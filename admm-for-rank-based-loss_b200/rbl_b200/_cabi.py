@@ -27,6 +27,11 @@ _SIGNATURES = {
     "rbl_prox_elementwise": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _c.c_int64, _c.c_double, _dp, _c.c_void_p]),
     "rbl_scatter_z": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_int, _c.c_double, _dp, _c.c_double, _dp, _dp,
                                  _c.c_void_p]),
+    "rbl_scatter_active": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_int, _c.c_double, _dp, _c.c_double, _dp, _dp,
+                                      _c.c_void_p]),
+    "rbl_grad_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _c.c_int64, _dp, _c.c_void_p]),
+    "rbl_gather_only": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
+    "rbl_active_count": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int32), _c.c_void_p]),
     "rbl_fused_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_fista_config": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_float)]),
     "rbl_fista_begin": (_c.c_int, [_c.c_void_p, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double, _c.c_int,

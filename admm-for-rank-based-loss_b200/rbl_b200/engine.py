@@ -75,8 +75,8 @@ class DeviceProblem:
                                                   self._stream()))
             torch.cuda.current_stream().synchronize()
             del Xd, yd
-            self._out4 = torch.zeros(8, dtype=torch.float64, device=self.device)
-            self._out4_host = torch.zeros(8, dtype=torch.float64).pin_memory()
+            self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
+            self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
             self._u_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
             self._u_glob = (torch.empty(self.n_global, dtype=torch.float64, device=self.device)
                             if self.world > 1 else self._u_local)
@@ -208,6 +208,11 @@ class AdmmEngine(DeviceProblem):
         self.gram_build_s = 0.0
         self._persistent = None
         self._fista_info_pending = False
+        # gradient pass: gather over the active rows (z != m) unless more than this fraction of rows is active
+        self.active_dense_frac = float(os.environ.get("RBL_ACTIVE_FRAC", "0.75"))
+        self._delta_valid = False
+        self._active_pending = False
+        self.active_stats = {"calls": 0, "rows": 0, "gathered": 0}
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
         self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
@@ -218,6 +223,7 @@ class AdmmEngine(DeviceProblem):
 
     # ---- state -------------------------------------------------------------------------------
     def set_state(self, w=None, z=None, lam=None):
+        self._delta_valid = False
         if w is not None:
             self.w.copy_(self.vec(w))
             self.Dw_valid = False
@@ -247,12 +253,19 @@ class AdmmEngine(DeviceProblem):
             self.gram_build_s = t0.elapsed_time(t1) * 1e-3
         return self.G
 
-    def _pass_at(self, w0, b):
-        """red0 = [D^T (b - D w0), ||b - D w0||^2] — the one pass over D a Gram-mode w-step makes."""
-        _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), w0.data_ptr(), b.data_ptr(),
-                                            self.r.data_ptr(), self.red0.data_ptr(), self._stream()))
+    def _pass_at(self, w0, b, use_active=False):
+        """red0 = [D^T (b - D w0), ||b - D w0||^2] — the one pass over D a Gram-mode w-step makes.  Right after
+        a z-step, b - D w0 = z - m is zero on every row the prox left alone: only the active rows are read."""
+        if use_active:
+            _cabi.check(self.lib.rbl_grad_pass(self.h, self.D.data_ptr(), w0.data_ptr(), b.data_ptr(),
+                                               self.r.data_ptr(), int(self.active_dense_frac * self.n_local),
+                                               self.red0.data_ptr(), self._stream()))
+            self._active_pending = True
+        else:
+            _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), w0.data_ptr(), b.data_ptr(),
+                                                self.r.data_ptr(), self.red0.data_ptr(), self._stream()))
+            self.fista_stats["d_passes"] += 1
         self.all_reduce(self.red0)
-        self.fista_stats["d_passes"] += 1
 
     # ---- z-step: margins -> sort -> PAV prox -> scatter (algorithms.py:88-106) -----------------
     def z_step(self, rho):
@@ -265,14 +278,22 @@ class AdmmEngine(DeviceProblem):
                                          self.perm.data_ptr(), s))
         _cabi.check(lib.rbl_pav_prox(self.h, self.loss_id, self.m_sorted.data_ptr(), float(rho),
                                      self.z_sorted.data_ptr(), s))
-        _cabi.check(lib.rbl_scatter_z(self.h, self.z_sorted.data_ptr(), self.perm.data_ptr(),
-                                      0 if self.clip is None else 1, 0.0 if self.clip is None else float(self.clip),
-                                      self.lam.data_ptr(), float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
+        if self.w_mode == "gram" and self.active_dense_frac > 0:
+            _cabi.check(lib.rbl_scatter_active(self.h, self.z_sorted.data_ptr(), self.m_sorted.data_ptr(),
+                                               self.perm.data_ptr(), 0 if self.clip is None else 1,
+                                               0.0 if self.clip is None else float(self.clip), self.lam.data_ptr(),
+                                               float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
+            self._delta_valid = True  # until w, z or lambda change
+        else:
+            _cabi.check(lib.rbl_scatter_z(self.h, self.z_sorted.data_ptr(), self.perm.data_ptr(),
+                                          0 if self.clip is None else 1,
+                                          0.0 if self.clip is None else float(self.clip), self.lam.data_ptr(),
+                                          float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
         return self.z
 
     # ---- w-step, l1: FISTA (fast_lasso.py:22-69 via algorithms.py:190-202) ---------------------
     def fista(self, w0, b, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_iter=5000, w_out=None,
-              r_out=None, want_info=True):
+              r_out=None, want_info=True, use_active=False):
         """Runs the device-resident FISTA state machine to completion; returns (w_out, info).
 
         `lam` keeps its Python type on purpose: a python float makes `lam/L_cur` a float32 quotient
@@ -290,7 +311,8 @@ class AdmmEngine(DeviceProblem):
         hi = (ctypes.c_int32 * 8)()
         hd = (ctypes.c_double * 4)()
         if self.w_mode == "gram":
-            return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info)
+            return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info,
+                                    use_active)
         # first batch: what the previous call needed (iteration counts drift slowly between ADMM
         # iterations), then small batches; steps enqueued after convergence exit immediately
         batch = max(self.fista_batch_min, self.fista_stats["last_passes"] - 1)
@@ -321,7 +343,8 @@ class AdmmEngine(DeviceProblem):
         st["d_passes"] += info["passes"]
         return w_out, info
 
-    def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info=True):
+    def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info=True,
+                    use_active=False):
         """FISTA on G = D^T D: one fused pass over D at the warm start, then one sweep over G per trial —
         the whole call is one persistent cooperative kernel when its state fits in shared memory."""
         lib, s = self.lib, self._stream()
@@ -330,7 +353,7 @@ class AdmmEngine(DeviceProblem):
             w_out = torch.empty(self.d, dtype=torch.float64, device=self.device)
         if w0.data_ptr() == w_out.data_ptr():
             raise ValueError("w0 and w_out must not alias in Gram mode")
-        self._pass_at(w0, b)
+        self._pass_at(w0, b, use_active)
         if self._persistent is None:
             self._persistent = bool(lib.rbl_gram_fista_persistent_ok(self.h)) and \
                 os.environ.get("RBL_GRAM_PERSISTENT", "1") != "0"
@@ -372,8 +395,9 @@ class AdmmEngine(DeviceProblem):
     def w_step_fista(self, lam, tol=7e-5, max_iter=5000):
         if self.w_mode == "gram":
             self.w_prev.copy_(self.w)
+            use_active, self._delta_valid = self._delta_valid, False
             _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w,
-                                 want_info=False)
+                                 want_info=False, use_active=use_active)
             self._r_matches_w = False
             return info
         self.w_prev.copy_(self.w)
@@ -419,7 +443,8 @@ class AdmmEngine(DeviceProblem):
         self.w_host.copy_(self.w)
         if self.w_mode == "gram":
             self.gram()
-            self._pass_at(self.w_prev, self.b)
+            use_active, self._delta_valid = self._delta_valid, False
+            self._pass_at(self.w_prev, self.b, use_active)
         torch.cuda.current_stream(self.device).synchronize()
         w0 = self.w_host.numpy().copy()
         rho, reg = float(rho), float(reg)
@@ -461,6 +486,14 @@ class AdmmEngine(DeviceProblem):
             took_sparse = bool(o[5].item())
             self.dual_stats["sparse" if took_sparse else "dense"] += 1
             self.dual_stats["nnz_last"] = int(o[4].item())
+            if self._active_pending:
+                self._active_pending = False
+                rows = int(o[8].item())
+                gathered = rows <= int(self.active_dense_frac * self.n_local)
+                self.active_stats["calls"] += 1
+                self.active_stats["rows"] += rows if gathered else self.n_local
+                self.active_stats["gathered"] += 1 if gathered else 0
+                self.fista_stats["d_passes"] += 0 if gathered else 1
             if self._fista_info_pending:
                 self._fista_info_pending = False
                 st = self.fista_stats

@@ -248,6 +248,7 @@ class ADMMmethod(Optimizer):
     def _w_subproblem(self):
         """reference :190-207 — standalone w-step on the current (z, lambda, rho); returns numpy d x 1"""
         e = self.engine
+        e._delta_valid = False  # b is rebuilt from the current (z, lambda, rho): not the z-step's z - m any more
         e.b.copy_(e.z + e.lam / float(self.rho))
         self._w_subproblem_device()
         return e.w.cpu().numpy().reshape(-1, 1)

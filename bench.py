@@ -253,26 +253,42 @@ def main():
     value = K / t_steps
     e2e_value = K / (t_steps + t_upload)
 
-    # ---- roofline of the dominant kernel: the fused D pass, timed alone on its stream -----------------
+    # ---- roofline of the D-reading kernels, each timed alone on its stream ------------------------------
     eng = solver.engine
     reps = 20
-    xd = eng.w.clone()
-    for _ in range(3):
-        _cabi.check(eng.lib.rbl_fused_pass(eng.h, eng.D.data_ptr(), xd.data_ptr(), eng.b.data_ptr(), eng.r.data_ptr(),
-                                           eng.red.data_ptr(), eng._stream()))
-    torch.cuda.synchronize()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record()
-    for _ in range(reps):
-        _cabi.check(eng.lib.rbl_fused_pass(eng.h, eng.D.data_ptr(), xd.data_ptr(), eng.b.data_ptr(), eng.r.data_ptr(),
-                                           eng.red.data_ptr(), eng._stream()))
-    p1.record()
-    torch.cuda.synchronize()
-    t_pass = p0.elapsed_time(p1) / 1e3 / reps
-    nl = hi - lo
-    alg_bytes = nl * d * 8 + (2 * nl + 2 * d) * 8  # D once; b in, r out; x in, g out  (DESIGN.md)
     peak, peak_kind = measured_peak_gbs()
+    nl = hi - lo
+
+    def time_kernel(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for _ in range(reps):
+            fn()
+        p1.record()
+        torch.cuda.synchronize()
+        return p0.elapsed_time(p1) / 1e3 / reps
+
+    xd = eng.w.clone()
+    t_pass = time_kernel(lambda: _cabi.check(eng.lib.rbl_fused_pass(
+        eng.h, eng.D.data_ptr(), xd.data_ptr(), eng.b.data_ptr(), eng.r.data_ptr(), eng.red.data_ptr(),
+        eng._stream())))
+    alg_bytes = nl * d * 8 + (2 * nl + 2 * d) * 8  # D once; b in, r out; x in, g out  (DESIGN.md)
     achieved = alg_bytes / t_pass / 1e9
+    gather = None
+    if eng.w_mode == "gram" and eng.active_dense_frac > 0:
+        import ctypes
+        eng.z_step(solver.rho)  # leaves the active-row list of the current state
+        cnt = ctypes.c_int32(0)
+        _cabi.check(eng.lib.rbl_active_count(eng.h, ctypes.byref(cnt), eng._stream()))
+        t_g = time_kernel(lambda: _cabi.check(eng.lib.rbl_gather_only(eng.h, eng.D.data_ptr(), eng._stream())))
+        g_bytes = cnt.value * (d * 8 + 12) + 2 * d * 8  # active rows of D + (row, delta) list; g out
+        gather = {"kernel": "rbl_gather_kernel (g = sum over ACTIVE rows of delta_i D_i, per-row TMA bulk copies)",
+                  "active_rows": cnt.value, "active_fraction": cnt.value / nl, "launch_ms": 1e3 * t_g,
+                  "algorithmic_bytes_per_launch": g_bytes, "achieved": g_bytes / t_g / 1e9,
+                  "frac": g_bytes / t_g / 1e9 / peak}
     # z-step alone (sort + PAV + scatter): 68 n bytes algorithmic
     torch.cuda.synchronize()
     z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -339,6 +355,10 @@ def main():
                    "fista_trials_in_timed_region": passes_timed,
                    "d_passes_in_timed_region": dpasses_timed,
                    "gram_build_s": solver.engine.gram_build_s,
+                   "active_rows": {**eng.active_stats, "note": "gradient pass reads only rows with z != m "
+                                   "(b - D w = z - m is exactly 0 elsewhere); rows = total rows read over `calls`"},
+                   "dual_pass": {**eng.dual_stats, "note": "D w reads only the sectors touched by nnz(w) when "
+                                 "w is sparse"},
                    "pass_tiles": {k: solver.engine.info[k] for k in ("pass_grid", "rows_per_tile", "pass_stages")}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes / K,
                 "d2h_bytes_per_step": (d + 4) * 8,
@@ -351,7 +371,8 @@ def main():
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": alg_bytes,
                      "launch_ms": 1e3 * t_pass,
-                     "pass_share_of_step": dpasses_timed * t_pass / t_steps},
+                     "pass_share_of_step": dpasses_timed * t_pass / t_steps,
+                     "gather_pass": gather},
         "zstep": {"ms": 1e3 * t_z, "keys_per_s": n / t_z, "algorithmic_bytes": 68 * n,
                   "frac_of_hbm_peak": 68 * n / t_z / 1e9 / peak},
         "cpu_baseline": cpu,

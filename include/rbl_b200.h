@@ -86,6 +86,25 @@ int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const do
 int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, int use_clip, double clip,
                   const double* lam, double rho, double* z, double* b, rbl_stream_t stream);
 
+/* rbl_scatter_z that also records the ACTIVE rows: those whose z differs from the margin m.  b - D w = z - m is
+ * exactly zero on every other row (sigma_i = 0 outside the pooled blocks; hinge margins below the kink), so the
+ * gradient pass of the w-step only has to read the active rows of D.  The list (local row, z - m) is kept in
+ * the handle in rank order (deterministic).  algorithms.py:103-104,192 */
+int rbl_scatter_active(rbl_handle_t h, const double* z_sorted, const double* m_sorted, const int32_t* perm,
+                       int use_clip, double clip, const double* lam, double rho, double* z, double* b,
+                       rbl_stream_t stream);
+/* red = [D^T (b - D w0) (d), ||b - D w0||^2] at the point w0 the last rbl_scatter_active was taken at
+ * (b = z + lambda/rho, m = D w0 - lambda/rho): a gather over the active rows when there are at most `dense_above`
+ * of them, else one streaming pass (chosen on the device; r is scratch for the latter).  fast_lasso.py:41-43,
+ * w_LBFGS.py:31-45 */
+int rbl_grad_pass(rbl_handle_t h, const double* D, const double* w0, const double* b, double* r, int64_t dense_above,
+                  double* red, rbl_stream_t stream);
+/* the gather kernel of rbl_grad_pass alone, on the current active-row list (per-CTA partials are left in
+ * handle scratch): lets bench.py time that kernel by itself */
+int rbl_gather_only(rbl_handle_t h, const double* D, rbl_stream_t stream);
+/* synchronises `stream`; *h_count = active rows of the last rbl_scatter_active (instrumentation) */
+int rbl_active_count(rbl_handle_t h, int32_t* h_count, rbl_stream_t stream);
+
 /* r = b - D x ; red[0..d) = D^T r ; red[d] = ||r||^2  (one pass over D).  w_LBFGS.py:31-45,
  * fast_lasso.py:41-43.  red must hold d + 2 doubles. */
 int rbl_fused_pass(rbl_handle_t h, const double* D, const double* x, const double* b, double* r, double* red,
@@ -137,7 +156,7 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
 
 /* Dw = D w with the dual update in the epilogue: lambda += rho (z - Dw);
  * out8 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1, nnz(w), sparse path taken (0/1),
- * FISTA iterations and sweeps of the last w-step].
+ * FISTA iterations and sweeps of the last w-step, active rows of the last rbl_scatter_active] (9 doubles).
  * algorithms.py:132-136.  The l1 w-step leaves exact zeros in w: when nnz(w) <= sparse_cap the product reads only
  * the nnz(w) touched 32-byte sectors of each row of D (chosen on the device, no host round trip), otherwise one
  * streaming pass over D.  sparse_cap = 0 forces the dense pass. */

@@ -208,3 +208,47 @@ def test_gram_build_eval_and_dual_pass(E, n, d):
         assert abs(o[2] - wv @ wv) <= 1e-13 * o[2] and abs(o[3] - np.abs(wv).sum()) <= 1e-13 * o[3]
         assert int(o[4]) == nnz and bool(o[5]) == (nnz <= cap), (nnz, cap, o[4:6])
     e.close()
+
+
+@pytest.mark.parametrize("wf,args,loss,n,d,frac", [
+    ("superquantile", [0.8], "binary_cross_entropy", 20000, 200, 0.75),   # 20% of the rows active -> gather
+    ("superquantile", [0.8], "binary_cross_entropy", 20000, 200, 0.05),   # same state, forced dense
+    ("aorr", [0.2, 0.8], "hinge", 5000, 101, 0.75),                       # hinge: margins below the kink drop out
+    ("erm", None, "binary_cross_entropy", 3000, 64, 0.75),                # every row active -> streaming pass
+    ("ehrm", None, "binary_cross_entropy", 4000, 50, 0.75),               # clip at B makes rows active
+])
+def test_active_row_gradient_pass(E, wf, args, loss, n, d, frac):
+    """After a z-step, b - D w = z - m vanishes on every row the prox left alone; rbl_grad_pass over the active
+    rows must give the same [D^T (b - D w), ||b - D w||^2] as the full fused pass (rounding only)."""
+    _, cabi = E
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d))
+    y = np.where(rng.random(n) > 0.5, 1.0, -1.0)
+    sig = O.spectrum(wf, n, args)
+    sig = sig[1] if isinstance(sig, tuple) else sig
+    e = _mk(E, X, y, loss=loss, sigma=sig, clip=-5.0 if wf == "ehrm" else None)
+    e.active_dense_frac = frac
+    rho = 0.05
+    e.set_state(w=rng.normal(size=d) * 0.05, z=np.zeros(n), lam=rng.normal(size=n) * 0.01)
+    e.z_step(rho)
+    if e.w_mode != "gram":
+        pytest.skip("active rows are a Gram-mode feature")
+    cnt = ctypes.c_int32(0)
+    cabi.check(e.lib.rbl_active_count(e.h, ctypes.byref(cnt), e._stream()))
+    z, m = e.z.cpu().numpy(), e.m.cpu().numpy()
+    assert cnt.value == int(np.count_nonzero(z != m))
+    if wf == "superquantile":
+        assert cnt.value < 0.35 * n          # the sigma = 0 ranks outside the pooled block are untouched
+    e.gram()
+    e._pass_at(e.w, e.b, use_active=True)
+    red_a = e.red0.cpu().numpy().copy()
+    e._pass_at(e.w, e.b, use_active=False)
+    red_f = e.red0.cpu().numpy().copy()
+    D = e.D[:, :d].cpu().numpy()
+    delta = z - m
+    gref = D.T @ delta
+    scale = np.abs(D).T @ np.abs(delta) + 1e-300
+    assert np.max(np.abs(red_a[:d] - gref) / scale) < 1e-14
+    assert np.max(np.abs(red_f[:d] - gref) / np.maximum(scale, np.abs(D).T @ np.abs(e.b.cpu().numpy()) * 1e-2)) < 1e-13
+    assert abs(red_a[d] - delta @ delta) <= 1e-13 * (delta @ delta)
+    e.close()
