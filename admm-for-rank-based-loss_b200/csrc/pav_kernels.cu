@@ -169,13 +169,12 @@ struct TreeParams {
 
 // one merge of two solved ranges by a full warp (shared- or global-memory values): the rounds of pav_merge_search_kary (pav_core.h, which the CPU
 // tests run with a loop over lanes) with one lane per probe — keep the two in sync
+// left half of the merge search: first p in [a, b-1] whose run joins the pooled block (full warp)
 template <class V, class PS, class PM>
-__device__ bool merge_kary_warp(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
-                                int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+__device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
+                                   int64_t b, int64_t c) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
-    if (!(val(b - 1) > val(b))) return false;
-    // ---- left
     int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
     bool first = true;
     while (lo < hi) {
@@ -228,13 +227,17 @@ __device__ bool merge_kary_warp(int loss, double rho, const V& val, const PS& ps
         }
         if (hi < lo) hi = lo;
     }
-    const int64_t lo_star = lo;
-    // ---- right
-    lo = b + 1;
-    hi = c;
-    xlo = a;
-    xhi = b;
-    first = true;
+    return lo;
+}
+
+// right half: first p in [b+1, c) whose run stays out of the pooled block, else c (full warp)
+template <class V, class PS, class PM>
+__device__ int64_t merge_kary_right(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
+                                    int64_t b, int64_t c) {
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    int64_t lo = b + 1, hi = c, xlo = a, xhi = b;
+    bool first = true;
     while (lo < hi) {
         const int64_t width = hi - lo;
         int active;
@@ -269,7 +272,17 @@ __device__ bool merge_kary_warp(int loss, double rho, const V& val, const PS& ps
         first = false;
         if (hi < lo) hi = lo;
     }
-    pav_kary_finish(loss, rho, val, ps, pm, a, c, lo_star, lo, lo_out, hi_out, v_out);
+    return lo;
+}
+
+// one merge of two solved ranges by a full warp: left search, right search, block value
+template <class V, class PS, class PM>
+__device__ bool merge_kary_warp(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
+                                int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+    if (!(val(b - 1) > val(b))) return false;
+    const int64_t lo_star = merge_kary_left(loss, rho, val, ps, pm, a, b, c);
+    const int64_t hi_star = merge_kary_right(loss, rho, val, ps, pm, a, b, c);
+    pav_kary_finish(loss, rho, val, ps, pm, a, c, lo_star, hi_star, lo_out, hi_out, v_out);
     return true;
 }
 
@@ -440,25 +453,34 @@ __global__ void sigma_ascents_kernel(const double* __restrict__ sigma, int64_t n
     }
 }
 
-// one warp: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1
-__global__ void __launch_bounds__(32) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
+// two warps: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1;
+// warp 0 searches the left end of the pooled block while warp 1 searches the right end (independent
+// dependent-load chains, ~50 us each at n = 1M)
+__global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
                                                            int nseg, SegBlocks* __restrict__ out) {
     __shared__ int s_nblk;
     __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
     __shared__ double s_v[kMaxSeg];
-    const int lane = threadIdx.x;
-    if (lane == 0) s_nblk = 0;
-    __syncwarp();
+    __shared__ int64_t s_end[2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_nblk = 0;
+    __syncthreads();
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
     PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
     ValOverlay val{P.val, &s_nblk, s_lo, s_hi, s_v};
     for (int j = 1; j < nseg; ++j) {
         const int64_t b = bounds[j], c = bounds[j + 1];
-        int64_t lo = 0, hi = 0;
-        double v = 0.0;
-        const bool merged = merge_kary_warp(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c, &lo, &hi, &v);
-        __syncwarp();
-        if (merged && lane == 0) {
+        const bool violated = val(b - 1) > val(b);  // block-uniform
+        if (violated) {
+            const int64_t e = warp == 0 ? merge_kary_left(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c)
+                                        : merge_kary_right(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c);
+            if (lane == 0) s_end[warp] = e;
+        }
+        __syncthreads();
+        if (violated && tid == 0) {
+            int64_t lo, hi;
+            double v;
+            pav_kary_finish(P.loss, P.rho, val, gps, gpm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
             int k2 = 0;
             const int nb = s_nblk;
@@ -474,9 +496,9 @@ __global__ void __launch_bounds__(32) pav_seg_merge_kernel(const TreeParams P, c
             s_v[k2] = v;
             s_nblk = k2 + 1;
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (lane == 0) {
+    if (tid == 0) {
         out->nblk = s_nblk;
         for (int k = 0; k < s_nblk; ++k) {
             out->lo[k] = s_lo[k];
@@ -594,7 +616,7 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.nchunks = nch;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
-        pav_seg_merge_kernel<<<1, 32, 0, s>>>(P, c->seg_bounds, c->nseg, blk);
+        pav_seg_merge_kernel<<<1, 64, 0, s>>>(P, c->seg_bounds, c->nseg, blk);
         RBL_LAUNCH_CHECK();
         pav_seg_fill_kernel<<<c->vec_grid, 256, 0, s>>>(blk, z_sorted);
         RBL_LAUNCH_CHECK();

@@ -134,6 +134,7 @@ RBL_HD double rbl_block_prox(int loss, double sbar, double mbar, double rho) {
     // so the root is only defined to ~eps*max(|z|,|mbar|).  Stopping on that (not on eps*|z|) matters:
     // roots near zero would otherwise jitter for the full iteration budget and stall their warp.
     const double floor_abs = 2.3e-16 * fabs(mbar);
+    double zprev = lo - 1.0;  // outside the bracket: never equal to an iterate
     for (int it = 0; it < 64; ++it) {
         double s = rbl_sigmoid(z);
         double g = sbar * s + rho * (z - mbar);
@@ -142,8 +143,12 @@ RBL_HD double rbl_block_prox(int loss, double sbar, double mbar, double rho) {
         double dg = sbar * s * (1.0 - s) + rho;
         double zn = z - g / dg;
         if (!(zn >= lo && zn <= hi)) zn = 0.5 * (lo + hi);
-        if (zn == z) break;
+        // zn == zprev: the iteration has collapsed onto two neighbouring doubles with residuals of opposite
+        // sign and would bounce between them for the whole budget (0.5% of the elements did, and each one
+        // stalled its warp for 64 rounds)
+        if (zn == z || zn == zprev) break;
         double dz = fabs(zn - z);
+        zprev = z;
         z = zn;
         if (dz <= fmax(2.3e-16 * fabs(z), floor_abs)) break;
     }

@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
 constexpr int kPT = 1024;
 constexpr int kPWarps = kPT / 32;
 constexpr int kPTile = kPT * kItems;  // 8192 keys
+constexpr size_t kPSortSmem = (size_t)(kPWarps * 257 + 256 + 256 + 8 + 2 * 16 * 256) * sizeof(uint32_t);
 
 struct PSortParams {
     const double* m;
@@ -204,11 +205,13 @@ __device__ __forceinline__ void sort_grid_barrier(unsigned int* ctr, unsigned in
 }
 
 __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSortParams p) {
-    __shared__ uint32_t cnt[kPWarps][257];
-    __shared__ uint32_t base[256];
-    __shared__ uint32_t tot[256];
-    __shared__ uint32_t part_tot[4][256], part_pre[4][256];
-    __shared__ uint32_t wtot[8];
+    extern __shared__ __align__(16) uint32_t psm[];
+    uint32_t(*cnt)[257] = reinterpret_cast<uint32_t(*)[257]>(psm);                       // [kPWarps][257]
+    uint32_t* base = psm + kPWarps * 257;  // [256]; 32 * 257 is a multiple of 4, so uint4 alignment holds
+    uint32_t* tot = base + 256;                                                          // [256]
+    uint32_t* wtot = tot + 256;                                                          // [8]
+    uint32_t(*part_tot)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8);             // [16][256]
+    uint32_t(*part_pre)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8 + 16 * 256);  // [16][256]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, me = blockIdx.x;
     const int64_t r0 = (int64_t)me * p.chunk;
@@ -277,22 +280,27 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
 
         // ---- phase 2: digit totals, counts of the CTAs before me, digit bases
         {
-            const int q = tid >> 8, dg = tid & 255;
-            const int c0 = (G * q) / 4, c1 = (G * (q + 1)) / 4;
-            uint32_t t = 0, pre = 0;
-            for (int c = c0; c < c1; ++c) {
-                const uint32_t v = __ldcg(&p.counts[(size_t)c * 256 + dg]);
-                t += v;
-                if (c < me) pre += v;
+            // 64 threads x uint4 cover one 256-digit row; 16 row groups; <= 10 independent loads per thread
+            const int q = tid >> 6, v4 = tid & 63;
+            const uint4* cp = reinterpret_cast<const uint4*>(p.counts);
+            uint4 t = make_uint4(0, 0, 0, 0), pre = make_uint4(0, 0, 0, 0);
+#pragma unroll 10
+            for (int c = q; c < G; c += 16) {
+                const uint4 v = __ldcg(&cp[(size_t)c * 64 + v4]);
+                t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+                if (c < me) { pre.x += v.x; pre.y += v.y; pre.z += v.z; pre.w += v.w; }
             }
-            part_tot[q][dg] = t;
-            part_pre[q][dg] = pre;
+            *reinterpret_cast<uint4*>(&part_tot[q][4 * v4]) = t;
+            *reinterpret_cast<uint4*>(&part_pre[q][4 * v4]) = pre;
         }
         __syncthreads();
         uint32_t dtot = 0, dpre = 0, x = 0;
         if (tid < 256) {
-            dtot = part_tot[0][tid] + part_tot[1][tid] + part_tot[2][tid] + part_tot[3][tid];
-            dpre = part_pre[0][tid] + part_pre[1][tid] + part_pre[2][tid] + part_pre[3][tid];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                dtot += part_tot[q][tid];
+                dpre += part_pre[q][tid];
+            }
             x = dtot;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
@@ -357,7 +365,10 @@ int rbl_sort_persistent_ok(rbl_ctx* c) {
     c->psort_ok = 0;
     int coop = 0, per_sm = 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_persistent_kernel, kPT, 0) != cudaSuccess ||
+    if (cudaFuncSetAttribute(radix_sort_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)kPSortSmem) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_sort_persistent_kernel, kPT, kPSortSmem) !=
+            cudaSuccess ||
         per_sm < 1) {
         cudaGetLastError();
         return 0;
@@ -386,7 +397,8 @@ int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted
     p.chunk = (n + G - 1) / G;
     RBL_CUDA(cudaMemsetAsync(c->gticket + 16, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
-    RBL_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_persistent_kernel, dim3(G), dim3(kPT), args, 0, s));
+    RBL_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_persistent_kernel, dim3(G), dim3(kPT), args,
+                                         kPSortSmem, s));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
