@@ -48,8 +48,9 @@ int rbl_gram_persist_config(rbl_ctx* c);
 int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
                          float L0, double tol, int max_iter, double* w_out, cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s);
-int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* w, const double* z, double* Dw, double* lam,
-                      double rho, int cap, cudaStream_t s);
+int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
+                      double* lam, double rho, int cap, cudaStream_t s);
+int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s);
 int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s);
 int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, const double* w_prev, double* out4,
                    cudaStream_t s);
@@ -598,13 +599,20 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
     return rbl_k_gram_eval(h, G, w0, red0, w, red_out, S(stream));
 }
 
-int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
-                  double* Dw, double* lam, double rho, int sparse_cap, double* out8, rbl_stream_t stream) {
+int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D && Dt, "null argument");
+    return rbl_k_transpose(h, D, Dt, S(stream));
+}
+
+int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const double* w, const double* w_prev,
+                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, double* out8,
+                  rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(D && w && z && Dw && lam && out8, "null argument");
     const int cap = sparse_cap < 0 ? 0 : sparse_cap;
     // exactly one of the two kernels does the work, chosen on the device from nnz(w): no host round trip
-    RBL_TRY(rbl_k_dual_sparse(h, D, w, z, Dw, lam, rho, cap, S(stream)));
+    RBL_TRY(rbl_k_dual_sparse(h, D, Dt, w, z, Dw, lam, rho, cap, S(stream)));
     RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho, h->sup_nnz, cap));
     return rbl_k_dual_finalize(h, cap, w, w_prev, out8, S(stream));
 }

@@ -176,7 +176,8 @@ __global__ void __launch_bounds__(kSortThreads) radix_scatter_kernel(
 constexpr int kPT = 1024;
 constexpr int kPWarps = kPT / 32;
 constexpr int kPTile = kPT * kItems;  // 8192 keys
-constexpr size_t kPSortSmem = (size_t)(kPWarps * 257 + 256 + 256 + 8 + 2 * 16 * 256) * sizeof(uint32_t);
+constexpr size_t kPSortSmem =
+    (size_t)(kPWarps * 257 + 256 + 256 + 8 + 2 * 16 * 256 + 256) * sizeof(uint32_t) + (size_t)kPTile * 12;
 
 struct PSortParams {
     const double* m;
@@ -212,6 +213,9 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
     uint32_t* wtot = tot + 256;                                                          // [8]
     uint32_t(*part_tot)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8);             // [16][256]
     uint32_t(*part_pre)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8 + 16 * 256);  // [16][256]
+    uint32_t* gbase = wtot + 8 + 32 * 256;                                               // [256]
+    uint64_t* skey = reinterpret_cast<uint64_t*>(gbase + 256);                           // [kPTile] (8-byte aligned)
+    uint32_t* sval = reinterpret_cast<uint32_t*>(skey + kPTile);                         // [kPTile]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, me = blockIdx.x;
     const int64_t r0 = (int64_t)me * p.chunk;
@@ -320,30 +324,68 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
         __syncthreads();
         for (int k = 0; k < ntile; ++k) {
             if (!single) rank_tile(k);
+            // tile-local digit starts (exclusive scan of the tile's digit counts), then per-warp local offsets;
+            // gbase[dg] = global start of this tile's run of digit dg minus its local start
+            uint32_t tcount = 0, xs = 0;
             if (tid < 256) {
-                uint32_t run = base[tid];
+#pragma unroll 8
+                for (int w = 0; w < kPWarps; ++w) tcount += cnt[w][tid];
+                xs = tcount;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
+                    if (lane >= o) xs += y;
+                }
+                if (lane == 31) wtot[warp] = xs;
+            }
+            __syncthreads();
+            if (tid < 256) {
+                uint32_t woff = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w)
+                    if (w < warp) woff += wtot[w];
+                const uint32_t lstart = woff + (xs - tcount);
+                uint32_t run = lstart;
 #pragma unroll 8
                 for (int w = 0; w < kPWarps; ++w) {
                     const uint32_t c = cnt[w][tid];
                     cnt[w][tid] = run;
                     run += c;
                 }
-                base[tid] = run;
+                gbase[tid] = base[tid] - lstart;
+                base[tid] += tcount;
             }
             __syncthreads();
-            const int64_t wbase = r0 + (int64_t)k * kPTile + (int64_t)warp * (kItems * 32);
+            // reorder the tile by digit in shared memory so that the global stores below are coalesced runs
+            // (8192 / 256 = 32 keys per digit on average) instead of 8-byte writes to random sectors
+            const int64_t tbase = r0 + (int64_t)k * kPTile;
+            const int tlen = (int)((r1 - tbase < kPTile) ? (r1 - tbase) : kPTile);
+            const int64_t wbase = tbase + (int64_t)warp * (kItems * 32);
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
                 const int64_t i = wbase + j * 32 + lane;
                 if (i < r1) {
                     const uint32_t dg = (uint32_t)((key[j] >> shift) & 0xff);
-                    const uint32_t pos = cnt[warp][dg] + rank[j];
+                    const uint32_t lpos = cnt[warp][dg] + rank[j];
+                    skey[lpos] = key[j];
+                    sval[lpos] = val[j];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int L = tid + j * kPT;
+                if (L < tlen) {
+                    const uint64_t kk = skey[L];
+                    const uint32_t vv = sval[L];
+                    const uint32_t dg = (uint32_t)((kk >> shift) & 0xff);
+                    const uint32_t pos = gbase[dg] + (uint32_t)L;
                     if (last) {
-                        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[pos] = rbl_bits_from_key(key[j]);
-                        if (p.perm_out) p.perm_out[pos] = (int32_t)val[j];
+                        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[pos] = rbl_bits_from_key(kk);
+                        if (p.perm_out) p.perm_out[pos] = (int32_t)vv;
                     } else {
-                        kout[pos] = key[j];
-                        vout[pos] = val[j];
+                        kout[pos] = kk;
+                        vout[pos] = vv;
                     }
                 }
             }

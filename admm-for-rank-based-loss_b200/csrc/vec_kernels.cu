@@ -482,30 +482,42 @@ __device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, i
     const int sub = lane % GS, grp = lane / GS;
     constexpr int GPW = 32 / GS;
     // warp-uniform loop bounds (the shuffles below need every lane of the warp): a warp owns GPW consecutive
-    // rows per step, 4 steps in flight
+    // rows per step, U steps in flight
     const int64_t wbase = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GPW;
     const int64_t gstride = (int64_t)gridDim.x * (blockDim.x >> 5) * GPW;
-    for (int64_t b0 = wbase; b0 < n; b0 += 4 * gstride) {
+    constexpr int U = 4;  // rows in flight per group
+    for (int64_t b0 = wbase; b0 < n; b0 += U * gstride) {
         const int64_t i0 = b0 + grp;
-        double a[4] = {0.0, 0.0, 0.0, 0.0};
+        double a[U], zv[U], lv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * gstride;
+            a[u] = 0.0;
+            zv[u] = 0.0;
+            lv[u] = 0.0;
+            if (sub == 0 && i < n) {  // issued now, consumed after the dot products
+                zv[u] = z[i];
+                lv[u] = lam[i];
+            }
+        }
         for (int k = sub; k < nnz; k += GS) {
             const int j = idx[k];
             const double wv = val[k];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const int64_t i = i0 + u * gstride;
                 if (i < n) a[u] = fma(__ldg(&D[i * ld + j]), wv, a[u]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
 #pragma unroll
             for (int o = GS / 2; o; o >>= 1) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
             const int64_t i = i0 + u * gstride;
             if (sub == 0 && i < n) {
-                const double res = z[i] - a[u];
+                const double res = zv[u] - a[u];
                 Dw[i] = a[u];
-                lam[i] = lam[i] + rho * res;
+                lam[i] = lv[u] + rho * res;
                 acc = fma(res, res, acc);
             }
         }
@@ -528,6 +540,96 @@ __global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restri
     else sparse_dual_rows<32>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// Same update from the TRANSPOSED copy Dt (d x n, row j = column j of D): the nnz touched columns are read as
+// contiguous n-vectors, so the traffic is nnz n 8 bytes of fully coalesced loads (80 MB at nnz = 10, n = 1M)
+// instead of one DRAM page activation per row of D (the sector gather above is activate-bound: ~2 TB/s).
+__global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __restrict__ Dt, int64_t n,
+                                                            const int32_t* __restrict__ idx,
+                                                            const double* __restrict__ val,
+                                                            const int* __restrict__ nnz_ptr, int cap,
+                                                            const double* __restrict__ z, double* __restrict__ Dw,
+                                                            double* __restrict__ lam, double rho,
+                                                            double* __restrict__ part) {
+    __shared__ double sh[33];
+    __shared__ int s_idx[256];
+    __shared__ double s_val[256];
+    const int nnz = *nnz_ptr;
+    if (nnz > cap) return;  // the dense pass handles it
+    double acc = 0.0;
+    for (int k0 = 0; k0 == 0 || k0 < nnz; k0 += 256) {  // nnz <= cap <= d/16: one chunk in practice
+        __syncthreads();
+        if (k0 + (int)threadIdx.x < nnz) {
+            s_idx[threadIdx.x] = idx[k0 + threadIdx.x];
+            s_val[threadIdx.x] = val[k0 + threadIdx.x];
+        }
+        __syncthreads();
+        const int kn = (nnz - k0 < 256) ? (nnz - k0) : 256;
+        const bool first = (k0 == 0), last_chunk = (k0 + 256 >= nnz);
+        for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n;
+             i += (int64_t)gridDim.x * blockDim.x * 2) {
+            const bool two = (i + 1 < n) && ((n & 1) == 0);  // double2 loads need 16-byte aligned columns
+            double a0 = first ? 0.0 : Dw[i], a1 = (two && !first) ? Dw[i + 1] : 0.0;
+            if (two) {
+#pragma unroll 4
+                for (int k = 0; k < kn; ++k) {
+                    const double2 v = __ldg(reinterpret_cast<const double2*>(Dt + (int64_t)s_idx[k] * n + i));
+                    a0 = fma(v.x, s_val[k], a0);
+                    a1 = fma(v.y, s_val[k], a1);
+                }
+            } else {
+                for (int k = 0; k < kn; ++k) a0 = fma(__ldg(Dt + (int64_t)s_idx[k] * n + i), s_val[k], a0);
+                if (i + 1 < n) {
+                    a1 = first ? 0.0 : Dw[i + 1];
+                    for (int k = 0; k < kn; ++k) a1 = fma(__ldg(Dt + (int64_t)s_idx[k] * n + i + 1), s_val[k], a1);
+                }
+            }
+            Dw[i] = a0;
+            if (i + 1 < n) Dw[i + 1] = a1;
+            if (last_chunk) {
+                const double r0 = z[i] - a0;
+                lam[i] = lam[i] + rho * r0;
+                acc = fma(r0, r0, acc);
+                if (i + 1 < n) {
+                    const double r1 = z[i + 1] - a1;
+                    lam[i + 1] = lam[i + 1] + rho * r1;
+                    acc = fma(r1, r1, acc);
+                }
+            }
+        }
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+// Dt = D^T (d x n) through a 32 x 33 shared-memory tile
+__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ D, int64_t ld, int64_t n, int d,
+                                                        double* __restrict__ Dt) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const int64_t ntr = (n + 31) / 32;
+    const int ntc = (d + 31) / 32;
+    for (int64_t t = blockIdx.x; t < ntr * ntc; t += gridDim.x) {
+        const int64_t tr = t / ntc;
+        const int tc = (int)(t - tr * ntc);
+        const int64_t r0 = tr * 32;
+        const int c0 = tc * 32;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int64_t r = r0 + ty + 8 * q;
+            const int c = c0 + tx;
+            tile[ty + 8 * q][tx] = (r < n && c < d) ? D[r * ld + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int c = c0 + ty + 8 * q;
+            const int64_t r = r0 + tx;
+            if (c < d && r < n) Dt[(int64_t)c * n + r] = tile[tx][ty + 8 * q];
+        }
+        __syncthreads();
+    }
 }
 
 // out8 = [||z - Dw||^2, ||w - w_prev||^2, ||w||^2, ||w||_1, nnz(w), 1 if the sparse kernel ran, k, sweeps]
@@ -657,12 +759,22 @@ int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const d
 }
 
 // support list, sparse kernel (gated nnz <= cap), then the caller launches the dense pass (gated nnz > cap)
-int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* w, const double* z, double* Dw, double* lam,
-                      double rho, int cap, cudaStream_t s) {
+int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
+                      double* lam, double rho, int cap, cudaStream_t s) {
     support_kernel<<<1, 1024, 0, s>>>(w, c->d, c->sup_idx, c->sup_val, c->sup_nnz);
     RBL_LAUNCH_CHECK();
-    sparse_dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(D, c->ld, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
-                                                          cap, z, Dw, lam, rho, c->vpart);
+    if (Dt)
+        sparse_dual_t_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
+                                                                cap, z, Dw, lam, rho, c->vpart);
+    else
+        sparse_dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(D, c->ld, c->n_local, c->sup_idx, c->sup_val,
+                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s) {
+    transpose_kernel<<<c->num_sms * 16, 256, 0, s>>>(D, c->ld, c->n_local, c->d, Dt);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -216,6 +216,9 @@ class AdmmEngine(DeviceProblem):
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
         self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
+        # transposed copy of D for the sparse-w dual pass: built once w has come out sparse twice, if it fits
+        self.Dt = None
+        self.transpose_ok = os.environ.get("RBL_TRANSPOSE", "1") != "0"
         if mode == "gram":
             self.gram()  # like the reference, which forms DTD in Optimizer.__init__ (algorithms.py:24)
         self._fista_eta = None
@@ -252,6 +255,16 @@ class AdmmEngine(DeviceProblem):
                 t1.synchronize()
             self.gram_build_s = t0.elapsed_time(t1) * 1e-3
         return self.G
+
+    def _build_transpose(self):
+        free, _ = torch.cuda.mem_get_info(self.device)
+        need = self.n_local * self.d * 8
+        if need + (2 << 30) > free:
+            self.transpose_ok = False  # not enough HBM left: keep the sector-gather kernel
+            return
+        with torch.cuda.device(self.device):
+            self.Dt = torch.empty((self.d, self.n_local), dtype=torch.float64, device=self.device)
+            _cabi.check(self.lib.rbl_build_transpose(self.h, self.D.data_ptr(), self.Dt.data_ptr(), self._stream()))
 
     def _pass_at(self, w0, b, use_active=False):
         """red0 = [D^T (b - D w0), ||b - D w0||^2] — the one pass over D a Gram-mode w-step makes.  Right after
@@ -464,7 +477,11 @@ class AdmmEngine(DeviceProblem):
         from_res = 1 if getattr(self, "_r_matches_w", False) else 0
         if not from_res:
             # Dw = D w with the multiplier update and ||z - Dw||^2 in the pass epilogue
-            _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(), self.w.data_ptr(), self.w_prev.data_ptr(),
+            if self.Dt is None and self.dual_stats["sparse"] >= 2 and self.transpose_ok:
+                self._build_transpose()
+            _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(),
+                                               0 if self.Dt is None else self.Dt.data_ptr(), self.w.data_ptr(),
+                                               self.w_prev.data_ptr(),
                                                self.z.data_ptr(), self.Dw.data_ptr(), self.lam.data_ptr(),
                                                float(rho), self.sparse_cap, self._out4.data_ptr(),
                                                self._stream()))

@@ -158,10 +158,16 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
  * out8 = [||z - Dw||^2 (local rows), ||w - w_prev||^2, ||w||^2, ||w||_1, nnz(w), sparse path taken (0/1),
  * FISTA iterations and sweeps of the last w-step, active rows of the last rbl_scatter_active] (9 doubles).
  * algorithms.py:132-136.  The l1 w-step leaves exact zeros in w: when nnz(w) <= sparse_cap the product reads only
- * the nnz(w) touched 32-byte sectors of each row of D (chosen on the device, no host round trip), otherwise one
- * streaming pass over D.  sparse_cap = 0 forces the dense pass. */
-int rbl_dual_pass(rbl_handle_t h, const double* D, const double* w, const double* w_prev, const double* z,
-                  double* Dw, double* lam, double rho, int sparse_cap, double* out8, rbl_stream_t stream);
+ * the nnz(w) touched columns (from the transposed copy Dt when given, else the touched 32-byte sectors of each row of
+ * D) — chosen on the device, no host round trip — otherwise one streaming pass over D.  sparse_cap = 0 forces the
+ * dense pass. */
+int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const double* w, const double* w_prev,
+                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, double* out8,
+                  rbl_stream_t stream);
+/* Dt = D^T as a dense d x n_local row-major copy (optional, 8 n d bytes).  With it the sparse-w branch of
+ * rbl_dual_pass reads the nnz(w) touched columns as contiguous n-vectors (coalesced) instead of one 32-byte sector
+ * per row and column (DRAM-activate bound).  Pass Dt = NULL to rbl_dual_pass when no copy is kept. */
+int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream);
 
 /* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
  * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].
