@@ -104,7 +104,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->gxs, 2 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->gvu, 2 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->gticket, 64));
-    RBL_TRY(dev_alloc(c, &c->gvu2, 4 * ld + 8));
+    RBL_TRY(dev_alloc(c, &c->gvu2, 16 * ld + 8));
     RBL_TRY(dev_alloc(c, &c->act_cta_count, (size_t)c->vec_grid + 8));
     RBL_TRY(dev_alloc(c, &c->act_row, nl + 8));
     RBL_TRY(dev_alloc(c, &c->act_delta, nl + 8));

@@ -92,8 +92,8 @@ struct rbl_ctx {
     // ---- Gram-mode w-step (gram_kernels.cu): q(beta_prev), right-hand sides, products, last-CTA ticket
     double *gq_prev, *gxs, *gvu;
     unsigned int* gticket;
-    double* gvu2;                       // [2][2][ld] parity-double-buffered products of the persistent kernel
-    int gp_checked, gp_grid, gp_rpc, gp_g_in_smem;  // persistent FISTA kernel shape (gp_grid = 0: unavailable)
+    double* gvu2;                       // [2][8][ld] parity-double-buffered products of the persistent kernel
+    int gp_checked, gp_grid, gp_rpc, gp_g_in_smem, gp_kc;  // persistent FISTA kernel shape (gp_grid = 0: unavailable)
     size_t gp_smem;
     const double *gram_w0, *gram_red0;  // caller-owned warm start and [g0, ss0] of the running FISTA call
     // ---- support of w (sparse D w in the dual pass): ascending column indices, values, count

@@ -308,9 +308,38 @@ __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int tar
     __syncthreads();
 }
 
+// sums of KC per-thread partials over the block, results valid in every thread (fixed order: deterministic and
+// identical in every CTA); sh holds KC * kGWarps doubles
+template <int KC>
+__device__ __forceinline__ void block_sum_vec(double (&v)[KC], double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < KC; ++c) v[c] = warp_sum(v[c]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < KC; ++c) sh[c * kGWarps + warp] = v[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < KC; ++c) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kGWarps; ++w) t += sh[c * kGWarps + w];
+        v[c] = t;
+    }
+}
+
+// KC line-search candidates per sweep.  The reference restarts L at 17 on every call and walks
+// L = 17 * 2.5^i up to ~lambda_max(G) ~ 1e6: ~13 rejected trials before the first accepted one.  All trial
+// points of one FISTA iteration depend only on (beta_p, g_p, L_i), so KC of them are formed at once, multiplied
+// by G in ONE sweep (KC right-hand sides Delta_i = beta_i - beta_p; G (beta_i - w0) = q_p + G Delta_i) and the
+// first i that passes the test is taken — the same accept/reject sequence as trying them one by one, at one
+// grid barrier per KC trials.
+template <int KC>
 __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(const GramPersist p) {
     extern __shared__ __align__(16) double psm[];
-    __shared__ double sh[kGWarps + 1];
+    __shared__ double sh[KC * kGWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = kGThreads;
     const int d = p.d;
     const int64_t ld = p.ldg;
@@ -322,9 +351,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     double* Q_P = BETA_PREV + ld;
     double* Q_PREV = Q_P + ld;
     double* G_P = Q_PREV + ld;
-    double* X0 = G_P + ld;
-    double* X1 = X0 + ld;
-    double* Gs = X1 + ld;  // [rpc][ld] when g_in_smem
+    double* DEL = G_P + ld;             // [KC][ld] candidate steps beta_i - beta_p
+    double* Gs = DEL + (size_t)KC * ld;  // [rpc][ld] when g_in_smem
     const int row0 = blockIdx.x * p.rpc;
     const int row1 = (row0 + p.rpc < d) ? row0 + p.rpc : d;
 
@@ -338,8 +366,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         Q_P[c] = 0.0;
         Q_PREV[c] = 0.0;
         G_P[c] = g;
-        X0[c] = 0.0;
-        X1[c] = 0.0;
+#pragma unroll
+        for (int q = 0; q < KC; ++q) DEL[(size_t)q * ld + c] = 0.0;  // padding columns stay zero
     }
     if (p.g_in_smem) {
         const int ld2 = (int)(ld >> 1);
@@ -348,101 +376,122 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         const int total = (row1 - row0) * ld2;
         for (int e = tid; e < total; e += nt) dst[e] = __ldg(&src[e]);
     }
-    float L_prev = p.L0, L_cur = __fmul_rn(p.L0, p.pow_tab[0]);
-    int i_k = 0, k = 0, done = 0, sweeps = 0, par = 0;
-    double t = 1.0, t1 = 0.0, crit = 0.0, rhs = 0.0, lhs = 0.0;
+    float L_prev = p.L0, L_acc = p.L0;
+    int i_k0 = 0, i_k = 0, k = 0, sweeps = 0, trials = 0, par = 0;
+    double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
     unsigned int target = 0;
     __syncthreads();
 
     while (true) {
-        // ---- trial: beta = soft(beta_p + g_p / L_cur, lam / L_cur)   (fast_lasso.py:47-49)
-        {
-            const double Ld = (double)L_cur;
-            const double thr = p.thr_f32 ? (double)__fdiv_rn((float)p.lam, L_cur) : p.lam / Ld;
-            double r1 = 0.0;
-            for (int c = tid; c < d; c += nt) {
-                const double bp = BETA_P[c], g = G_P[c];
-                const double bs = bp + g / Ld;
-                const double mag = fmax(fabs(bs) - thr, 0.0);
-                const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
-                const double bn = mag * sgn;
-                BETA[c] = bn;
-                const double df = bn - bp;
-                X0[c] = bn - W0[c];
-                X1[c] = df;
-                r1 = fma(df, df, r1);
-            }
-            r1 = block_sum(r1, sh);  // ends with a __syncthreads: X0, X1 complete
-            rhs = Ld * r1;
+        // ---- KC candidates: beta_i = soft(beta_p + g_p / L_i, lam / L_i), L_i = L_prev * eta^(i_k0 + i)
+        float Lc[KC];
+        double Ld[KC], thr[KC], r1[KC];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) {
+            const int ii = i_k0 + q;
+            Lc[q] = __fmul_rn(L_prev, p.pow_tab[ii < 127 ? ii : 127]);  // fast_lasso.py:46
+            Ld[q] = (double)Lc[q];
+            thr[q] = p.thr_f32 ? (double)__fdiv_rn((float)p.lam, Lc[q]) : p.lam / Ld[q];
+            r1[q] = 0.0;
         }
-        // ---- products of my rows with both right-hand sides
-        double* vu = p.vu + (size_t)par * 2 * ld;
+        for (int c = tid; c < d; c += nt) {
+            const double bp = BETA_P[c], g = G_P[c];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                const double bs = bp + g / Ld[q];  // :47
+                const double mag = fmax(fabs(bs) - thr[q], 0.0);
+                const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+                const double df = mag * sgn - bp;  // :49-50
+                DEL[(size_t)q * ld + c] = df;
+                r1[q] = fma(df, df, r1[q]);
+            }
+        }
+        block_sum_vec<KC>(r1, sh);  // its barriers also publish DEL
+        // ---- u_i = G Delta_i for my rows
+        double* vu = p.vu + (size_t)par * KC * ld;
         for (int row = row0 + warp; row < row1; row += kGWarps) {
             const double2* g2 = p.g_in_smem ? reinterpret_cast<const double2*>(Gs + (size_t)(row - row0) * ld)
                                             : reinterpret_cast<const double2*>(p.G + (size_t)row * ld);
-            const double2* x0 = reinterpret_cast<const double2*>(X0);
-            const double2* x1 = reinterpret_cast<const double2*>(X1);
             const int ld2 = (int)(ld >> 1);
-            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
-#pragma unroll 4
+            double ax[KC], ay[KC];
+#pragma unroll
+            for (int q = 0; q < KC; ++q) ax[q] = ay[q] = 0.0;
             for (int c2 = lane; c2 < ld2; c2 += 32) {
                 const double2 g = p.g_in_smem ? g2[c2] : __ldg(&g2[c2]);
-                const double2 xa = x0[c2], xb = x1[c2];
-                a0 = fma(g.x, xa.x, a0);
-                a1 = fma(g.y, xa.y, a1);
-                b0 = fma(g.x, xb.x, b0);
-                b1 = fma(g.y, xb.y, b1);
+#pragma unroll
+                for (int q = 0; q < KC; ++q) {
+                    const double2 x = reinterpret_cast<const double2*>(DEL + (size_t)q * ld)[c2];
+                    ax[q] = fma(g.x, x.x, ax[q]);
+                    ay[q] = fma(g.y, x.y, ay[q]);
+                }
             }
-            const double a = warp_sum(a0 + a1), b = warp_sum(b0 + b1);
-            if (lane == 0) {
-                __stcg(&vu[row], a);
-                __stcg(&vu[ld + row], b);
+#pragma unroll
+            for (int q = 0; q < KC; ++q) {
+                const double a = warp_sum(ax[q] + ay[q]);
+                if (lane == 0) __stcg(&vu[(size_t)q * ld + row], a);
             }
         }
         ++sweeps;
         target += gridDim.x;
         grid_barrier(p.bar, target);
-        // ---- control flow, identical in every CTA (fast_lasso.py:50-65)
-        {
-            double a = 0.0;
-            for (int c = tid; c < d; c += nt) a = fma(X1[c], __ldcg(&vu[ld + c]), a);
-            lhs = block_sum(a, sh);
+        // ---- line search, identical in every CTA: first i with NOT (Delta_i.G Delta_i > L_i ||Delta_i||^2)
+        double lhs[KC];
+#pragma unroll
+        for (int q = 0; q < KC; ++q) lhs[q] = 0.0;
+        for (int c = tid; c < d; c += nt) {
+#pragma unroll
+            for (int q = 0; q < KC; ++q) lhs[q] = fma(DEL[(size_t)q * ld + c], __ldcg(&vu[(size_t)q * ld + c]), lhs[q]);
         }
-        if (lhs > rhs) {  // LHS > RHS  <=>  D.G D > L ||D||^2; false for NaN like the reference
-            ++i_k;
-            L_cur = __fmul_rn(L_prev, p.pow_tab[i_k < 127 ? i_k : 127]);
-        } else {
-            L_prev = L_cur;
-            const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;
-            t1 = (t - 1.0) / tnext;
-            double a2 = 0.0;
-            for (int c = tid; c < d; c += nt) {
-                const double df = BETA[c] - BETA_PREV[c];
-                a2 = fma(df, df, a2);
-            }
-            crit = sqrt(block_sum(a2, sh));
-            ++k;
-            if (crit < p.tol || k >= p.max_iter) {
-                done = 1;
-            } else {
-                t = tnext;
-                for (int c = tid; c < d; c += nt) {
-                    const double bc = BETA[c];
-                    const double v = __ldcg(&vu[c]);
-                    const double df = bc - BETA_PREV[c];
-                    BETA_P[c] = bc + t1 * df;
-                    const double qp = v + t1 * (v - Q_PREV[c]);
-                    Q_P[c] = qp;
-                    Q_PREV[c] = v;
-                    G_P[c] = G0[c] - qp;
-                    BETA_PREV[c] = bc;
-                }
-                i_k = 0;
-                L_cur = __fmul_rn(L_prev, p.pow_tab[0]);
-            }
-        }
-        if (done) break;
+        block_sum_vec<KC>(lhs, sh);
+        int acc_q = -1;
+#pragma unroll
+        for (int q = 0; q < KC; ++q)
+            if (acc_q < 0 && !(lhs[q] > Ld[q] * r1[q])) acc_q = q;  // cond = (LHS > RHS), false for NaN (:56)
         par ^= 1;
+        if (acc_q < 0) {  // all KC rejected: next KC candidates from the same (beta_p, g_p)
+            i_k0 += KC;
+            trials += KC;
+            __syncthreads();
+            continue;
+        }
+        i_k = i_k0 + acc_q;
+        trials += acc_q + 1;
+        L_acc = Lc[acc_q];
+        lhs_acc = lhs[acc_q];
+        rhs_acc = Ld[acc_q] * r1[acc_q];
+        const double Lda = Ld[acc_q], thra = thr[acc_q];
+        const double* ua = vu + (size_t)acc_q * ld;
+        L_prev = L_acc;                                              // :58
+        const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;  // :59
+        t1 = (t - 1.0) / tnext;                                      // :61
+        double a2[1] = {0.0};
+        for (int c = tid; c < d; c += nt) {
+            const double bp = BETA_P[c], g = G_P[c];
+            const double bs = bp + g / Lda;  // the accepted trial point, same expression as above
+            const double mag = fmax(fabs(bs) - thra, 0.0);
+            const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+            const double bn = mag * sgn;
+            BETA[c] = bn;
+            const double df = bn - BETA_PREV[c];  // :60
+            a2[0] = fma(df, df, a2[0]);
+        }
+        block_sum_vec<1>(a2, sh);
+        crit = sqrt(a2[0]);  // :63
+        ++k;
+        if (crit < p.tol || k >= p.max_iter) break;
+        t = tnext;
+        for (int c = tid; c < d; c += nt) {
+            const double bc = BETA[c];
+            const double v = Q_P[c] + __ldcg(&ua[c]);      // G (beta - w0) = G (beta_p - w0) + G Delta
+            const double df = bc - BETA_PREV[c];
+            BETA_P[c] = bc + t1 * df;                      // :62
+            const double qp = v + t1 * (v - Q_PREV[c]);    // G (beta_p - w0): affine in beta
+            Q_P[c] = qp;
+            Q_PREV[c] = v;
+            G_P[c] = G0[c] - qp;                           // D^T (b - D beta_p), :41-43
+            BETA_PREV[c] = bc;
+        }
+        i_k0 = 0;
         __syncthreads();
     }
     if (blockIdx.x == 0) {
@@ -454,20 +503,20 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         if (tid == 0) {
             FistaState* st = p.st;
             st->t = t;
-            st->rhs = rhs;
+            st->rhs = rhs_acc;
             st->t1 = t1;
             st->crit = crit;
-            st->ss_last = lhs;
+            st->ss_last = lhs_acc;
             st->tol = p.tol;
             st->lam = p.lam;
             st->L_prev = L_prev;
-            st->L_cur = L_cur;
+            st->L_cur = L_acc;
             st->i_k = i_k;
             st->k = k;
             st->max_iter = p.max_iter;
             st->done = 1;
-            st->passes = sweeps;
-            st->trials = sweeps;
+            st->passes = sweeps;   // sweeps over G (each carries KC candidates)
+            st->trials = trials;   // line-search trials consumed, as the reference would count them
             st->thr_f32 = p.thr_f32;
         }
     }
@@ -727,6 +776,30 @@ int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cu
 }
 
 // ---- persistent FISTA: shape + launch ----------------------------------------------------------------------
+template <int KC>
+static bool gp_try(rbl_ctx* c, int dev_max, int grid, int rpc) {
+    const size_t vec_bytes = (size_t)(8 + KC) * c->ld * sizeof(double);
+    if (vec_bytes + 2048 > (size_t)dev_max) return false;
+    const size_t g_bytes = (size_t)rpc * c->ld * sizeof(double);
+    const int g_in = (vec_bytes + g_bytes + 2048 <= (size_t)dev_max) ? 1 : 0;
+    const size_t smem = vec_bytes + (g_in ? g_bytes : 0);
+    if (cudaFuncSetAttribute(gram_fista_persistent_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_fista_persistent_kernel<KC>, kGThreads, smem) !=
+            cudaSuccess || per_sm * c->num_sms < grid) {
+        cudaGetLastError();
+        return false;
+    }
+    c->gp_kc = KC;
+    c->gp_g_in_smem = g_in;
+    c->gp_smem = smem;
+    return true;
+}
+
 // returns 0 if the persistent kernel cannot hold its state in shared memory (caller uses the per-trial launches)
 int rbl_gram_persist_config(rbl_ctx* c) {
     if (c->gp_checked) return c->gp_grid > 0;
@@ -735,26 +808,14 @@ int rbl_gram_persist_config(rbl_ctx* c) {
     int dev_max = 0, coop = 0;
     if (cudaDeviceGetAttribute(&dev_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device) != cudaSuccess || !coop) return 0;
-    const size_t vec_bytes = 10 * (size_t)c->ld * sizeof(double);
-    if (vec_bytes + 1024 > (size_t)dev_max) return 0;
     int grid = c->num_sms;
     if (grid > c->d) grid = c->d;
     const int rpc = (c->d + grid - 1) / grid;
     grid = (c->d + rpc - 1) / rpc;
-    const size_t g_bytes = (size_t)rpc * c->ld * sizeof(double);
-    c->gp_g_in_smem = (vec_bytes + g_bytes + 1024 <= (size_t)dev_max) ? 1 : 0;
-    c->gp_smem = vec_bytes + (c->gp_g_in_smem ? g_bytes : 0);
-    if (cudaFuncSetAttribute(gram_fista_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)c->gp_smem) != cudaSuccess) {
-        cudaGetLastError();
+    // as many candidates per sweep as fit next to the state; G rows in shared memory if they fit as well
+    if (!(gp_try<8>(c, dev_max, grid, rpc) || gp_try<4>(c, dev_max, grid, rpc) || gp_try<2>(c, dev_max, grid, rpc) ||
+          gp_try<1>(c, dev_max, grid, rpc)))
         return 0;
-    }
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_fista_persistent_kernel, kGThreads, c->gp_smem) !=
-            cudaSuccess || per_sm * c->num_sms < grid) {
-        cudaGetLastError();
-        return 0;
-    }
     c->gp_rpc = rpc;
     c->gp_grid = grid;
     return 1;
@@ -783,8 +844,11 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
     p.max_iter = max_iter;
     RBL_CUDA(cudaMemsetAsync(c->gticket + 8, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
-    RBL_CUDA(cudaLaunchCooperativeKernel((const void*)gram_fista_persistent_kernel, dim3(c->gp_grid), dim3(kGThreads),
-                                         args, c->gp_smem, s));
+    const void* fn = c->gp_kc == 8   ? (const void*)gram_fista_persistent_kernel<8>
+                     : c->gp_kc == 4 ? (const void*)gram_fista_persistent_kernel<4>
+                     : c->gp_kc == 2 ? (const void*)gram_fista_persistent_kernel<2>
+                                     : (const void*)gram_fista_persistent_kernel<1>;
+    RBL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->gp_grid), dim3(kGThreads), args, c->gp_smem, s));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -76,7 +76,12 @@ def test_fista_vs_reference_golden_and_oracle(golden_dir, w_mode):
             assert np.linalg.norm(w - wo) <= 1e-11 * max(np.linalg.norm(wo), 1e-3), lam
             assert np.linalg.norm(w - g[key]) <= 1e-11 * max(np.linalg.norm(g[key]), 1e-3), lam
             # stream: one pass over D per trial (+1 initial); gram: one sweep over G per trial
-            assert info["passes"] == (info["trials"] if w_mode == "gram" else 1 + info["trials"])
+            # (the persistent kernel carries up to 8 line-search candidates per sweep)
+            if w_mode == "gram":
+                # the oracle counts matvecs: 2 per iteration + 1 per line-search trial
+                assert info["passes"] <= info["trials"] == oinfo["passes"] - 2 * oinfo["iters"]
+            else:
+                assert info["passes"] == 1 + info["trials"]
 
 
 def test_l2_step_vs_reference_golden(golden_dir):
