@@ -284,9 +284,21 @@ int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, d
     return rbl_k_pav(h, loss, m_sorted, rho, z_sorted, S(stream));
 }
 
+int rbl_bind_scalars(rbl_handle_t h, const double* d_scal) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    h->scal = d_scal;
+    return RBL_OK;
+}
+
 int rbl_sort_config(rbl_handle_t h, int legacy) {
     RBL_REQUIRE(h != nullptr, "null handle");
     h->sort_legacy = legacy ? 1 : 0;
+    return RBL_OK;
+}
+
+int rbl_sort_debug(rbl_handle_t h, uint64_t* d_stamps) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    h->sort_dbg = (unsigned long long*)d_stamps;
     return RBL_OK;
 }
 

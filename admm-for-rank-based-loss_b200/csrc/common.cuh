@@ -112,6 +112,7 @@ struct rbl_ctx {
     int sort_tiles;
     uint32_t* sort_counts;  // [num_sms][256] per-CTA digit counts of the persistent sort
     int psort_checked, psort_ok, sort_legacy;
+    unsigned long long* sort_dbg;  // dev tool: phase timestamps of the persistent sort (null: off)
     // ---- PAV
     int chunk_log2;
     int64_t nchunks;
@@ -122,6 +123,7 @@ struct rbl_ctx {
     unsigned int* node_cnt;  // merge-tree arrival counters (self-cleaning)
     double* sigma;          // n_global, rank order (the sigma the PAV uses: alphas, or betas for EHRM)
     double* val;            // n_global block values
+    const double* scal;     // caller-owned device scalars [rho, lam_fista, thr_f32] (rbl_bind_scalars) or null
     int has_sigma;
     int nseg;               // runs of non-increasing sigma (0: too many, use the merge tree)
     int force_tree;         // testing: always take the merge tree

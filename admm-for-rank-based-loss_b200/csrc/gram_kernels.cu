@@ -292,6 +292,7 @@ struct GramPersist {
     double lam, tol;
     float L0;
     int thr_f32, max_iter;
+    const double* scal;   // device block [rho, lam, thr_f32] overriding lam / thr_f32 when bound (may be null)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
@@ -376,6 +377,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         const int total = (row1 - row0) * ld2;
         for (int e = tid; e < total; e += nt) dst[e] = __ldg(&src[e]);
     }
+    const double lam_ = p.scal ? p.scal[1] : p.lam;
+    const int thr_f32_ = p.scal ? (p.scal[2] != 0.0 ? 1 : 0) : p.thr_f32;
     float L_prev = p.L0, L_acc = p.L0;
     int i_k0 = 0, i_k = 0, k = 0, sweeps = 0, trials = 0, par = 0;
     double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
@@ -391,7 +394,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             const int ii = i_k0 + q;
             Lc[q] = __fmul_rn(L_prev, p.pow_tab[ii < 127 ? ii : 127]);  // fast_lasso.py:46
             Ld[q] = (double)Lc[q];
-            thr[q] = p.thr_f32 ? (double)__fdiv_rn((float)p.lam, Lc[q]) : p.lam / Ld[q];
+            thr[q] = thr_f32_ ? (double)__fdiv_rn((float)lam_, Lc[q]) : lam_ / Ld[q];
             r1[q] = 0.0;
         }
         for (int c = tid; c < d; c += nt) {
@@ -508,7 +511,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             st->crit = crit;
             st->ss_last = lhs_acc;
             st->tol = p.tol;
-            st->lam = p.lam;
+            st->lam = lam_;
             st->L_prev = L_prev;
             st->L_cur = L_acc;
             st->i_k = i_k;
@@ -517,7 +520,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             st->done = 1;
             st->passes = sweeps;   // sweeps over G (each carries KC candidates)
             st->trials = trials;   // line-search trials consumed, as the reference would count them
-            st->thr_f32 = p.thr_f32;
+            st->thr_f32 = thr_f32_;
         }
     }
 }
@@ -842,6 +845,7 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
     p.L0 = L0;
     p.thr_f32 = thr_f32;
     p.max_iter = max_iter;
+    p.scal = c->scal;
     RBL_CUDA(cudaMemsetAsync(c->gticket + 8, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
     const void* fn = c->gp_kc == 8   ? (const void*)gram_fista_persistent_kernel<8>

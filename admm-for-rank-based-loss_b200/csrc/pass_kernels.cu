@@ -85,6 +85,7 @@ struct PassParams {
     uint32_t stage_stride;  // bytes, multiple of 128
     double* lam;            // RBL_PASS_DUAL: multiplier updated in place, b = z
     double rho;
+    const double* scal;     // device scalar block overriding rho when bound (may be null)
     const int* gate_nnz;    // RBL_PASS_DUAL: run only if *gate_nnz > gate_cap (w too dense for the sparse path)
     int gate_cap;
 };
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
     if ((mode == RBL_PASS_DUAL || mode == RBL_PASS_FUSED) && p.gate_nnz && *p.gate_nnz <= p.gate_cap) return;
     const bool fused = (mode == RBL_PASS_FUSED || mode == RBL_PASS_FISTA);
     const bool dual = (mode == RBL_PASS_DUAL);
+    const double rho = p.scal ? p.scal[0] : p.rho;
     const int R = p.R, S = p.stages;
     const int64_t ld = p.ld;
     const int ld2 = (int)(ld >> 1);
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
                 // lambda += rho (z - D w), partial ||z - D w||^2 (algorithms.py:132,135) in the matvec epilogue
                 const double res = bv - dot;
                 out[row0 + tid] = dot;
-                p.lam[row0 + tid] = lv + p.rho * res;
+                p.lam[row0 + tid] = lv + rho * res;
                 ss = fma(res, res, ss);
             } else {
                 out[row0 + tid] = dot;
@@ -450,6 +452,7 @@ int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, cons
     p.rho = rho;
     p.gate_nnz = gate_nnz;
     p.gate_cap = gate_cap;
+    p.scal = c->scal;
     p.D = D;
     p.ld = c->ld;
     p.n = c->n_local;

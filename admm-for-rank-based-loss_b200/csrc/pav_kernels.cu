@@ -79,8 +79,10 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
                                                                    double* __restrict__ tot_hi,
                                                                    double* __restrict__ tot_lo,
                                                                    const double* __restrict__ sigma, int loss,
-                                                                   double rho, double* __restrict__ prox_out) {
+                                                                   double rho, double* __restrict__ prox_out,
+                                                                   const double* __restrict__ scal) {
     __shared__ double sh[16];
+    if (scal) rho = scal[0];
     const int64_t base = (int64_t)blockIdx.x * kChunk;
     const int64_t i0 = base + (int64_t)threadIdx.x * kPer;
     double v[kPer];
@@ -157,6 +159,7 @@ struct ChunkSmem {
 struct TreeParams {
     int loss;
     double rho;
+    const double* scal;  // device scalar block (rho first) overriding `rho` when bound; may be null
     const double* sigma;
     const double* m;
     int64_t n;
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(kPavThreads, 3) pav_chunk_kernel(const TreePar
     ChunkSmem& S = *reinterpret_cast<ChunkSmem*>(smem_raw);
     const int tid = threadIdx.x;
     const int loss = P.loss;
-    const double rho = P.rho;
+    const double rho = P.scal ? P.scal[0] : P.rho;
     const int64_t n = P.n;
     const int64_t base = (int64_t)blockIdx.x * kChunk;
     const int len = (int)((n - base < kChunk) ? (n - base) : kChunk);
@@ -372,7 +375,7 @@ __global__ void __launch_bounds__(kPavThreads) pav_tree_kernel(const TreeParams 
     __shared__ double s_v;
     const int tid = threadIdx.x;
     const int loss = P.loss;
-    const double rho = P.rho;
+    const double rho = P.scal ? P.scal[0] : P.rho;
     const int64_t n = P.n;
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
     PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
@@ -463,6 +466,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
     __shared__ double s_v[kMaxSeg];
     __shared__ int64_t s_end[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double rho = P.scal ? P.scal[0] : P.rho;
     if (tid == 0) s_nblk = 0;
     __syncthreads();
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
@@ -472,15 +476,15 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
         const int64_t b = bounds[j], c = bounds[j + 1];
         const bool violated = val(b - 1) > val(b);  // block-uniform
         if (violated) {
-            const int64_t e = warp == 0 ? merge_kary_left(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c)
-                                        : merge_kary_right(P.loss, P.rho, val, gps, gpm, (int64_t)0, b, c);
+            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, gps, gpm, (int64_t)0, b, c)
+                                        : merge_kary_right(P.loss, rho, val, gps, gpm, (int64_t)0, b, c);
             if (lane == 0) s_end[warp] = e;
         }
         __syncthreads();
         if (violated && tid == 0) {
             int64_t lo, hi;
             double v;
-            pav_kary_finish(P.loss, P.rho, val, gps, gpm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            pav_kary_finish(P.loss, rho, val, gps, gpm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
             int k2 = 0;
             const int nb = s_nblk;
@@ -542,7 +546,7 @@ int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double*
     const int64_t nch = (n + kChunk - 1) / kChunk;
     (void)c;
     chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(x, n, loc_hi, loc_lo, tot_hi, tot_lo, nullptr, 0, 0.0,
-                                                             nullptr);
+                                                             nullptr, nullptr);
     RBL_LAUNCH_CHECK();
     chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(tot_hi, tot_lo, nch, off_hi, off_lo);
     RBL_LAUNCH_CHECK();
@@ -594,7 +598,7 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     const bool few = c->nseg > 0 && !c->force_tree;
     chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(m_sorted, n, c->pm_loc_hi, c->pm_loc_lo, c->ch_tot_hi,
                                                              c->ch_tot_lo, c->sigma, loss, rho,
-                                                             few ? z_sorted : nullptr);
+                                                             few ? z_sorted : nullptr, c->scal);
     RBL_LAUNCH_CHECK();
     if (few && c->nseg == 1) return RBL_OK;  // sigma never steps up (ERM): the element prox is the answer
     chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
@@ -602,6 +606,7 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     TreeParams P;
     P.loss = loss;
     P.rho = rho;
+    P.scal = c->scal;
     P.sigma = c->sigma;
     P.m = m_sorted;
     P.n = n;

@@ -177,7 +177,7 @@ constexpr int kPT = 1024;
 constexpr int kPWarps = kPT / 32;
 constexpr int kPTile = kPT * kItems;  // 8192 keys
 constexpr size_t kPSortSmem =
-    (size_t)(kPWarps * 257 + 256 + 256 + 8 + 2 * 16 * 256 + 256) * sizeof(uint32_t) + (size_t)kPTile * 12;
+    (size_t)(kPWarps * 257 + 256 + 256 + 8 + 2 * 16 * 256 + 3 * 256) * sizeof(uint32_t) + (size_t)kPTile * 12;
 
 struct PSortParams {
     const double* m;
@@ -189,6 +189,7 @@ struct PSortParams {
     double* sorted_out;
     int32_t* perm_out;
     int64_t chunk;
+    unsigned long long* dbg;  // optional [8][6] globaltimer stamps of CTA 0 (dev tool)
 };
 
 __device__ __forceinline__ void sort_grid_barrier(unsigned int* ctr, unsigned int target) {
@@ -214,7 +215,9 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
     uint32_t(*part_tot)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8);             // [16][256]
     uint32_t(*part_pre)[256] = reinterpret_cast<uint32_t(*)[256]>(wtot + 8 + 16 * 256);  // [16][256]
     uint32_t* gbase = wtot + 8 + 32 * 256;                                               // [256]
-    uint64_t* skey = reinterpret_cast<uint64_t*>(gbase + 256);                           // [kPTile] (8-byte aligned)
+    uint32_t* tcnt = gbase + 256;                                                        // [256]
+    uint32_t* lstart = tcnt + 256;                                                       // [256]
+    uint64_t* skey = reinterpret_cast<uint64_t*>(lstart + 256);                          // [kPTile] (8-byte aligned)
     uint32_t* sval = reinterpret_cast<uint32_t*>(skey + kPTile);                         // [kPTile]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, me = blockIdx.x;
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
     uint64_t key[kItems];
     uint32_t val[kItems];
     uint16_t rank[kItems];
+    uint32_t qoff = 0;
 
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
@@ -238,20 +242,37 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
         uint32_t* vout = (pass & 1) ? p.vB : p.vA;
 
         auto rank_tile = [&](int k) {
-            for (int q = tid; q < kPWarps * 257; q += kPT) (&cnt[0][0])[q] = 0;
-            __syncthreads();
+            // all loads of the tile first (independent, L1-bypassing: other CTAs rewrote these buffers earlier
+            // in this launch), zero the counters while they are in flight
             const int64_t wbase = r0 + (int64_t)k * kPTile + (int64_t)warp * (kItems * 32);
 #pragma unroll
             for (int j = 0; j < kItems; ++j) {
                 const int64_t i = wbase + j * 32 + lane;
                 const bool ok = i < r1;
-                // L1-bypassing loads: other CTAs rewrote these buffers earlier in this launch
                 key[j] = ok ? (from_double ? rbl_key_from_bits(reinterpret_cast<const uint64_t*>(kin)[i])
                                            : __ldcg(reinterpret_cast<const unsigned long long*>(kin) + i))
                             : 0ull;
                 val[j] = ok ? (vin ? __ldcg(vin + i) : (uint32_t)i) : 0u;
+            }
+            {
+                uint4* c4 = reinterpret_cast<uint4*>(&cnt[0][0]);  // 32 * 257 words = 2056 uint4
+                for (int q = tid; q < kPWarps * 257 / 4; q += kPT) c4[q] = make_uint4(0, 0, 0, 0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int j = 0; j < kItems; ++j) {
+                const int64_t i = wbase + j * 32 + lane;
+                const bool ok = i < r1;
                 const uint32_t dg = ok ? (uint32_t)((key[j] >> shift) & 0xff) : 256u;
-                const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+                // peers = lanes holding the same digit, from 9 ballots (MATCH.ANY serialises over the ~30
+                // distinct digits of a warp and was the single largest cost of a pass)
+                uint32_t peers = 0xffffffffu;
+#pragma unroll
+                for (int bit = 0; bit < 9; ++bit) {
+                    const bool set = (dg >> bit) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, set);
+                    peers &= set ? bal : ~bal;
+                }
                 const int leader = __ffs(peers) - 1;
                 uint32_t basec = 0;
                 if (lane == leader) {
@@ -265,22 +286,35 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
             __syncthreads();
         };
 
+        auto stamp = [&](int slot) {
+            if (p.dbg && blockIdx.x == 0 && tid == 0) {
+                unsigned long long t;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+                p.dbg[pass * 6 + slot] = t;
+            }
+        };
+        stamp(0);
         // ---- phase 1: digit counts of my range
         if (tid < 256) tot[tid] = 0;
         for (int k = 0; k < ntile; ++k) {
             rank_tile(k);
-            if (tid < 256) {
+            {   // 4 threads per digit, 8 warps' counters each (bank-conflict free: 257-word rows)
+                const int dg = tid >> 2, q = tid & 3;
                 uint32_t t = 0;
-#pragma unroll 8
-                for (int w = 0; w < kPWarps; ++w) t += cnt[w][tid];
-                tot[tid] += t;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) t += cnt[8 * q + w][dg];
+                t += __shfl_xor_sync(0xffffffffu, t, 1);
+                t += __shfl_xor_sync(0xffffffffu, t, 2);
+                if (q == 0) tot[dg] += t;
             }
             if (!single) __syncthreads();
         }
         __syncthreads();
         if (tid < 256) __stcg(&p.counts[(size_t)me * 256 + tid], tot[tid]);
+        stamp(1);
         target += G;
         sort_grid_barrier(p.bar, target);
+        stamp(2);
 
         // ---- phase 2: digit totals, counts of the CTAs before me, digit bases
         {
@@ -322,38 +356,62 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
             base[tid] = woff + (x - dtot) + dpre;
         }
         __syncthreads();
+        stamp(3);
         for (int k = 0; k < ntile; ++k) {
             if (!single) rank_tile(k);
             // tile-local digit starts (exclusive scan of the tile's digit counts), then per-warp local offsets;
             // gbase[dg] = global start of this tile's run of digit dg minus its local start
-            uint32_t tcount = 0, xs = 0;
-            if (tid < 256) {
-#pragma unroll 8
-                for (int w = 0; w < kPWarps; ++w) tcount += cnt[w][tid];
-                xs = tcount;
+            {
+                const int dg = tid >> 2, q = tid & 3;
+                uint32_t sq = 0;
 #pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t y = __shfl_up_sync(0xffffffffu, xs, o);
-                    if (lane >= o) xs += y;
-                }
-                if (lane == 31) wtot[warp] = xs;
+                for (int w = 0; w < 8; ++w) sq += cnt[8 * q + w][dg];
+                // exclusive prefix over the 4 warp groups of this digit, and the digit's tile count
+                uint32_t inc = sq;
+                uint32_t y = __shfl_up_sync(0xffffffffu, inc, 1, 4);
+                if (q >= 1) inc += y;
+                y = __shfl_up_sync(0xffffffffu, inc, 2, 4);
+                if (q >= 2) inc += y;
+                const uint32_t tcount = __shfl_sync(0xffffffffu, inc, 3, 4);
+                qoff = inc - sq;
+                if (q == 0) tcnt[dg] = tcount;
             }
             __syncthreads();
-            if (tid < 256) {
-                uint32_t woff = 0;
+            if (warp == 0) {  // 256-wide exclusive scan by one warp: 8 digits per lane
+                uint32_t v[8], run = 0;
 #pragma unroll
-                for (int w = 0; w < 8; ++w)
-                    if (w < warp) woff += wtot[w];
-                const uint32_t lstart = woff + (xs - tcount);
-                uint32_t run = lstart;
-#pragma unroll 8
-                for (int w = 0; w < kPWarps; ++w) {
-                    const uint32_t c = cnt[w][tid];
-                    cnt[w][tid] = run;
+                for (int e = 0; e < 8; ++e) {
+                    v[e] = tcnt[lane * 8 + e];
+                    run += v[e];
+                }
+                uint32_t x = run;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if (lane >= o) x += y;
+                }
+                uint32_t ex = x - run;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    lstart[lane * 8 + e] = ex;
+                    ex += v[e];
+                }
+            }
+            __syncthreads();
+            {
+                const int dg = tid >> 2, q = tid & 3;
+                const uint32_t ls = lstart[dg];
+                uint32_t run = ls + qoff;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) {
+                    const uint32_t c = cnt[8 * q + w][dg];
+                    cnt[8 * q + w][dg] = run;
                     run += c;
                 }
-                gbase[tid] = base[tid] - lstart;
-                base[tid] += tcount;
+                if (q == 0) {
+                    gbase[dg] = base[dg] - ls;
+                    base[dg] += tcnt[dg];
+                }
             }
             __syncthreads();
             // reorder the tile by digit in shared memory so that the global stores below are coalesced runs
@@ -391,10 +449,12 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
             }
             __syncthreads();
         }
+        stamp(4);
         if (!last) {
             target += G;
             sort_grid_barrier(p.bar, target);
         }
+        stamp(5);
     }
 }
 
@@ -437,6 +497,7 @@ int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted
     p.sorted_out = sorted_out;
     p.perm_out = perm_out;
     p.chunk = (n + G - 1) / G;
+    p.dbg = c->sort_dbg;
     RBL_CUDA(cudaMemsetAsync(c->gticket + 16, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
     RBL_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_persistent_kernel, dim3(G), dim3(kPT), args,

@@ -259,8 +259,12 @@ __global__ void fista_result_kernel(const FistaState* st, const double* beta, in
 }
 
 // ---- margins m = D w - lambda / rho (algorithms.py:89) from a maintained Dw ----------------------
+// `scal` (here and below, may be null): device block [rho, lam_fista, thr_f32] bound with rbl_bind_scalars — when
+// present it overrides the by-value scalar so that a captured CUDA graph of the iteration can be replayed with
+// new values
 __global__ void margins_kernel(const double* __restrict__ Dw, const double* __restrict__ lam, double rho, int64_t n,
-                               double* __restrict__ m) {
+                               double* __restrict__ m, const double* __restrict__ scal) {
+    if (scal) rho = scal[0];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         m[i] = Dw[i] - lam[i] / rho;
 }
@@ -269,7 +273,8 @@ __global__ void margins_kernel(const double* __restrict__ Dw, const double* __re
 __global__ void scatter_kernel(const double* __restrict__ zs, const int32_t* __restrict__ perm, int64_t n_global,
                                int64_t row_lo, int64_t n_local, int use_clip, double clip,
                                const double* __restrict__ lam, double rho, double* __restrict__ z,
-                               double* __restrict__ b) {
+                               double* __restrict__ b, const double* __restrict__ scal) {
+    if (scal) rho = scal[0];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_global;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = (int64_t)perm[i] - row_lo;
@@ -307,8 +312,10 @@ __device__ __forceinline__ bool active_item(const double* __restrict__ zs, const
 __global__ void __launch_bounds__(kActThreads) scatter_active_kernel(
     const double* __restrict__ zs, const double* __restrict__ ms, const int32_t* __restrict__ perm, int64_t n_global,
     int64_t row_lo, int64_t n_local, int use_clip, double clip, const double* __restrict__ lam, double rho,
-    double* __restrict__ z, double* __restrict__ b, int64_t chunk, int* __restrict__ cta_count) {
+    double* __restrict__ z, double* __restrict__ b, int64_t chunk, int* __restrict__ cta_count,
+    const double* __restrict__ scal) {
     __shared__ int wcount[kActThreads / 32];
+    if (scal) rho = scal[0];
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
     const int64_t r1 = (r0 + chunk < n_global) ? r0 + chunk : n_global;
     int cnt = 0;
@@ -530,10 +537,12 @@ __global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restri
                                                           const int* __restrict__ nnz_ptr, int cap,
                                                           const double* __restrict__ z, double* __restrict__ Dw,
                                                           double* __restrict__ lam, double rho,
-                                                          double* __restrict__ part) {
+                                                          double* __restrict__ part,
+                                                          const double* __restrict__ scal) {
     __shared__ double sh[33];
     const int nnz = *nnz_ptr;
     if (nnz > cap) return;  // the dense pass handles it
+    if (scal) rho = scal[0];
     double acc = 0.0;
     if (nnz <= 8) sparse_dual_rows<8>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
     else if (nnz <= 16) sparse_dual_rows<16>(D, ld, n, idx, val, nnz, z, Dw, lam, rho, acc);
@@ -551,9 +560,11 @@ __global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __rest
                                                             const int* __restrict__ nnz_ptr, int cap,
                                                             const double* __restrict__ z, double* __restrict__ Dw,
                                                             double* __restrict__ lam, double rho,
-                                                            double* __restrict__ part) {
+                                                            double* __restrict__ part,
+                                                            const double* __restrict__ scal) {
     __shared__ double sh[33];
     __shared__ int s_idx[256];
+    if (scal) rho = scal[0];
     __shared__ double s_val[256];
     const int nnz = *nnz_ptr;
     if (nnz > cap) return;  // the dense pass handles it
@@ -722,7 +733,7 @@ int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s)
 }
 
 int rbl_k_margins(rbl_ctx* c, const double* Dw, const double* lam, double rho, double* m, cudaStream_t s) {
-    margins_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dw, lam, rho, c->n_local, m);
+    margins_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dw, lam, rho, c->n_local, m, c->scal);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -730,7 +741,7 @@ int rbl_k_margins(rbl_ctx* c, const double* Dw, const double* lam, double rho, d
 int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_clip, double clip, const double* lam,
                   double rho, double* z, double* b, cudaStream_t s) {
     scatter_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(zs, perm, c->n_global, c->row_lo, c->n_local, use_clip, clip,
-                                                      lam, rho, z, b);
+                                                      lam, rho, z, b, c->scal);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -740,7 +751,7 @@ int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const i
     const int grid = c->vec_grid;
     const int64_t chunk = (c->n_global + grid - 1) / grid;
     scatter_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
-                                                      clip, lam, rho, z, b, chunk, c->act_cta_count);
+                                                      clip, lam, rho, z, b, chunk, c->act_cta_count, c->scal);
     RBL_LAUNCH_CHECK();
     compact_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
                                                       clip, chunk, c->act_cta_count, c->act_row, c->act_delta,
@@ -765,10 +776,10 @@ int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const doubl
     RBL_LAUNCH_CHECK();
     if (Dt)
         sparse_dual_t_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
-                                                                cap, z, Dw, lam, rho, c->vpart);
+                                                                cap, z, Dw, lam, rho, c->vpart, c->scal);
     else
         sparse_dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(D, c->ld, c->n_local, c->sup_idx, c->sup_val,
-                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart);
+                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart, c->scal);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -22,6 +22,8 @@ _SIGNATURES = {
     "rbl_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_double, _dp, _c.c_void_p]),
     "rbl_sort_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_pav_prox": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_bind_scalars": (_c.c_int, [_c.c_void_p, _dp]),
+    "rbl_sort_debug": (_c.c_int, [_c.c_void_p, _dp]),
     "rbl_sort_config": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "rbl_pav_config": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_int32)]),
     "rbl_prox_elementwise": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _c.c_int64, _c.c_double, _dp, _c.c_void_p]),

@@ -77,6 +77,7 @@ class DeviceProblem:
             del Xd, yd
             self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
             self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
+            self._out4_np = self._out4_host.numpy()
             self._u_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
             self._u_glob = (torch.empty(self.n_global, dtype=torch.float64, device=self.device)
                             if self.world > 1 else self._u_local)
@@ -104,7 +105,7 @@ class DeviceProblem:
     @property
     def launches(self):
         """kernels launched through librbl_b200 by this process (bench.py's gpu_launches)"""
-        return int(self.lib.rbl_launch_count())
+        return int(self.lib.rbl_launch_count()) + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_launches", 0)
 
     def close(self):
         if getattr(self, "h", None) is not None and self.h.value:
@@ -213,10 +214,14 @@ class AdmmEngine(DeviceProblem):
         self._delta_valid = False
         self._active_pending = False
         self.active_stats = {"calls": 0, "rows": 0, "gathered": 0}
+        # CUDA-graph replay of the whole iteration (iteration_fista)
+        self.graph_ok = os.environ.get("RBL_GRAPH", "1") != "0"
+        self.graph_mgpu = os.environ.get("RBL_GRAPH_MGPU", "0") != "0"  # capture the NCCL collectives as well
+        self._graph, self._graph_key, self._iters_eager = None, None, 0
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
         self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
-        # transposed copy of D for the sparse-w dual pass: built once w has come out sparse twice, if it fits
+        # transposed copy of D for the sparse-w dual pass: built once w has come out sparse, if it fits
         self.Dt = None
         self.transpose_ok = os.environ.get("RBL_TRANSPOSE", "1") != "0"
         if mode == "gram":
@@ -227,6 +232,7 @@ class AdmmEngine(DeviceProblem):
     # ---- state -------------------------------------------------------------------------------
     def set_state(self, w=None, z=None, lam=None):
         self._delta_valid = False
+        self._iters_eager = 0  # a few eager iterations again before the graph path resumes
         if w is not None:
             self.w.copy_(self.vec(w))
             self.Dw_valid = False
@@ -472,13 +478,11 @@ class AdmmEngine(DeviceProblem):
         return {"nit": int(res.nit), "nfev": int(res.nfev)}
 
     # ---- dual update + residuals (algorithms.py:132-136) -----------------------------------------
-    def dual_step(self, rho):
-        """lambda += rho (z - D w); returns (||z - D w||_2, ||w - w_prev||_2)."""
+    def _dual_launch(self, rho):
+        """enqueue the dual update and the read-back of its 128-byte result; no host synchronisation"""
         from_res = 1 if getattr(self, "_r_matches_w", False) else 0
         if not from_res:
             # Dw = D w with the multiplier update and ||z - Dw||^2 in the pass epilogue
-            if self.Dt is None and self.dual_stats["sparse"] >= 2 and self.transpose_ok:
-                self._build_transpose()
             _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(),
                                                0 if self.Dt is None else self.Dt.data_ptr(), self.w.data_ptr(),
                                                self.w_prev.data_ptr(),
@@ -497,25 +501,109 @@ class AdmmEngine(DeviceProblem):
             self.all_reduce(self._out4[:1])
         self._out4_host.copy_(self._out4, non_blocking=True)
         self.w_host.copy_(self.w, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
-        o = self._out4_host
+        return from_res
+
+    def _dual_finish(self, from_res):
+        """after the stream has been synchronised: bookkeeping from the read-back, residual norms"""
+        o = self._out4_np  # numpy view of the pinned read-back buffer
         if not from_res:
-            took_sparse = bool(o[5].item())
-            self.dual_stats["sparse" if took_sparse else "dense"] += 1
-            self.dual_stats["nnz_last"] = int(o[4].item())
+            took_sparse = o[5] != 0.0
+            ds = self.dual_stats
+            ds["sparse" if took_sparse else "dense"] += 1
+            ds["nnz_last"] = int(o[4])
+            st = self.fista_stats
             if self._active_pending:
                 self._active_pending = False
-                rows = int(o[8].item())
+                rows = int(o[8])
                 gathered = rows <= int(self.active_dense_frac * self.n_local)
-                self.active_stats["calls"] += 1
-                self.active_stats["rows"] += rows if gathered else self.n_local
-                self.active_stats["gathered"] += 1 if gathered else 0
-                self.fista_stats["d_passes"] += 0 if gathered else 1
+                a = self.active_stats
+                a["calls"] += 1
+                a["rows"] += rows if gathered else self.n_local
+                a["gathered"] += 1 if gathered else 0
+                st["d_passes"] += 0 if gathered else 1
             if self._fista_info_pending:
                 self._fista_info_pending = False
-                st = self.fista_stats
-                st["iters"] += int(o[6].item())
-                st["passes"] += int(o[7].item())
-                st["last_passes"] = int(o[7].item())
-            self.fista_stats["d_passes"] += 0 if took_sparse else 1
-        return float(np.sqrt(o[0].item())), float(np.sqrt(o[1].item()))
+                st["iters"] += int(o[6])
+                st["passes"] += int(o[7])
+                st["last_passes"] = int(o[7])
+            st["d_passes"] += 0 if took_sparse else 1
+        return float(np.sqrt(o[0])), float(np.sqrt(o[1]))
+
+    def dual_step(self, rho):
+        """lambda += rho (z - D w); returns (||z - D w||_2, ||w - w_prev||_2)."""
+        if (self.Dt is None and self.dual_stats["sparse"] >= 1 and self.transpose_ok
+                and not getattr(self, "_r_matches_w", False)):
+            self._build_transpose()
+        from_res = self._dual_launch(rho)
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._dual_finish(from_res)
+
+    # ---- one whole ADMM iteration with the FISTA w-step, replayed as a CUDA graph ------------------------
+    def iteration_fista(self, rho, lam, tol=7e-5, max_iter=5000):
+        """z-step, l1 w-step, dual step (algorithms.py:119-136).  Every data-dependent branch of the Gram-mode
+        iteration is taken on the device, so the launch sequence is static: after a few eager iterations it is
+        captured once as a CUDA graph and replayed with the per-iteration scalars (rho, lam) refreshed in a
+        device block (rbl_bind_scalars) — ~20 launches become one.  Returns (primal, dual)."""
+        thr_f32 = 1.0 if type(lam) is float or isinstance(lam, (int, np.float32)) else 0.0
+        key = (float(tol), int(max_iter))
+        can_graph = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
+                     and self._persistent is True
+                     and self._iters_eager >= 2 and self.Dw_valid and (self.Dt is not None or not self.transpose_ok
+                                                     or self.dual_stats["sparse"] < 1)
+                     and not getattr(self, "_r_matches_w", False))
+        if can_graph and (self._graph is None or self._graph_key != key):
+            self._capture_iteration(key)
+        if can_graph and self._graph is not None:
+            sh = self._scal_np
+            sh[0], sh[1], sh[2] = float(rho), float(lam), thr_f32
+            self._graph.replay()
+            self._graph_replays += 1
+            self.Dw_valid, self._delta_valid, self._r_matches_w = True, False, False
+            self._active_pending = self._fista_info_pending = True
+            self.fista_stats["calls"] += 1
+            torch.cuda.current_stream(self.device).synchronize()
+            return self._dual_finish(0)
+        self._iters_eager += 1
+        self.z_step(rho)
+        self.w_step_fista(lam, tol=tol, max_iter=max_iter)
+        return self.dual_step(rho)
+
+    def _capture_iteration(self, key):
+        tol, max_iter = key
+        dev = self.device
+        if not hasattr(self, "scal"):
+            self.scal = torch.zeros(4, dtype=torch.float64, device=dev)
+            self.scal_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+            self._scal_np = self.scal_host.numpy()
+        torch.cuda.current_stream(dev).synchronize()
+        stats = (dict(self.fista_stats), dict(self.dual_stats), dict(self.active_stats))
+        g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.rbl_launch_count())
+        _cabi.check(self.lib.rbl_bind_scalars(self.h, self.scal.data_ptr()))
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_cap_stream"):
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        try:
+            # capture_begin / capture_end directly (torch.cuda.graph() would also run gc.collect and
+            # empty_cache: tens of milliseconds in the middle of a solve)
+            self._cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self._cap_stream):
+                g.capture_begin()
+                try:
+                    self.scal.copy_(self.scal_host, non_blocking=True)
+                    self.Dw_valid = True
+                    self.z_step(1.0)                                   # by-value scalars are ignored while bound
+                    self.w_step_fista(1.0, tol=tol, max_iter=max_iter)
+                    self._dual_launch(1.0)
+                finally:
+                    g.capture_end()
+            cur.wait_stream(self._cap_stream)
+            self._graph, self._graph_key = g, key
+            self._graph_launches, self._graph_replays = int(self.lib.rbl_launch_count()) - n0, 0
+        except Exception:  # noqa: BLE001 — capture unsupported here: stay on eager launches
+            self._graph, self.graph_ok = None, False
+        finally:
+            _cabi.check(self.lib.rbl_bind_scalars(self.h, 0))
+            # capture only records the launches: restore the bookkeeping it touched
+            self.fista_stats, self.dual_stats, self.active_stats = stats
+            self._active_pending = self._fista_info_pending = False

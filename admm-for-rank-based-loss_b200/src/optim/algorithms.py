@@ -144,18 +144,24 @@ class Optimizer:
         return time.time()
 
     def main_loop(self, i, t_start, verbose):
-        t1 = self._sync_timer()
-        self.engine.z_step(self.rho)
-        t2 = self._sync_timer()
-        if self.store:
-            self.z_time.append(t2 - t1 + self.z_time[i])
+        if not self.store and self._whole_iteration_on_device():
+            # z-step, FISTA w-step and dual step as one device-side sequence (a CUDA graph after warm-up)
+            alpha = self.reg / (2 * self.rho * self.num_row)
+            primal_feasibility, dual_feasibility = self.engine.iteration_fista(
+                self.rho, alpha * self.num_row, tol=self.w_tol, max_iter=self.fista_max_iter)
+        else:
+            t1 = self._sync_timer()
+            self.engine.z_step(self.rho)
+            t2 = self._sync_timer()
+            if self.store:
+                self.z_time.append(t2 - t1 + self.z_time[i])
 
-        self._w_subproblem_device()
-        if self.store:
-            self.w_time.append(self._sync_timer() - t2 + self.w_time[i])
+            self._w_subproblem_device()
+            if self.store:
+                self.w_time.append(self._sync_timer() - t2 + self.w_time[i])
 
-        # Lagrange multiplier update + stopping criterion (:132-136), fused on the device
-        primal_feasibility, dual_feasibility = self.engine.dual_step(self.rho)
+            # Lagrange multiplier update + stopping criterion (:132-136), fused on the device
+            primal_feasibility, dual_feasibility = self.engine.dual_step(self.rho)
         self._w = self.engine.w_host.numpy().reshape(-1, 1).copy()
         self.primal_feasibility, self.dual_feasibility = primal_feasibility, dual_feasibility
         if primal_feasibility < self.tol and dual_feasibility < self.tol:
@@ -186,6 +192,9 @@ class Optimizer:
             self.test_losses.append(self.test_objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
             self.time_array.append(time.time() - t_start)
 
+        return False
+
+    def _whole_iteration_on_device(self):
         return False
 
     def _w_subproblem_device(self):
@@ -233,6 +242,9 @@ class ADMMmethod(Optimizer):
 
     def _z_subproblem(self):
         return super(ADMMmethod, self).z_subproblem()
+
+    def _whole_iteration_on_device(self):
+        return self.w_flag == 1 and self.engine.w_mode == "gram"
 
     def _w_subproblem_device(self):
         if self.w_flag == 1:

@@ -42,6 +42,13 @@ const char* rbl_last_error(void);
 /* kernels launched through the library by this process (instrumentation for bench.py) */
 int64_t rbl_launch_count(void);
 
+/* Per-iteration scalars from DEVICE memory: d_scal = [rho, lam of the FISTA call, thr_f32 (0/1)] (3 doubles, caller
+ * owned).  While bound (non-NULL), rbl_margins, rbl_pav_prox, rbl_scatter_*, rbl_dual_pass and rbl_gram_fista_run read
+ * these instead of their by-value arguments, so the host layer can capture one ADMM iteration as a CUDA graph and
+ * replay it after updating d_scal (the rho schedule of algorithms.py:147-157 changes rho every iteration).
+ * NULL unbinds. */
+int rbl_bind_scalars(rbl_handle_t h, const double* d_scal);
+
 /* handle + scratch.  Replaces the state set up in Optimizer.__init__ (algorithms.py:20-75). */
 int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global, int64_t row_lo, int32_t d,
                int64_t ld);
@@ -66,6 +73,9 @@ int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho,
 int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream);
 /* legacy != 0: three launches per radix pass instead of the single persistent cooperative kernel (testing) */
 int rbl_sort_config(rbl_handle_t h, int legacy);
+/* dev tool: d_stamps (48 x u64, device) receives %globaltimer at 6 phase boundaries of each of the 8 passes of
+ * the persistent sort (CTA 0); NULL switches it off */
+int rbl_sort_debug(rbl_handle_t h, uint64_t* d_stamps);
 
 /* z_sorted = argmin_{z1<=..<=zn} sum sigma_i loss(z_i) + rho/2 (z_i - m_i)^2.  pav.py:54-178,
  * individual_solver.py:90-130, PAV_cpt.py:169-293 (with sigma = betas; clip in rbl_scatter_z) */
