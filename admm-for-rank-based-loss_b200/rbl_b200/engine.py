@@ -108,6 +108,11 @@ class DeviceProblem:
         return int(self.lib.rbl_launch_count()) + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_launches", 0)
 
     def close(self):
+        # a captured iteration graph holds NCCL work in a row-sharded job: drop it before the handle (and before
+        # the caller destroys the process group)
+        if getattr(self, "_graph", None) is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph = None
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.rbl_destroy(self.h)
             self.h = ctypes.c_void_p()
@@ -216,7 +221,7 @@ class AdmmEngine(DeviceProblem):
         self.active_stats = {"calls": 0, "rows": 0, "gathered": 0}
         # CUDA-graph replay of the whole iteration (iteration_fista)
         self.graph_ok = os.environ.get("RBL_GRAPH", "1") != "0"
-        self.graph_mgpu = os.environ.get("RBL_GRAPH_MGPU", "0") != "0"  # capture the NCCL collectives as well
+        self.graph_mgpu = os.environ.get("RBL_GRAPH_MGPU", "1") != "0"  # capture the NCCL collectives as well
         self._graph, self._graph_key, self._iters_eager = None, None, 0
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))

@@ -331,9 +331,16 @@ def main():
             t_e2e = float(tt[0])
         e2e_value, e2e_iters = it2 / t_e2e, it2
 
-    if rank != 0:
+    def shutdown():
+        # release the captured iteration graph (it holds NCCL work) before the process group goes away
+        solver.engine.close()
+        torch.cuda.synchronize()
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
+
+    if rank != 0:
+        shutdown()
         return
 
     cpu = None
@@ -405,9 +412,8 @@ def main():
         "cpu_baseline": cpu,
         "solve": solve,
     }
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":
