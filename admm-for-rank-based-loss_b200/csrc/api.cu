@@ -1,4 +1,5 @@
 // api.cu — the C ABI declared in include/rbl_b200.h: handle, scratch, and thin launch wrappers.
+#include <math.h>
 #include <stdarg.h>
 #include <string.h>
 
@@ -627,6 +628,51 @@ int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const doubl
     RBL_TRY(rbl_k_dual_sparse(h, D, Dt, w, z, Dw, lam, rho, cap, S(stream)));
     RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho, h->sup_nnz, cap));
     return rbl_k_dual_finalize(h, cap, w, w_prev, out8, S(stream));
+}
+
+// ---- native outer loop over a captured iteration graph (algorithms.py:119-157 host logic) -------------------
+int rbl_admm_run(rbl_handle_t h, void* graph_exec, rbl_stream_t stream, double* h_scal, const double* h_out,
+                 int32_t max_iters, double tol, double reg, int64_t num_row, int32_t num_feature,
+                 int64_t dense_above, double rho, int32_t rho_is_pyfloat, rbl_run_stats* out) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(graph_exec && h_scal && h_out && out && max_iters >= 0, "bad arguments");
+    memset(out, 0, sizeof(*out));
+    const double rho_cap = 217.0 * (double)num_feature;  // algorithms.py:153-157
+    int pyfloat = rho_is_pyfloat ? 1 : 0;
+    for (int it = 0; it < max_iters; ++it) {
+        // lam = alpha * n with alpha = reg / (2 rho n), in the reference's operation order (:192-193,200)
+        const double alpha = reg / (2.0 * rho * (double)num_row);
+        h_scal[0] = rho;
+        h_scal[1] = alpha * (double)num_row;
+        h_scal[2] = pyfloat ? 1.0 : 0.0;  // python-float lam: float32 threshold quotient (NEP 50), else float64
+        RBL_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, S(stream)));
+        RBL_CUDA(cudaStreamSynchronize(S(stream)));
+        const double primal = sqrt(h_out[0]), dual = sqrt(h_out[1]);
+        out->iters = it + 1;
+        out->primal = primal;
+        out->dual = dual;
+        out->nnz_last = (int32_t)h_out[4];
+        if (h_out[5] != 0.0) ++out->sparse_dual; else ++out->dense_dual;
+        out->fista_iters += (int64_t)h_out[6];
+        out->fista_sweeps += (int64_t)h_out[7];
+        out->last_sweeps = (int32_t)h_out[7];
+        const int64_t rows = (int64_t)h_out[8];
+        if (rows <= dense_above) {
+            ++out->gathered;
+            out->rows_read += rows;
+        } else {
+            out->rows_read += h->n_local;
+        }
+        if (primal < tol && dual < tol) {  // :137 — before the rho update, like the reference
+            out->converged = 1;
+            break;
+        }
+        rho = fmin(rho * (primal > 1e-2 ? 1.02 : 1.07), rho_cap);  // :153-157
+        pyfloat = 0;                                               // np.min returns np.float64
+    }
+    out->rho = rho;
+    out->rho_is_pyfloat = pyfloat;
+    return RBL_OK;
 }
 
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,

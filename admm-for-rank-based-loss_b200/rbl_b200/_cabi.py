@@ -8,6 +8,15 @@ from . import build as _build
 _c = ctypes
 _dp = _c.c_void_p  # device pointers travel as integers (tensor.data_ptr())
 
+class RunStats(_c.Structure):
+    """rbl_run_stats (include/rbl_b200.h)"""
+    _fields_ = [("rho", _c.c_double), ("primal", _c.c_double), ("dual", _c.c_double), ("iters", _c.c_int32),
+                ("converged", _c.c_int32), ("rho_is_pyfloat", _c.c_int32), ("nnz_last", _c.c_int32),
+                ("last_sweeps", _c.c_int32), ("pad", _c.c_int32), ("fista_iters", _c.c_int64),
+                ("fista_sweeps", _c.c_int64), ("sparse_dual", _c.c_int64), ("dense_dual", _c.c_int64),
+                ("gathered", _c.c_int64), ("rows_read", _c.c_int64)]
+
+
 _SIGNATURES = {
     "rbl_version": (_c.c_int, []),
     "rbl_last_error": (_c.c_char_p, []),
@@ -22,6 +31,9 @@ _SIGNATURES = {
     "rbl_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_double, _dp, _c.c_void_p]),
     "rbl_sort_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_pav_prox": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_admm_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32,
+                                _c.c_double, _c.c_double, _c.c_int64, _c.c_int32, _c.c_int64, _c.c_double,
+                                _c.c_int32, _c.POINTER(RunStats)]),
     "rbl_bind_scalars": (_c.c_int, [_c.c_void_p, _dp]),
     "rbl_sort_debug": (_c.c_int, [_c.c_void_p, _dp]),
     "rbl_sort_config": (_c.c_int, [_c.c_void_p, _c.c_int]),

@@ -573,6 +573,46 @@ class AdmmEngine(DeviceProblem):
         self.w_step_fista(lam, tol=tol, max_iter=max_iter)
         return self.dual_step(rho)
 
+    def graph_ready(self, tol=7e-5, max_iter=5000):
+        """True once the iteration graph exists (capturing it now if the engine state allows it)"""
+        key = (float(tol), int(max_iter))
+        ok = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
+              and self._persistent is True and self._iters_eager >= 2 and self.Dw_valid
+              and (self.Dt is not None or not self.transpose_ok or self.dual_stats["sparse"] < 1)
+              and not getattr(self, "_r_matches_w", False))
+        if ok and (self._graph is None or self._graph_key != key):
+            self._capture_iteration(key)
+        return ok and self._graph is not None
+
+    def run_fista_iterations(self, n_iters, rho, reg, num_row, num_feature, tol, w_tol=7e-5, fista_max_iter=5000):
+        """up to n_iters ADMM iterations (stopping at the reference's stop test) in the library's native loop
+        over the captured iteration graph; returns the rbl_run_stats, or None if the graph is not available"""
+        if n_iters <= 0 or not self.graph_ready(w_tol, fista_max_iter):
+            return None
+        st = _cabi.RunStats()
+        pyfloat = 1 if type(rho) is float else 0
+        _cabi.check(self.lib.rbl_admm_run(self.h, ctypes.c_void_p(self._graph.raw_cuda_graph_exec()), self._stream(),
+                                          ctypes.c_void_p(self.scal_host.data_ptr()),
+                                          ctypes.c_void_p(self._out4_host.data_ptr()), int(n_iters), float(tol),
+                                          float(reg), int(num_row), int(num_feature),
+                                          int(self.active_dense_frac * self.n_local), float(rho), pyfloat,
+                                          ctypes.byref(st)))
+        self._graph_replays += st.iters
+        self.Dw_valid, self._delta_valid, self._r_matches_w = True, False, False
+        fs, ds, a = self.fista_stats, self.dual_stats, self.active_stats
+        fs["calls"] += st.iters
+        fs["iters"] += st.fista_iters
+        fs["passes"] += st.fista_sweeps
+        fs["last_passes"] = st.last_sweeps
+        fs["d_passes"] += (st.iters - st.gathered) + st.dense_dual
+        ds["sparse"] += st.sparse_dual
+        ds["dense"] += st.dense_dual
+        ds["nnz_last"] = st.nnz_last
+        a["calls"] += st.iters
+        a["rows"] += st.rows_read
+        a["gathered"] += st.gathered
+        return st
+
     def _capture_iteration(self, key):
         tol, max_iter = key
         dev = self.device
@@ -584,6 +624,7 @@ class AdmmEngine(DeviceProblem):
         stats = (dict(self.fista_stats), dict(self.dual_stats), dict(self.active_stats))
         g = torch.cuda.CUDAGraph()
         n0 = int(self.lib.rbl_launch_count())
+        self._graph = None
         _cabi.check(self.lib.rbl_bind_scalars(self.h, self.scal.data_ptr()))
         cur = torch.cuda.current_stream(dev)
         if not hasattr(self, "_cap_stream"):

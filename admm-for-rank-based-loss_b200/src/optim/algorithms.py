@@ -265,13 +265,43 @@ class ADMMmethod(Optimizer):
         self._w_subproblem_device()
         return e.w.cpu().numpy().reshape(-1, 1)
 
+    def advance(self, i0, n_iters, verbose=False, t_start=0.0):
+        """Iterations i0 .. i0 + n_iters - 1 of the reference loop (:209-216); returns (next i, converged).
+        Extension used by main_loop and bench.py: once the engine has captured the iteration as a CUDA graph the
+        iterations between two verbose prints run in the library's native loop (rbl_admm_run) — same host logic
+        as Optimizer.main_loop (stop test, rho schedule), no interpreter in between."""
+        i, end = i0, i0 + n_iters
+        while i < end:
+            st = None
+            if not self.store and self._whole_iteration_on_device():
+                # run up to and including the next iteration that prints (i % 10 == 0), natively
+                stop = end if not verbose else min(end, i + 1 if i % 10 == 0 else (i // 10 + 1) * 10 + 1)
+                st = self.engine.run_fista_iterations(stop - i, self.rho, self.reg, self.num_row, self.num_feature,
+                                                      self.tol, self.w_tol, self.fista_max_iter)
+            if st is None:
+                if super(ADMMmethod, self).main_loop(i, t_start, verbose):
+                    return i + 1, True
+                i += 1
+                continue
+            i += st.iters
+            last = i - 1
+            self._w = self.engine.w_host.numpy().reshape(-1, 1).copy()
+            self.primal_feasibility, self.dual_feasibility = st.primal, st.dual
+            if not st.rho_is_pyfloat:
+                self.rho = np.float64(st.rho)
+            if st.converged:
+                print('algorithm converges within tolerance')
+                print('iter_num=', last, 'primal_feasibility: ', st.primal, 'dual_feasibility: ', st.dual)
+                print('loss=', self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+                return i, True
+            if verbose and last % 10 == 0:
+                print('iter_num=', last, 'primal_feasibility: ', st.primal, 'dual_feasibility: ', st.dual)
+                print('loss=', self.objective.get_arrogate_loss(torch.from_numpy(self.w).double()))
+        return i, False
+
     def main_loop(self, verbose=True):
         t_start = time.time()
-
-        for i in range(self.max_iter):
-            if super(ADMMmethod, self).main_loop(i, t_start, verbose):
-                break
-
+        self.advance(0, self.max_iter, verbose, t_start)
         return self.w
 
     def final_res(self):

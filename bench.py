@@ -224,8 +224,7 @@ def main():
     w0_ev, w1_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0_ev.record()
     with quiet:
-        for it in range(W):
-            done = Optimizer.main_loop(solver, it, 0.0, False) or done
+        _, done = solver.advance(0, W)
     w1_ev.record()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -236,8 +235,8 @@ def main():
     dpasses1 = solver.engine.fista_stats["d_passes"]
     ev[2].record()
     with quiet:
-        for it in range(W, W + K):
-            done = Optimizer.main_loop(solver, it, 0.0, False) or done
+        it_next, done2 = solver.advance(W, K)
+    done = done or done2
     ev[3].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -309,9 +308,8 @@ def main():
         s0.record()
         it2 = W + K
         with quiet:
-            while not done and it2 < 1000:
-                done = Optimizer.main_loop(solver, it2, 0.0, False)
-                it2 += 1
+            if not done:
+                it2, done = solver.advance(W + K, 1000 - (W + K))
         s1.record()
         barrier()
         t_tail = s0.elapsed_time(s1) / 1e3

@@ -179,6 +179,29 @@ int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const doubl
  * per row and column (DRAM-activate bound).  Pass Dt = NULL to rbl_dual_pass when no copy is kept. */
 int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream);
 
+/* ---- native outer loop.  The host layer captures ONE ADMM iteration (z-step, FISTA w-step, dual step, read-back of
+ * out8/out9 into pinned memory) as a CUDA graph whose first node copies the pinned scalar block h_scal =
+ * [rho, lam, thr_f32] to the block bound with rbl_bind_scalars.  rbl_admm_run then replays it up to max_iters
+ * times with the reference's host logic in between (algorithms.py:137-157): stop test ||z - Dw|| < tol and
+ * ||w - w_prev|| < tol, rho <- min(rho * (1.02 if primal > 1e-2 else 1.07), 217 d), lam = (reg / (2 rho n)) n.
+ * One cudaGraphLaunch + one stream synchronise per iteration, no interpreter in the loop. */
+typedef struct rbl_run_stats {
+    double rho;             /* rho to use for the NEXT iteration (unchanged by a converged iteration) */
+    double primal, dual;    /* residual norms of the last iteration run */
+    int32_t iters;          /* iterations run */
+    int32_t converged;      /* stop test met at the last iteration */
+    int32_t rho_is_pyfloat; /* still the caller's python-float rho (no update happened) */
+    int32_t nnz_last;       /* nnz(w) after the last iteration */
+    int32_t last_sweeps;    /* sweeps over G of the last FISTA call */
+    int32_t pad;
+    int64_t fista_iters, fista_sweeps;   /* totals over the run */
+    int64_t sparse_dual, dense_dual;     /* which dual-pass branch ran */
+    int64_t gathered, rows_read;         /* gradient passes that gathered active rows; rows of D read in total */
+} rbl_run_stats;
+int rbl_admm_run(rbl_handle_t h, void* graph_exec /* cudaGraphExec_t */, rbl_stream_t stream, double* h_scal,
+                 const double* h_out, int32_t max_iters, double tol, double reg, int64_t num_row,
+                 int32_t num_feature, int64_t dense_above, double rho, int32_t rho_is_pyfloat, rbl_run_stats* out);
+
 /* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
  * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].
  * One pass over D serves 8 instances at a time (multi-RHS fused pass on the FP64 tensor-core path). */

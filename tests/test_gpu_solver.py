@@ -269,3 +269,41 @@ def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw
     o.w = s.w.reshape(-1).copy()
     assert abs(obj - o.objective()) < 1e-11 * abs(obj)
     s.engine.close()
+
+
+def test_native_loop_equals_per_iteration_loop(w_mode):
+    """ADMMmethod.main_loop runs the captured iteration graph in the library's native loop (rbl_admm_run: stop test,
+    rho schedule, lam in C); stepping the same solve one Optimizer.main_loop call at a time must give the same
+    iterates bit for bit, the same rho and the same stopping iteration."""
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    rng = np.random.default_rng(11)
+    n, d = 4000, 60
+    X = rng.normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:5] = rng.normal(size=5)
+    y = np.sign(X @ ws + 0.1 * rng.normal(size=n)).reshape(-1, 1)
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.01, args=[0.8], max_iter=60,
+              tol=1e-3)
+    a = ADMMmethod(X, y, **kw)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        wa = a.main_loop(verbose=True)
+    b = ADMMmethod(X, y, **kw)
+    it_b = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(60):
+            if Optimizer.main_loop(b, i, 0.0, False):
+                it_b = i
+                break
+    np.testing.assert_array_equal(wa, b.w)
+    np.testing.assert_array_equal(a.z, b.z)
+    assert float(a.rho) == float(b.rho)
+    out = buf.getvalue()
+    assert "iter_num= 0 " in out and "iter_num= 10 " in out          # verbose prints every 10th iteration
+    if it_b is not None:
+        assert f"iter_num= {it_b} " in out and "algorithm converges within tolerance" in out
+    if w_mode == "gram":
+        assert a.engine._graph is not None and a.engine._graph_replays > 0
+    a.engine.close()
+    b.engine.close()
