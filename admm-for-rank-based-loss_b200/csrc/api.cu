@@ -47,12 +47,14 @@ int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double*
 size_t rbl_gram_scratch_doubles(rbl_ctx* c);
 int rbl_gram_persist_config(rbl_ctx* c);
 int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
-                         float L0, double tol, int max_iter, double* w_out, cudaStream_t s);
+                         float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
+                         cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s);
 int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
-                      double* lam, double rho, int cap, cudaStream_t s);
+                      double* lam, double rho, int cap, int support_ready, cudaStream_t s);
 int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s);
-int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s);
+int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, double* w_copy,
+                        cudaStream_t s);
 int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, const double* w_prev, double* out4,
                    cudaStream_t s);
 
@@ -344,7 +346,9 @@ int rbl_grad_pass(rbl_handle_t h, const double* D, const double* w0, const doubl
     RBL_TRY(rbl_launch_pass(h, RBL_PASS_FUSED, D, w0, b, r, nullptr, nullptr, S(stream), nullptr, 0.0, h->act_total,
                             cap));
     RBL_TRY(rbl_k_reduce_partials(h, 0, nullptr, S(stream)));
-    RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 1) * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    if (red != h->red)  // rbl_fista_bind_red(h, red) makes the reduction land in the caller's buffer directly
+        RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 1) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 S(stream)));
     return RBL_OK;
 }
 
@@ -368,7 +372,9 @@ int rbl_fused_pass(rbl_handle_t h, const double* D, const double* x, const doubl
     RBL_REQUIRE(D && x && b && r && red, "null argument");
     RBL_TRY(rbl_launch_pass(h, RBL_PASS_FUSED, D, x, b, r, nullptr, nullptr, S(stream)));
     RBL_TRY(rbl_k_reduce_partials(h, 0, nullptr, S(stream)));
-    RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 2) * sizeof(double), cudaMemcpyDeviceToDevice, S(stream)));
+    if (red != h->red)
+        RBL_CUDA(cudaMemcpyAsync(red, h->red, (size_t)(h->d + 2) * sizeof(double), cudaMemcpyDeviceToDevice,
+                                 S(stream)));
     return RBL_OK;
 }
 
@@ -575,16 +581,18 @@ int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, cons
 }
 
 int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
-                       float L0, double tol, int max_iter, double* w_out, rbl_stream_t stream) {
+                       float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
+                       rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(G && w0 && red0 && max_iter > 0, "bad arguments");
-    RBL_REQUIRE(w0 != w_out, "w0 and w_out must not alias");
+    RBL_REQUIRE(w_prev_out == nullptr || w_prev_out != w_out, "w_prev_out and w_out must not alias");
     if (!rbl_gram_persist_config(h)) {
         rbl_set_error("persistent FISTA kernel unavailable for d = %d (state does not fit in shared memory or no "
                       "cooperative launch); use rbl_gram_fista_begin/steps", h->d);
         return RBL_ERR_UNSUPPORTED;
     }
-    return rbl_k_gram_fista_run(h, G, w0, red0, lam, thr_f32, L0, tol, max_iter, w_out, S(stream));
+    return rbl_k_gram_fista_run(h, G, w0, red0, lam, thr_f32, L0, tol, max_iter, w_out, w_prev_out, with_support,
+                                S(stream));
 }
 
 int rbl_gram_fista_persistent_ok(rbl_handle_t h) {
@@ -619,15 +627,15 @@ int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_
 }
 
 int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const double* w, const double* w_prev,
-                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, double* out8,
-                  rbl_stream_t stream) {
+                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, int support_ready,
+                  double* out8, double* w_copy, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(D && w && z && Dw && lam && out8, "null argument");
     const int cap = sparse_cap < 0 ? 0 : sparse_cap;
     // exactly one of the two kernels does the work, chosen on the device from nnz(w): no host round trip
-    RBL_TRY(rbl_k_dual_sparse(h, D, Dt, w, z, Dw, lam, rho, cap, S(stream)));
+    RBL_TRY(rbl_k_dual_sparse(h, D, Dt, w, z, Dw, lam, rho, cap, support_ready, S(stream)));
     RBL_TRY(rbl_launch_pass(h, RBL_PASS_DUAL, D, w, z, Dw, nullptr, nullptr, S(stream), lam, rho, h->sup_nnz, cap));
-    return rbl_k_dual_finalize(h, cap, w, w_prev, out8, S(stream));
+    return rbl_k_dual_finalize(h, cap, w, w_prev, out8, w_copy, S(stream));
 }
 
 // ---- native outer loop over a captured iteration graph (algorithms.py:119-157 host logic) -------------------

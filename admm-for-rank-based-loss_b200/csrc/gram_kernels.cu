@@ -284,8 +284,12 @@ struct GramPersist {
     const double* red0;
     double* vu;           // [2 (parity)][2][ldg]
     double* beta_out;     // global copy of the final iterate (handle-internal)
-    double* w_out;        // caller's w (may be null)
-    unsigned int* bar;    // zeroed before the launch
+    double* w_out;        // caller's w (may be null; may alias w0: it is written after the last grid barrier)
+    double* w_prev_out;   // receives w0 (may be null)
+    int32_t* sup_idx;     // ascending support of the result (may be null): indices, values, count
+    double* sup_val;
+    int* sup_nnz;
+    unsigned int* bar;    // [0] barrier counter, [1] exit ticket; both zero on entry and on exit
     const float* pow_tab;
     int rpc;
     int g_in_smem;
@@ -502,6 +506,33 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             const double b = BETA[c];
             p.beta_out[c] = b;
             if (p.w_out) p.w_out[c] = b;
+            if (p.w_prev_out) p.w_prev_out[c] = W0[c];
+        }
+        if (p.sup_idx) {  // ascending support of beta for the sparse dual pass (saves the support kernel)
+            __shared__ int s_wc[kGWarps];
+            int base = 0;
+            for (int c0 = 0; c0 < d; c0 += nt) {
+                const int c = c0 + tid;
+                const double v = (c < d) ? BETA[c] : 0.0;
+                const bool nz = (v != 0.0);
+                const unsigned m = __ballot_sync(0xffffffffu, nz);
+                __syncthreads();
+                if (lane == 0) s_wc[warp] = __popc(m);
+                __syncthreads();
+                int off = base, tot = 0;
+#pragma unroll
+                for (int w = 0; w < kGWarps; ++w) {
+                    if (w < warp) off += s_wc[w];
+                    tot += s_wc[w];
+                }
+                if (nz) {
+                    const int k2 = off + __popc(m & ((1u << lane) - 1u));
+                    p.sup_idx[k2] = c;
+                    p.sup_val[k2] = v;
+                }
+                base += tot;
+            }
+            if (tid == 0) *p.sup_nnz = base;
         }
         if (tid == 0) {
             FistaState* st = p.st;
@@ -521,6 +552,16 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             st->passes = sweeps;   // sweeps over G (each carries KC candidates)
             st->trials = trials;   // line-search trials consumed, as the reference would count them
             st->thr_f32 = thr_f32_;
+        }
+    }
+    // leave the barrier words clean for the next launch: the last CTA out resets them (no memset node needed)
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int tk = atomicAdd(p.bar + 1, 1u);
+        if (tk == gridDim.x - 1) {
+            p.bar[0] = 0u;
+            p.bar[1] = 0u;
+            __threadfence();
         }
     }
 }
@@ -825,8 +866,13 @@ int rbl_gram_persist_config(rbl_ctx* c) {
 }
 
 int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
-                         float L0, double tol, int max_iter, double* w_out, cudaStream_t s) {
+                         float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
+                         cudaStream_t s) {
     GramPersist p;
+    p.w_prev_out = w_prev_out;
+    p.sup_idx = with_support ? c->sup_idx : nullptr;
+    p.sup_val = c->sup_val;
+    p.sup_nnz = c->sup_nnz;
     p.G = G;
     p.ldg = c->ld;
     p.d = c->d;
@@ -846,7 +892,6 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
     p.thr_f32 = thr_f32;
     p.max_iter = max_iter;
     p.scal = c->scal;
-    RBL_CUDA(cudaMemsetAsync(c->gticket + 8, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
     const void* fn = c->gp_kc == 8   ? (const void*)gram_fista_persistent_kernel<8>
                      : c->gp_kc == 4 ? (const void*)gram_fista_persistent_kernel<4>

@@ -168,6 +168,7 @@ struct TreeParams {
     double* val;
     unsigned int* node_cnt;
     int64_t nchunks;
+    double *pm_off_hi_w, *pm_off_lo_w;  // writable views of pm_off_* (the few-segment merge kernel scans them itself)
 };
 
 // one merge of two solved ranges by a full warp (shared- or global-memory values): the rounds of pav_merge_search_kary (pav_core.h, which the CPU
@@ -468,7 +469,53 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double rho = P.scal ? P.scal[0] : P.rho;
     if (tid == 0) s_nblk = 0;
-    __syncthreads();
+    {   // exclusive scan of the chunk totals of the margins (what chunk_offsets_kernel does for the tree route):
+        // 64 threads x contiguous slices, double-double throughout
+        __shared__ double s_wh[2], s_wl[2];
+        const int64_t nch = P.nchunks;
+        const int64_t per = (nch + 63) / 64;
+        const int64_t c0 = (int64_t)tid * per;
+        dd_t run = dd_make(0.0);
+        for (int64_t c = c0; c < c0 + per && c < nch; ++c) {
+            dd_t t;
+            t.hi = P.pm_tot_hi[c];
+            t.lo = P.pm_tot_lo[c];
+            run = dd_add(run, t);
+        }
+        dd_t x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            dd_t y = shfl_up_dd(x, o);
+            if (lane >= o) x = dd_add(y, x);
+        }
+        if (lane == 31) {
+            s_wh[warp] = x.hi;
+            s_wl[warp] = x.lo;
+        }
+        __syncthreads();
+        dd_t incl_prev = shfl_up_dd(x, 1);
+        if (lane == 0) incl_prev = dd_make(0.0);
+        dd_t ex = incl_prev;
+        if (warp == 1) {
+            dd_t w0t;
+            w0t.hi = s_wh[0];
+            w0t.lo = s_wl[0];
+            ex = dd_add(w0t, ex);
+        }
+        for (int64_t c = c0; c < c0 + per && c < nch; ++c) {
+            P.pm_off_hi_w[c] = ex.hi;
+            P.pm_off_lo_w[c] = ex.lo;
+            dd_t t;
+            t.hi = P.pm_tot_hi[c];
+            t.lo = P.pm_tot_lo[c];
+            ex = dd_add(ex, t);
+        }
+        if (tid == 63) {  // grand total closes the offsets (thread 63 owns the last slice, possibly empty)
+            P.pm_off_hi_w[nch] = ex.hi;
+            P.pm_off_lo_w[nch] = ex.lo;
+        }
+    }
+    __syncthreads();  // offsets (global memory, this CTA's own writes) and s_nblk visible
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
     PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
     ValOverlay val{P.val, &s_nblk, s_lo, s_hi, s_v};
@@ -601,8 +648,10 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
                                                              few ? z_sorted : nullptr, c->scal);
     RBL_LAUNCH_CHECK();
     if (few && c->nseg == 1) return RBL_OK;  // sigma never steps up (ERM): the element prox is the answer
-    chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
-    RBL_LAUNCH_CHECK();
+    if (!few) {
+        chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(c->ch_tot_hi, c->ch_tot_lo, nch, c->pm_off_hi, c->pm_off_lo);
+        RBL_LAUNCH_CHECK();
+    }
     TreeParams P;
     P.loss = loss;
     P.rho = rho;
@@ -619,6 +668,8 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.val = z_sorted;
     P.node_cnt = c->node_cnt;
     P.nchunks = nch;
+    P.pm_off_hi_w = c->pm_off_hi;
+    P.pm_off_lo_w = c->pm_off_lo;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
         pav_seg_merge_kernel<<<1, 64, 0, s>>>(P, c->seg_bounds, c->nseg, blk);

@@ -185,7 +185,7 @@ struct PSortParams {
     uint64_t *kA, *kB;
     uint32_t *vA, *vB;
     uint32_t* counts;    // [grid][256]
-    unsigned int* bar;   // zeroed before the launch
+    unsigned int* bar;   // [0] barrier counter, [1] exit ticket; both zero on entry and on exit
     double* sorted_out;
     int32_t* perm_out;
     int64_t chunk;
@@ -456,6 +456,15 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
         }
         stamp(5);
     }
+    // leave the barrier words clean for the next launch: the last CTA out resets them (no memset node needed)
+    if (tid == 0) {
+        const unsigned int tk = atomicAdd(p.bar + 1, 1u);
+        if (tk == gridDim.x - 1) {
+            p.bar[0] = 0u;
+            p.bar[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 }  // namespace
@@ -498,7 +507,6 @@ int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted
     p.perm_out = perm_out;
     p.chunk = (n + G - 1) / G;
     p.dbg = c->sort_dbg;
-    RBL_CUDA(cudaMemsetAsync(c->gticket + 16, 0, sizeof(unsigned int), s));
     void* args[] = {(void*)&p};
     RBL_CUDA(cudaLaunchCooperativeKernel((const void*)radix_sort_persistent_kernel, dim3(G), dim3(kPT), args,
                                          kPSortSmem, s));

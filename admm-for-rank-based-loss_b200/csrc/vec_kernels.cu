@@ -651,7 +651,8 @@ __global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __res
                                                              const double* __restrict__ w_prev, int d,
                                                              const FistaState* __restrict__ st,
                                                              const int* __restrict__ act_total,
-                                                             double* __restrict__ out) {
+                                                             double* __restrict__ out,
+                                                             double* __restrict__ w_copy) {
     __shared__ double sh[33];
     const int nnz = *nnz_ptr;
     const bool sparse = nnz <= cap;
@@ -663,6 +664,7 @@ __global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __res
     double dd = 0.0, w2 = 0.0, w1 = 0.0;
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
         const double wc = w[c];
+        if (w_copy) w_copy[c] = wc;  // e.g. pinned host memory: the iterate travels with the residuals
         if (w_prev) {
             const double df = wc - w_prev[c];
             dd = fma(df, df, dd);
@@ -771,9 +773,11 @@ int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const d
 
 // support list, sparse kernel (gated nnz <= cap), then the caller launches the dense pass (gated nnz > cap)
 int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
-                      double* lam, double rho, int cap, cudaStream_t s) {
-    support_kernel<<<1, 1024, 0, s>>>(w, c->d, c->sup_idx, c->sup_val, c->sup_nnz);
-    RBL_LAUNCH_CHECK();
+                      double* lam, double rho, int cap, int support_ready, cudaStream_t s) {
+    if (!support_ready) {
+        support_kernel<<<1, 1024, 0, s>>>(w, c->d, c->sup_idx, c->sup_val, c->sup_nnz);
+        RBL_LAUNCH_CHECK();
+    }
     if (Dt)
         sparse_dual_t_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
                                                                 cap, z, Dw, lam, rho, c->vpart, c->scal);
@@ -790,9 +794,10 @@ int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s) {
     return RBL_OK;
 }
 
-int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, cudaStream_t s) {
+int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, double* w_copy,
+                        cudaStream_t s) {
     dual_finalize_kernel<<<1, 1024, 0, s>>>(c->sspart, c->pass_grid, c->vpart, c->vec_grid, c->sup_nnz, cap, w,
-                                            w_prev, c->d, c->fista, c->act_total, out8);
+                                            w_prev, c->d, c->fista, c->act_total, out8, w_copy);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

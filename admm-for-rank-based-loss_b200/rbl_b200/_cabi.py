@@ -61,12 +61,12 @@ _SIGNATURES = {
                                         _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_persistent_ok": (_c.c_int, [_c.c_void_p]),
     "rbl_gram_fista_run": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double,
-                                      _c.c_int, _dp, _c.c_void_p]),
+                                      _c.c_int, _dp, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_result": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
-    "rbl_dual_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _c.c_double, _c.c_int, _dp,
-                                 _c.c_void_p]),
+    "rbl_dual_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_int,
+                                 _dp, _dp, _c.c_void_p]),
     "rbl_build_transpose": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
     "rbl_batch_create": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "rbl_fista_batch_begin": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _c.POINTER(_c.c_double), _c.POINTER(_c.c_int32),

@@ -237,6 +237,7 @@ class AdmmEngine(DeviceProblem):
     # ---- state -------------------------------------------------------------------------------
     def set_state(self, w=None, z=None, lam=None):
         self._delta_valid = False
+        self._support_ready = False
         self._iters_eager = 0  # a few eager iterations again before the graph path resumes
         if w is not None:
             self.w.copy_(self.vec(w))
@@ -259,6 +260,8 @@ class AdmmEngine(DeviceProblem):
                 self.G = torch.empty((self.d, self.ld), dtype=torch.float64, device=self.device)
                 self.red0 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
                 self.red1 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
+                # reductions of the gradient pass land in red0 directly (no copy node)
+                _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red0.data_ptr()))
                 t0.record()
                 _cabi.check(self.lib.rbl_gram_build(self.h, self.D.data_ptr(), self.G.data_ptr(), self._stream()))
                 self.all_reduce(self.G)
@@ -317,7 +320,7 @@ class AdmmEngine(DeviceProblem):
 
     # ---- w-step, l1: FISTA (fast_lasso.py:22-69 via algorithms.py:190-202) ---------------------
     def fista(self, w0, b, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_iter=5000, w_out=None,
-              r_out=None, want_info=True, use_active=False):
+              r_out=None, want_info=True, use_active=False, w_prev_out=None):
         """Runs the device-resident FISTA state machine to completion; returns (w_out, info).
 
         `lam` keeps its Python type on purpose: a python float makes `lam/L_cur` a float32 quotient
@@ -336,7 +339,7 @@ class AdmmEngine(DeviceProblem):
         hd = (ctypes.c_double * 4)()
         if self.w_mode == "gram":
             return self._fista_gram(w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info,
-                                    use_active)
+                                    use_active, w_prev_out)
         # first batch: what the previous call needed (iteration counts drift slowly between ADMM
         # iterations), then small batches; steps enqueued after convergence exit immediately
         batch = max(self.fista_batch_min, self.fista_stats["last_passes"] - 1)
@@ -368,23 +371,26 @@ class AdmmEngine(DeviceProblem):
         return w_out, info
 
     def _fista_gram(self, w0, b, lam, thr_f32, L, tol, max_iter, w_out, r_out, hi, hd, want_info=True,
-                    use_active=False):
+                    use_active=False, w_prev_out=None):
         """FISTA on G = D^T D: one fused pass over D at the warm start, then one sweep over G per trial —
         the whole call is one persistent cooperative kernel when its state fits in shared memory."""
         lib, s = self.lib, self._stream()
         G = self.gram()
         if w_out is None:
             w_out = torch.empty(self.d, dtype=torch.float64, device=self.device)
-        if w0.data_ptr() == w_out.data_ptr():
-            raise ValueError("w0 and w_out must not alias in Gram mode")
-        self._pass_at(w0, b, use_active)
         if self._persistent is None:
             self._persistent = bool(lib.rbl_gram_fista_persistent_ok(self.h)) and \
                 os.environ.get("RBL_GRAM_PERSISTENT", "1") != "0"
+        if w0.data_ptr() == w_out.data_ptr() and not self._persistent:
+            raise ValueError("w0 and w_out must not alias in Gram mode without the persistent kernel")
+        self._pass_at(w0, b, use_active)
         if self._persistent:
+            # the kernel also emits w_prev (= w0) and the support of the result for the sparse dual pass
             _cabi.check(lib.rbl_gram_fista_run(self.h, G.data_ptr(), w0.data_ptr(), self.red0.data_ptr(), float(lam),
                                                thr_f32, float(np.float32(L)), float(tol), int(max_iter),
-                                               w_out.data_ptr(), s))
+                                               w_out.data_ptr(), 0 if w_prev_out is None else w_prev_out.data_ptr(),
+                                               1, s))
+            self._support_ready = w_out.data_ptr() == self.w.data_ptr()
             if want_info:
                 _cabi.check(lib.rbl_fista_poll(self.h, s, hi, hd))
         else:
@@ -418,10 +424,14 @@ class AdmmEngine(DeviceProblem):
 
     def w_step_fista(self, lam, tol=7e-5, max_iter=5000):
         if self.w_mode == "gram":
-            self.w_prev.copy_(self.w)
             use_active, self._delta_valid = self._delta_valid, False
-            _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w,
-                                 want_info=False, use_active=use_active)
+            if self._persistent:  # in place: the kernel reads w, writes the new w and the old one to w_prev
+                _, info = self.fista(self.w, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w,
+                                     want_info=False, use_active=use_active, w_prev_out=self.w_prev)
+            else:
+                self.w_prev.copy_(self.w)
+                _, info = self.fista(self.w_prev, self.b, lam, tol=tol, max_iter=max_iter, w_out=self.w,
+                                     want_info=False, use_active=use_active)
             self._r_matches_w = False
             return info
         self.w_prev.copy_(self.w)
@@ -486,14 +496,17 @@ class AdmmEngine(DeviceProblem):
     def _dual_launch(self, rho):
         """enqueue the dual update and the read-back of its 128-byte result; no host synchronisation"""
         from_res = 1 if getattr(self, "_r_matches_w", False) else 0
+        direct = not from_res and self.world == 1  # residuals and w written straight into pinned host memory
         if not from_res:
             # Dw = D w with the multiplier update and ||z - Dw||^2 in the pass epilogue
+            sup_ready, self._support_ready = (1 if getattr(self, "_support_ready", False) else 0), False
             _cabi.check(self.lib.rbl_dual_pass(self.h, self.D.data_ptr(),
                                                0 if self.Dt is None else self.Dt.data_ptr(), self.w.data_ptr(),
                                                self.w_prev.data_ptr(),
                                                self.z.data_ptr(), self.Dw.data_ptr(), self.lam.data_ptr(),
-                                               float(rho), self.sparse_cap, self._out4.data_ptr(),
-                                               self._stream()))
+                                               float(rho), self.sparse_cap, sup_ready,
+                                               self._out4_host.data_ptr() if direct else self._out4.data_ptr(),
+                                               self.w_host.data_ptr() if direct else 0, self._stream()))
         else:
             _cabi.check(self.lib.rbl_dual_update(self.h, self.z.data_ptr(), self.Dw.data_ptr(), self.b.data_ptr(),
                                                  self.r.data_ptr(), from_res, self.lam.data_ptr(), float(rho),
@@ -501,6 +514,8 @@ class AdmmEngine(DeviceProblem):
                                                  self._stream()))
         self.Dw_valid = True
         self._r_matches_w = False
+        if direct:
+            return from_res
         if self.world > 1:
             # only the primal term is a partial sum over row shards
             self.all_reduce(self._out4[:1])

@@ -156,8 +156,11 @@ int rbl_gram_fista_steps(rbl_handle_t h, const double* G, int nsteps, rbl_stream
  * one grid barrier per trial, no host round trip): runs to convergence, leaves w_out (may be NULL) and the
  * final state for rbl_fista_poll.  rbl_gram_fista_persistent_ok() == 0 (large d): use begin/steps instead. */
 int rbl_gram_fista_persistent_ok(rbl_handle_t h);
+/* w_out may alias w0 (it is written after the last grid barrier); w_prev_out (may be NULL) receives w0;
+ * with_support != 0 also leaves the ascending support of the result in the handle for rbl_dual_pass(support_ready) */
 int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
-                       float L0, double tol, int max_iter, double* w_out, rbl_stream_t stream);
+                       float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
+                       rbl_stream_t stream);
 int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream);
 /* red_out = [D^T (b - D w) (d), ||b - D w||^2, 0] at any w, from G, w0, red0 (same layout as rbl_fused_pass):
  * the f/g evaluation of w_LBFGS.py:31-45 */
@@ -171,9 +174,12 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
  * the nnz(w) touched columns (from the transposed copy Dt when given, else the touched 32-byte sectors of each row of
  * D) — chosen on the device, no host round trip — otherwise one streaming pass over D.  sparse_cap = 0 forces the
  * dense pass. */
+/* support_ready != 0: the support of w was left in the handle by rbl_gram_fista_run(with_support).  out8 and
+ * w_copy (may be NULL; receives w) may point to pinned host memory (unified addressing): the residuals and the
+ * iterate then reach the host without a copy node. */
 int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const double* w, const double* w_prev,
-                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, double* out8,
-                  rbl_stream_t stream);
+                  const double* z, double* Dw, double* lam, double rho, int sparse_cap, int support_ready,
+                  double* out8, double* w_copy, rbl_stream_t stream);
 /* Dt = D^T as a dense d x n_local row-major copy (optional, 8 n d bytes).  With it the sparse-w branch of
  * rbl_dual_pass reads the nnz(w) touched columns as contiguous n-vectors (coalesced) instead of one 32-byte sector
  * per row and column (DRAM-activate bound).  Pass Dt = NULL to rbl_dual_pass when no copy is kept. */

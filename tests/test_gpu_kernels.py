@@ -202,8 +202,8 @@ def test_gram_build_eval_and_dual_pass(E, n, d):
             e._build_transpose()
             np.testing.assert_array_equal(e.Dt.cpu().numpy(), X.T)
         cabi.check(e.lib.rbl_dual_pass(e.h, e.D.data_ptr(), e.Dt.data_ptr() if use_t else 0, wd2.data_ptr(),
-                                       w0d.data_ptr(), zd.data_ptr(), Dw.data_ptr(), lamd.data_ptr(), 0.37, cap,
-                                       e._out4.data_ptr(), e._stream()))
+                                       w0d.data_ptr(), zd.data_ptr(), Dw.data_ptr(), lamd.data_ptr(), 0.37, cap, 0,
+                                       e._out4.data_ptr(), 0, e._stream()))
         dw = X @ wv
         scale = np.abs(X) @ np.abs(wv) + 1e-300
         assert np.max(np.abs(Dw.cpu().numpy() - dw) / scale) < 1e-14, (nnz, cap)
