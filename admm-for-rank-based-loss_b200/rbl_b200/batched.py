@@ -2,13 +2,21 @@
 grid, several seeds / warm starts — that share ONE design matrix resident in HBM.
 
 The reference has no counterpart (one `ADMMmethod` object per instance; the oracle for this mode is a
-Python loop over it).  Here the w-steps of all active instances advance together: every pass over D
-serves 8 instances at once (multi-RHS fused pass on the FP64 tensor-core path, csrc/batch_kernels.cu),
-each instance keeping its own device-resident FISTA state machine, rho schedule and stop test, so ragged
-iteration counts cost nothing but the masked lanes.  z-steps (sort + PAV) run per instance with the
-single-instance kernels.  Across GPUs instances are sharded with NO communication
-(`torch.distributed` is only used to gather the d x B result at the end).
+Python loop over it).  Two formulations:
+
+* mode "gram" (default wherever the single-instance engine runs its w-step on G = D^T D): D, G and D^T are
+  resident ONCE; every instance is a light child engine (own handle, state and scratch) whose whole ADMM
+  iteration is a captured CUDA graph — active-row gradient gather, persistent FISTA on G, sparse dual pass —
+  and the graphs of different instances are replayed concurrently on a pool of streams, so the latency-bound
+  kernels of one instance (sort, PAV merge, FISTA barriers) overlap with the bandwidth-bound ones of another.
+* mode "stream": the w-steps of all active instances advance together, every pass over D serving 8 instances
+  at once (multi-RHS fused pass on the FP64 tensor-core path, csrc/batch_kernels.cu), each instance keeping
+  its own device-resident FISTA state machine; z-steps run per instance on worker streams.
+
+Either way each instance has its own rho schedule and stop test (ragged iteration counts), and across GPUs
+instances are sharded with NO communication (`torch.distributed` only gathers the d x B result at the end).
 """
+import os
 import ctypes
 
 import numpy as np
@@ -71,7 +79,7 @@ class BatchedADMM:
     """
 
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l1_regs=None, B_clip=None, args=None,
-                 w0s=None, max_iter=200, tol=1e-4, device=None, group=None, shard=True, z_streams=8):
+                 w0s=None, max_iter=200, tol=1e-4, device=None, group=None, shard=True, z_streams=8, mode=None):
         if l1_regs is None or len(l1_regs) == 0:
             raise ValueError("l1_regs: one l1 regulariser per instance is required (batched mode is the l1/FISTA path)")
         if B_clip is not None and weight_function != "ehrm":
@@ -124,6 +132,15 @@ class BatchedADMM:
         self.primal = np.full(self.B, np.inf)
         self.dual = np.full(self.B, np.inf)
         self.fista_passes = 0   # passes over D (each serves up to 8 instances)
+        mode = (mode or os.environ.get("RBL_BATCH_MODE", "auto")).lower()
+        if mode not in ("auto", "gram", "stream"):
+            raise ValueError(f"mode must be auto, gram or stream (got {mode!r})")
+        self.mode = e.w_mode if mode == "auto" else mode
+        if self.mode == "gram" and e.w_mode != "gram":
+            raise ValueError("batched mode 'gram' needs the engine in Gram mode (d <= 4096, n >= 2d)")
+        if self.mode == "gram":
+            self._init_gram(w0s, z_streams)
+            return
         if self.B:
             _cabi.check(e.lib.rbl_batch_create(e.h, self.B))
             tab = _pow_table(np.float32(2.5))
@@ -132,6 +149,66 @@ class BatchedADMM:
                 e.matvec(self.W[j], self.DW[j])
             torch.cuda.current_stream(e.device).synchronize()
             self.zworkers = [ZWorker(n, e.sigma, e.loss_id, e.clip, e.device) for _ in range(min(z_streams, self.B))]
+
+    # ---- Gram formulation: one child engine per instance, graphs replayed concurrently ----------------
+    def _init_gram(self, w0s, n_streams):
+        e, n, d = self.eng, self.n, self.d
+        # the big per-slot matrices of the stream formulation are not needed
+        self.Z = self.LAM = self.DW = self.Bv = self.R = None
+        self.inst = []
+        for j in range(self.B):
+            c = AdmmEngine.child(e)
+            reg = float(self.regs[j])
+            lam0 = 0.1 * reg / n
+            w_init = (np.asarray(w0s)[self.i_lo + j] if w0s is not None else np.full(d, 0.001 * reg / d / n))
+            c.set_state(w=w_init, z=np.full(n, lam0), lam=np.full(n, lam0))
+            self.inst.append(c)
+        self.active = list(range(self.B))
+        self.streams = [torch.cuda.Stream(device=e.device) for _ in range(max(1, min(n_streams, self.B)))]
+        torch.cuda.current_stream(e.device).synchronize()
+
+    def _step_gram(self):
+        e = self.eng
+        if not self.active:
+            return 0
+        main = torch.cuda.current_stream(e.device)
+        ready = torch.cuda.Event()
+        ready.record(main)
+        for k, j in enumerate(self.active):
+            st = self.streams[k % len(self.streams)]
+            if k < len(self.streams):
+                st.wait_event(ready)
+            reg = float(self.regs[j])
+            alpha = reg / (2 * self.rho[j] * self.n)   # algorithms.py:192-193,200
+            with torch.cuda.stream(st):
+                self.inst[j].iteration_fista(self.rho[j], alpha * self.n, sync=False)
+        for st in self.streams:
+            st.synchronize()
+        still = []
+        for j in self.active:
+            pf, df = self.inst[j].finish_iteration()
+            self.primal[j], self.dual[j] = pf, df
+            self.iters[j] += 1
+            if pf < self.tol and df < self.tol:
+                self.converged[j] = True
+            else:
+                self.rho[j] = np.min((self.rho[j] * (1.02 if pf > 1e-2 else 1.07), 217 * self.d))
+                still.append(j)
+        self.active = still
+        self.n_active = len(still)
+        return self.n_active
+
+    @property
+    def last_fista_info(self):
+        """{instance: (FISTA iterations, 1 + line-search trials, final L)} of the last step"""
+        if self.mode != "gram":
+            return self._last_fista_info
+        out = {}
+        hi, hd = (ctypes.c_int32 * 8)(), (ctypes.c_double * 4)()
+        for j, c in enumerate(self.inst):
+            _cabi.check(c.lib.rbl_fista_poll(c.h, c._stream(), hi, hd))
+            out[j] = (int(hi[1]), 1 + int(hi[3]), float(hd[1]))
+        return out
 
     # ------------------------------------------------------------------------------------------
     def _swap_slots(self, a, b):
@@ -146,6 +223,8 @@ class BatchedADMM:
 
     def step(self):
         """one ADMM iteration of every active instance; returns the number still active"""
+        if self.mode == "gram":
+            return self._step_gram()
         e, lib = self.eng, self.eng.lib
         Ba = self.n_active
         if Ba == 0:
@@ -190,7 +269,7 @@ class BatchedADMM:
             batch = 4
         self._last_steps = max(passes[a] for a in range(Ba))
         self.last_fista_iters = {self.slot_of[a]: int(its[a]) for a in range(Ba)}
-        self.last_fista_info = {self.slot_of[a]: (int(its[a]), int(passes[a]), float(Ls[a])) for a in range(Ba)}
+        self._last_fista_info = {self.slot_of[a]: (int(its[a]), int(passes[a]), float(Ls[a])) for a in range(Ba)}
         self.fista_passes += self._last_steps * ((Ba + 7) // 8)
         _cabi.check(lib.rbl_fista_batch_result(e.h, Ba, self.W.data_ptr(), self.R.data_ptr(), s()))
         # ---- dual updates + residuals, per instance (algorithms.py:132-136)
@@ -231,14 +310,20 @@ class BatchedADMM:
     def close(self):
         for zw in getattr(self, "zworkers", []):
             zw.close()
+        for c in getattr(self, "inst", []):
+            c.close()
         self.eng.close()
 
     def result(self, gather=True):
         """d x B matrix of solutions, columns in the order of `l1_regs` (all ranks' instances if gathered)"""
         W_local = np.zeros((self.d, self.B))
-        Wh = self.W.cpu().numpy()
-        for slot, j in enumerate(self.slot_of):
-            W_local[:, j] = Wh[slot]
+        if self.mode == "gram":
+            for j, c in enumerate(self.inst):
+                W_local[:, j] = c.w.cpu().numpy()
+        else:
+            Wh = self.W.cpu().numpy()
+            for slot, j in enumerate(self.slot_of):
+                W_local[:, j] = Wh[slot]
         if self.world == 1 or not gather:
             return W_local
         out = [None] * self.world
@@ -247,14 +332,17 @@ class BatchedADMM:
 
     def state(self, j):
         """(w, z, lambda, rho) of local instance j as numpy arrays (for inspection / lockstep tests)"""
+        if self.mode == "gram":
+            c = self.inst[j]
+            return (c.w.cpu().numpy(), c.z.cpu().numpy(), c.lam.cpu().numpy(), self.rho[j])
         slot = self.slot_of.index(j)
         return (self.W[slot].cpu().numpy(), self.Z[slot].cpu().numpy(), self.LAM[slot].cpu().numpy(), self.rho[slot])
 
     def objective(self, j):
         """rank-weighted objective of local instance j (objective.py:71-87)"""
         e = self.eng
-        slot = self.slot_of.index(j)
         if not hasattr(self, "_sig_dev"):
             self._sig_dev = e.vec(self.sigma_a)
-        risk, w2, w1 = e.objective_terms(self.W[slot].contiguous(), self._sig_dev, self.loss)
+        wj = self.inst[j].w if self.mode == "gram" else self.W[self.slot_of.index(j)].contiguous()
+        risk, w2, w1 = e.objective_terms(wj, self._sig_dev, self.loss)
         return risk + 0.5 * float(self.regs[j]) * w1

@@ -49,8 +49,29 @@ class DeviceProblem:
     """D = -y (.) X resident in HBM (row-major, padded to an even leading dimension) plus the library
     handle that owns the scratch for passes, sort and PAV over it."""
 
-    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None):
+    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None, _share=None):
         self.lib = _cabi.load()
+        self._parent = _share
+        if _share is not None:
+            # another solver instance over the SAME design matrix (batched mode): own handle, scratch and state,
+            # D / G / D^T borrowed from the parent
+            p = _share
+            self.device, self.group, self.world, self.rank = p.device, p.group, p.world, p.rank
+            self.n_local, self.d, self.n_global, self.row_lo, self.ld = p.n_local, p.d, p.n_global, p.row_lo, p.ld
+            with torch.cuda.device(self.device):
+                h = ctypes.c_void_p()
+                _cabi.check(self.lib.rbl_create(ctypes.byref(h), self.device.index or 0, self.n_local, self.n_global,
+                                                self.row_lo, self.d, self.ld))
+                self.h = h
+                self.D = p.D
+                self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
+                self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
+                self._out4_np = self._out4_host.numpy()
+                self._u_local = torch.empty(self.n_local, dtype=torch.float64, device=self.device)
+                self._u_glob = (torch.empty(self.n_global, dtype=torch.float64, device=self.device)
+                                if self.world > 1 else self._u_local)
+            self.info = dict(p.info)
+            return
         self.device = _require_cuda(device)
         self.group = group
         if row_lo is None:  # unsharded: this process holds every row
@@ -172,6 +193,11 @@ class DeviceProblem:
 class AdmmEngine(DeviceProblem):
     """ADMM state and the three sub-steps on the device."""
 
+    @classmethod
+    def child(cls, parent):
+        """a further solver instance over the parent's design matrix (shares D, G = D^T D and D^T)"""
+        return cls(None, None, parent.loss, parent.sigma, clip=parent.clip, _share=parent)
+
     def __init__(self, X, y, loss, sigma, clip=None, **kw):
         super().__init__(X, y, **kw)
         if loss not in LOSS_IDS:
@@ -253,6 +279,12 @@ class AdmmEngine(DeviceProblem):
 
     # ---- Gram matrix (algorithms.py:24), built on first use ------------------------------------------
     def gram(self):
+        if self.G is None and self._parent is not None:
+            with torch.cuda.device(self.device):
+                self.G = self._parent.gram()
+                self.red0 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
+                self.red1 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
+                _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red0.data_ptr()))
         if self.G is None:
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
@@ -271,6 +303,11 @@ class AdmmEngine(DeviceProblem):
         return self.G
 
     def _build_transpose(self):
+        if self._parent is not None:
+            if self._parent.Dt is None and self._parent.transpose_ok:
+                self._parent._build_transpose()
+            self.Dt, self.transpose_ok = self._parent.Dt, self._parent.transpose_ok
+            return
         free, _ = torch.cuda.mem_get_info(self.device)
         need = self.n_local * self.d * 8
         if need + (2 << 30) > free:
@@ -559,11 +596,13 @@ class AdmmEngine(DeviceProblem):
         return self._dual_finish(from_res)
 
     # ---- one whole ADMM iteration with the FISTA w-step, replayed as a CUDA graph ------------------------
-    def iteration_fista(self, rho, lam, tol=7e-5, max_iter=5000):
+    def iteration_fista(self, rho, lam, tol=7e-5, max_iter=5000, sync=True):
         """z-step, l1 w-step, dual step (algorithms.py:119-136).  Every data-dependent branch of the Gram-mode
         iteration is taken on the device, so the launch sequence is static: after a few eager iterations it is
         captured once as a CUDA graph and replayed with the per-iteration scalars (rho, lam) refreshed in a
-        device block (rbl_bind_scalars) — ~20 launches become one.  Returns (primal, dual)."""
+        device block (rbl_bind_scalars) — ~20 launches become one.  Returns (primal, dual); with sync=False the
+        work is only enqueued on the current stream (batched mode: many instances in flight) and the caller
+        synchronises that stream before finish_iteration()."""
         thr_f32 = 1.0 if type(lam) is float or isinstance(lam, (int, np.float32)) else 0.0
         key = (float(tol), int(max_iter))
         can_graph = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
@@ -581,12 +620,26 @@ class AdmmEngine(DeviceProblem):
             self.Dw_valid, self._delta_valid, self._r_matches_w = True, False, False
             self._active_pending = self._fista_info_pending = True
             self.fista_stats["calls"] += 1
+            self._inflight = 0
+            if not sync:
+                return None
             torch.cuda.current_stream(self.device).synchronize()
             return self._dual_finish(0)
         self._iters_eager += 1
         self.z_step(rho)
         self.w_step_fista(lam, tol=tol, max_iter=max_iter)
-        return self.dual_step(rho)
+        if (self.Dt is None and self.dual_stats["sparse"] >= 1 and self.transpose_ok
+                and not getattr(self, "_r_matches_w", False)):
+            self._build_transpose()
+        self._inflight = self._dual_launch(rho)
+        if not sync:
+            return None
+        torch.cuda.current_stream(self.device).synchronize()
+        return self._dual_finish(self._inflight)
+
+    def finish_iteration(self):
+        """after the stream of an iteration_fista(sync=False) call has been synchronised: (primal, dual)"""
+        return self._dual_finish(self._inflight)
 
     def graph_ready(self, tol=7e-5, max_iter=5000):
         """True once the iteration graph exists (capturing it now if the engine state allows it)"""

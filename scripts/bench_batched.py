@@ -19,6 +19,8 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--n", type=int, default=100_000)
     ap.add_argument("--d", type=int, default=1000)
+    ap.add_argument("--mode", default="gram", choices=["gram", "stream"])
+    ap.add_argument("--streams", type=int, default=8)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -33,7 +35,7 @@ def main():
     y = torch.sign(X @ ws + 0.1 * torch.randn(a.n, generator=g, dtype=torch.float64, device=dev)); y[y == 0] = 1
     regs = np.logspace(-4, 0, a.instances)
     b = BatchedADMM(X, y.reshape(-1, 1), "superquantile", "binary_cross_entropy", l1_regs=list(regs), args=[0.8],
-                    max_iter=10_000, tol=1e-6)
+                    max_iter=10_000, tol=1e-6, mode=a.mode, z_streams=a.streams)
     del X
     e = b.eng
     for _ in range(3):
@@ -49,8 +51,28 @@ def main():
     t1.record(); torch.cuda.synchronize()
     dt = t0.elapsed_time(t1) / 1e3
     passes = b.fista_passes - p0
-    # the multi-RHS pass alone: 8 instances per launch
     B = b.B
+    if a.mode == "gram":
+        out = {"workload": f"batched lambda-grid SRM superquantile(0.8) BCE l1 in [1e-4,1], n={a.n} d={a.d}, "
+                           f"{a.instances} instances over {world} GPU(s) (BASELINE configs[4])",
+               "mode": "gram: one child engine per instance, iteration graphs replayed concurrently on "
+                       f"{len(b.streams)} streams", "instances_per_gpu": B, "admm_iterations_timed": a.iters,
+               "instance_iterations_per_s_per_gpu": B * a.iters / dt, "ms_per_batched_iteration": 1e3 * dt / a.iters,
+               "graphs": sum(1 for c in b.inst if c._graph is not None),
+               "active_rows_mean": float(np.mean([c.active_stats["rows"] / max(1, c.active_stats["calls"])
+                                                  for c in b.inst])),
+               "nnz_last": [int(c.dual_stats["nnz_last"]) for c in b.inst][:8]}
+        if world > 1:
+            v = torch.tensor([out["instance_iterations_per_s_per_gpu"]], device=dev, dtype=torch.float64)
+            torch.distributed.all_reduce(v)
+            out["instance_iterations_per_s_total"] = float(v[0])
+        if rank == 0:
+            print(json.dumps(out))
+        b.close()
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    # the multi-RHS pass alone: 8 instances per launch
     lams = (ctypes.c_double * B)(*([1.0] * B)); flags = (ctypes.c_int32 * B)(*([0] * B))
     _cabi.check(e.lib.rbl_fista_batch_begin(e.h, B, b.W.data_ptr(), lams, flags, 17.0, 0.0, 100000, e._stream()))
     _cabi.check(e.lib.rbl_fista_batch_steps(e.h, B, e.D.data_ptr(), b.Bv.data_ptr(), 2, e._stream()))

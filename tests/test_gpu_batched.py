@@ -57,7 +57,8 @@ def test_batched_fista_matches_oracle_per_instance(n, d, B):
     e.close()
 
 
-def test_batched_admm_matches_independent_solves(golden_dir):
+@pytest.mark.parametrize("mode", ["gram", "stream"])
+def test_batched_admm_matches_independent_solves(golden_dir, mode):
     """Lockstep: before every ADMM iteration each oracle instance is put in the batched solver's state, then
     both step once.  With identical inner (FISTA) branch decisions — same iteration count, same number of
     line-search trials, same final L — the iterates agree to 1e-9.  When a line-search test `LHS > RHS`
@@ -70,7 +71,8 @@ def test_batched_admm_matches_independent_solves(golden_dir):
     X, y = d2["X"], d2["y"]
     regs = [0.3, 0.1, 0.03, 0.01, 0.003, 0.001, 0.0003, 0.05, 0.02, 0.007]
     for wf, args in [("superquantile", [0.8]), ("erm", None)]:
-        b = BatchedADMM(X, y, wf, "binary_cross_entropy", l1_regs=regs, args=args, max_iter=30, tol=1e-7)
+        b = BatchedADMM(X, y, wf, "binary_cross_entropy", l1_regs=regs, args=args, max_iter=30, tol=1e-7, mode=mode)
+        assert b.mode == mode
         orc = [O.OracleADMM(X, y, wf, "binary_cross_entropy", l1_reg=r, args=args, max_iter=30, tol=1e-7,
                             small_lasso=False) for r in regs]
         flips = 0
@@ -96,7 +98,8 @@ def test_batched_admm_matches_independent_solves(golden_dir):
         b.close()
 
 
-def test_batched_admm_ragged_convergence():
+@pytest.mark.parametrize("mode", ["gram", "stream"])
+def test_batched_admm_ragged_convergence(mode):
     """instances converge at different iterations; finished ones retire without disturbing the others"""
     from rbl_b200.batched import BatchedADMM
 
@@ -107,7 +110,7 @@ def test_batched_admm_ragged_convergence():
     ws[:4] = rng.normal(size=4)
     y = np.sign(X @ ws + 0.1 * rng.normal(size=n)).reshape(-1, 1)
     regs = [1.0, 0.5, 0.2, 0.05, 0.01]
-    b = BatchedADMM(X, y, "erm", "binary_cross_entropy", l1_regs=regs, max_iter=400, tol=1e-5)
+    b = BatchedADMM(X, y, "erm", "binary_cross_entropy", l1_regs=regs, max_iter=400, tol=1e-5, mode=mode)
     with contextlib.redirect_stdout(io.StringIO()):
         W = b.main_loop()
     assert b.converged.all() and len(set(b.iters.tolist())) > 1       # ragged
