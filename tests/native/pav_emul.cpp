@@ -63,6 +63,72 @@ extern "C" int emul_pav(int loss, int64_t n, const double* sigma, const double* 
     return 0;
 }
 
+// ---- few-segment route (csrc/pav_kernels.cu: pav_seg_merge_kernel): level-0 solved ranges are the maximal runs
+// of ranks where sigma does not increase; (#runs - 1) merges of the solved prefix with the next run over a value
+// array with pending pooled blocks laid over it; one fill at the end.
+struct ValOverlayHost {
+    const double* p;
+    const std::vector<int64_t>* lo;
+    const std::vector<int64_t>* hi;
+    const std::vector<double>* v;
+    double operator()(int64_t i) const {
+        for (size_t k = 0; k < lo->size(); ++k)
+            if (i >= (*lo)[k] && i < (*hi)[k]) return (*v)[k];
+        return p[i];
+    }
+};
+
+extern "C" int emul_pav_fewseg(int loss, int64_t n, const double* sigma, const double* m, double rho, int chunk_log2,
+                               double* val, int64_t* n_runs) {
+    const int64_t CH = int64_t(1) << chunk_log2;
+    const int64_t nch = (n + CH - 1) / CH;
+    for (int64_t i = 0; i < n; ++i) val[i] = rbl_block_prox(loss, sigma[i], m[i], rho);
+    std::vector<int64_t> bounds{0};
+    for (int64_t i = 1; i < n; ++i)
+        if (sigma[i] > sigma[i - 1]) bounds.push_back(i);
+    bounds.push_back(n);
+    if (n_runs) *n_runs = (int64_t)bounds.size() - 1;
+    // chunked double-double prefixes of sigma and m, exactly as the device lays them out
+    std::vector<double> lsh(n + 1), lsl(n + 1), lmh(n + 1), lml(n + 1);
+    std::vector<double> osh(nch + 1), osl(nch + 1), omh(nch + 1), oml(nch + 1);
+    dd_t ts = dd_make(0.0), tm = dd_make(0.0);
+    for (int64_t ch = 0; ch < nch; ++ch) {
+        osh[ch] = ts.hi; osl[ch] = ts.lo; omh[ch] = tm.hi; oml[ch] = tm.lo;
+        int64_t base = ch * CH, len = (n - base < CH) ? n - base : CH;
+        dd_t as = dd_make(0.0), am = dd_make(0.0);
+        for (int64_t i = 0; i < len; ++i) {
+            lsh[base + i] = as.hi; lsl[base + i] = as.lo; lmh[base + i] = am.hi; lml[base + i] = am.lo;
+            as = dd_add_d(as, sigma[base + i]);
+            am = dd_add_d(am, m[base + i]);
+        }
+        if (len < CH) { lsh[base + len] = as.hi; lsl[base + len] = as.lo; lmh[base + len] = am.hi; lml[base + len] = am.lo; }
+        ts = dd_add(ts, as);
+        tm = dd_add(tm, am);
+    }
+    osh[nch] = ts.hi; osl[nch] = ts.lo; omh[nch] = tm.hi; oml[nch] = tm.lo;
+    PrefixChunked ps{lsh.data(), lsl.data(), osh.data(), osl.data(), chunk_log2};
+    PrefixChunked pm{lmh.data(), lml.data(), omh.data(), oml.data(), chunk_log2};
+    std::vector<int64_t> blo, bhi;
+    std::vector<double> bv;
+    ValOverlayHost ov{val, &blo, &bhi, &bv};
+    for (size_t j = 1; j + 1 < bounds.size(); ++j) {
+        const int64_t b = bounds[j], c = bounds[j + 1];
+        int64_t lo, hi;
+        double vv;
+        if (!pav_merge_search_kary(loss, rho, ov, ps, pm, (int64_t)0, b, c, &lo, &hi, &vv)) continue;
+        std::vector<int64_t> nlo, nhi;
+        std::vector<double> nv;
+        for (size_t k = 0; k < blo.size(); ++k) {
+            if (blo[k] >= lo && bhi[k] <= hi) continue;  // swallowed whole
+            nlo.push_back(blo[k]); nhi.push_back(bhi[k]); nv.push_back(bv[k]);
+        }
+        nlo.push_back(lo); nhi.push_back(hi); nv.push_back(vv);
+        blo = nlo; bhi = nhi; bv = nv;
+    }
+    for (size_t k = 0; k < blo.size(); ++k) fill(val, blo[k], bhi[k], bv[k]);
+    return 0;
+}
+
 extern "C" uint64_t emul_key(double x) { uint64_t b; memcpy(&b, &x, 8); return rbl_key_from_bits(b); }
 extern "C" double emul_unkey(uint64_t k) { uint64_t b = rbl_bits_from_key(k); double x; memcpy(&x, &b, 8); return x; }
 extern "C" double emul_prox(int loss, double s, double m, double rho) { return rbl_block_prox(loss, s, m, rho); }

@@ -307,3 +307,38 @@ def test_native_loop_equals_per_iteration_loop(w_mode):
         assert a.engine._graph is not None and a.engine._graph_replays > 0
     a.engine.close()
     b.engine.close()
+
+
+def test_full_size_gram_route_equals_stream_route(w_mode, monkeypatch):
+    """BASELINE config-2 row count (n = 1M; d = 32 keeps it small): eight ADMM iterations with the w-step on
+    G = D^T D, the active-row gradient gather, the sparse dual pass and the replayed iteration graph must give the
+    iterates of the formulation that streams all of D for every FISTA trial — the size-independent property that
+    ties the fast route to the straightforward one at full n."""
+    if w_mode != "gram":
+        pytest.skip("runs both routes itself")
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    rng = np.random.default_rng(3)
+    n, d = 1_000_000, 32
+    X = rng.standard_normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:4] = rng.normal(size=4)
+    y = np.sign(X @ ws + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.01, args=[0.8], max_iter=8,
+              tol=1e-12)
+    res = {}
+    monkeypatch.setenv("RBL_SPARSE_CAP", "16")  # default d // 16 = 2 would keep this small d on the dense dual pass
+    for mode in ("gram", "stream"):
+        monkeypatch.setenv("RBL_W_MODE", mode)
+        s = ADMMmethod(X, y, **kw)
+        assert s.engine.w_mode == mode
+        with contextlib.redirect_stdout(io.StringIO()):
+            for i in range(8):
+                Optimizer.main_loop(s, i, 0.0, False)
+        res[mode] = (s.w.copy(), s.z.copy(), float(s.rho), dict(s.engine.active_stats), dict(s.engine.dual_stats),
+                     s.engine._graph is not None)
+        s.engine.close()
+    (wg, zg, rg, act, dual, graphed), (wst, zst, rst, _, _, _) = res["gram"], res["stream"]
+    assert _rel(wg, wst) < 1e-9 and _rel(zg, zst) < 1e-9 and rg == rst
+    assert graphed and act["gathered"] >= 4 and dual["sparse"] >= 4     # the fast route really ran
+    assert act["rows"] < 0.8 * act["calls"] * n                        # and read fewer rows than full passes

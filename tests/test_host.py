@@ -73,6 +73,8 @@ def _emul_lib():
     dp = ctypes.POINTER(ctypes.c_double)
     lib.emul_pav.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_int, dp,
                              ctypes.POINTER(ctypes.c_int64)]
+    lib.emul_pav_fewseg.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_int, dp,
+                                    ctypes.POINTER(ctypes.c_int64)]
     lib.emul_key.restype = ctypes.c_uint64
     lib.emul_key.argtypes = [ctypes.c_double]
     lib.emul_unkey.restype = ctypes.c_double
@@ -110,6 +112,47 @@ def test_device_pav_logic_matches_stack_pav_on_cpu():
                      z.ctypes.data_as(dp), None)
         assert np.max(np.abs(z - zo)) <= 1e-13 * max(1.0, np.max(np.abs(zo))), (trial, n, loss, kind)
         assert np.all(np.diff(z) >= 0)
+
+
+def test_few_segment_pav_route_matches_stack_pav_on_cpu():
+    """The few-segment route of the device PAV (level-0 ranges = runs of non-increasing sigma, merges over a lazily
+    overlaid value array, csrc/pav_kernels.cu) emulated on the host from the same header vs the oracle's stack PAV
+    — spectra with few runs (erm, superquantile, aorr, step functions) and, for the logic, arbitrary ones."""
+    lib = _emul_lib()
+    dp = ctypes.POINTER(ctypes.c_double)
+    rng = np.random.default_rng(23)
+    for trial in range(1200):
+        n = int(rng.integers(1, 500))
+        loss = ["binary_cross_entropy", "hinge"][trial % 2]
+        kind = trial % 6
+        m = np.sort(rng.normal(size=n) * 10 ** rng.uniform(-3, 1.5))
+        if kind == 0:
+            sig = np.ones(n) / n
+        elif kind == 1:
+            sig = O.spectrum("superquantile", n, [rng.uniform(0.05, 0.97)])
+        elif kind == 2:
+            sig = O.spectrum("aorr", n, [0.2, 0.8]) if n >= 5 else np.ones(n) / n
+        elif kind == 3:  # a few random steps up and down
+            sig = np.repeat(np.abs(rng.normal(size=5)) * (rng.random(5) > 0.3), -(-n // 5))[:n]
+        elif kind == 4:  # non-increasing pieces with a few jumps up
+            sig = np.sort(np.abs(rng.normal(size=n)))[::-1].copy()
+            for cut in rng.integers(0, n, size=3):
+                sig[cut:] += abs(rng.normal())
+        else:            # many runs: the route is not used on the device here, but the logic must still hold
+            sig = O.spectrum("extremile", n, [rng.uniform(1, 4)])
+        if trial % 7 == 0:
+            m = np.round(m, 1)
+        rho = 10 ** rng.uniform(-6, 1)
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        zo = O.pav_prox(loss, sig, m, rho)
+        z = np.empty_like(m)
+        runs = ctypes.c_int64(0)
+        lib.emul_pav_fewseg(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m.ctypes.data_as(dp), rho,
+                            int(rng.integers(1, 8)), z.ctypes.data_as(dp), ctypes.byref(runs))
+        assert np.max(np.abs(z - zo)) <= 1e-13 * max(1.0, np.max(np.abs(zo))), (trial, n, loss, kind, runs.value)
+        assert np.all(np.diff(z) >= 0)
+        if kind in (0, 1, 2):
+            assert runs.value <= 3, (kind, runs.value)
 
 
 def test_radix_key_transform_is_order_preserving():
