@@ -70,11 +70,25 @@ void rbl_set_error(const char* fmt, ...) {
 
 namespace {
 
+// Handle scratch is ONE slab: ctx_alloc runs twice, first measuring (alloc_mode 1), then carving pointers out of a
+// single cudaMalloc + cudaMemset (alloc_mode 2) — ~60 separate cudaMalloc/cudaMemset pairs used to cost ~0.1 s of
+// every solver construction.  Later additions (batched buffers) allocate directly (alloc_mode 0) and are tracked.
 template <class T>
 int dev_alloc(rbl_ctx* c, T** p, size_t count) {
     const size_t bytes = ((count ? count : 1) * sizeof(T) + 255) & ~(size_t)255;
+    if (c->alloc_mode == 1) {
+        c->slab_bytes += bytes;
+        *p = nullptr;
+        return RBL_OK;
+    }
+    if (c->alloc_mode == 2) {
+        *p = reinterpret_cast<T*>(c->slab + c->slab_off);
+        c->slab_off += bytes;
+        return RBL_OK;
+    }
     RBL_CUDA(cudaMalloc((void**)p, bytes));
     RBL_CUDA(cudaMemset(*p, 0, bytes));
+    if (c->n_extra < 32) c->extra[c->n_extra++] = (void*)*p;
     c->bytes += bytes;
     return RBL_OK;
 }
@@ -91,7 +105,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->sspart, (size_t)c->pass_grid));
     RBL_TRY(dev_alloc(c, &c->vpart, (size_t)4 * c->vec_grid));
     RBL_TRY(dev_alloc(c, &c->fista, 1));
-    RBL_CUDA(cudaMallocHost((void**)&c->fista_host, 2 * sizeof(FistaState)));
+    if (c->alloc_mode != 1) RBL_CUDA(cudaMallocHost((void**)&c->fista_host, 2 * sizeof(FistaState)));
     RBL_TRY(dev_alloc(c, &c->pow_tab, 128));
     RBL_TRY(dev_alloc(c, &c->beta, ld + 8));
     RBL_TRY(dev_alloc(c, &c->beta_p, ld + 8));
@@ -147,18 +161,26 @@ int ctx_alloc(rbl_ctx* c) {
 }
 
 void ctx_free(rbl_ctx* c) {
-    void* ptrs[] = {c->gpart,     c->sspart,    c->vpart,     c->fista,     c->pow_tab,   c->beta,      c->beta_p,
-                    c->beta_prev, c->g_p,       c->g_prev,    c->rbuf[0],   c->rbuf[1],   c->red_own,   c->c0part,
-                    c->keysA,     c->keysB,     c->valsA,     c->valsB,     c->tile_hist, c->ps_loc_hi, c->ps_loc_lo,
-                    c->ps_off_hi, c->ps_off_lo, c->ps_tot_hi, c->ps_tot_lo, c->pm_loc_hi, c->pm_loc_lo, c->pm_off_hi,
-                    c->pm_off_lo, c->ch_tot_hi, c->ch_tot_lo, c->sigma,     c->obj_tmp,   c->node_cnt,  c->gq_prev,   c->gxs,       c->gvu,
-                    c->gticket,   c->sup_idx,   c->sup_val,   c->sup_nnz,
-                    c->gvu2,      c->seg_count, c->seg_bounds, c->seg_blocks,
-                    c->sort_counts, c->act_cta_count, c->act_row, c->act_delta, c->act_total};
-    for (void* p : ptrs)
-        if (p) cudaFree(p);
+    if (c->slab) cudaFree(c->slab);
+    for (int i = 0; i < c->n_extra; ++i)
+        if (c->extra[i]) cudaFree(c->extra[i]);
     if (c->fista_host) cudaFreeHost(c->fista_host);
     if (c->bfista_host) cudaFreeHost(c->bfista_host);
+}
+
+int ctx_alloc_slab(rbl_ctx* c) {
+    c->alloc_mode = 1;
+    c->slab_bytes = 0;
+    int rc = ctx_alloc(c);
+    if (rc != RBL_OK) return rc;
+    RBL_CUDA(cudaMalloc((void**)&c->slab, c->slab_bytes));
+    RBL_CUDA(cudaMemset(c->slab, 0, c->slab_bytes));
+    c->bytes += c->slab_bytes;
+    c->alloc_mode = 2;
+    c->slab_off = 0;
+    rc = ctx_alloc(c);
+    c->alloc_mode = 0;
+    return rc;
 }
 
 inline cudaStream_t S(rbl_stream_t s) { return (cudaStream_t)s; }
@@ -191,17 +213,20 @@ int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global,
     RBL_REQUIRE(device >= 0 && device < ndev, "no CUDA device %d (found %d); this library has no CPU path", device,
                 ndev);
     RBL_CUDA(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    RBL_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) {
-        rbl_set_error("device %d is sm_%d%d; librbl_b200 is built for sm_100a (B200) only", device, prop.major,
-                      prop.minor);
+    // attributes one by one: cudaGetDeviceProperties fills ~100 fields and costs tens of milliseconds
+    int cc_major = 0, cc_minor = 0, num_sms = 0;
+    RBL_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    RBL_CUDA(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+    RBL_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
+    if (cc_major < 10) {
+        rbl_set_error("device %d is sm_%d%d; librbl_b200 is built for sm_100a (B200) only", device, cc_major,
+                      cc_minor);
         return RBL_ERR_UNSUPPORTED;
     }
     rbl_ctx* c = new rbl_ctx();
     memset(c, 0, sizeof(*c));
     c->device = device;
-    c->num_sms = prop.multiProcessorCount;
+    c->num_sms = num_sms;
     c->n_local = n_local;
     c->n_global = n_global;
     c->row_lo = row_lo;
@@ -209,7 +234,7 @@ int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global,
     c->ld = ld;
     c->vec_grid = c->num_sms * 4;
     int rc = rbl_pass_configure(c);
-    if (rc == RBL_OK) rc = ctx_alloc(c);
+    if (rc == RBL_OK) rc = ctx_alloc_slab(c);
     if (rc != RBL_OK) {
         ctx_free(c);
         delete c;

@@ -142,6 +142,11 @@ struct rbl_ctx {
     // ---- objective
     double* obj_tmp;        // n_global
     size_t bytes;           // total scratch allocated
+    char* slab;             // all handle scratch lives in one allocation (api.cu: ctx_alloc_slab)
+    size_t slab_bytes, slab_off;
+    int alloc_mode;         // 0 direct cudaMalloc, 1 measuring, 2 carving
+    void* extra[32];        // direct allocations made after creation (batched mode)
+    int n_extra;
 };
 
 // ---- launchers implemented in the kernel translation units --------------------------------------

@@ -83,19 +83,27 @@ class DeviceProblem:
         self.n_local, self.d = int(X.shape[0]), int(X.shape[1])
         self.n_global, self.row_lo = int(n_global), int(row_lo)
         self.ld = self.d + (self.d & 1)
+        import time as _time
+        self.build_times = {}
         with torch.cuda.device(self.device):
+            t0 = _time.perf_counter()
             h = ctypes.c_void_p()
             _cabi.check(self.lib.rbl_create(ctypes.byref(h), self.device.index or 0, self.n_local, self.n_global,
                                             self.row_lo, self.d, self.ld))
             self.h = h
+            t1 = _time.perf_counter()
             Xd = self._to_device(X).reshape(self.n_local, self.d)
             yd = self._to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not torch.is_tensor(y)
                                  else y.reshape(-1).to(torch.float64))
+            torch.cuda.current_stream().synchronize()
+            t2 = _time.perf_counter()
             self.D = torch.empty((self.n_local, self.ld), dtype=torch.float64, device=self.device)
             _cabi.check(self.lib.rbl_build_design(self.h, Xd.data_ptr(), self.d, yd.data_ptr(), self.D.data_ptr(),
                                                   self._stream()))
             torch.cuda.current_stream().synchronize()
+            t3 = _time.perf_counter()
             del Xd, yd
+            self.build_times.update(handle_scratch_s=t1 - t0, h2d_s=t2 - t1, design_s=t3 - t2)
             self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
             self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
             self._out4_np = self._out4_host.numpy()
@@ -199,7 +207,10 @@ class AdmmEngine(DeviceProblem):
         return cls(None, None, parent.loss, parent.sigma, clip=parent.clip, _share=parent)
 
     def __init__(self, X, y, loss, sigma, clip=None, **kw):
+        import time as _time
+        _t0 = _time.perf_counter()
         super().__init__(X, y, **kw)
+        _t1 = _time.perf_counter()
         if loss not in LOSS_IDS:
             raise ValueError(f"Unrecognized loss '{loss}'! Options: ['binary_cross_entropy', 'hinge']")
         self.loss, self.loss_id = loss, LOSS_IDS[loss]
@@ -255,8 +266,13 @@ class AdmmEngine(DeviceProblem):
         # transposed copy of D for the sparse-w dual pass: built once w has come out sparse, if it fits
         self.Dt = None
         self.transpose_ok = os.environ.get("RBL_TRANSPOSE", "1") != "0"
+        torch.cuda.current_stream(dev).synchronize()
+        _t2 = _time.perf_counter()
         if mode == "gram":
             self.gram()  # like the reference, which forms DTD in Optimizer.__init__ (algorithms.py:24)
+        if hasattr(self, "build_times"):
+            self.build_times.update(problem_total_s=_t1 - _t0, state_and_spectrum_s=_t2 - _t1,
+                                    gram_total_s=_time.perf_counter() - _t2)
         self._fista_eta = None
         self.fista_batch_min = int(os.environ.get("RBL_FISTA_BATCH", "4"))
 

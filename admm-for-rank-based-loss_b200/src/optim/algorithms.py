@@ -28,6 +28,7 @@ class Optimizer:
                  B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None):
         # _shard (extension, not in the reference): dict(row_lo=, n_global=[, group=]) when X, y are this
         # rank's contiguous rows of a row-sharded problem (one process per GPU, torch.distributed/NCCL)
+        _t0 = time.perf_counter()
         X = np.asarray(X)
         y = np.asarray(y)
         _shard = _shard or {}
@@ -77,6 +78,8 @@ class Optimizer:
         nl = self.engine.n_local
         self.engine.set_state(w=w_init, z=np.full(nl, lam0), lam=np.full(nl, lam0))
         self._w = w_init.astype(np.float64)
+        if hasattr(self.engine, "build_times"):
+            self.engine.build_times["constructor_total_s"] = time.perf_counter() - _t0
         self.fista_max_iter = 5000
         self.last_info = {}
 

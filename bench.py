@@ -197,7 +197,6 @@ def main():
     y_host.copy_(y_dev)
     del X_dev, y_dev
     torch.cuda.synchronize()
-    torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
@@ -207,6 +206,21 @@ def main():
     kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=L1_REG, args=[Q],
               max_iter=100_000, tol=TOL)
     shard = dict(row_lo=lo, n_global=n) if world > 1 else {}
+
+    # ---- process warm-up (untimed): a tiny solve of the same kind, so that the one-off costs of a fresh process —
+    # librbl_b200's module load on its first call, lazy loading of each kernel on its first launch, function
+    # attributes — are not charged to the end-to-end figure (the CUDA context itself is already up: the data above
+    # was generated on the device).  Same d, hence the same kernel instantiations; 4096 rows.
+    rng_w = np.random.default_rng(5)
+    Xw = rng_w.standard_normal((4096, d))
+    yw = np.sign(Xw @ planted_wstar(d) + 0.1 * rng_w.standard_normal(4096)).reshape(-1, 1)
+    yw[yw == 0] = 1.0
+    with contextlib.redirect_stdout(io.StringIO()):
+        warm = ADMMmethod(Xw, yw, **{**kw, "max_iter": 8})
+        warm.advance(0, 8)
+    warm.engine.close()
+    del warm, Xw, yw
+    torch.cuda.synchronize()
 
     # ---- upload + build (e2e part 1): pinned host -> HBM, D = -y (.) X -------------------------------
     barrier()
@@ -325,6 +339,9 @@ def main():
         solve = {"iterations": it2, "converged": bool(done),
                  "time_to_1e-6_s": round(t_warm + t_steps + t_tail, 3),
                  "time_to_1e-6_s_incl_upload": round(t_upload + t_warm + t_steps + t_tail, 3), "objective": obj, "nnz_w": int(np.count_nonzero(solver.w)),
+                 "phases_s": {"warmup_iterations_0_to_%d" % (W - 1): round(t_warm, 4),
+                              "timed_%d_iterations" % K: round(t_steps, 4),
+                              "continuation_to_stop_test": round(t_tail, 4)},
                  "primal": solver.primal_feasibility, "dual": solver.dual_feasibility,
                  "fista_passes_total": eng.fista_stats["passes"], "fista_calls": eng.fista_stats["calls"]}
         # degenerate-benchmark guard: the solve must do real work
@@ -364,9 +381,20 @@ def main():
     if gather is not None and eng.active_stats["gathered"] > 0:
         # the D-reading kernel of the step is the active-row gather; the streaming pass is kept for reference
         g_launches = K  # one gradient pass per ADMM iteration
+        traffic, traffic_note = None, "no ncu capture on file"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gather_traffic.json")))
+            per_row = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["active_rows"]
+            traffic = per_row * gather["active_rows"]
+            traffic_note = ("dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of this "
+                            "kernel (%d active rows: %.4f GB), scaled per active row to this launch; "
+                            "profiles/r01_gather_traffic.json" % (tj["active_rows"],
+                                                                  (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / 1e9))
+        except Exception:  # noqa: BLE001
+            pass
         roofline = {"bound": "hbm", "kernel": gather["kernel"], "achieved": gather["achieved"], "peak": peak,
-                    "peak_kind": peak_kind, "unit": "GB/s", "frac": gather["frac"], "traffic": None,
-                    "traffic_note": "ncu dram__bytes_read+write per launch: profiles/ (same state, --set full)",
+                    "peak_kind": peak_kind, "unit": "GB/s", "frac": gather["frac"], "traffic": traffic,
+                    "traffic_note": traffic_note,
                     "algorithmic_bytes_per_launch": gather["algorithmic_bytes_per_launch"],
                     "launch_ms": gather["launch_ms"], "active_rows": gather["active_rows"],
                     "active_fraction": gather["active_fraction"],
@@ -394,6 +422,7 @@ def main():
                    "fista_trials_in_timed_region": passes_timed,
                    "d_passes_in_timed_region": dpasses_timed,
                    "gram_build_s": solver.engine.gram_build_s,
+                   "build_times_s": {k: round(v, 4) for k, v in solver.engine.build_times.items()},
                    "active_rows": {**eng.active_stats, "note": "gradient pass reads only rows with z != m "
                                    "(b - D w = z - m is exactly 0 elsewhere); rows = total rows read over `calls`"},
                    "dual_pass": {**eng.dual_stats, "note": "D w reads only the sectors touched by nnz(w) when "
