@@ -7,7 +7,8 @@
 #include "common.cuh"
 
 // launchers defined in the kernel translation units
-int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, cudaStream_t s);
+int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
+                       cudaStream_t s);
 int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStream_t s);
 int rbl_k_fista_update(rbl_ctx* c, cudaStream_t s);
 int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s);
@@ -44,12 +45,13 @@ int rbl_k_gram_fista_steps(rbl_ctx* c, const double* G, int nsteps, cudaStream_t
 int rbl_k_gram_result(rbl_ctx* c, double* w_out, cudaStream_t s);
 int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double* red0, const double* w,
                     double* red_out, cudaStream_t s);
-size_t rbl_gram_scratch_doubles(rbl_ctx* c);
+size_t rbl_gram_scratch_doubles(rbl_ctx* c, int64_t nrows);
 int rbl_gram_persist_config(rbl_ctx* c);
 int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
                          float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
                          cudaStream_t s);
-int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s);
+int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate, double* G, double* scratch,
+                     cudaStream_t s);
 int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
                       double* lam, double rho, int cap, int support_ready, cudaStream_t s);
 int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s);
@@ -269,7 +271,14 @@ int rbl_info(rbl_handle_t h, int64_t* o) {
 int rbl_build_design(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(X && y && D && ldx >= h->d, "bad arguments");
-    return rbl_k_build_design(h, X, ldx, y, D, S(stream));
+    return rbl_k_build_design(h, X, ldx, y, D, h->n_local, S(stream));
+}
+
+int rbl_build_design_rows(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
+                          rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(X && y && D && ldx >= h->d && nrows >= 0 && nrows <= h->n_local, "bad arguments");
+    return nrows ? rbl_k_build_design(h, X, ldx, y, D, nrows, S(stream)) : RBL_OK;
 }
 
 int rbl_set_spectrum(rbl_handle_t h, const double* sigma, rbl_stream_t stream) {
@@ -576,15 +585,26 @@ int rbl_fista_batch_result(rbl_handle_t h, int B, double* w_out, double* r_out, 
 }
 
 // ---- Gram mode (gram_kernels.cu) ------------------------------------------------------------------
+static int gram_rows(rbl_handle_t h, const double* D, int64_t nrows, int accumulate, double* G, cudaStream_t s) {
+    double* scratch = nullptr;
+    const size_t bytes = rbl_gram_scratch_doubles(h, nrows) * sizeof(double);
+    RBL_CUDA(cudaMallocAsync((void**)&scratch, bytes, s));
+    int rc = rbl_k_gram_build(h, D, nrows, accumulate, G, scratch, s);
+    RBL_CUDA(cudaFreeAsync(scratch, s));
+    return rc;
+}
+
 int rbl_gram_build(rbl_handle_t h, const double* D, double* G, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(D && G, "null argument");
-    double* scratch = nullptr;
-    const size_t bytes = rbl_gram_scratch_doubles(h) * sizeof(double);
-    RBL_CUDA(cudaMallocAsync((void**)&scratch, bytes, S(stream)));
-    int rc = rbl_k_gram_build(h, D, G, scratch, S(stream));
-    RBL_CUDA(cudaFreeAsync(scratch, S(stream)));
-    return rc;
+    return gram_rows(h, D, h->n_local, 0, G, S(stream));
+}
+
+int rbl_gram_accumulate(rbl_handle_t h, const double* D_rows, int64_t nrows, int accumulate, double* G,
+                        rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(D_rows && G && nrows > 0 && nrows <= h->n_local, "bad arguments");
+    return gram_rows(h, D_rows, nrows, accumulate, G, S(stream));
 }
 
 int rbl_gram_fista_begin(rbl_handle_t h, const double* G, const double* w0, const double* red0, double lam,

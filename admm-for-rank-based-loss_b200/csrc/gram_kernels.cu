@@ -683,7 +683,7 @@ __global__ void __launch_bounds__(256) gram_syrk_kernel(const SyrkParams p) {
 
 // fixed-order sum of the split-K partials; the lower triangle is mirrored so G is exactly symmetric
 __global__ void gram_syrk_reduce_kernel(const double* __restrict__ part, int nslab, int npairs, int d, int64_t ldg,
-                                        double* __restrict__ G) {
+                                        double* __restrict__ G, int accumulate) {
     int ti, tj;
     pair_to_tiles(blockIdx.x, &ti, &tj);
     for (int e = threadIdx.x; e < kST * kST; e += blockDim.x) {
@@ -693,6 +693,7 @@ __global__ void gram_syrk_reduce_kernel(const double* __restrict__ part, int nsl
         for (int k = 0; k < nslab; ++k) s += part[((size_t)k * npairs + blockIdx.x) * (kST * kST) + e];
         const int i = ti * kST + li, j = tj * kST + lj;
         if (i < d && j < d) {
+            if (accumulate) s += G[(size_t)i * ldg + j];  // chunked build: same value on both sides of the diagonal
             G[(size_t)i * ldg + j] = s;
             G[(size_t)j * ldg + i] = s;
         }
@@ -783,38 +784,40 @@ int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double*
 }
 
 // scratch doubles rbl_k_gram_build needs for its split-K partials
-static void syrk_shape(rbl_ctx* c, int* ntile, int* npairs, int* nslab) {
+static void syrk_shape(rbl_ctx* c, int64_t nrows, int* ntile, int* npairs, int* nslab) {
     *ntile = (c->d + kST - 1) / kST;
     *npairs = *ntile * (*ntile + 1) / 2;
     // enough CTAs to fill the machine ~4x over, at least 256 rows per slab
     int64_t want = ((int64_t)c->num_sms * 4 + *npairs - 1) / *npairs;
-    const int64_t max_slabs = (c->n_local + 255) / 256;
+    const int64_t max_slabs = (nrows + 255) / 256;
     if (want > max_slabs) want = max_slabs;
     if (want < 1) want = 1;
     if (want > 64) want = 64;
     *nslab = (int)want;
 }
 
-size_t rbl_gram_scratch_doubles(rbl_ctx* c) {
+size_t rbl_gram_scratch_doubles(rbl_ctx* c, int64_t nrows) {
     int ntile, npairs, nslab;
-    syrk_shape(c, &ntile, &npairs, &nslab);
+    syrk_shape(c, nrows, &ntile, &npairs, &nslab);
     return (size_t)nslab * npairs * kST * kST;
 }
 
-int rbl_k_gram_build(rbl_ctx* c, const double* D, double* G, double* scratch, cudaStream_t s) {
+// G (+)= D_rows^T D_rows over `nrows` rows starting at D (accumulate != 0 adds to the G already there)
+int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate, double* G, double* scratch,
+                     cudaStream_t s) {
     SyrkParams p;
     int npairs;
-    syrk_shape(c, &p.ntile, &npairs, &p.nslab);
+    syrk_shape(c, nrows, &p.ntile, &npairs, &p.nslab);
     p.D = D;
     p.ld = c->ld;
-    p.n = c->n_local;
+    p.n = nrows;
     p.d = c->d;
     p.part = scratch;
-    RBL_CUDA(cudaMemsetAsync(G, 0, (size_t)c->d * c->ld * sizeof(double), s));
+    if (!accumulate) RBL_CUDA(cudaMemsetAsync(G, 0, (size_t)c->d * c->ld * sizeof(double), s));
     dim3 grid(npairs, p.nslab);
     gram_syrk_kernel<<<grid, 256, 0, s>>>(p);
     RBL_LAUNCH_CHECK();
-    gram_syrk_reduce_kernel<<<npairs, 256, 0, s>>>(scratch, p.nslab, npairs, c->d, c->ld, G);
+    gram_syrk_reduce_kernel<<<npairs, 256, 0, s>>>(scratch, p.nslab, npairs, c->d, c->ld, G, accumulate);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

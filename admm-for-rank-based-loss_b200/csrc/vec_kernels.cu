@@ -703,8 +703,9 @@ __global__ void objective_kernel(const double* __restrict__ u_sorted, const doub
 }  // namespace
 
 // ---- host launchers ----------------------------------------------------------------------------
-int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, cudaStream_t s) {
-    build_design_kernel<<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, D, c->ld, c->n_local, c->d);
+int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
+                       cudaStream_t s) {
+    build_design_kernel<<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, D, c->ld, nrows, c->d);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -26,6 +26,7 @@ _SIGNATURES = {
     "rbl_destroy": (_c.c_int, [_c.c_void_p]),
     "rbl_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int64)]),
     "rbl_build_design": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _dp, _dp, _c.c_void_p]),
+    "rbl_build_design_rows": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _dp, _dp, _c.c_int64, _c.c_void_p]),
     "rbl_set_spectrum": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
     "rbl_matvec": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_margins": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_double, _dp, _c.c_void_p]),
@@ -57,6 +58,7 @@ _SIGNATURES = {
     "rbl_fista_poll": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int32), _c.POINTER(_c.c_double)]),
     "rbl_fista_result": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
     "rbl_gram_build": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
+    "rbl_gram_accumulate": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _c.c_int, _dp, _c.c_void_p]),
     "rbl_gram_fista_begin": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_float, _c.c_double,
                                         _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_persistent_ok": (_c.c_int, [_c.c_void_p]),

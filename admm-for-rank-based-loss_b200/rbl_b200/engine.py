@@ -49,7 +49,7 @@ class DeviceProblem:
     """D = -y (.) X resident in HBM (row-major, padded to an even leading dimension) plus the library
     handle that owns the scratch for passes, sort and PAV over it."""
 
-    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None, _share=None):
+    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None, _share=None, _want_gram=False):
         self.lib = _cabi.load()
         self._parent = _share
         if _share is not None:
@@ -92,17 +92,26 @@ class DeviceProblem:
                                             self.row_lo, self.d, self.ld))
             self.h = h
             t1 = _time.perf_counter()
-            Xd = self._to_device(X).reshape(self.n_local, self.d)
+            self.G = None
             yd = self._to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not torch.is_tensor(y)
                                  else y.reshape(-1).to(torch.float64))
-            torch.cuda.current_stream().synchronize()
-            t2 = _time.perf_counter()
             self.D = torch.empty((self.n_local, self.ld), dtype=torch.float64, device=self.device)
-            _cabi.check(self.lib.rbl_build_design(self.h, Xd.data_ptr(), self.d, yd.data_ptr(), self.D.data_ptr(),
-                                                  self._stream()))
-            torch.cuda.current_stream().synchronize()
-            t3 = _time.perf_counter()
-            del Xd, yd
+            chunk = int(os.environ.get("RBL_PIPELINE_ROWS", "0")) or max(4096, (256 << 20) // (8 * self.d))  # ~256 MB
+            if (not torch.is_tensor(X)) and self.n_local >= 4 * chunk and os.environ.get("RBL_PIPELINE", "1") != "0":
+                # host array: upload X chunk by chunk on a copy stream while the previous chunk is turned into rows
+                # of D = -y*X and (Gram mode) accumulated into G = D^T D — the 2 n d^2 flop of G hide behind PCIe
+                self._upload_pipelined(X, yd, chunk, _want_gram)
+                t2 = t3 = _time.perf_counter()
+            else:
+                Xd = self._to_device(X).reshape(self.n_local, self.d)
+                torch.cuda.current_stream().synchronize()
+                t2 = _time.perf_counter()
+                _cabi.check(self.lib.rbl_build_design(self.h, Xd.data_ptr(), self.d, yd.data_ptr(),
+                                                      self.D.data_ptr(), self._stream()))
+                torch.cuda.current_stream().synchronize()
+                t3 = _time.perf_counter()
+                del Xd
+            del yd
             self.build_times.update(handle_scratch_s=t1 - t0, h2d_s=t2 - t1, design_s=t3 - t2)
             self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
             self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
@@ -114,6 +123,36 @@ class DeviceProblem:
         _cabi.check(self.lib.rbl_info(self.h, info))
         self.info = dict(zip(["num_sms", "pass_grid", "rows_per_tile", "pass_stages", "pass_smem", "scratch_bytes",
                               "vec_grid", "pav_chunk"], list(info)))
+
+    def _upload_pipelined(self, X, yd, chunk, want_gram):
+        n, d, dev = self.n_local, self.d, self.device
+        Xt = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64)).reshape(n, d)  # no copy for fp64 C-order
+        main = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty((chunk, d), dtype=torch.float64, device=dev) for _ in range(2)]
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        consumed = [torch.cuda.Event(), torch.cuda.Event()]
+        if want_gram:
+            self.G = torch.empty((d, self.ld), dtype=torch.float64, device=dev)
+        copy_stream.wait_stream(main)
+        ms = ctypes.c_void_p(main.cuda_stream)
+        for k, r0 in enumerate(range(0, n, chunk)):
+            r1, b = min(n, r0 + chunk), k % 2
+            with torch.cuda.stream(copy_stream):
+                if k >= 2:
+                    copy_stream.wait_event(consumed[b])
+                stage[b][: r1 - r0].copy_(Xt[r0:r1], non_blocking=True)
+                copied[b].record(copy_stream)
+            main.wait_event(copied[b])
+            Dk = self.D[r0:r1]
+            _cabi.check(self.lib.rbl_build_design_rows(self.h, stage[b].data_ptr(), d, yd[r0:].data_ptr(),
+                                                       Dk.data_ptr(), r1 - r0, ms))
+            if want_gram:
+                _cabi.check(self.lib.rbl_gram_accumulate(self.h, Dk.data_ptr(), r1 - r0, 1 if k else 0,
+                                                         self.G.data_ptr(), ms))
+            consumed[b].record(main)
+        main.synchronize()
+        self.gram_during_upload = bool(want_gram)
 
     # ---- plumbing ----------------------------------------------------------------------------
     def _stream(self):
@@ -209,6 +248,11 @@ class AdmmEngine(DeviceProblem):
     def __init__(self, X, y, loss, sigma, clip=None, **kw):
         import time as _time
         _t0 = _time.perf_counter()
+        if kw.get("_share") is None and X is not None:
+            # the w-step formulation is known from the shape alone: let the upload accumulate G on the way
+            n_g, d_ = int(kw.get("n_global") or np.shape(X)[0]), int(np.shape(X)[1])
+            m_ = os.environ.get("RBL_W_MODE", "auto").lower()
+            kw["_want_gram"] = (m_ == "gram") or (m_ == "auto" and d_ <= 4096 and n_g >= 2 * d_)
         super().__init__(X, y, **kw)
         _t1 = _time.perf_counter()
         if loss not in LOSS_IDS:
@@ -247,7 +291,8 @@ class AdmmEngine(DeviceProblem):
         if mode == "auto":
             mode = "gram" if (d <= 4096 and ng >= 2 * d) else "stream"
         self.w_mode = mode
-        self.G = None
+        if not hasattr(self, "G"):
+            self.G = None
         self.gram_build_s = 0.0
         self._persistent = None
         self._fista_info_pending = False
@@ -301,21 +346,27 @@ class AdmmEngine(DeviceProblem):
                 self.red0 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
                 self.red1 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
                 _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red0.data_ptr()))
+            self._gram_reduced = True
         if self.G is None:
             t0 = torch.cuda.Event(enable_timing=True)
             t1 = torch.cuda.Event(enable_timing=True)
             with torch.cuda.device(self.device):
                 self.G = torch.empty((self.d, self.ld), dtype=torch.float64, device=self.device)
+                t0.record()
+                _cabi.check(self.lib.rbl_gram_build(self.h, self.D.data_ptr(), self.G.data_ptr(), self._stream()))
+                t1.record()
+                t1.synchronize()
+            self.gram_build_s = t0.elapsed_time(t1) * 1e-3
+            self._gram_reduced = False
+        if not getattr(self, "_gram_reduced", False):
+            self.all_reduce(self.G)  # row shards: G is the sum of the per-rank Grams
+            self._gram_reduced = True
+        if not hasattr(self, "red0"):
+            with torch.cuda.device(self.device):
                 self.red0 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
                 self.red1 = torch.zeros(self.d + 2, dtype=torch.float64, device=self.device)
                 # reductions of the gradient pass land in red0 directly (no copy node)
                 _cabi.check(self.lib.rbl_fista_bind_red(self.h, self.red0.data_ptr()))
-                t0.record()
-                _cabi.check(self.lib.rbl_gram_build(self.h, self.D.data_ptr(), self.G.data_ptr(), self._stream()))
-                self.all_reduce(self.G)
-                t1.record()
-                t1.synchronize()
-            self.gram_build_s = t0.elapsed_time(t1) * 1e-3
         return self.G
 
     def _build_transpose(self):

@@ -60,6 +60,11 @@ int rbl_info(rbl_handle_t h, int64_t* h_out);
 /* D = -y (.) X, zero padding up to ld.  algorithms.py:23 */
 int rbl_build_design(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, rbl_stream_t stream);
 
+/* the same for `nrows` rows only (X, y, D point at the first of them): lets the host layer build D chunk by chunk
+ * while the next chunk of X is still in flight over PCIe */
+int rbl_build_design_rows(rbl_handle_t h, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
+                          rbl_stream_t stream);
+
 /* rank-order spectrum sigma (n_global) used by the PAV: alphas, or betas for EHRM.  algorithms.py:74-75 */
 int rbl_set_spectrum(rbl_handle_t h, const double* sigma, rbl_stream_t stream);
 
@@ -146,6 +151,10 @@ int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t 
  * G is row-major d x ld (same leading dimension as D), exactly symmetric. */
 /* G = D^T D over this rank's rows (FP64 tensor cores); a row-sharded host layer all-reduces it once */
 int rbl_gram_build(rbl_handle_t h, const double* D, double* G, rbl_stream_t stream);
+/* G (+)= D_rows^T D_rows over `nrows` rows starting at D_rows (accumulate = 0 overwrites G): the chunked form of
+ * rbl_gram_build, overlapped with the upload of the design matrix */
+int rbl_gram_accumulate(rbl_handle_t h, const double* D_rows, int64_t nrows, int accumulate, double* G,
+                        rbl_stream_t stream);
 /* FISTA (fast_lasso.py:22-69) on G: same trial points, same accept/reject rule (LHS - RHS = D.G D - L||D||^2),
  * same float32 L schedule; state polled with rbl_fista_poll (passes = sweeps over G).  w0 and red0 are
  * caller-owned and must stay valid until the call converges. */

@@ -258,3 +258,30 @@ def test_active_row_gradient_pass(E, wf, args, loss, n, d, frac):
     assert np.max(np.abs(red_f[:d] - gref) / np.maximum(scale, np.abs(D).T @ np.abs(e.b.cpu().numpy()) * 1e-2)) < 1e-13
     assert abs(red_a[d] - delta @ delta) <= 1e-13 * (delta @ delta)
     e.close()
+
+
+def test_pipelined_upload_builds_the_same_design_and_gram(E, monkeypatch):
+    """Host arrays are uploaded chunk by chunk while D = -y*X and G = D^T D are built behind the copy
+    (engine._upload_pipelined); D must be bit-identical to the one-shot build and G equal up to the summation
+    order of the chunks."""
+    engine, _ = E
+    rng = np.random.default_rng(8)
+    n, d = 21001, 65   # odd d: padded leading dimension; ragged last chunk
+    X = rng.normal(size=(n, d))
+    y = np.where(rng.random(n) > 0.5, 1.0, -1.0)
+    monkeypatch.setenv("RBL_W_MODE", "gram")
+    monkeypatch.setenv("RBL_PIPELINE_ROWS", "4096")
+    a = engine.AdmmEngine(X, y, "binary_cross_entropy", np.ones(n) / n)
+    assert getattr(a, "gram_during_upload", False)
+    monkeypatch.setenv("RBL_PIPELINE", "0")
+    b = engine.AdmmEngine(X, y, "binary_cross_entropy", np.ones(n) / n)
+    assert not getattr(b, "gram_during_upload", False)
+    np.testing.assert_array_equal(a.D.cpu().numpy(), b.D.cpu().numpy())
+    np.testing.assert_array_equal(a.D[:, :d].cpu().numpy(), -y[:, None] * X)
+    Ga, Gb = a.gram()[:, :d].cpu().numpy(), b.gram()[:, :d].cpu().numpy()
+    ref = X.T @ X
+    assert np.max(np.abs(Ga - ref)) < 1e-13 * np.max(np.abs(ref)) and np.max(np.abs(Gb - ref)) < 1e-13 * np.max(np.abs(ref))
+    np.testing.assert_array_equal(Ga, Ga.T)
+    assert float(a.G[:, d:].abs().sum()) == 0.0
+    a.close()
+    b.close()
