@@ -66,7 +66,7 @@ def test_matvec_and_fused_pass(E, n, d):
     e.close()
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100003, 1 << 20])
+@pytest.mark.parametrize("n", [1, 2, 31, 4096, 4097, 100003, 1 << 20, 4_000_037])
 def test_sort_bit_exact_vs_stable_argsort(E, n):
     rng = np.random.default_rng(n)
     e = _mk(E, np.zeros((n, 2)))
@@ -79,12 +79,18 @@ def test_sort_bit_exact_vs_stable_argsort(E, n):
     cases["special"] = sp
     for name, m in cases.items():
         md = e.vec(m)
-        E[1].check(e.lib.rbl_sort_margins(e.h, md.data_ptr(), e.m_sorted.data_ptr(), e.perm.data_ptr(), e._stream()))
-        perm = e.perm.cpu().numpy()
-        ms = e.m_sorted.cpu().numpy()
         ref = np.argsort(m, kind="stable")
-        np.testing.assert_array_equal(perm, ref, err_msg=name)          # bit-exact permutation
-        np.testing.assert_array_equal(ms, m[ref] + 0.0, err_msg=name)   # -0.0 is canonicalised to +0.0
+        # both implementations: the persistent cooperative kernel (default) and the three-launches-per-pass one
+        for legacy in (0, 1):
+            E[1].check(e.lib.rbl_sort_config(e.h, legacy))
+            e.perm.zero_()
+            e.m_sorted.zero_()
+            E[1].check(e.lib.rbl_sort_margins(e.h, md.data_ptr(), e.m_sorted.data_ptr(), e.perm.data_ptr(),
+                                              e._stream()))
+            perm = e.perm.cpu().numpy()
+            ms = e.m_sorted.cpu().numpy()
+            np.testing.assert_array_equal(perm, ref, err_msg=f"{name} legacy={legacy}")         # bit-exact permutation
+            np.testing.assert_array_equal(ms, m[ref] + 0.0, err_msg=f"{name} legacy={legacy}")  # -0.0 -> +0.0
     e.close()
 
 

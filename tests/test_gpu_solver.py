@@ -58,8 +58,14 @@ def test_zstep_vs_reference_golden_and_oracle(golden_dir):
         s.engine.close()
 
 
-def test_fista_vs_reference_golden_and_oracle(golden_dir, w_mode):
+@pytest.mark.parametrize("persistent", [True, False])
+def test_fista_vs_reference_golden_and_oracle(golden_dir, w_mode, persistent, monkeypatch):
     from src.util.fast_lasso import FISTA
+
+    if not persistent:
+        if w_mode != "gram":
+            pytest.skip("the persistent kernel is a Gram-mode feature")
+        monkeypatch.setenv("RBL_GRAM_PERSISTENT", "0")  # one launch per line-search trial (what large d falls back to)
 
     g = _load(golden_dir, "fista.npz")
     d = _load(golden_dir, "data_300x40.npz")
