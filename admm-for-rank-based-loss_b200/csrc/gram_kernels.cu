@@ -297,6 +297,7 @@ struct GramPersist {
     float L0;
     int thr_f32, max_iter;
     const double* scal;   // device block [rho, lam, thr_f32] overriding lam / thr_f32 when bound (may be null)
+    unsigned long long* dbg;  // dev tool: %globaltimer stamps of CTA 0 (null: off)
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned int* ctr, unsigned int target) {
@@ -388,6 +389,15 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
     unsigned int target = 0;
     __syncthreads();
+    int dbg_n = 0;
+    auto stamp = [&]() {
+        if (p.dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 60) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            p.dbg[1 + dbg_n++] = tt;
+        }
+    };
+    stamp();
 
     while (true) {
         // ---- KC candidates: beta_i = soft(beta_p + g_p / L_i, lam / L_i), L_i = L_prev * eta^(i_k0 + i)
@@ -414,6 +424,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             }
         }
         block_sum_vec<KC>(r1, sh);  // its barriers also publish DEL
+        stamp();
         // ---- u_i = G Delta_i for my rows
         double* vu = p.vu + (size_t)par * KC * ld;
         for (int row = row0 + warp; row < row1; row += kGWarps) {
@@ -439,8 +450,10 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             }
         }
         ++sweeps;
+        stamp();
         target += gridDim.x;
         grid_barrier(p.bar, target);
+        stamp();
         // ---- line search, identical in every CTA: first i with NOT (Delta_i.G Delta_i > L_i ||Delta_i||^2)
         double lhs[KC];
 #pragma unroll
@@ -450,6 +463,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             for (int q = 0; q < KC; ++q) lhs[q] = fma(DEL[(size_t)q * ld + c], __ldcg(&vu[(size_t)q * ld + c]), lhs[q]);
         }
         block_sum_vec<KC>(lhs, sh);
+        stamp();
         int acc_q = -1;
 #pragma unroll
         for (int q = 0; q < KC; ++q)
@@ -500,7 +514,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         }
         i_k0 = 0;
         __syncthreads();
+        stamp();
     }
+    stamp();
     if (blockIdx.x == 0) {
         for (int c = tid; c < d; c += nt) {
             const double b = BETA[c];
@@ -556,6 +572,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     }
     // leave the barrier words clean for the next launch: the last CTA out resets them (no memset node needed)
     __syncthreads();
+    stamp();
+    if (p.dbg && blockIdx.x == 0 && tid == 0) p.dbg[0] = (unsigned long long)dbg_n;
     if (tid == 0) {
         const unsigned int tk = atomicAdd(p.bar + 1, 1u);
         if (tk == gridDim.x - 1) {
@@ -895,6 +913,7 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
     p.thr_f32 = thr_f32;
     p.max_iter = max_iter;
     p.scal = c->scal;
+    p.dbg = c->sort_dbg;  // shared dev-tool buffer (rbl_sort_debug)
     void* args[] = {(void*)&p};
     const void* fn = c->gp_kc == 8   ? (const void*)gram_fista_persistent_kernel<8>
                      : c->gp_kc == 4 ? (const void*)gram_fista_persistent_kernel<4>

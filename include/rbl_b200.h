@@ -78,8 +78,9 @@ int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho,
 int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream);
 /* legacy != 0: three launches per radix pass instead of the single persistent cooperative kernel (testing) */
 int rbl_sort_config(rbl_handle_t h, int legacy);
-/* dev tool: d_stamps (48 x u64, device) receives %globaltimer at 6 phase boundaries of each of the 8 passes of
- * the persistent sort (CTA 0); NULL switches it off */
+/* dev tool: d_stamps (64 x u64, device) receives %globaltimer stamps of CTA 0 — the persistent sort writes 6 phase
+ * boundaries for each of its 8 passes ([pass][6]), the persistent Gram-FISTA kernel a count in [0] followed by its
+ * phase boundaries (scripts/sort_phases.py, scripts/fista_phases.py); NULL switches it off */
 int rbl_sort_debug(rbl_handle_t h, uint64_t* d_stamps);
 
 /* z_sorted = argmin_{z1<=..<=zn} sum sigma_i loss(z_i) + rho/2 (z_i - m_i)^2.  pav.py:54-178,
