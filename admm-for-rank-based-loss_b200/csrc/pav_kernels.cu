@@ -169,6 +169,7 @@ struct TreeParams {
     unsigned int* node_cnt;
     int64_t nchunks;
     double *pm_off_hi_w, *pm_off_lo_w;  // writable views of pm_off_* (the few-segment merge kernel scans them itself)
+    unsigned long long* dbg;            // dev tool: %globaltimer stamps (null: off)
 };
 
 // one merge of two solved ranges by a full warp (shared- or global-memory values): the rounds of pav_merge_search_kary (pav_core.h, which the CPU
@@ -468,6 +469,15 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
     __shared__ int64_t s_end[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double rho = P.scal ? P.scal[0] : P.rho;
+    int dbg_n = 0;
+    auto stamp = [&]() {
+        if (P.dbg && tid == 0 && dbg_n < 60) {
+            unsigned long long tt;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tt));
+            P.dbg[1 + dbg_n++] = tt;
+        }
+    };
+    stamp();
     if (tid == 0) s_nblk = 0;
     {   // exclusive scan of the chunk totals of the margins (what chunk_offsets_kernel does for the tree route):
         // 64 threads x contiguous slices, double-double throughout
@@ -516,6 +526,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
         }
     }
     __syncthreads();  // offsets (global memory, this CTA's own writes) and s_nblk visible
+    stamp();
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
     PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
     ValOverlay val{P.val, &s_nblk, s_lo, s_hi, s_v};
@@ -528,6 +539,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
             if (lane == 0) s_end[warp] = e;
         }
         __syncthreads();
+        stamp();
         if (violated && tid == 0) {
             int64_t lo, hi;
             double v;
@@ -548,7 +560,9 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
             s_nblk = k2 + 1;
         }
         __syncthreads();
+        stamp();
     }
+    if (P.dbg && tid == 0) P.dbg[0] = (unsigned long long)dbg_n;
     if (tid == 0) {
         out->nblk = s_nblk;
         for (int k = 0; k < s_nblk; ++k) {
@@ -670,6 +684,7 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.nchunks = nch;
     P.pm_off_hi_w = c->pm_off_hi;
     P.pm_off_lo_w = c->pm_off_lo;
+    P.dbg = c->sort_dbg;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
         pav_seg_merge_kernel<<<1, 64, 0, s>>>(P, c->seg_bounds, c->nseg, blk);
