@@ -21,7 +21,10 @@ int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const i
                          double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s);
 int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
                     cudaStream_t s);
-int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s);
+int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s,
+               const int32_t* prev_perm = nullptr);
+int rbl_ss_buckets(int64_t n);
+size_t rbl_ss_slots(int64_t n);
 int rbl_sort_tiles(int64_t n);
 int rbl_pav_chunk_log2();
 int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double* loc_lo, double* tot_hi,
@@ -138,6 +141,11 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->valsB, ng));
     RBL_TRY(dev_alloc(c, &c->tile_hist, (size_t)256 * c->sort_tiles + 256 + 8));
     RBL_TRY(dev_alloc(c, &c->sort_counts, (size_t)256 * c->num_sms));
+    c->ss_nb = rbl_ss_buckets(c->n_global);
+    RBL_TRY(dev_alloc(c, &c->ss_bkey, rbl_ss_slots(c->n_global)));
+    RBL_TRY(dev_alloc(c, &c->ss_bval, rbl_ss_slots(c->n_global)));
+    RBL_TRY(dev_alloc(c, &c->ss_count, (size_t)4096 + 8));
+    RBL_TRY(dev_alloc(c, &c->ss_flag, 16));
     c->chunk_log2 = rbl_pav_chunk_log2();
     c->nchunks = (c->n_global + ((int64_t)1 << c->chunk_log2) - 1) >> c->chunk_log2;
     const size_t nch = (size_t)c->nchunks;
@@ -311,6 +319,13 @@ int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t*
     return rbl_k_sort(h, m, h->n_global, m_sorted, perm, S(stream));
 }
 
+int rbl_sort_margins_near(rbl_handle_t h, const double* m, const int32_t* prev_perm, double* m_sorted,
+                          int32_t* perm, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(m && (m_sorted || perm), "null argument");
+    return rbl_k_sort(h, m, h->n_global, m_sorted, perm, S(stream), prev_perm);
+}
+
 int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, double* z_sorted,
                  rbl_stream_t stream) {
     RBL_ENTER(h);
@@ -329,7 +344,21 @@ int rbl_bind_scalars(rbl_handle_t h, const double* d_scal) {
 
 int rbl_sort_config(rbl_handle_t h, int legacy) {
     RBL_REQUIRE(h != nullptr, "null handle");
-    h->sort_legacy = legacy ? 1 : 0;
+    h->sort_legacy = (legacy & 1) ? 1 : 0;
+    h->ss_off = (legacy & 2) ? 1 : 0;
+    return RBL_OK;
+}
+
+int rbl_sort_stats(rbl_handle_t h, rbl_stream_t stream, int32_t* h_out) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(h_out != nullptr, "null argument");
+    int tmp[8];
+    RBL_CUDA(cudaMemcpyAsync(tmp, h->ss_flag, sizeof(tmp), cudaMemcpyDeviceToHost, S(stream)));
+    RBL_CUDA(cudaStreamSynchronize(S(stream)));
+    h_out[0] = h->ss_nb;
+    h_out[1] = tmp[4];  // route of the last hinted call: 1 buckets, 2 LSD fallback, 0 none yet
+    h_out[2] = tmp[5];  // its largest bucket
+    h_out[3] = tmp[0];  // overflow flag right now (0 between calls)
     return RBL_OK;
 }
 

@@ -190,6 +190,11 @@ struct PSortParams {
     int32_t* perm_out;
     int64_t chunk;
     unsigned long long* dbg;  // optional [8][6] globaltimer stamps of CTA 0 (dev tool)
+    const int* gate;          // run only if *gate != 0 (the splitter sort overflowed); null: always run
+    int* ss_flag;             // splitter-sort state cleaned up on exit when gated: overflow flag,
+    uint32_t* ss_count;       //   bucket counts [ss_nb]
+    int ss_nb;
+    int* ss_stats;            // [0] route of the last hinted call (1 buckets, 2 LSD fallback), [1] largest bucket
 };
 
 __device__ __forceinline__ void sort_grid_barrier(unsigned int* ctr, unsigned int target) {
@@ -221,6 +226,7 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
     uint32_t* sval = reinterpret_cast<uint32_t*>(skey + kPTile);                         // [kPTile]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, me = blockIdx.x;
+    if (p.gate && *p.gate == 0) return;  // the splitter sort handled this call (every CTA sees the same flag)
     const int64_t r0 = (int64_t)me * p.chunk;
     const int64_t r1 = (r0 + p.chunk < p.n) ? r0 + p.chunk : p.n;
     const int ntile = r0 < r1 ? (int)((r1 - r0 + kPTile - 1) / kPTile) : 0;
@@ -457,12 +463,267 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
         stamp(5);
     }
     // leave the barrier words clean for the next launch: the last CTA out resets them (no memset node needed)
+    if (p.gate) {  // fallback run: leave the splitter sort's counters and flag clean for the next call
+        if (me == 0 && tid == 0) {
+            p.ss_stats[0] = 2;
+            p.ss_stats[1] = 0;
+        }
+        __syncthreads();
+        for (int b = me * kPT + tid; b < p.ss_nb; b += G * kPT) {
+            atomicMax(&p.ss_stats[1], (int)p.ss_count[b]);
+            p.ss_count[b] = 0u;
+        }
+        __threadfence();
+        __syncthreads();
+    }
     if (tid == 0) {
         const unsigned int tk = atomicAdd(p.bar + 1, 1u);
         if (tk == gridDim.x - 1) {
             p.bar[0] = 0u;
             p.bar[1] = 0u;
+            if (p.gate) *p.ss_flag = 0;
             __threadfence();
+        }
+    }
+}
+
+// ---- splitter sort: partition by the PREVIOUS rank order, then sort every bucket in shared memory -----------
+// Between two ADMM iterations the rank order of the margins changes little (even when their values shift or scale
+// a lot, as they do while rho is small): the rows that sat at B - 1 evenly spaced ranks in the last z-step are read
+// at their NEW values, sorted, and used as splitters — B buckets of ~n/B keys each (B = 512 at n = 1M; measured
+// along a solve: largest bucket <= 2.1x the mean from iteration 3 on, <= 1.1x from iteration 10).  One pass
+// scatters (key, index) into per-bucket slots (arrival order is irrelevant), then one CTA per bucket sorts its
+// <= 4096 keys in shared memory by (key, index) — a total order that equals the stable sort order — and writes
+// its slice of the output at the prefix of the bucket counts.  No grid barrier and two launches instead of the
+// 16 barriers of the LSD sort.  If any bucket would overflow (first call, margins all equal, a jump in the data)
+// the partition raises a device flag: the bucket kernel exits and the gated LSD kernel runs instead.
+constexpr int kSSCap = 4096;       // slots per bucket
+constexpr int kSSThreads = 1024;
+constexpr int kSSItems = 4;        // keys per thread in the partition kernel
+
+struct SSParams {
+    const double* m;
+    int64_t n;
+    const int32_t* prev_perm;   // permutation of an earlier call (splitters: today's keys of the rows that sat at
+                                // evenly spaced ranks then)
+    int nb;                     // buckets (power of two, <= 4096)
+    uint64_t* bkey;             // [nb][kSSCap]
+    uint32_t* bval;
+    uint32_t* count;            // [nb], zero on entry
+    int* flag;                  // overflow flag, zero on entry
+    unsigned int* ticket;       // last-CTA ticket of the bucket kernel, zero on entry
+    int* stats;                 // [0] route taken, [1] largest bucket (instrumentation)
+    double* sorted_out;
+    int32_t* perm_out;
+};
+
+__global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams p) {
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int nb2 = 16;  // the splitter array is sorted by a power-of-two network: pad with maximal keys
+    while (nb2 < p.nb) nb2 <<= 1;
+    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);          // [nb2] spl[j] = first key of bucket j (spl[0] = 0)
+    uint32_t* hist = reinterpret_cast<uint32_t*>(spl + nb2);   // [nb] tile counts, then tile bases
+    const int tid = threadIdx.x, nb = p.nb;
+    for (int j = tid; j < nb2; j += kSSThreads) {
+        uint64_t k = 0ull;
+        if (j >= nb) {
+            k = 0xffffffffffffffffull;
+        } else if (j > 0) {
+            const int64_t pos = (int64_t)(((__int128)j * p.n) / nb);
+            int64_t row = p.prev_perm[pos];
+            row = row < 0 ? 0 : (row >= p.n ? p.n - 1 : row);
+            k = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[row]);
+        }
+        spl[j] = k;
+        if (j < nb) hist[j] = 0u;
+    }
+    __syncthreads();
+    // the sampled rows kept their order almost everywhere: a bitonic network puts the splitters in exact order
+    // (every CTA sorts its own copy; nb2 <= 4096, warp-local stages for distances <= 32)
+    {
+        const int warp = tid >> 5, lane = tid & 31, npair = nb2 >> 1;
+        auto cx = [&](int t, int j, int k) {
+            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
+            const uint64_t a = spl[i], b2 = spl[l];
+            if ((a > b2) == ((i & k) == 0)) {
+                spl[i] = b2;
+                spl[l] = a;
+            }
+        };
+        for (int k = 2; k <= nb2; k <<= 1) {
+            int j = k >> 1;
+            for (; j > 32; j >>= 1) {
+                for (int t = tid; t < npair; t += kSSThreads) cx(t, j, k);
+                __syncthreads();
+            }
+            for (int t0 = warp * 32; t0 < npair; t0 += kSSThreads) {
+                for (int jj = j; jj > 0; jj >>= 1) {
+                    if (t0 + lane < npair) cx(t0 + lane, jj, k);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) spl[0] = 0ull;  // bucket 0 starts at the smallest key (the 0 placed there sorted to the front)
+        __syncthreads();
+    }
+    const int64_t base = (int64_t)blockIdx.x * (kSSThreads * kSSItems);
+    uint64_t key[kSSItems];
+    int bkt[kSSItems];
+    uint32_t rnk[kSSItems];
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q) {
+        const int64_t i = base + q * kSSThreads + tid;
+        bkt[q] = -1;
+        if (i < p.n) {
+            key[q] = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[i]);
+            int lo = 0, hi = nb;  // largest j with spl[j] <= key (spl[0] = 0 always qualifies)
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (spl[mid] <= key[q]) lo = mid; else hi = mid;
+            }
+            bkt[q] = lo;
+            rnk[q] = atomicAdd(&hist[lo], 1u);
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < nb; j += kSSThreads) {
+        const uint32_t c = hist[j];
+        hist[j] = c ? atomicAdd(&p.count[j], c) : 0u;  // reserve this tile's range in bucket j
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q) {
+        if (bkt[q] >= 0) {
+            const uint32_t slot = hist[bkt[q]] + rnk[q];
+            if (slot < (uint32_t)kSSCap) {
+                const size_t at = (size_t)bkt[q] * kSSCap + slot;
+                p.bkey[at] = key[q];
+                p.bval[at] = (uint32_t)(base + q * kSSThreads + tid);
+            } else {
+                *p.flag = 1;  // overflow: the LSD sort takes this call
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p) {
+    extern __shared__ __align__(16) unsigned char bsm[];
+    uint64_t* sk = reinterpret_cast<uint64_t*>(bsm);         // [kSSCap]
+    uint32_t* sv = reinterpret_cast<uint32_t*>(sk + kSSCap);  // [kSSCap]
+    __shared__ uint32_t s_part[32];
+    __shared__ uint32_t s_off;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x, nb = p.nb;
+    if (*p.flag) return;  // overflow: nothing here is valid (the gated LSD kernel cleans up)
+    const uint32_t cnt = p.count[b];
+    {   // output offset = sum of the counts of the buckets before mine
+        uint32_t a = 0;
+        for (int j = tid; j < b; j += kSSThreads) a += p.count[j];
+        for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) s_part[warp] = a;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < kSSThreads / 32; ++w) t += s_part[w];
+            s_off = t;
+        }
+    }
+    int N2 = 64;  // at least one full warp of pairs
+    while (N2 < (int)cnt) N2 <<= 1;
+    for (int i = tid; i < N2; i += kSSThreads) {
+        const bool ok = i < (int)cnt;
+        sk[i] = ok ? p.bkey[(size_t)b * kSSCap + i] : 0xffffffffffffffffull;  // sentinels sort last
+        sv[i] = ok ? p.bval[(size_t)b * kSSCap + i] : 0xffffffffu;
+    }
+    __syncthreads();
+    // bitonic network on (key, index): a total order, identical to the stable order of the keys.  Stages with
+    // distance j > 32 run in shared memory across the block.  The stages with j <= 32 of every phase k stay inside
+    // blocks of 64 consecutive elements: a warp takes such a block into registers (2 elements per lane: x and
+    // x + 32), runs them with shuffles, and writes the block back once — one shared-memory round trip per phase
+    // instead of one per stage (the all-shared-memory version moved 72 x 24 B per key and was bound by it).
+    const int npair = N2 >> 1;
+    auto cmpx = [&](int t, int j, int k) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+        const int l = i | j;
+        const bool up = ((i & k) == 0);
+        const uint64_t ka = sk[i], kb = sk[l];
+        const uint32_t va = sv[i], vb = sv[l];
+        const bool gt = (ka > kb) || (ka == kb && va > vb);
+        if (gt == up) {
+            sk[i] = kb; sk[l] = ka;
+            sv[i] = vb; sv[l] = va;
+        }
+    };
+    for (int k = 2; k <= N2; k <<= 1) {
+        int j = k >> 1;
+        for (; j > 32; j >>= 1) {  // pairs span warps: block-wide stages
+            for (int t = tid; t < npair; t += kSSThreads) cmpx(t, j, k);
+            __syncthreads();
+        }
+        for (int blk = warp; blk < (N2 >> 6); blk += kSSThreads / 32) {
+            const int g0 = (blk << 6) + lane, g1 = g0 + 32;
+            uint64_t k0 = sk[g0], k1 = sk[g1];
+            uint32_t v0 = sv[g0], v1 = sv[g1];
+            const bool up = ((g0 & k) == 0);  // k >= 64 here or the whole block shares the direction bit pattern
+            int jj = j;
+            if (jj == 32) {  // partner of x is x + 32: both in this lane
+                const bool up0 = (k > 32) ? up : true;  // k == 64: direction from bit 6; (k <= 32 never has jj == 32)
+                const bool gt = (k0 > k1) || (k0 == k1 && v0 > v1);
+                if (gt == up0) {
+                    const uint64_t tk = k0; k0 = k1; k1 = tk;
+                    const uint32_t tv = v0; v0 = v1; v1 = tv;
+                }
+                jj = 16;
+            }
+            for (; jj > 0; jj >>= 1) {
+                // element g (g0 or g1): direction from bit k of g, lower of its pair iff bit jj of g is clear
+                const uint64_t ok0 = __shfl_xor_sync(0xffffffffu, k0, jj), ok1 = __shfl_xor_sync(0xffffffffu, k1, jj);
+                const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
+                const bool lower = (lane & jj) == 0;
+                const bool upa = ((g0 & k) == 0), upb = ((g1 & k) == 0);
+                {
+                    const bool mine_gt = (k0 > ok0) || (k0 == ok0 && v0 > ov0);
+                    const bool keep_min = (lower == upa);
+                    if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
+                }
+                {
+                    const bool mine_gt = (k1 > ok1) || (k1 == ok1 && v1 > ov1);
+                    const bool keep_min = (lower == upb);
+                    if (mine_gt == keep_min) { k1 = ok1; v1 = ov1; }
+                }
+            }
+            sk[g0] = k0; sk[g1] = k1;
+            sv[g0] = v0; sv[g1] = v1;
+        }
+        __syncthreads();
+    }
+    const uint32_t off = s_off;
+    for (int i = tid; i < (int)cnt; i += kSSThreads) {
+        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[off + i] = rbl_bits_from_key(sk[i]);
+        if (p.perm_out) p.perm_out[off + i] = (int32_t)sv[i];
+    }
+    // last CTA out clears the counters for the next call (every CTA has read all the counts it needs by now)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int tk = atomicAdd(p.ticket, 1u);
+        s_off = (tk == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (s_off) {
+        uint32_t mx = 0;
+        for (int j = tid; j < nb; j += kSSThreads) {
+            mx = max(mx, p.count[j]);
+            p.count[j] = 0u;
+        }
+        for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        if (lane == 0) s_part[warp] = mx;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < kSSThreads / 32; ++w) mx = max(mx, s_part[w]);
+            p.stats[0] = 1;
+            p.stats[1] = (int)mx;
+            *p.ticket = 0u;
         }
     }
 }
@@ -489,8 +750,13 @@ int rbl_sort_persistent_ok(rbl_ctx* c) {
 }
 
 int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out,
-                          cudaStream_t s) {
+                          cudaStream_t s, int gated) {
     PSortParams p;
+    p.gate = gated ? c->ss_flag : nullptr;
+    p.ss_flag = c->ss_flag;
+    p.ss_count = c->ss_count;
+    p.ss_nb = c->ss_nb;
+    p.ss_stats = c->ss_flag + 4;
     int G = c->num_sms;
     const int64_t min_chunk = 2048;  // do not spread tiny sorts over the whole machine
     if ((int64_t)G * min_chunk > n) G = (int)((n + min_chunk - 1) / min_chunk);
@@ -516,10 +782,62 @@ int rbl_k_sort_persistent(rbl_ctx* c, const double* m, int64_t n, double* sorted
 
 int rbl_sort_tiles(int64_t n) { return (int)((n + kTile - 1) / kTile); }
 
-// sorted_out / perm_out may be null when only one of them is wanted (objective: keys only)
-int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s) {
+// buckets of the splitter sort for n keys (0: n too small to bother)
+int rbl_ss_buckets(int64_t n) {
+    if (n < 65536) return 0;
+    // mean load n / nb in (512, 1024]: >= 4x headroom to the 4096-slot cap for buckets that grow because the rank
+    // order moved.  Measured on B200 (us, LSD vs this): n = 100k 114 / 34, 1M 144 / 128, 2M 322 / 340, 4M 603 / 683 —
+    // above ~1M keys the LSD sort wins, so this route is for n <= 2^20.
+    int nb = 16;
+    while ((int64_t)nb * 1024 < n && nb < 1024) nb <<= 1;
+    if ((int64_t)nb * 1024 < n) return 0;
+    return nb;
+}
+
+size_t rbl_ss_slots(int64_t n) { return (size_t)rbl_ss_buckets(n) * kSSCap; }
+
+// sorted_out / perm_out may be null when only one of them is wanted (objective: keys only).
+// prev_perm (may be null): permutation of an earlier, similar call — enables the splitter sort with the LSD sort
+// as the device-gated fallback.
+int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s,
+               const int32_t* prev_perm) {
     if (n <= 0) return RBL_OK;
-    if (!c->sort_legacy && rbl_sort_persistent_ok(c)) return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s);
+    const bool persistent = !c->sort_legacy && rbl_sort_persistent_ok(c);
+    if (persistent && prev_perm && c->ss_nb > 0 && n == c->n_global && !c->ss_off) {
+        SSParams q;
+        q.m = m;
+        q.n = n;
+        q.prev_perm = prev_perm;
+        q.nb = c->ss_nb;
+        q.bkey = c->ss_bkey;
+        q.bval = c->ss_bval;
+        q.count = c->ss_count;
+        q.flag = c->ss_flag;
+        q.ticket = c->gticket + 24;
+        q.stats = c->ss_flag + 4;
+        q.sorted_out = sorted_out;
+        q.perm_out = perm_out;
+        const int tiles = (int)((n + kSSThreads * kSSItems - 1) / (kSSThreads * kSSItems));
+        int nb2 = 16;
+        while (nb2 < q.nb) nb2 <<= 1;
+        const size_t smem = (size_t)nb2 * sizeof(uint64_t) + (size_t)q.nb * sizeof(uint32_t);
+        static size_t attr = 0;
+        if (smem > 48 * 1024 && smem > attr) {
+            RBL_CUDA(cudaFuncSetAttribute(ss_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr = smem;
+        }
+        ss_partition_kernel<<<tiles, kSSThreads, smem, s>>>(q);
+        RBL_LAUNCH_CHECK();
+        static bool battr = false;
+        if (!battr) {
+            RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSCap * 12));
+            battr = true;
+        }
+        ss_bucket_kernel<<<q.nb, kSSThreads, kSSCap * 12, s>>>(q);
+        RBL_LAUNCH_CHECK();
+        return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 1);  // runs only if the flag was raised
+    }
+    if (persistent) return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 0);
     const int ntiles = rbl_sort_tiles(n);
     if (ntiles > c->sort_tiles) {
         rbl_set_error("sort of %lld keys exceeds the handle's capacity", (long long)n);

@@ -296,6 +296,8 @@ class AdmmEngine(DeviceProblem):
         self.gram_build_s = 0.0
         self._persistent = None
         self._fista_info_pending = False
+        self._sorted_valid = False
+        self.splitter_sort = os.environ.get("RBL_SPLITTER_SORT", "1") != "0"
         # gradient pass: gather over the active rows (z != m) unless more than this fraction of rows is active
         self.active_dense_frac = float(os.environ.get("RBL_ACTIVE_FRAC", "0.75"))
         self._delta_valid = False
@@ -405,8 +407,14 @@ class AdmmEngine(DeviceProblem):
             self.refresh_Dw()
         _cabi.check(lib.rbl_margins(self.h, self.Dw.data_ptr(), self.lam.data_ptr(), float(rho), self.m.data_ptr(), s))
         self.gather_rows(self.m, self.m_glob)
-        _cabi.check(lib.rbl_sort_margins(self.h, self.m_glob.data_ptr(), self.m_sorted.data_ptr(),
-                                         self.perm.data_ptr(), s))
+        if self._sorted_valid and self.splitter_sort:
+            # the rank order of the previous z-step supplies the splitters of this one
+            _cabi.check(lib.rbl_sort_margins_near(self.h, self.m_glob.data_ptr(), self.perm.data_ptr(),
+                                                  self.m_sorted.data_ptr(), self.perm.data_ptr(), s))
+        else:
+            _cabi.check(lib.rbl_sort_margins(self.h, self.m_glob.data_ptr(), self.m_sorted.data_ptr(),
+                                             self.perm.data_ptr(), s))
+            self._sorted_valid = True
         _cabi.check(lib.rbl_pav_prox(self.h, self.loss_id, self.m_sorted.data_ptr(), float(rho),
                                      self.z_sorted.data_ptr(), s))
         if self.w_mode == "gram" and self.active_dense_frac > 0:

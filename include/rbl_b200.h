@@ -76,7 +76,18 @@ int rbl_margins(rbl_handle_t h, const double* Dw, const double* lam, double rho,
 
 /* stable ascending key-index sort of n_global margins.  algorithms.py:92-93 */
 int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t* perm, rbl_stream_t stream);
-/* legacy != 0: three launches per radix pass instead of the single persistent cooperative kernel (testing) */
+/* The same sort with a hint: prev_perm = the permutation an EARLIER call returned on similar data (e.g. the previous
+ * ADMM iteration; may alias perm, may be NULL; n_global entries).  The rows that sat at B - 1 evenly spaced ranks
+ * then, read at their new values and sorted, split the new keys into B ~ n/2048 buckets, each sorted by (key,
+ * index) in shared memory by one CTA — two launches, no grid barrier, the same bit-exact stable permutation.  If a
+ * bucket would overflow its 4096 slots (stale or useless hint) the LSD sort runs instead, chosen on the device. */
+int rbl_sort_margins_near(rbl_handle_t h, const double* m, const int32_t* prev_perm, double* m_sorted,
+                          int32_t* perm, rbl_stream_t stream);
+/* synchronises `stream`; h_out[0..4) = buckets B of the splitter sort for this n (0: not used), route the last
+ * rbl_sort_margins_near call took (1 buckets, 2 LSD fallback, 0 none yet), its largest bucket, overflow flag now */
+int rbl_sort_stats(rbl_handle_t h, rbl_stream_t stream, int32_t* h_out);
+/* bit 0: three launches per radix pass instead of the single persistent cooperative kernel; bit 1: never use the
+ * splitter sort (testing) */
 int rbl_sort_config(rbl_handle_t h, int legacy);
 /* dev tool: d_stamps (64 x u64, device) receives %globaltimer stamps of CTA 0 — the persistent sort writes 6 phase
  * boundaries for each of its 8 passes ([pass][6]), the persistent Gram-FISTA kernel a count in [0] followed by its

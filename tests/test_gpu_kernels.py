@@ -94,6 +94,55 @@ def test_sort_bit_exact_vs_stable_argsort(E, n):
     e.close()
 
 
+@pytest.mark.parametrize("n", [70001, 1 << 20, 3_000_017])
+def test_splitter_sort_bit_exact_and_falls_back(E, n):
+    """rbl_sort_margins_near: buckets from the previous rank order + per-bucket shared-memory sort must give the
+    same bit-exact stable permutation as the LSD sort — with a good hint (same data, moved / shifted / scaled data),
+    with heavy ties, and with useless hints, where the device-side fallback to the LSD sort runs."""
+    _, cabi = E
+    rng = np.random.default_rng(n)
+    e = _mk(E, np.zeros((n, 2)))
+    nseg = ctypes.c_int32(0)
+    base = rng.normal(size=n)
+
+    st = (ctypes.c_int32 * 4)()
+
+    def sort_near(m, hint_perm, route=None):
+        md, hd = e.vec(m), torch.from_numpy(np.ascontiguousarray(hint_perm, dtype=np.int32)).to(e.device)
+        e.perm.zero_()
+        e.m_sorted.zero_()
+        cabi.check(e.lib.rbl_sort_margins_near(e.h, md.data_ptr(), hd.data_ptr(), e.m_sorted.data_ptr(),
+                                               e.perm.data_ptr(), e._stream()))
+        ref = np.argsort(m, kind="stable")
+        np.testing.assert_array_equal(e.perm.cpu().numpy(), ref)
+        np.testing.assert_array_equal(e.m_sorted.cpu().numpy(), m[ref] + 0.0)
+        cabi.check(e.lib.rbl_sort_stats(e.h, e._stream(), st))
+        assert st[3] == 0
+        assert (st[0] > 0) == (n <= (1 << 20))     # larger sorts always take the LSD route
+        if route is not None and st[0] > 0:
+            assert st[1] == route, (route, list(st))
+
+    hint = np.argsort(base, kind="stable")
+    sort_near(base, hint, 1)                                           # exact hint: the bucket route
+    assert st[0] == 0 or st[2] <= -(-n // st[0]) + 1                   # perfectly balanced buckets
+    sort_near(base + 1e-4 * rng.normal(size=n), hint, 1)               # the margins moved a little (ranks by ~100)
+    sort_near(base + 1e-2 * rng.normal(size=n), hint)                  # moved a lot: either route, same answer
+    sort_near(base * 1e3 + 5e3, hint, 1)                               # shifted and scaled: same ranks, still fast
+    sort_near(np.round(base, 2), hint)                                 # ~600 distinct values: long runs of ties
+    sort_near(base, np.arange(n))                                      # useless hint (identity)
+    sort_near(base, np.zeros(n, dtype=np.int32), 2)                    # degenerate hint (all row 0) -> LSD
+    sort_near(np.full(n, 0.25), hint, 2)                               # all keys equal -> LSD
+    sort_near(-base, hint, 1)                                          # reversed order: splitters get sorted
+    sort_near(base, hint, 1)                                           # and the fast path works again afterwards
+    # in place, as the engine calls it: the hint IS the output buffer of the previous call
+    md = e.vec(base + 2e-3 * rng.normal(size=n))
+    cabi.check(e.lib.rbl_sort_margins_near(e.h, md.data_ptr(), e.perm.data_ptr(), e.m_sorted.data_ptr(),
+                                           e.perm.data_ptr(), e._stream()))
+    mm = md.cpu().numpy()
+    np.testing.assert_array_equal(e.perm.cpu().numpy(), np.argsort(mm, kind="stable"))
+    e.close()
+
+
 SPECTRA = [("erm", None), ("superquantile", [0.8]), ("aorr", [0.2, 0.8]), ("extremile", [2.5]), ("esrm", [1.5]),
            ("ehrm", None)]
 
