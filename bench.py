@@ -113,6 +113,18 @@ def cpu_iters_per_sec(n_full, d, rows, warmup, iters):
     the same recipe; ADMM cost is linear in rows (matvec-bound), so iterations/s is scaled by rows/n_full."""
     from oracle import rbl_oracle as O
 
+    # all host cores for BLAS, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 per rank)
+    cores = os.cpu_count() or 1
+    try:
+        import torch
+        torch.set_num_threads(cores)
+    except Exception:  # noqa: BLE001
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        cpu_iters_per_sec._limits = threadpool_limits(limits=cores)  # kept alive: applies process-wide
+    except Exception:  # noqa: BLE001
+        pass
     X, y = gen_rows_numpy(0, rows, d)
     o = O.OracleADMM(X, y, "superquantile", "binary_cross_entropy", l1_reg=L1_REG, args=[Q], max_iter=10_000,
                      tol=TOL)
