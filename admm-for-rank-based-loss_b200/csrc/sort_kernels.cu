@@ -481,7 +481,13 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
         if (tk == gridDim.x - 1) {
             p.bar[0] = 0u;
             p.bar[1] = 0u;
-            if (p.gate) *p.ss_flag = 0;
+            if (p.gate) {
+                // overflow this call: do not try the bucket route for the next few calls (the rank order is still
+                // moving fast, typically the first ~10 ADMM iterations); otherwise count the pause down
+                int* cool = p.ss_flag + 1;
+                *cool = (*cool > 0) ? *cool - 1 : 4;
+                *p.ss_flag = 0;
+            }
             __threadfence();
         }
     }
@@ -510,7 +516,7 @@ struct SSParams {
     uint64_t* bkey;             // [nb][kSSCap]
     uint32_t* bval;
     uint32_t* count;            // [nb], zero on entry
-    int* flag;                  // overflow flag, zero on entry
+    int* flag;                  // [0] overflow flag, zero on entry; [1] calls left to pause after an overflow
     unsigned int* ticket;       // last-CTA ticket of the bucket kernel, zero on entry
     int* stats;                 // [0] route taken, [1] largest bucket (instrumentation)
     double* sorted_out;
@@ -524,6 +530,10 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
     uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);          // [nb2] spl[j] = first key of bucket j (spl[0] = 0)
     uint32_t* hist = reinterpret_cast<uint32_t*>(spl + nb2);   // [nb] tile counts, then tile bases
     const int tid = threadIdx.x, nb = p.nb;
+    if (p.flag[1] > 0) {  // pausing after a recent overflow: straight to the LSD kernel
+        if (blockIdx.x == 0 && tid == 0) p.flag[0] = 1;
+        return;
+    }
     for (int j = tid; j < nb2; j += kSSThreads) {
         uint64_t k = 0ull;
         if (j >= nb) {

@@ -126,14 +126,16 @@ def test_splitter_sort_bit_exact_and_falls_back(E, n):
     sort_near(base, hint, 1)                                           # exact hint: the bucket route
     assert st[0] == 0 or st[2] <= -(-n // st[0]) + 1                   # perfectly balanced buckets
     sort_near(base + 1e-4 * rng.normal(size=n), hint, 1)               # the margins moved a little (ranks by ~100)
-    sort_near(base + 1e-2 * rng.normal(size=n), hint)                  # moved a lot: either route, same answer
     sort_near(base * 1e3 + 5e3, hint, 1)                               # shifted and scaled: same ranks, still fast
+    sort_near(-base, hint, 1)                                          # reversed order: splitters get sorted
+    sort_near(base + 1e-2 * rng.normal(size=n), hint)                  # moved a lot: either route, same answer
     sort_near(np.round(base, 2), hint)                                 # ~600 distinct values: long runs of ties
     sort_near(base, np.arange(n))                                      # useless hint (identity)
     sort_near(base, np.zeros(n, dtype=np.int32), 2)                    # degenerate hint (all row 0) -> LSD
     sort_near(np.full(n, 0.25), hint, 2)                               # all keys equal -> LSD
-    sort_near(-base, hint, 1)                                          # reversed order: splitters get sorted
-    sort_near(base, hint, 1)                                           # and the fast path works again afterwards
+    for _ in range(5):                                                 # after an overflow the bucket route pauses
+        sort_near(base, hint)                                          # for 4 calls (still exact, via LSD) ...
+    sort_near(base, hint, 1)                                           # ... and then works again
     # in place, as the engine calls it: the hint IS the output buffer of the previous call
     md = e.vec(base + 2e-3 * rng.normal(size=n))
     cabi.check(e.lib.rbl_sort_margins_near(e.h, md.data_ptr(), e.perm.data_ptr(), e.m_sorted.data_ptr(),
