@@ -1,6 +1,7 @@
 // api.cu — the C ABI declared in include/rbl_b200.h: handle, scratch, and thin launch wrappers.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/rbl_b200.h"
@@ -65,6 +66,12 @@ int rbl_k_finalize(rbl_ctx* c, const double* part, int np, const double* w, cons
 
 static thread_local char g_err[512] = "";
 long long g_rbl_launches = 0;
+// measured on B200 inside the replayed iteration graph: 1409.8 it/s with programmatic dependent launch vs 1409.5
+// without — the graph already removes the launch gaps it would hide, so it is opt-in (RBL_PDL=1)
+int g_rbl_pdl = [] {
+    const char* e = getenv("RBL_PDL");
+    return (e && e[0] == '1') ? 1 : 0;
+}();
 
 void rbl_set_error(const char* fmt, ...) {
     va_list ap;

@@ -23,6 +23,31 @@ void rbl_set_error(const char* fmt, ...);
     } while (0)
 
 extern long long g_rbl_launches;  // kernels launched by this process through the library
+extern int g_rbl_pdl;             // programmatic dependent launch for the kernels of the iteration (RBL_PDL=1: on)
+
+// Programmatic dependent launch: the kernel may be scheduled while its predecessor in the stream is still
+// draining, and waits (rbl_pdl_wait, first statement of the kernel) until that predecessor has completed and
+// flushed before it touches memory.  Meant to hide the launch latency between the ~15 short kernels of one ADMM
+// iteration in eager (non-graph) runs; opt-in, see api.cu.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void rbl_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t rbl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                  Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_rbl_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 #define RBL_LAUNCH_CHECK()             \
     do {                               \
         ++g_rbl_launches;              \

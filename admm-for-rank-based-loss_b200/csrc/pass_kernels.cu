@@ -97,6 +97,7 @@ constexpr int kMaxRows = 64;
 // XJ : double2 of x held per lane;  WPR : warps cooperating on one row;  CJ : double2 columns per thread
 template <int XJ, int WPR, int CJ>
 __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams p) {
+    rbl_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -286,6 +287,7 @@ struct GatherParams {
 
 template <int CJ>
 __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherParams p) {
+    rbl_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int count = *p.count;
@@ -388,7 +390,7 @@ int launch_gather_t(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
                                       (int)c->pass_smem));
         attr_smem = c->pass_smem;
     }
-    rbl_gather_kernel<CJ><<<c->pass_grid, kThreads, c->pass_smem, s>>>(p);
+    RBL_CUDA(rbl_launch_pdl(rbl_gather_kernel<CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -401,7 +403,7 @@ int launch_t(rbl_ctx* c, const PassParams& p, cudaStream_t s) {
                                       (int)c->pass_smem));
         attr_smem = c->pass_smem;
     }
-    rbl_pass_kernel<XJ, WPR, CJ><<<c->pass_grid, kThreads, c->pass_smem, s>>>(p);
+    RBL_CUDA(rbl_launch_pdl(rbl_pass_kernel<XJ, WPR, CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
                                                                    const double* __restrict__ sigma, int loss,
                                                                    double rho, double* __restrict__ prox_out,
                                                                    const double* __restrict__ scal) {
+    rbl_pdl_wait();
     __shared__ double sh[16];
     if (scal) rho = scal[0];
     const int64_t base = (int64_t)blockIdx.x * kChunk;
@@ -463,6 +464,7 @@ __global__ void sigma_ascents_kernel(const double* __restrict__ sigma, int64_t n
 // dependent-load chains, ~50 us each at n = 1M)
 __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
                                                            int nseg, SegBlocks* __restrict__ out) {
+    rbl_pdl_wait();
     __shared__ int s_nblk;
     __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
     __shared__ double s_v[kMaxSeg];
@@ -574,6 +576,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
 }
 
 __global__ void pav_seg_fill_kernel(const SegBlocks* __restrict__ blk, double* __restrict__ val) {
+    rbl_pdl_wait();
     const int nb = blk->nblk;
     for (int k = 0; k < nb; ++k) {
         const int64_t lo = blk->lo[k], hi = blk->hi[k];
@@ -606,8 +609,8 @@ int rbl_k_prefix(rbl_ctx* c, const double* x, int64_t n, double* loc_hi, double*
                  double* tot_lo, double* off_hi, double* off_lo, cudaStream_t s) {
     const int64_t nch = (n + kChunk - 1) / kChunk;
     (void)c;
-    chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(x, n, loc_hi, loc_lo, tot_hi, tot_lo, nullptr, 0, 0.0,
-                                                             nullptr, nullptr);
+    RBL_CUDA(rbl_launch_pdl(chunk_prefix_kernel, dim3((unsigned)nch), dim3(kPavThreads), 0, s, x, n, loc_hi, loc_lo, tot_hi, tot_lo, nullptr, 0, 0.0,
+                                                             nullptr, nullptr));
     RBL_LAUNCH_CHECK();
     chunk_offsets_kernel<<<1, kPavThreads, 0, s>>>(tot_hi, tot_lo, nch, off_hi, off_lo);
     RBL_LAUNCH_CHECK();
@@ -657,9 +660,9 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
         attr_set = true;
     }
     const bool few = c->nseg > 0 && !c->force_tree;
-    chunk_prefix_kernel<<<(unsigned)nch, kPavThreads, 0, s>>>(m_sorted, n, c->pm_loc_hi, c->pm_loc_lo, c->ch_tot_hi,
+    RBL_CUDA(rbl_launch_pdl(chunk_prefix_kernel, dim3((unsigned)nch), dim3(kPavThreads), 0, s, m_sorted, n, c->pm_loc_hi, c->pm_loc_lo, c->ch_tot_hi,
                                                              c->ch_tot_lo, c->sigma, loss, rho,
-                                                             few ? z_sorted : nullptr, c->scal);
+                                                             few ? z_sorted : nullptr, c->scal));
     RBL_LAUNCH_CHECK();
     if (few && c->nseg == 1) return RBL_OK;  // sigma never steps up (ERM): the element prox is the answer
     if (!few) {
@@ -687,9 +690,9 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.dbg = c->sort_dbg;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
-        pav_seg_merge_kernel<<<1, 64, 0, s>>>(P, c->seg_bounds, c->nseg, blk);
+        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(64), 0, s, P, c->seg_bounds, c->nseg, blk));
         RBL_LAUNCH_CHECK();
-        pav_seg_fill_kernel<<<c->vec_grid, 256, 0, s>>>(blk, z_sorted);
+        RBL_CUDA(rbl_launch_pdl(pav_seg_fill_kernel, dim3(c->vec_grid), dim3(256), 0, s, blk, z_sorted));
         RBL_LAUNCH_CHECK();
         return RBL_OK;
     }

@@ -524,6 +524,7 @@ struct SSParams {
 };
 
 __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams p) {
+    rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char ssm[];
     int nb2 = 16;  // the splitter array is sorted by a power-of-two network: pad with maximal keys
     while (nb2 < p.nb) nb2 <<= 1;
@@ -618,6 +619,7 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
 }
 
 __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p) {
+    rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char bsm[];
     uint64_t* sk = reinterpret_cast<uint64_t*>(bsm);         // [kSSCap]
     uint32_t* sv = reinterpret_cast<uint32_t*>(sk + kSSCap);  // [kSSCap]
@@ -836,14 +838,14 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
             RBL_CUDA(cudaFuncSetAttribute(ss_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
-        ss_partition_kernel<<<tiles, kSSThreads, smem, s>>>(q);
+        RBL_CUDA(rbl_launch_pdl(ss_partition_kernel, dim3(tiles), dim3(kSSThreads), smem, s, q));
         RBL_LAUNCH_CHECK();
         static bool battr = false;
         if (!battr) {
             RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSCap * 12));
             battr = true;
         }
-        ss_bucket_kernel<<<q.nb, kSSThreads, kSSCap * 12, s>>>(q);
+        RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSSThreads), kSSCap * 12, s, q));
         RBL_LAUNCH_CHECK();
         return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 1);  // runs only if the flag was raised
     }

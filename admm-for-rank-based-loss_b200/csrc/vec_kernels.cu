@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const double* __re
                                                               const double* __restrict__ c0part, int nparts, int nc0,
                                                               int64_t ld, int d, double* __restrict__ red,
                                                               const FistaState* st) {
+    rbl_pdl_wait();
     // 32 columns x 8 row-slices per CTA: coalesced 256-byte row segments, 8 independent partial sums per
     // column combined in a fixed order (slice 0..7) => deterministic
     __shared__ double sh[8][33];
@@ -264,6 +265,7 @@ __global__ void fista_result_kernel(const FistaState* st, const double* beta, in
 // new values
 __global__ void margins_kernel(const double* __restrict__ Dw, const double* __restrict__ lam, double rho, int64_t n,
                                double* __restrict__ m, const double* __restrict__ scal) {
+    rbl_pdl_wait();
     if (scal) rho = scal[0];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         m[i] = Dw[i] - lam[i] / rho;
@@ -314,6 +316,7 @@ __global__ void __launch_bounds__(kActThreads) scatter_active_kernel(
     int64_t row_lo, int64_t n_local, int use_clip, double clip, const double* __restrict__ lam, double rho,
     double* __restrict__ z, double* __restrict__ b, int64_t chunk, int* __restrict__ cta_count,
     const double* __restrict__ scal) {
+    rbl_pdl_wait();
     __shared__ int wcount[kActThreads / 32];
     if (scal) rho = scal[0];
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
@@ -343,6 +346,7 @@ __global__ void __launch_bounds__(kActThreads) compact_active_kernel(
     const double* __restrict__ zs, const double* __restrict__ ms, const int32_t* __restrict__ perm, int64_t n_global,
     int64_t row_lo, int64_t n_local, int use_clip, double clip, int64_t chunk, const int* __restrict__ cta_count,
     int32_t* __restrict__ act_row, double* __restrict__ act_delta, int* __restrict__ act_total) {
+    rbl_pdl_wait();
     __shared__ int sh[kActThreads / 32 + 1];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -539,6 +543,7 @@ __global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restri
                                                           double* __restrict__ lam, double rho,
                                                           double* __restrict__ part,
                                                           const double* __restrict__ scal) {
+    rbl_pdl_wait();
     __shared__ double sh[33];
     const int nnz = *nnz_ptr;
     if (nnz > cap) return;  // the dense pass handles it
@@ -562,6 +567,7 @@ __global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __rest
                                                             double* __restrict__ lam, double rho,
                                                             double* __restrict__ part,
                                                             const double* __restrict__ scal) {
+    rbl_pdl_wait();
     __shared__ double sh[33];
     __shared__ int s_idx[256];
     if (scal) rho = scal[0];
@@ -653,6 +659,7 @@ __global__ void __launch_bounds__(1024) dual_finalize_kernel(const double* __res
                                                              const int* __restrict__ act_total,
                                                              double* __restrict__ out,
                                                              double* __restrict__ w_copy) {
+    rbl_pdl_wait();
     __shared__ double sh[33];
     const int nnz = *nnz_ptr;
     const bool sparse = nnz <= cap;
@@ -713,8 +720,8 @@ int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y
 int rbl_k_reduce_partials(rbl_ctx* c, int with_c0, const FistaState* st, cudaStream_t s) {
     const int threads = 256;
     const int blocks = (c->d + 31) / 32;
-    reduce_partials_kernel<<<blocks, threads, 0, s>>>(c->gpart, c->sspart, with_c0 ? c->c0part : nullptr,
-                                                      c->pass_grid, c->vec_grid, c->ld, c->d, c->red, st);
+    RBL_CUDA(rbl_launch_pdl(reduce_partials_kernel, dim3(blocks), dim3(threads), 0, s, c->gpart, c->sspart, with_c0 ? c->c0part : nullptr,
+                                                      c->pass_grid, c->vec_grid, c->ld, c->d, c->red, st));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -736,7 +743,7 @@ int rbl_k_fista_result(rbl_ctx* c, double* w_out, double* r_out, cudaStream_t s)
 }
 
 int rbl_k_margins(rbl_ctx* c, const double* Dw, const double* lam, double rho, double* m, cudaStream_t s) {
-    margins_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dw, lam, rho, c->n_local, m, c->scal);
+    RBL_CUDA(rbl_launch_pdl(margins_kernel, dim3(c->vec_grid), dim3(kVecThreads), 0, s, Dw, lam, rho, c->n_local, m, c->scal));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -753,12 +760,12 @@ int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const i
                          double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s) {
     const int grid = c->vec_grid;
     const int64_t chunk = (c->n_global + grid - 1) / grid;
-    scatter_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
-                                                      clip, lam, rho, z, b, chunk, c->act_cta_count, c->scal);
+    RBL_CUDA(rbl_launch_pdl(scatter_active_kernel, dim3(grid), dim3(kActThreads), 0, s, zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
+                                                      clip, lam, rho, z, b, chunk, c->act_cta_count, c->scal));
     RBL_LAUNCH_CHECK();
-    compact_active_kernel<<<grid, kActThreads, 0, s>>>(zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
+    RBL_CUDA(rbl_launch_pdl(compact_active_kernel, dim3(grid), dim3(kActThreads), 0, s, zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
                                                       clip, chunk, c->act_cta_count, c->act_row, c->act_delta,
-                                                      c->act_total);
+                                                      c->act_total));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -780,11 +787,11 @@ int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const doubl
         RBL_LAUNCH_CHECK();
     }
     if (Dt)
-        sparse_dual_t_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
-                                                                cap, z, Dw, lam, rho, c->vpart, c->scal);
+        RBL_CUDA(rbl_launch_pdl(sparse_dual_t_kernel, dim3(c->vec_grid), dim3(kVecThreads), 0, s, Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
+                                                                cap, z, Dw, lam, rho, c->vpart, c->scal));
     else
-        sparse_dual_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(D, c->ld, c->n_local, c->sup_idx, c->sup_val,
-                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart, c->scal);
+        RBL_CUDA(rbl_launch_pdl(sparse_dual_kernel, dim3(c->vec_grid), dim3(kVecThreads), 0, s, D, c->ld, c->n_local, c->sup_idx, c->sup_val,
+                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart, c->scal));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -797,8 +804,8 @@ int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s) {
 
 int rbl_k_dual_finalize(rbl_ctx* c, int cap, const double* w, const double* w_prev, double* out8, double* w_copy,
                         cudaStream_t s) {
-    dual_finalize_kernel<<<1, 1024, 0, s>>>(c->sspart, c->pass_grid, c->vpart, c->vec_grid, c->sup_nnz, cap, w,
-                                            w_prev, c->d, c->fista, c->act_total, out8, w_copy);
+    RBL_CUDA(rbl_launch_pdl(dual_finalize_kernel, dim3(1), dim3(1024), 0, s, c->sspart, c->pass_grid, c->vpart, c->vec_grid, c->sup_nnz, cap, w,
+                                            w_prev, c->d, c->fista, c->act_total, out8, w_copy));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
