@@ -67,6 +67,28 @@ def main():
     chk = [torch.zeros_like(red) for _ in range(world)]
     dist.all_gather(chk, red)
     assert all(torch.equal(chk[0], c) for c in chk)
+    # ---- Gram-mode data flow (engine.gram / _pass_at / dual pass): G = sum of the per-rank D_l^T D_l (one
+    # all-reduce at construction); g0 = D^T (z - m) from each rank's ACTIVE rows only (z != m), all-reduced;
+    # the FISTA trial identities on G; the primal residual as an all-reduced scalar
+    G = torch.from_numpy(Dl.T @ Dl)
+    dist.all_reduce(G)
+    assert np.allclose(G.numpy(), D.T @ D, rtol=1e-13, atol=1e-12)
+    delta_l = z_local - m[lo:hi]
+    act = np.flatnonzero(delta_l != 0.0)
+    assert 0 < len(act) < (hi - lo)                       # superquantile: most rows are untouched by the prox
+    g0 = torch.from_numpy(np.concatenate([Dl[act].T @ delta_l[act], [delta_l[act] @ delta_l[act]]]))
+    dist.all_reduce(g0)
+    assert np.allclose(g0[:d].numpy(), D.T @ r, rtol=1e-11, atol=1e-12)        # b - D w == z - m
+    assert abs(float(g0[d]) - r @ r) < 1e-10 * (r @ r)
+    beta = w + 1e-2 * rng.normal(size=d)                  # same on every rank (same generator state)
+    g_beta = g0[:d].numpy() - G.numpy() @ (beta - w)      # D^T (b - D beta) = g0 - G (beta - w)
+    assert np.allclose(g_beta, D.T @ (b - D @ beta), rtol=1e-10, atol=1e-11)
+    dl = beta - w
+    ss = float(g0[d]) - 2 * dl @ g0[:d].numpy() + dl @ (G.numpy() @ dl)
+    assert abs(ss - np.sum((b - D @ beta) ** 2)) < 1e-10 * ss
+    prim = torch.tensor([float(np.sum((z_local - Dl @ beta) ** 2))], dtype=torch.float64)
+    dist.all_reduce(prim)
+    assert abs(float(prim[0]) - np.sum((z_ref - D @ beta) ** 2)) < 1e-11 * float(prim[0])
     dist.barrier()
     print("OK", rank)
     dist.destroy_process_group()
