@@ -383,8 +383,11 @@ class AdmmEngine(DeviceProblem):
             self.transpose_ok = False  # not enough HBM left: keep the sector-gather kernel
             return
         with torch.cuda.device(self.device):
-            self.Dt = torch.empty((self.d, self.n_local), dtype=torch.float64, device=self.device)
-            _cabi.check(self.lib.rbl_build_transpose(self.h, self.D.data_ptr(), self.Dt.data_ptr(), self._stream()))
+            Dt = torch.empty((self.d, self.n_local), dtype=torch.float64, device=self.device)
+            _cabi.check(self.lib.rbl_build_transpose(self.h, self.D.data_ptr(), Dt.data_ptr(), self._stream()))
+            # one-off: finish before publishing it — child engines (batched mode) read it from other streams
+            torch.cuda.current_stream(self.device).synchronize()
+            self.Dt = Dt
 
     def _pass_at(self, w0, b, use_active=False):
         """red0 = [D^T (b - D w0), ||b - D w0||^2] — the one pass over D a Gram-mode w-step makes.  Right after
