@@ -348,3 +348,27 @@ def test_full_size_gram_route_equals_stream_route(w_mode, monkeypatch):
     assert _rel(wg, wst) < 1e-9 and _rel(zg, zst) < 1e-9 and rg == rst
     assert graphed and act["gathered"] >= 4 and dual["sparse"] >= 4     # the fast route really ran
     assert act["rows"] < 0.8 * act["calls"] * n                        # and read fewer rows than full passes
+
+
+@pytest.mark.parametrize("n,d", [(33, 1), (50, 7), (200, 3), (1000, 129), (700, 255), (5000, 2)])
+def test_odd_and_tiny_shapes_in_lockstep_with_the_oracle(n, d, w_mode):
+    """odd d (padded leading dimension), d = 1, n barely above 2d, tiny n: 12 ADMM iterations of the l1 path in
+    lockstep with the oracle, both w-step formulations (persistent FISTA grid = min(#SMs, d) CTAs)."""
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    rng = np.random.default_rng(n * 7 + d)
+    X = rng.normal(size=(n, d))
+    ws = rng.normal(size=d) * (rng.random(d) < 0.5)
+    y = np.sign(X @ ws + 0.3 * rng.normal(size=n) + 1e-12).reshape(-1, 1)
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.02, args=[0.7], max_iter=12,
+              tol=1e-12)
+    s = ADMMmethod(X, y, **kw)
+    o = O.OracleADMM(X, y, small_lasso=False, **kw)
+    for i in range(12):
+        o.w, o.z, o.lam, o.rho = s.w.reshape(-1).copy(), s.z.reshape(-1).copy(), s.lagrangian.reshape(-1).copy(), s.rho
+        with contextlib.redirect_stdout(io.StringIO()):
+            Optimizer.main_loop(s, i, 0.0, False)
+        o.step()
+        assert _rel(s.z, o.z) < 1e-9, (n, d, i)
+        assert _rel(s.w, o.w) < 1e-9 or np.linalg.norm(s.w.reshape(-1) - o.w) < 1e-9, (n, d, i, _rel(s.w, o.w))
+    s.engine.close()
