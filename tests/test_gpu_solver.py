@@ -372,3 +372,31 @@ def test_odd_and_tiny_shapes_in_lockstep_with_the_oracle(n, d, w_mode):
         assert _rel(s.z, o.z) < 1e-9, (n, d, i)
         assert _rel(s.w, o.w) < 1e-9 or np.linalg.norm(s.w.reshape(-1) - o.w) < 1e-9, (n, d, i, _rel(s.w, o.w))
     s.engine.close()
+
+
+@pytest.mark.parametrize("n,d", [(5000, 2050), (9000, 4096)])
+def test_wide_problems_in_lockstep_with_the_oracle(n, d, w_mode):
+    """d = 2050 (persistent FISTA with fewer candidates per sweep, G rows read from L2) and d = 4096 (state does not
+    fit in shared memory: one launch per line-search trial): 6 iterations in lockstep with the oracle."""
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    rng = np.random.default_rng(d)
+    X = rng.normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:8] = rng.normal(size=8)
+    y = np.sign(X @ ws + 0.1 * rng.normal(size=n)).reshape(-1, 1)
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.05, args=[0.8], max_iter=6,
+              tol=1e-12)
+    s = ADMMmethod(X, y, **kw)
+    assert s.engine.w_mode == w_mode
+    o = O.OracleADMM(X, y, small_lasso=False, **kw)
+    for i in range(6):
+        o.w, o.z, o.lam, o.rho = s.w.reshape(-1).copy(), s.z.reshape(-1).copy(), s.lagrangian.reshape(-1).copy(), s.rho
+        with contextlib.redirect_stdout(io.StringIO()):
+            Optimizer.main_loop(s, i, 0.0, False)
+        o.step()
+        assert _rel(s.z, o.z) < 1e-9, (n, d, i)
+        assert _rel(s.w, o.w) < 1e-9 or np.linalg.norm(s.w.reshape(-1) - o.w) < 1e-9, (n, d, i, _rel(s.w, o.w))
+    if w_mode == "gram":
+        assert s.engine._persistent == (d <= 2050)
+    s.engine.close()
