@@ -793,7 +793,10 @@ class AdmmEngine(DeviceProblem):
             cur.wait_stream(self._cap_stream)
             self._graph, self._graph_key = g, key
             self._graph_launches, self._graph_replays = int(self.lib.rbl_launch_count()) - n0, 0
-        except Exception:  # noqa: BLE001 — capture unsupported here: stay on eager launches
+        except Exception as exc:  # noqa: BLE001 — capture unsupported here: stay on eager launches
+            import warnings
+            warnings.warn(f"rbl_b200: CUDA graph capture of the ADMM iteration failed ({exc!r}); "
+                          "continuing with eager launches", RuntimeWarning, stacklevel=2)
             self._graph, self.graph_ok = None, False
         finally:
             _cabi.check(self.lib.rbl_bind_scalars(self.h, 0))
