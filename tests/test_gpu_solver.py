@@ -203,8 +203,23 @@ def test_full_size_properties():
         assert np.all(np.diff(z) >= 0)                               # isotonic
         zo = O.pav_prox("binary_cross_entropy", sig, ms, rho)        # the C oracle handles 1M in < 1 s
         assert np.max(np.abs(z - zo)) < 1e-12 * max(1.0, np.max(np.abs(zo)))
-        # idempotence of the projection part: with sigma = 0 the prox of an isotonic vector is itself
     e.close()
+    # idempotence / fixed points at full size: with sigma = 0 the prox is the projection of an already sorted vector
+    # onto the isotonic cone, i.e. the vector itself, bit for bit, on both PAV routes; the scatter then returns the
+    # margins to row order exactly (z == m), so no row is active
+    import ctypes
+    e0 = AdmmEngine(np.zeros((n, 2)), np.ones(n), "binary_cross_entropy", np.zeros(n))
+    for force_tree in (0, 1):
+        _cabi.check(e0.lib.rbl_pav_config(e0.h, force_tree, None))
+        e0.set_state(w=np.zeros(2), z=np.zeros(n), lam=-m * 0.5)      # margins = D w - lam / rho = m at rho = 0.5
+        e0.z_step(0.5)
+        np.testing.assert_array_equal(e0.z_sorted.cpu().numpy(), np.sort(m))
+        np.testing.assert_array_equal(e0.z.cpu().numpy(), m)
+        if e0.w_mode == "gram":
+            cnt = ctypes.c_int32(-1)
+            _cabi.check(e0.lib.rbl_active_count(e0.h, ctypes.byref(cnt), e0._stream()))
+            assert cnt.value == 0
+    e0.close()
 
 
 def test_smooth_admm_vs_oracle_and_reference(golden_dir):
