@@ -384,8 +384,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     }
     const double lam_ = p.scal ? p.scal[1] : p.lam;
     const int thr_f32_ = p.scal ? (p.scal[2] != 0.0 ? 1 : 0) : p.thr_f32;
+    __shared__ float s_pow[128];
+    for (int i = tid; i < 128; i += nt) s_pow[i] = p.pow_tab[i];
     float L_prev = p.L0, L_acc = p.L0;
     int i_k0 = 0, i_k = 0, k = 0, sweeps = 0, trials = 0, par = 0;
+    // candidates evaluated per sweep: all KC while L climbs from L0 (the first iteration of a call rejects ~12
+    // candidates), 2 once an iteration has been accepted (L_prev is then right and i = 0 passes almost always);
+    // a sweep whose candidates are all rejected widens the next one again
+    int kc = KC;
     double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
     unsigned int target = 0;
     __syncthreads();
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
 #pragma unroll
         for (int q = 0; q < KC; ++q) {
             const int ii = i_k0 + q;
-            Lc[q] = __fmul_rn(L_prev, p.pow_tab[ii < 127 ? ii : 127]);  // fast_lasso.py:46
+            Lc[q] = __fmul_rn(L_prev, s_pow[ii < 127 ? ii : 127]);  // fast_lasso.py:46
             Ld[q] = (double)Lc[q];
             thr[q] = thr_f32_ ? (double)__fdiv_rn((float)lam_, Lc[q]) : lam_ / Ld[q];
             r1[q] = 0.0;
@@ -415,6 +421,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             const double bp = BETA_P[c], g = G_P[c];
 #pragma unroll
             for (int q = 0; q < KC; ++q) {
+                if (q >= kc) break;
                 const double bs = bp + g / Ld[q];  // :47
                 const double mag = fmax(fabs(bs) - thr[q], 0.0);
                 const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
@@ -438,6 +445,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
                 const double2 g = p.g_in_smem ? g2[c2] : __ldg(&g2[c2]);
 #pragma unroll
                 for (int q = 0; q < KC; ++q) {
+                    if (q >= kc) break;
                     const double2 x = reinterpret_cast<const double2*>(DEL + (size_t)q * ld)[c2];
                     ax[q] = fma(g.x, x.x, ax[q]);
                     ay[q] = fma(g.y, x.y, ay[q]);
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
             }
 #pragma unroll
             for (int q = 0; q < KC; ++q) {
+                if (q >= kc) break;
                 const double a = warp_sum(ax[q] + ay[q]);
                 if (lane == 0) __stcg(&vu[(size_t)q * ld + row], a);
             }
