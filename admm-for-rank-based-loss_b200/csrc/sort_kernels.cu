@@ -506,6 +506,10 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
 constexpr int kSSCap = 4096;       // slots per bucket
 constexpr int kSSThreads = 1024;
 constexpr int kSSItems = 4;        // keys per thread in the partition kernel
+#ifndef RBL_SB_THREADS
+#define RBL_SB_THREADS 512
+#endif
+constexpr int kSBThreads = RBL_SB_THREADS;  // bucket kernel: a 1024-key bucket has 512 pairs per stage
 
 struct SSParams {
     const double* m;
@@ -618,7 +622,7 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
     }
 }
 
-__global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p) {
+__global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char bsm[];
     uint64_t* sk = reinterpret_cast<uint64_t*>(bsm);         // [kSSCap]
@@ -630,19 +634,33 @@ __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p)
     const uint32_t cnt = p.count[b];
     {   // output offset = sum of the counts of the buckets before mine
         uint32_t a = 0;
-        for (int j = tid; j < b; j += kSSThreads) a += p.count[j];
+        for (int j = tid; j < b; j += kSBThreads) a += p.count[j];
         for (int o = 16; o; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
         if (lane == 0) s_part[warp] = a;
         __syncthreads();
         if (tid == 0) {
             uint32_t t = 0;
-            for (int w = 0; w < kSSThreads / 32; ++w) t += s_part[w];
+            for (int w = 0; w < kSBThreads / 32; ++w) t += s_part[w];
             s_off = t;
         }
     }
-    int N2 = 64;  // at least one full warp of pairs
-    while (N2 < (int)cnt) N2 <<= 1;
-    for (int i = tid; i < N2; i += kSSThreads) {
+    // The network needs power-of-two lengths, and the loads sit just around one (mean n / nb ~ 1000): rounding
+    // 1030 keys up to 2048 would cost 2.4x.  The keys are split into a head A of Na keys (the largest power of two
+    // <= cnt) and a tail B padded to Nb < Na slots; both are sorted by the same network (B only joins the phases
+    // k <= Nb) and every key then finds its output slot by one binary search in the other part.
+    int Na = 64;  // at least one full warp of pairs
+    while (Na * 2 <= (int)cnt) Na <<= 1;
+    int Nb = 0;
+    if ((int)cnt > Na) {
+        Nb = 64;
+        while (Nb < (int)cnt - Na) Nb <<= 1;
+        if (Nb >= Na) {  // no saving: one network over 2 Na
+            Na <<= 1;
+            Nb = 0;
+        }
+    }
+    const int N2 = Na + Nb;
+    for (int i = tid; i < N2; i += kSBThreads) {
         const bool ok = i < (int)cnt;
         sk[i] = ok ? p.bkey[(size_t)b * kSSCap + i] : 0xffffffffffffffffull;  // sentinels sort last
         sv[i] = ok ? p.bval[(size_t)b * kSSCap + i] : 0xffffffffu;
@@ -653,7 +671,6 @@ __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p)
     // blocks of 64 consecutive elements: a warp takes such a block into registers (2 elements per lane: x and
     // x + 32), runs them with shuffles, and writes the block back once — one shared-memory round trip per phase
     // instead of one per stage (the all-shared-memory version moved 72 x 24 B per key and was bound by it).
-    const int npair = N2 >> 1;
     auto cmpx = [&](int t, int j, int k) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
         const int l = i | j;
@@ -666,53 +683,81 @@ __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p)
             sv[i] = vb; sv[l] = va;
         }
     };
-    for (int k = 2; k <= N2; k <<= 1) {
-        int j = k >> 1;
-        for (; j > 32; j >>= 1) {  // pairs span warps: block-wide stages
-            for (int t = tid; t < npair; t += kSSThreads) cmpx(t, j, k);
+    // register stages of phase k from distance j0 (<= 32) down to 1 on the 64 keys a warp holds
+    auto warp_stages = [&](int g0, int g1, int k, int j0, uint64_t& k0, uint64_t& k1, uint32_t& v0, uint32_t& v1) {
+        const bool upa = ((g0 & k) == 0), upb = ((g1 & k) == 0);
+        int jj = j0;
+        if (jj == 32) {  // partner of x is x + 32: both in this lane (k >= 64: one direction for the pair)
+            const bool gt = (k0 > k1) || (k0 == k1 && v0 > v1);
+            if (gt == upa) {
+                const uint64_t tk = k0; k0 = k1; k1 = tk;
+                const uint32_t tv = v0; v0 = v1; v1 = tv;
+            }
+            jj = 16;
+        }
+        for (; jj > 0; jj >>= 1) {
+            // element g (g0 or g1): direction from bit k of g, lower of its pair iff bit jj of g is clear
+            const uint64_t ok0 = __shfl_xor_sync(0xffffffffu, k0, jj), ok1 = __shfl_xor_sync(0xffffffffu, k1, jj);
+            const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
+            const bool lower = (lane & jj) == 0;
+            {
+                const bool mine_gt = (k0 > ok0) || (k0 == ok0 && v0 > ov0);
+                const bool keep_min = (lower == upa);
+                if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
+            }
+            {
+                const bool mine_gt = (k1 > ok1) || (k1 == ok1 && v1 > ov1);
+                const bool keep_min = (lower == upb);
+                if (mine_gt == keep_min) { k1 = ok1; v1 = ov1; }
+            }
+        }
+    };
+    // phases k = 2 .. 64 never leave a block of 64 keys: one load, 21 stages in registers, one store
+    for (int blk = warp; blk < (N2 >> 6); blk += kSBThreads / 32) {
+        const int g0 = (blk << 6) + lane, g1 = g0 + 32;
+        uint64_t k0 = sk[g0], k1 = sk[g1];
+        uint32_t v0 = sv[g0], v1 = sv[g1];
+#pragma unroll
+        for (int k = 2; k <= 64; k <<= 1) warp_stages(g0, g1, k, k >> 1, k0, k1, v0, v1);
+        sk[g0] = k0; sk[g1] = k1;
+        sv[g0] = v0; sv[g1] = v1;
+    }
+    __syncthreads();
+    for (int k = 128; k <= Na; k <<= 1) {
+        // B starts at a multiple of 2 Nb, so (i & k) gives it the same directions as a network of its own
+        const int lim = (k <= Nb) ? N2 : Na, npair = lim >> 1;
+        for (int j = k >> 1; j > 32; j >>= 1) {  // pairs span warps: block-wide stages
+            for (int t = tid; t < npair; t += kSBThreads) cmpx(t, j, k);
             __syncthreads();
         }
-        for (int blk = warp; blk < (N2 >> 6); blk += kSSThreads / 32) {
+        for (int blk = warp; blk < (lim >> 6); blk += kSBThreads / 32) {
             const int g0 = (blk << 6) + lane, g1 = g0 + 32;
             uint64_t k0 = sk[g0], k1 = sk[g1];
             uint32_t v0 = sv[g0], v1 = sv[g1];
-            const bool up = ((g0 & k) == 0);  // k >= 64 here or the whole block shares the direction bit pattern
-            int jj = j;
-            if (jj == 32) {  // partner of x is x + 32: both in this lane
-                const bool up0 = (k > 32) ? up : true;  // k == 64: direction from bit 6; (k <= 32 never has jj == 32)
-                const bool gt = (k0 > k1) || (k0 == k1 && v0 > v1);
-                if (gt == up0) {
-                    const uint64_t tk = k0; k0 = k1; k1 = tk;
-                    const uint32_t tv = v0; v0 = v1; v1 = tv;
-                }
-                jj = 16;
-            }
-            for (; jj > 0; jj >>= 1) {
-                // element g (g0 or g1): direction from bit k of g, lower of its pair iff bit jj of g is clear
-                const uint64_t ok0 = __shfl_xor_sync(0xffffffffu, k0, jj), ok1 = __shfl_xor_sync(0xffffffffu, k1, jj);
-                const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
-                const bool lower = (lane & jj) == 0;
-                const bool upa = ((g0 & k) == 0), upb = ((g1 & k) == 0);
-                {
-                    const bool mine_gt = (k0 > ok0) || (k0 == ok0 && v0 > ov0);
-                    const bool keep_min = (lower == upa);
-                    if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
-                }
-                {
-                    const bool mine_gt = (k1 > ok1) || (k1 == ok1 && v1 > ov1);
-                    const bool keep_min = (lower == upb);
-                    if (mine_gt == keep_min) { k1 = ok1; v1 = ov1; }
-                }
-            }
+            warp_stages(g0, g1, k, 32, k0, k1, v0, v1);
             sk[g0] = k0; sk[g1] = k1;
             sv[g0] = v0; sv[g1] = v1;
         }
         __syncthreads();
     }
     const uint32_t off = s_off;
-    for (int i = tid; i < (int)cnt; i += kSSThreads) {
-        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[off + i] = rbl_bits_from_key(sk[i]);
-        if (p.perm_out) p.perm_out[off + i] = (int32_t)sv[i];
+    for (int i = tid; i < (int)cnt; i += kSBThreads) {
+        const uint64_t ki = sk[i];
+        const uint32_t vi = sv[i];
+        int pos = i;
+        if (Nb) {  // + the keys of the other part that sort before mine ((key, index) pairs are all distinct)
+            const bool inA = i < Na;
+            int lo = inA ? Na : 0, hi = inA ? (int)cnt : Na;
+            const int first = lo;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const uint64_t km = sk[mid];
+                if (km < ki || (km == ki && sv[mid] < vi)) lo = mid + 1; else hi = mid;
+            }
+            pos = (inA ? i : i - Na) + (lo - first);
+        }
+        if (p.sorted_out) reinterpret_cast<uint64_t*>(p.sorted_out)[off + pos] = rbl_bits_from_key(ki);
+        if (p.perm_out) p.perm_out[off + pos] = (int32_t)vi;
     }
     // last CTA out clears the counters for the next call (every CTA has read all the counts it needs by now)
     __threadfence();
@@ -724,7 +769,7 @@ __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p)
     __syncthreads();
     if (s_off) {
         uint32_t mx = 0;
-        for (int j = tid; j < nb; j += kSSThreads) {
+        for (int j = tid; j < nb; j += kSBThreads) {
             mx = max(mx, p.count[j]);
             p.count[j] = 0u;
         }
@@ -732,7 +777,7 @@ __global__ void __launch_bounds__(kSSThreads) ss_bucket_kernel(const SSParams p)
         if (lane == 0) s_part[warp] = mx;
         __syncthreads();
         if (tid == 0) {
-            for (int w = 1; w < kSSThreads / 32; ++w) mx = max(mx, s_part[w]);
+            for (int w = 1; w < kSBThreads / 32; ++w) mx = max(mx, s_part[w]);
             p.stats[0] = 1;
             p.stats[1] = (int)mx;
             *p.ticket = 0u;
@@ -845,7 +890,7 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
             RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSCap * 12));
             battr = true;
         }
-        RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSSThreads), kSSCap * 12, s, q));
+        RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSBThreads), kSSCap * 12, s, q));
         RBL_LAUNCH_CHECK();
         return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 1);  // runs only if the flag was raised
     }
