@@ -56,6 +56,10 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
                          cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate, double* G, double* scratch,
                      cudaStream_t s);
+size_t rbl_k_metrics_scratch_bytes(int num_sms);
+int rbl_k_test_metrics(int num_sms, const double* X, int64_t n, int64_t d, int64_t ld, const double* w,
+                       const double* y, const int32_t* group, int loss, double threshold, double* out16,
+                       void* scratch, cudaStream_t s);
 int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const double* w, const double* z, double* Dw,
                       double* lam, double rho, int cap, int support_ready, cudaStream_t s);
 int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s);
@@ -779,6 +783,39 @@ int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double*
     RBL_REQUIRE(margins && sigma && out4, "null argument");
     RBL_TRY(rbl_k_sort(h, margins, h->n_global, h->obj_tmp, nullptr, S(stream)));
     return rbl_k_objective(h, h->obj_tmp, sigma, loss, w, out4, S(stream));
+}
+
+// ---- test-set metrics (no handle: a test set has its own row count) -------------------------------------------
+static int metrics_device(int device, int* num_sms) {
+    int ndev = 0, cc_major = 0;
+    RBL_CUDA(cudaGetDeviceCount(&ndev));
+    RBL_REQUIRE(device >= 0 && device < ndev, "no CUDA device %d (found %d); this library has no CPU path", device,
+                ndev);
+    RBL_CUDA(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+    RBL_REQUIRE(cc_major >= 10, "device %d is not sm_100 class; librbl_b200 is built for sm_100a (B200) only", device);
+    RBL_CUDA(cudaDeviceGetAttribute(num_sms, cudaDevAttrMultiProcessorCount, device));
+    return RBL_OK;
+}
+
+int rbl_metrics_scratch_bytes(int device, int64_t* bytes) {
+    RBL_REQUIRE(bytes != nullptr, "null argument");
+    int num_sms = 0;
+    RBL_TRY(metrics_device(device, &num_sms));
+    *bytes = (int64_t)rbl_k_metrics_scratch_bytes(num_sms);
+    return RBL_OK;
+}
+
+int rbl_test_metrics(int device, const double* X, int64_t n, int64_t d, int64_t ld, const double* w,
+                     const double* y, const int32_t* group, int loss, double threshold, double* out16,
+                     void* scratch, rbl_stream_t stream) {
+    RBL_REQUIRE(X && w && y && out16 && scratch, "null argument");
+    RBL_REQUIRE(n > 0 && d > 0 && ld >= d, "bad shape: n=%lld d=%lld ld=%lld", (long long)n, (long long)d,
+                (long long)ld);
+    RBL_REQUIRE(loss == RBL_LOSS_BCE || loss == RBL_LOSS_HINGE, "unknown loss id %d", loss);
+    int num_sms = 0;
+    RBL_TRY(metrics_device(device, &num_sms));
+    RBL_CUDA(cudaSetDevice(device));
+    return rbl_k_test_metrics(num_sms, X, n, d, ld, w, y, group, loss, threshold, out16, scratch, S(stream));
 }
 
 }  // extern "C"

@@ -255,6 +255,23 @@ int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b
 int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double* sigma, const double* w,
                   double* out4, rbl_stream_t stream);
 
+/* ---- test-set metrics: the step after the path (no handle — a test set has its own row count) ----------------
+ * One pass over X (row-major n x d, leading dimension ld) yields every number that
+ * src/util/calculate_acc.py:3-19 (calculate_accuracy) and src/util/fair_metric.py:3-40 (calculate_statistics)
+ * derive their results from:
+ *   out16[0]  rows whose prediction equals the label (BCE: +1 iff sigmoid(x.w) >= threshold, else -1;
+ *             hinge: always +1, as the reference ships it, calculate_acc.py:14-15)
+ *   out16[1]  n
+ *   out16[2 + 6 g + k], group g in {0, 1}:  k = 0 rows, 1 predicted positive, 2 TP, 3 FN, 4 TN, 5 FP
+ *   out16[14] sum b,  out16[15] sum b log b,  b = sigmoid(x.w) - y01 + 1     (Theil index, fair_metric.py:35-38)
+ * y holds the labels as doubles (-1 / +1); group (int32, may be NULL: all rows in group 0).  Counts are exact
+ * integers in doubles; the two sums are reduced in a fixed order.  scratch: rbl_metrics_scratch_bytes() bytes of
+ * device memory, zeroed once before the first call (the call leaves it ready for the next). */
+int rbl_metrics_scratch_bytes(int device, int64_t* bytes);
+int rbl_test_metrics(int device, const double* X, int64_t n, int64_t d, int64_t ld, const double* w,
+                     const double* y, const int32_t* group, int loss, double threshold, double* out16,
+                     void* scratch, rbl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -172,5 +172,44 @@ def main():
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
 
+
+
+def metrics():
+    """tests/golden/metrics.npz: calculate_acc.py / fair_metric.py of the reference on seeded inputs
+    (`python -m oracle.gen_golden metrics`; does not touch the other fixtures)."""
+    import importlib
+    import sys
+
+    from oracle import ref_shim
+
+    ref_shim.load()
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    try:
+        acc_mod = importlib.import_module("src.util.calculate_acc")
+        fair_mod = importlib.import_module("src.util.fair_metric")
+    finally:
+        sys.path.remove(ref_shim.REF_ROOT)
+    rng = np.random.default_rng(20261019)
+    n, d = 700, 24
+    X = rng.normal(size=(n, d))
+    w_true = rng.normal(size=d)
+    y = np.where(X @ w_true + 0.8 * rng.normal(size=n) > 0, 1, -1).reshape(-1, 1)
+    group = (rng.random(n) < 0.35 + 0.2 * (y.reshape(-1) > 0)).astype(int)   # group membership correlated with y
+    out = {"X": X, "y": y, "group": group}
+    for k, scale in enumerate((1.0, 0.2, 3.0)):
+        w = (w_true * scale + 0.5 * rng.normal(size=d)).reshape(-1, 1)
+        out[f"w{k}"] = w
+        for thr in (0.5, 0.3, 0.8):
+            out[f"ref_acc_bce_{k}_{thr}"] = np.array(acc_mod.calculate_accuracy(w, X, y, threshold=thr))
+            out[f"ref_stats_{k}_{thr}"] = np.array(fair_mod.calculate_statistics(w, X, y, group, threshold=thr),
+                                                   dtype=np.float64)
+        out[f"ref_acc_hinge_{k}"] = np.array(acc_mod.calculate_accuracy(w, X, y, loss="hinge"))
+    out["nw"] = np.array(3)
+    np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
+    print("metrics.npz", os.path.getsize(os.path.join(OUT, "metrics.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    import sys as _sys
+
+    metrics() if "metrics" in _sys.argv[1:] else (main(), metrics())

@@ -449,3 +449,69 @@ class OracleSmoothADMM(OracleADMM):
         if self.w_flag == 1:  # :257-258
             self.w = np.sign(self.w) * np.where((np.abs(self.w) - self.t) > 0, np.abs(self.w) - self.t, 0)
         return self.w
+
+
+# ---------------------------------------------------------------------------------------
+# test-set metrics — the step after the path: calculate_acc.py:3-19, fair_metric.py:3-40
+# ---------------------------------------------------------------------------------------
+def class_probs(w, X):
+    """sigmoid(X w), evaluated on the stable side of 0 (calculate_acc.py:5-8, fair_metric.py:4-7)."""
+    p = np.asarray(X, dtype=np.float64) @ np.asarray(w, dtype=np.float64).reshape(-1)
+    e = np.exp(-np.abs(p))
+    return np.where(p >= 0, 1.0 / (1.0 + e), e / (e + 1.0))
+
+
+def calculate_accuracy(w, X_test, y_test, threshold=0.5, loss="binary_cross_entropy"):
+    """calculate_acc.py:3-19.  BCE: predict +1 iff sigmoid(x.w) >= threshold, else -1.  hinge: the reference maps
+    (x.w >= 0) to {1, 0} and then rewrites the zeros to 1 (:14-15), so every prediction is +1 and the value is the
+    share of positive labels — reproduced as shipped."""
+    y = np.asarray(y_test).reshape(-1)
+    if loss == "binary_cross_entropy":
+        pred = np.where(class_probs(w, X_test) >= threshold, 1, -1)
+    elif loss == "hinge":
+        pred = np.ones(len(y), dtype=int)
+    else:
+        raise ValueError(f"loss '{loss}' is not supported! Options: ['binary_cross_entropy','hinge']")
+    return float(np.mean(pred == y))
+
+
+def confusion_by_group(w, X_test, label_test, group_test, threshold=0.5):
+    """per group g in {0, 1}: [size, predicted positive, TP, FN, TN, FP] (fair_metric.py:11-24), plus
+    sum(b), sum(b log b) for b = prob - y01 + 1 (:35-38)."""
+    prob = class_probs(w, X_test)
+    pred = prob >= threshold
+    y01 = np.asarray(label_test).reshape(-1) == 1          # :9-10 (labels -1 -> 0)
+    grp = np.asarray(group_test).reshape(-1)
+    out = np.zeros((2, 6))
+    for g in (0, 1):
+        sel = grp == g
+        out[g] = [sel.sum(), (pred & sel).sum(), (pred & y01 & sel).sum(), (~pred & y01 & sel).sum(),
+                  (~pred & ~y01 & sel).sum(), (pred & ~y01 & sel).sum()]
+    b = prob - y01 + 1.0
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return out, float(b.sum()), float(np.sum(b * np.log(b)))
+
+
+def statistics_from_counts(counts, sum_b, sum_blogb, n):
+    """SPD, DI, EOD, AOD, TI, FNRD from the confusion counts (fair_metric.py:13-40).  Group 0 is the reference
+    group ("G1"), group 1 the other ("G2").  TI = mean((b/mu) log(b/mu)) = sum(b log b)/(n mu) - log(mu).
+    Empty classes divide by zero exactly as numpy does in the reference (nan / inf, no exception)."""
+    c = np.asarray(counts, dtype=np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        size, pp, tp, fn, tn, fp = (c[:, k] for k in range(6))
+        gp = pp / size
+        spd = gp[1] - gp[0]
+        di = np.inf if gp[0] == 0 else gp[1] / gp[0]
+        tpr, fpr, fnr = tp / (tp + fn), fp / (fp + tn), fn / (tp + fn)
+        eod = tpr[1] - tpr[0]
+        aod = 0.5 * (fpr[1] - fpr[0] + eod)
+        mu = np.float64(sum_b) / n
+        ti = np.float64(sum_blogb) / (n * mu) - np.log(mu)
+        fnrd = fnr[1] - fnr[0]
+    return float(spd), float(di), float(eod), float(aod), float(ti), float(fnrd)
+
+
+def calculate_statistics(w, X_test, label_test, group_test, threshold=0.5):
+    """fair_metric.py:3-40 -> (SPD, DI, EOD, AOD, TI, FNRD)."""
+    counts, sb, sbl = confusion_by_group(w, X_test, label_test, group_test, threshold)
+    return statistics_from_counts(counts, sb, sbl, len(np.asarray(label_test).reshape(-1)))

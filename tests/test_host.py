@@ -180,3 +180,25 @@ def test_row_sharded_collectives_on_gloo():
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
     assert all("OK" in o for o in outs), outs
+
+
+def test_fair_statistics_host_formulas_match_reference(golden_dir):
+    """rbl_b200.metrics.statistics_from_counts (the host half of calculate_statistics) on confusion counts produced by
+    the oracle, against the reference's own outputs in tests/golden/metrics.npz (fair_metric.py:13-40)."""
+    from oracle import rbl_oracle as O
+    from rbl_b200.metrics import statistics_from_counts
+
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    X, y, grp = g["X"], g["y"], g["group"]
+    n = X.shape[0]
+    for k in range(int(g["nw"])):
+        for thr in (0.5, 0.3, 0.8):
+            counts, sb, sbl = O.confusion_by_group(g[f"w{k}"], X, y, grp, thr)
+            c = np.zeros(16)
+            c[1], c[2:14], c[14], c[15] = n, counts.reshape(-1), sb, sbl
+            np.testing.assert_allclose(statistics_from_counts(c), g[f"ref_stats_{k}_{thr}"], rtol=1e-13, atol=1e-14)
+    # empty classes: nan / inf as in the reference, no exception
+    c = np.zeros(16)
+    c[1], c[2], c[8], c[14], c[15] = 4, 2, 2, 4.0, 0.0
+    spd, di, *_ = statistics_from_counts(c)
+    assert spd == 0.0 and di == np.inf

@@ -201,3 +201,21 @@ def test_smooth_admm_tracks_reference(golden_dir):
     assert np.linalg.norm(w - ref) < 2e-3 * np.linalg.norm(ref)
     assert abs(o.objective() - float(g["sadmm_erm_l1_obj"])) < 5e-5
     assert np.count_nonzero(w) == np.count_nonzero(ref)
+
+
+def test_metrics_match_reference(golden_dir):
+    """calculate_accuracy / calculate_statistics restatements against the reference's own functions
+    (calculate_acc.py, fair_metric.py) on the seeded inputs of oracle/gen_golden.py::metrics."""
+    g = _load(golden_dir, "metrics.npz")
+    X, y, grp = g["X"], g["y"], g["group"]
+    for k in range(int(g["nw"])):
+        w = g[f"w{k}"]
+        for thr in (0.5, 0.3, 0.8):
+            # counts are integers: the accuracy is exact
+            assert O.calculate_accuracy(w, X, y, threshold=thr) == float(g[f"ref_acc_bce_{k}_{thr}"])
+            # rates are ratios of the same integers (exact); TI sums n terms in another order: 1e-13
+            np.testing.assert_allclose(O.calculate_statistics(w, X, y, grp, threshold=thr), g[f"ref_stats_{k}_{thr}"],
+                                       rtol=1e-13, atol=1e-14)
+        assert O.calculate_accuracy(w, X, y, loss="hinge") == float(g[f"ref_acc_hinge_{k}"])
+    with pytest.raises(ValueError):
+        O.calculate_accuracy(g["w0"], X, y, loss="multinomial_cross_entropy")
