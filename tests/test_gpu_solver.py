@@ -180,6 +180,42 @@ def test_driver_style_run_with_store(golden_dir):
         ADMMmethod(d["X"], d["y"], "erm", "binary_cross_entropy")                          # no regulariser
 
 
+def test_aorr_and_ehrm_driver_flows_with_test_metrics():
+    """run_AoRR_fixed.py:152-156 and run_EHRM.py:36-41 end to end on the drop-in names: solver with an intercept
+    column, start_store on the test split with its own spectrum args, main_loop, final_res, calculate_accuracy and
+    calculate_statistics — every number against the oracle on the same w."""
+    from src.optim.algorithms import ADMMmethod
+    from src.util.calculate_acc import calculate_accuracy
+    from src.util.fair_metric import calculate_statistics
+
+    rng = np.random.default_rng(77)
+    n, nt, d = 900, 600, 9
+    Xa = rng.normal(size=(n + nt, d))
+    ws = rng.normal(size=d)
+    ya = np.where(Xa @ ws + 0.7 * rng.normal(size=n + nt) > 0, 1, -1).reshape(-1, 1)
+    grp = (rng.random(n + nt) < 0.4).astype(int)
+    X, Xt = np.hstack([Xa[:n], np.ones((n, 1))]), np.hstack([Xa[n:], np.ones((nt, 1))])
+    y, yt, gt = ya[:n], ya[n:], grp[n:]
+    for wf, loss, args, targs, B in (("aorr_dc", "hinge", [500, 10], [1, 0], None),
+                                     ("ehrm", "binary_cross_entropy", None, None, -5)):
+        s = ADMMmethod(X, y, wf, loss, l2_reg=1e-4 if wf == "aorr_dc" else 0.01, B=B, args=args, max_iter=25)
+        s.start_store(Xt, yt, wf, loss, l2_reg=1e-4 if wf == "aorr_dc" else 0.01, B=B, args=targs)
+        with contextlib.redirect_stdout(io.StringIO()):
+            s.main_loop(verbose=False)
+        w, t, tr, te = s.final_res()
+        assert w.shape == (d + 1, 1) and len(t) == len(tr) == len(te) and np.all(np.isfinite(te))
+        sig_t = O.spectrum(wf, nt, targs)
+        sig_t = sig_t[0] if isinstance(sig_t, tuple) else sig_t
+        ref_te = O.objective(-yt * Xt, w, sig_t, loss, l2_reg=1e-4 if wf == "aorr_dc" else 0.01)
+        assert abs(te[-1] - ref_te) < 1e-10 * max(1.0, abs(ref_te))
+        acc = calculate_accuracy(w.reshape(-1, 1), Xt, yt, threshold=0.5, loss=loss)
+        assert acc == O.calculate_accuracy(w, Xt, yt, 0.5, loss)
+        if wf == "ehrm":
+            np.testing.assert_allclose(calculate_statistics(w.reshape(-1, 1), Xt, yt, gt),
+                                       O.calculate_statistics(w, Xt, yt, gt), rtol=1e-12, atol=1e-13)
+        s.engine.close()
+
+
 def test_full_size_properties():
     """BASELINE config-2 sized z-step (n = 1M): size-independent properties instead of an oracle run."""
     from rbl_b200 import _cabi
@@ -258,6 +294,9 @@ def test_smooth_admm_vs_oracle_and_reference(golden_dir):
     ("C4 twin hinge", 2400, 200, "aorr", [0.2, 0.8], "hinge", None, dict(l2_reg=1e-4), True),
     ("C4 twin bce", 2400, 200, "aorr", [0.2, 0.8], "binary_cross_entropy", None, dict(l2_reg=1e-4), True),
     ("extremile", 3000, 40, "extremile", [2.0], "hinge", None, dict(l1_reg=0.05), False),
+    # run_AoRR_fixed.py:109-155: aorr_dc with [k, m] as counts (titanic-like: n ~ 800, k = 500, m = 10), intercept
+    ("AoRR fixed hinge", 800, 12, "aorr_dc", [500, 10], "hinge", None, dict(l2_reg=1e-4), True),
+    ("AoRR fixed bce", 800, 12, "aorr_dc", [500, 10], "binary_cross_entropy", None, dict(l2_reg=1e-4), True),
 ])
 def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw, intercept):
     """Reduced-n twins of BASELINE configs 2-4 on planted data, 30 ADMM iterations in lockstep
