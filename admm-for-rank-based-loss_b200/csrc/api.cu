@@ -56,6 +56,11 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
                          cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate, double* G, double* scratch,
                      cudaStream_t s);
+int rbl_k_standardize_scratch_doubles(int num_sms, int64_t ld, int64_t* out);
+int rbl_k_standardize(int num_sms, double* X, int64_t n, int64_t ld, double* mean, double* scale, double* scratch,
+                      cudaStream_t s);
+int rbl_k_gather_rows(int num_sms, const double* X, int64_t ld_in, const int64_t* idx, int64_t n_out, int64_t d,
+                      double* out, int64_t ld_out, cudaStream_t s);
 size_t rbl_k_metrics_scratch_bytes(int num_sms);
 int rbl_k_test_metrics(int num_sms, const double* X, int64_t n, int64_t d, int64_t ld, const double* w,
                        const double* y, const int32_t* group, int loss, double threshold, double* out16,
@@ -816,6 +821,45 @@ int rbl_test_metrics(int device, const double* X, int64_t n, int64_t d, int64_t 
     RBL_TRY(metrics_device(device, &num_sms));
     RBL_CUDA(cudaSetDevice(device));
     return rbl_k_test_metrics(num_sms, X, n, d, ld, w, y, group, loss, threshold, out16, scratch, S(stream));
+}
+
+// ---- data ingest on the device (the step before the path) ------------------------------------------------------
+int rbl_standardize_scratch_bytes(int device, int64_t ld, int64_t* bytes) {
+    RBL_REQUIRE(bytes != nullptr && ld > 0 && ld % 2 == 0, "bad argument (ld must be even)");
+    int num_sms = 0;
+    RBL_TRY(metrics_device(device, &num_sms));
+    int64_t doubles = 0;
+    rbl_k_standardize_scratch_doubles(num_sms, ld, &doubles);
+    *bytes = doubles * (int64_t)sizeof(double);
+    return RBL_OK;
+}
+
+int rbl_standardize_columns(int device, double* X, int64_t n, int64_t d, int64_t ld, double* mean_out,
+                            double* scale_out, void* scratch, rbl_stream_t stream) {
+    RBL_REQUIRE(X && mean_out && scale_out && scratch, "null argument");
+    RBL_REQUIRE(n > 0 && d > 0 && ld >= d && ld % 2 == 0, "bad shape: n=%lld d=%lld ld=%lld (ld must be even)",
+                (long long)n, (long long)d, (long long)ld);
+    RBL_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(mean_out) % 16 == 0 &&
+                    reinterpret_cast<uintptr_t>(scale_out) % 16 == 0,
+                "X, mean_out and scale_out must be 16-byte aligned");
+    int num_sms = 0;
+    RBL_TRY(metrics_device(device, &num_sms));
+    RBL_CUDA(cudaSetDevice(device));
+    return rbl_k_standardize(num_sms, X, n, ld, mean_out, scale_out, reinterpret_cast<double*>(scratch), S(stream));
+}
+
+int rbl_gather_rows(int device, const double* X, int64_t ld_in, const int64_t* idx, int64_t n_out, int64_t d,
+                    double* out, int64_t ld_out, rbl_stream_t stream) {
+    RBL_REQUIRE(X && idx && out, "null argument");
+    RBL_REQUIRE(n_out > 0 && d > 0 && ld_in >= d && ld_out >= d && ld_in % 2 == 0 && ld_out % 2 == 0,
+                "bad shape: n_out=%lld d=%lld ld_in=%lld ld_out=%lld (leading dimensions must be even)",
+                (long long)n_out, (long long)d, (long long)ld_in, (long long)ld_out);
+    RBL_REQUIRE(reinterpret_cast<uintptr_t>(X) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0,
+                "X and out must be 16-byte aligned");
+    int num_sms = 0;
+    RBL_TRY(metrics_device(device, &num_sms));
+    RBL_CUDA(cudaSetDevice(device));
+    return rbl_k_gather_rows(num_sms, X, ld_in, idx, n_out, d, out, ld_out, S(stream));
 }
 
 }  // extern "C"

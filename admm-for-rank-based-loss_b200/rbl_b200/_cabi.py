@@ -82,6 +82,11 @@ _SIGNATURES = {
     "rbl_dual_update": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _c.c_int, _dp, _c.c_double, _dp, _dp, _dp,
                                    _c.c_void_p]),
     "rbl_objective": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _dp, _dp, _c.c_void_p]),
+    "rbl_standardize_scratch_bytes": (_c.c_int, [_c.c_int, _c.c_int64, _c.POINTER(_c.c_int64)]),
+    "rbl_standardize_columns": (_c.c_int, [_c.c_int, _dp, _c.c_int64, _c.c_int64, _c.c_int64, _dp, _dp, _dp,
+                                           _c.c_void_p]),
+    "rbl_gather_rows": (_c.c_int, [_c.c_int, _dp, _c.c_int64, _dp, _c.c_int64, _c.c_int64, _dp, _c.c_int64,
+                                   _c.c_void_p]),
     "rbl_metrics_scratch_bytes": (_c.c_int, [_c.c_int, _c.POINTER(_c.c_int64)]),
     "rbl_test_metrics": (_c.c_int, [_c.c_int, _dp, _c.c_int64, _c.c_int64, _c.c_int64, _dp, _dp, _dp, _c.c_int,
                                     _c.c_double, _dp, _dp, _c.c_void_p]),

@@ -29,8 +29,9 @@ class Optimizer:
         # _shard (extension, not in the reference): dict(row_lo=, n_global=[, group=]) when X, y are this
         # rank's contiguous rows of a row-sharded problem (one process per GPU, torch.distributed/NCCL)
         _t0 = time.perf_counter()
-        X = np.asarray(X)
-        y = np.asarray(y)
+        if not torch.is_tensor(X):  # a (device) tensor is taken as it is: no copy back to the host
+            X = np.asarray(X)
+        y = y.detach().cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
         _shard = _shard or {}
         self.num_row = int(_shard.get("n_global", X.shape[0]))
         self.num_feature = X.shape[1]
@@ -121,7 +122,9 @@ class Optimizer:
     def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                     B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):
         # X, y both are test set.
-        self.test_objective = rankbasedObjective(torch.from_numpy(np.asarray(X)), torch.from_numpy(np.asarray(y)),
+        Xt = X if torch.is_tensor(X) else torch.from_numpy(np.asarray(X))
+        yt = y if torch.is_tensor(y) else torch.from_numpy(np.asarray(y))
+        self.test_objective = rankbasedObjective(Xt, yt,
                                                  weight_function, loss, l2_reg, l1_reg, B, n_class, args)
         self.w_time = [0]
         self.z_time = [0]

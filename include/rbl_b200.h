@@ -272,6 +272,19 @@ int rbl_test_metrics(int device, const double* X, int64_t n, int64_t d, int64_t 
                      const double* y, const int32_t* group, int loss, double threshold, double* out16,
                      void* scratch, rbl_stream_t stream);
 
+/* ---- data ingest on the device: the step before the path (no handle) ------------------------------------------
+ * rbl_standardize_columns: X <- (X - mean) / std per column, in place — `preprocessing.scale(X)` of
+ * src/util/load_data.py:115 (scikit-learn semantics: population std, columns with std < 10 eps keep scale 1).
+ * X is row-major n x d with an EVEN leading dimension ld (padding columns must be zero and stay zero);
+ * mean_out / scale_out receive ld doubles each.  scratch: rbl_standardize_scratch_bytes(device, ld) bytes.
+ * rbl_gather_rows: out[i, :] = X[idx[i], :] for i < n_out (int64 row indices on the device) — the row selection of
+ * the drivers' train_test_split (run_SRM.py:26). */
+int rbl_standardize_scratch_bytes(int device, int64_t ld, int64_t* bytes);
+int rbl_standardize_columns(int device, double* X, int64_t n, int64_t d, int64_t ld, double* mean_out,
+                            double* scale_out, void* scratch, rbl_stream_t stream);
+int rbl_gather_rows(int device, const double* X, int64_t ld_in, const int64_t* idx, int64_t n_out, int64_t d,
+                    double* out, int64_t ld_out, rbl_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,82 @@
+"""GPU parity: device-side data ingest (rbl_standardize_columns, rbl_gather_rows through the C ABI) against
+scikit-learn's own `preprocessing.scale` and `train_test_split` — the third-party calls the reference's
+load_data.py:115 / run_SRM.py:26 make."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n,d", [(1, 2), (5, 1), (1000, 7), (4097, 64), (30001, 200), (20000, 1001), (300, 5000)])
+def test_standardize_matches_sklearn_scale(n, d):
+    from sklearn import preprocessing
+
+    from rbl_b200 import ingest
+
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d)) * rng.uniform(0.1, 30.0, size=d) + rng.normal(size=d) * 5.0
+    if d > 2:
+        X[:, 1] = 3.25          # constant column: std 0 -> scale stays 1, result exactly 0
+    ref = preprocessing.scale(X)
+    Xp, dd = ingest.to_device_padded(X)
+    mean, scale = ingest.standardize_(Xp, dd)
+    got = Xp[:, :d].cpu().numpy()
+    # same formulas, other summation order: mean and std agree to ~1e-15 relative, the quotient to ~1e-14 absolute
+    np.testing.assert_allclose(mean.cpu().numpy(), X.mean(axis=0), rtol=1e-13, atol=1e-14)
+    sd = X.std(axis=0)
+    sd[sd < 10 * np.finfo(float).eps] = 1.0
+    np.testing.assert_allclose(scale.cpu().numpy(), sd, rtol=1e-13)
+    np.testing.assert_allclose(got, ref, rtol=0, atol=2e-12)
+    if d > 2:
+        assert np.all(got[:, 1] == 0.0)
+    if Xp.shape[1] != d:
+        assert torch.all(Xp[:, d] == 0)          # the padding column stays zero
+    # idempotent up to rounding: standardised data has mean 0 and std 1
+    m2, s2 = ingest.standardize_(Xp, dd)
+    keep = np.ones(d, dtype=bool)
+    if d > 2:
+        keep[1] = False
+    if n > 1:
+        assert np.max(np.abs(m2.cpu().numpy())) < 1e-13 and np.max(np.abs(s2.cpu().numpy()[keep] - 1)) < 1e-12
+
+
+def test_split_matches_sklearn_and_feeds_the_solver():
+    from sklearn.model_selection import train_test_split
+
+    from rbl_b200 import ingest
+    from src.optim.algorithms import ADMMmethod
+    from src.util.load_data import get_data
+
+    X, y = get_data("synthetic", num_row=3000, num_feature=41, seed=17)               # host path (reference recipe)
+    Xd, yd = get_data("synthetic", num_row=3000, num_feature=41, seed=17, device="cuda")  # device standardisation
+    assert np.array_equal(y, yd)
+    np.testing.assert_allclose(Xd.cpu().numpy(), X, rtol=0, atol=2e-12)
+    Xtr, Xte, ytr, yte = train_test_split(X, y, test_size=0.4, random_state=17)
+    Xp, d = ingest.to_device_padded(X)
+    got = ingest.train_test_split_device(Xp, y, test_size=0.4, random_state=17, d=d)
+    np.testing.assert_array_equal(got[0][:, :d].cpu().numpy(), Xtr)     # same rows, bit for bit
+    np.testing.assert_array_equal(got[1][:, :d].cpu().numpy(), Xte)
+    np.testing.assert_array_equal(got[2], ytr)
+    np.testing.assert_array_equal(got[3], yte)
+    with pytest.raises(IndexError):
+        ingest.split_rows(Xp, np.array([0, 3000]))
+    # the device tensors go straight into the solver: same iterates as from the host arrays
+    s1 = ADMMmethod(Xtr, ytr, "superquantile", "binary_cross_entropy", l2_reg=0.01, args=[0.8], max_iter=8)
+    s2 = ADMMmethod(got[0][:, :d], ytr, "superquantile", "binary_cross_entropy", l2_reg=0.01, args=[0.8], max_iter=8)
+    w1, w2 = s1.main_loop(verbose=False), s2.main_loop(verbose=False)
+    np.testing.assert_array_equal(w1, w2)
+    s1.engine.close()
+    s2.engine.close()
+
+
+def test_standardize_full_size_properties():
+    """2 M x 500 (8 GB): column means 0 and stds 1 after the pass, to rounding; untouched padding not applicable."""
+    from rbl_b200 import ingest
+
+    n, d = 2_000_000, 500
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    X = torch.randn((n, d), dtype=torch.float64, device="cuda", generator=gen) * 7.0 + 2.5
+    ingest.standardize_(X)
+    assert float(X.mean(dim=0).abs().max()) < 1e-12
+    assert float((X.std(dim=0, unbiased=False) - 1).abs().max()) < 1e-12
