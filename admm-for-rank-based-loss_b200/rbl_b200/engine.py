@@ -225,10 +225,13 @@ class DeviceProblem:
         _cabi.check(self.lib.rbl_matvec(self.h, self.D.data_ptr(), x.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def objective_terms(self, w, sigma, loss):
-        """(sum_i sigma_i loss(u_(i)), ||w||^2, ||w||_1) for u = D w  (objective.py:71-87)"""
-        self.matvec(w, self._u_local)
-        self.gather_rows(self._u_local, self._u_glob)
+    def objective_terms(self, w, sigma, loss, u_local=None):
+        """(sum_i sigma_i loss(u_(i)), ||w||^2, ||w||_1) for u = D w  (objective.py:71-87).
+        u_local: the margins D w of this rank's rows when the caller already holds them (no pass over D)"""
+        if u_local is None:
+            self.matvec(w, self._u_local)
+            u_local = self._u_local
+        self.gather_rows(u_local, self._u_glob)
         _cabi.check(self.lib.rbl_objective(self.h, LOSS_IDS[loss], self._u_glob.data_ptr(), sigma.data_ptr(),
                                            w.data_ptr(), self._out4.data_ptr(), self._stream()))
         self._out4_host.copy_(self._out4, non_blocking=True)

@@ -228,6 +228,21 @@ class _LazyObjective(rankbasedObjective):
         self.problem = engine
         self._alphas_dev = engine.vec(self.alphas)
 
+    def get_arrogate_loss(self, w, include_reg=True):
+        """objective.py:71-87.  Right after a dual step the engine holds D w for exactly this w (the per-iteration
+        train loss of start_store, algorithms.py:160): the margins are reused and no pass over D is made."""
+        eng = self.problem
+        wt = w if torch.is_tensor(w) else torch.from_numpy(np.ascontiguousarray(w))
+        if (getattr(eng, "Dw_valid", False) and not wt.is_cuda and wt.numel() == eng.d
+                and torch.equal(wt.reshape(-1).to(torch.float64), eng.w_host.reshape(-1))):
+            risk, w2, w1 = eng.objective_terms(eng.w, self._alphas_dev, self.loss_name, u_local=eng.Dw)
+            if self.l2_reg and include_reg:
+                risk += 0.5 * self.l2_reg * w2
+            if self.l1_reg and include_reg:
+                risk += 0.5 * self.l1_reg * w1
+            return risk
+        return super().get_arrogate_loss(w, include_reg)
+
 
 class _Deferred:
     def vec(self, a):

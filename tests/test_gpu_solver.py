@@ -208,6 +208,14 @@ def test_aorr_and_ehrm_driver_flows_with_test_metrics():
         sig_t = sig_t[0] if isinstance(sig_t, tuple) else sig_t
         ref_te = O.objective(-yt * Xt, w, sig_t, loss, l2_reg=1e-4 if wf == "aorr_dc" else 0.01)
         assert abs(te[-1] - ref_te) < 1e-10 * max(1.0, abs(ref_te))
+        # the per-iteration train loss reuses the engine's D w (no extra pass over D): same value
+        sig = O.spectrum(wf, n, args)
+        sig = sig[0] if isinstance(sig, tuple) else sig
+        ref_tr = O.objective(-y * X, w, sig, loss, l2_reg=1e-4 if wf == "aorr_dc" else 0.01)
+        assert abs(tr[-1] - ref_tr) < 1e-10 * max(1.0, abs(ref_tr))
+        from src.optim.objective import rankbasedObjective
+        fresh = rankbasedObjective.get_arrogate_loss(s.objective, torch.from_numpy(w).double())  # with its own pass
+        assert abs(fresh - tr[-1]) < 1e-12 * max(1.0, abs(fresh))
         acc = calculate_accuracy(w.reshape(-1, 1), Xt, yt, threshold=0.5, loss=loss)
         assert acc == O.calculate_accuracy(w, Xt, yt, 0.5, loss)
         if wf == "ehrm":
