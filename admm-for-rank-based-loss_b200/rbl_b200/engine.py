@@ -173,14 +173,16 @@ class DeviceProblem:
     @property
     def launches(self):
         """kernels launched through librbl_b200 by this process (bench.py's gpu_launches)"""
-        return int(self.lib.rbl_launch_count()) + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_launches", 0)
+        return (int(self.lib.rbl_launch_count())
+                + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_launches", 0)
+                + getattr(self, "_graph_l2_replays", 0) * getattr(self, "_graph_l2_launches", 0))
 
     def close(self):
         # a captured iteration graph holds NCCL work in a row-sharded job: drop it before the handle (and before
         # the caller destroys the process group)
-        if getattr(self, "_graph", None) is not None:
+        if getattr(self, "_graph", None) is not None or getattr(self, "_graph_l2", None) is not None:
             torch.cuda.synchronize(self.device)
-            self._graph = None
+            self._graph = self._graph_l2 = None
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.rbl_destroy(self.h)
             self.h = ctypes.c_void_p()
@@ -311,6 +313,7 @@ class AdmmEngine(DeviceProblem):
         self.graph_ok = os.environ.get("RBL_GRAPH", "1") != "0"
         self.graph_mgpu = os.environ.get("RBL_GRAPH_MGPU", "1") != "0"  # capture the NCCL collectives as well
         self._graph, self._graph_key, self._iters_eager = None, None, 0
+        self._graph_l2, self._graph_l2_active, self._iters_eager_l2, self._pre_done = None, False, 0, False
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
         self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
@@ -332,6 +335,7 @@ class AdmmEngine(DeviceProblem):
         self._delta_valid = False
         self._support_ready = False
         self._iters_eager = 0  # a few eager iterations again before the graph path resumes
+        self._iters_eager_l2, self._pre_done = 0, False
         if w is not None:
             self.w.copy_(self.vec(w))
             self.Dw_valid = False
@@ -584,6 +588,79 @@ class AdmmEngine(DeviceProblem):
         self.lbfgs_evals += 1
         return f, g
 
+    def _warm_start_pass(self):
+        """what every L-BFGS w-step starts from: w_prev = w (device and host) and, in Gram mode,
+        red0 = [D^T (b - D w), ||b - D w||^2] from the one pass over D (active rows only right after a z-step)"""
+        self.w_prev.copy_(self.w)
+        self.w_host.copy_(self.w, non_blocking=True)
+        if self.w_mode == "gram":
+            self.gram()
+            use_active, self._delta_valid = self._delta_valid, False
+            self._pass_at(self.w_prev, self.b, use_active)
+
+    def z_and_grad(self, rho):
+        """z-step + the warm-start pass of an L-BFGS w-step (l2 and smoothed-l1 problems).  In Gram mode the launch
+        sequence is static (every data-dependent branch is taken on the device), so after two eager iterations
+        it is captured as a CUDA graph and replayed with rho refreshed in the device scalar block: ~20 launches
+        become one; the host then only drives scipy's L-BFGS-B over rbl_gram_eval."""
+        can_graph = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
+                     and self._iters_eager_l2 >= 2 and self.Dw_valid and self.G is not None
+                     and not getattr(self, "_r_matches_w", False))
+        if can_graph and self._graph_l2 is None:
+            self._capture_l2()
+        if can_graph and self._graph_l2 is not None:
+            self._scal_np[0] = float(rho)
+            self._graph_l2.replay()
+            self._graph_l2_replays += 1
+            self._delta_valid, self._pre_done = False, True
+            self._active_pending = self._graph_l2_active
+            return
+        self._iters_eager_l2 += 1
+        self.z_step(rho)
+        self._warm_start_pass()
+        self._pre_done = True
+
+    def _ensure_scalars(self):
+        if not hasattr(self, "scal"):
+            self.scal = torch.zeros(4, dtype=torch.float64, device=self.device)
+            self.scal_host = torch.zeros(4, dtype=torch.float64).pin_memory()
+            self._scal_np = self.scal_host.numpy()
+
+    def _capture_l2(self):
+        dev = self.device
+        self._ensure_scalars()
+        torch.cuda.current_stream(dev).synchronize()
+        stats = (dict(self.fista_stats), dict(self.dual_stats), dict(self.active_stats))
+        g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.rbl_launch_count())
+        _cabi.check(self.lib.rbl_bind_scalars(self.h, self.scal.data_ptr()))
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_cap_stream"):
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        try:
+            self._cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self._cap_stream):
+                g.capture_begin()
+                try:
+                    self.scal.copy_(self.scal_host, non_blocking=True)
+                    self.z_step(1.0)                      # by-value scalars are ignored while bound
+                    self._graph_l2_active = bool(self._delta_valid)
+                    self._warm_start_pass()
+                finally:
+                    g.capture_end()
+            cur.wait_stream(self._cap_stream)
+            self._graph_l2 = g
+            self._graph_l2_launches, self._graph_l2_replays = int(self.lib.rbl_launch_count()) - n0, 0
+        except Exception as exc:  # noqa: BLE001 — capture unsupported here: stay on eager launches
+            import warnings
+            warnings.warn(f"rbl_b200: CUDA graph capture of the z-step + gradient pass failed ({exc!r}); "
+                          "continuing with eager launches", RuntimeWarning, stacklevel=2)
+            self._graph_l2, self.graph_ok = None, False
+        finally:
+            _cabi.check(self.lib.rbl_bind_scalars(self.h, 0))
+            self.fista_stats, self.dual_stats, self.active_stats = stats
+            self._active_pending = False
+
     def w_step_lbfgs(self, rho, reg, maxiter=1000, reg_fg=None):
         """scipy L-BFGS-B (host, d-vector control logic) over the fused device pass.
         reg_fg=None: the l2 problem of w_LBFGS.py:31-53; otherwise a smooth regulariser (sADMM)."""
@@ -592,12 +669,9 @@ class AdmmEngine(DeviceProblem):
         if not hasattr(self, "_wtmp"):
             self._wtmp = torch.zeros(self.d, dtype=torch.float64, device=self.device)
             self.lbfgs_evals = 0
-        self.w_prev.copy_(self.w)
-        self.w_host.copy_(self.w)
-        if self.w_mode == "gram":
-            self.gram()
-            use_active, self._delta_valid = self._delta_valid, False
-            self._pass_at(self.w_prev, self.b, use_active)
+        pre_done, self._pre_done = getattr(self, "_pre_done", False), False
+        if not pre_done:  # (z_and_grad has already made the warm-start pass, inside its graph)
+            self._warm_start_pass()
         torch.cuda.current_stream(self.device).synchronize()
         w0 = self.w_host.numpy().copy()
         rho, reg = float(rho), float(reg)
@@ -766,10 +840,7 @@ class AdmmEngine(DeviceProblem):
     def _capture_iteration(self, key):
         tol, max_iter = key
         dev = self.device
-        if not hasattr(self, "scal"):
-            self.scal = torch.zeros(4, dtype=torch.float64, device=dev)
-            self.scal_host = torch.zeros(4, dtype=torch.float64).pin_memory()
-            self._scal_np = self.scal_host.numpy()
+        self._ensure_scalars()
         torch.cuda.current_stream(dev).synchronize()
         stats = (dict(self.fista_stats), dict(self.dual_stats), dict(self.active_stats))
         g = torch.cuda.CUDAGraph()

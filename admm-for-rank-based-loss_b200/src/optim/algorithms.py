@@ -157,7 +157,13 @@ class Optimizer:
                 self.rho, alpha * self.num_row, tol=self.w_tol, max_iter=self.fista_max_iter)
         else:
             t1 = self._sync_timer()
-            self.engine.z_step(self.rho)
+            if not self.store and self._w_step_is_lbfgs():
+                # z-step and the warm-start pass of the L-BFGS w-step as one device-side sequence (a CUDA graph
+                # after warm-up); with start_store the two steps stay apart so that z_time / w_time keep their
+                # meaning
+                self.engine.z_and_grad(self.rho)
+            else:
+                self.engine.z_step(self.rho)
             t2 = self._sync_timer()
             if self.store:
                 self.z_time.append(t2 - t1 + self.z_time[i])
@@ -202,6 +208,9 @@ class Optimizer:
 
     def _whole_iteration_on_device(self):
         return False
+
+    def _w_step_is_lbfgs(self):
+        return self.w_flag == 2
 
     def _w_subproblem_device(self):
         """w-step leaving the result on the device (the numpy view is refreshed by the dual step)."""
@@ -348,6 +357,9 @@ class smoothADMMmethod(Optimizer):
 
     def _z_subproblem(self):
         return super(smoothADMMmethod, self).z_subproblem()
+
+    def _w_step_is_lbfgs(self):
+        return self.w_flag in (1, 2)  # the Huber-smoothed l1 problem goes through L-BFGS-B as well (:247-251)
 
     def _w_subproblem_device(self):
         if self.w_flag == 1:
