@@ -59,7 +59,7 @@ class DeviceTestSet:
         lid = _loss_id(loss)
         with torch.cuda.device(self.device):
             if torch.is_tensor(w) and w.is_cuda:
-                wd = w.reshape(-1).to(torch.float64)
+                wd = w.reshape(-1).to(device=self.device, dtype=torch.float64).contiguous()
             else:
                 wh = torch.from_numpy(np.ascontiguousarray(np.asarray(w, dtype=np.float64).reshape(-1)))
                 self._w.copy_(wh, non_blocking=False)

@@ -39,6 +39,24 @@ def test_product_fails_loudly_without_gpu():
 
     with pytest.raises(RblError):
         ADMMmethod(np.zeros((8, 2)), np.ones((8, 1)), l1_reg=0.1)
+    # the steps either side of the loop have no CPU path either
+    from rbl_b200 import ingest
+    from src.util.calculate_acc import calculate_accuracy
+    from src.util.fair_metric import calculate_statistics
+    from src.util.load_data import get_data
+
+    with pytest.raises(RblError):
+        calculate_accuracy(np.zeros((2, 1)), np.zeros((8, 2)), np.ones((8, 1)))
+    with pytest.raises(RblError):
+        calculate_statistics(np.zeros((2, 1)), np.zeros((8, 2)), np.ones((8, 1)), np.zeros(8, dtype=int))
+    with pytest.raises(RblError):
+        ingest.to_device_padded(np.zeros((8, 3)))
+    with pytest.raises(RblError):
+        get_data("synthetic", num_row=50, num_feature=20, seed=1, device="cuda")
+    with pytest.raises(ValueError, match="is not supported"):   # argument errors come first, as in the reference
+        calculate_accuracy(np.zeros((2, 1)), np.zeros((8, 2)), np.ones((8, 1)), loss="nope")
+    X, y = get_data("synthetic", num_row=50, num_feature=20, seed=1)   # the reference's host recipe still works
+    assert X.shape == (50, 20) and set(np.unique(y)) == {-1, 1} and abs(X.mean()) < 1e-12
 
 
 def test_product_never_imports_the_oracle():
