@@ -205,6 +205,15 @@ def metrics():
                                                    dtype=np.float64)
         out[f"ref_acc_hinge_{k}"] = np.array(acc_mod.calculate_accuracy(w, X, y, loss="hinge"))
     out["nw"] = np.array(3)
+    # split_group.py:3-25 (run_EHRM.py:25): row ids recovered by splitting X = arange(n)
+    sys.path.insert(0, ref_shim.REF_ROOT)
+    try:
+        split_mod = importlib.import_module("src.util.split_group")
+    finally:
+        sys.path.remove(ref_shim.REF_ROOT)
+    ids = np.arange(n).reshape(-1, 1)
+    tr, te, ytr, yte, gtr, gte = split_mod.train_test_split_group(ids, y, group, test_size=0.4, random_state=17)
+    out["ref_split_train_ids"], out["ref_split_test_ids"] = tr.reshape(-1), te.reshape(-1)
     np.savez_compressed(os.path.join(OUT, "metrics.npz"), **out)
     print("metrics.npz", os.path.getsize(os.path.join(OUT, "metrics.npz")))
 

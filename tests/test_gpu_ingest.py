@@ -80,3 +80,20 @@ def test_standardize_full_size_properties():
     ingest.standardize_(X)
     assert float(X.mean(dim=0).abs().max()) < 1e-12
     assert float((X.std(dim=0, unbiased=False) - 1).abs().max()) < 1e-12
+
+
+def test_split_group_on_device_rows_match_host_split():
+    """run_EHRM.py:25 flow with a device-resident X: same rows as the host split, labels and groups alongside."""
+    from src.util.split_group import train_test_split_group
+
+    rng = np.random.default_rng(5)
+    n, d = 1201, 13
+    X = rng.normal(size=(n, d))
+    y = np.where(rng.random(n) > 0.5, 1, -1).reshape(-1, 1)
+    grp = (rng.random(n) < 0.3).astype(int)
+    host = train_test_split_group(X, y, grp, test_size=0.4, random_state=17)
+    dev = train_test_split_group(torch.from_numpy(X).cuda(), y, grp, test_size=0.4, random_state=17)
+    np.testing.assert_array_equal(dev[0].cpu().numpy(), host[0])
+    np.testing.assert_array_equal(dev[1].cpu().numpy(), host[1])
+    for a, b in zip(dev[2:], host[2:]):
+        np.testing.assert_array_equal(a, b)

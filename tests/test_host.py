@@ -220,3 +220,19 @@ def test_fair_statistics_host_formulas_match_reference(golden_dir):
     c[1], c[2], c[8], c[14], c[15] = 4, 2, 2, 4.0, 0.0
     spd, di, *_ = statistics_from_counts(c)
     assert spd == 0.0 and di == np.inf
+
+
+def test_split_group_matches_reference(golden_dir):
+    """src/util/split_group.py mirror against the row ids the reference's own function produced
+    (tests/golden/metrics.npz, oracle/gen_golden.py::metrics)."""
+    from src.util.split_group import train_test_split_group
+
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    X, y, grp = g["X"], g["y"], g["group"]
+    Xtr, Xte, ytr, yte, gtr, gte = train_test_split_group(X, y, grp, test_size=0.4, random_state=17)
+    tr, te = g["ref_split_train_ids"], g["ref_split_test_ids"]
+    assert len(te) == int(len(X) * 0.4) and len(tr) + len(te) == len(X)
+    np.testing.assert_array_equal(Xtr, X[tr])
+    np.testing.assert_array_equal(Xte, X[te])
+    np.testing.assert_array_equal(ytr, y[tr])
+    np.testing.assert_array_equal(gte, grp[te])
