@@ -21,11 +21,15 @@ def _loss_id(loss):
 
 
 class DeviceTestSet:
-    """X (n x d, numpy or torch, host or device), y (n or n x 1, labels -1 / +1), group (n, {0, 1}; optional)."""
+    """X (n x d, numpy or torch, host or device), y (n or n x 1, labels -1 / +1), group (n, {0, 1}; optional).
+    sharded=True (one process per GPU, torch.distributed initialised): X, y, group are THIS rank's rows of the
+    test set; all 16 numbers are sums over rows, so one all-reduce of 128 bytes gives every rank the metrics of the
+    whole set."""
 
-    def __init__(self, X, y, group=None, device=None):
+    def __init__(self, X, y, group=None, device=None, sharded=False, dist_group=None):
         self.lib = _cabi.load()
         self.device = _require_cuda(device)
+        self.sharded, self.dist_group = bool(sharded), dist_group
         with torch.cuda.device(self.device):
             Xt = X if torch.is_tensor(X) else torch.from_numpy(np.ascontiguousarray(X, dtype=np.float64))
             if Xt.dim() != 2:
@@ -75,6 +79,8 @@ class DeviceTestSet:
     def counts(self, w, threshold=0.5, loss="binary_cross_entropy"):
         """-> numpy[16], layout of rbl_test_metrics (include/rbl_b200.h)."""
         out = self.launch(w, threshold, loss)
+        if self.sharded:
+            torch.distributed.all_reduce(out, group=self.dist_group)  # every entry is a sum over rows
         self._out_host.copy_(out, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         return self._out_host.numpy().copy()

@@ -89,6 +89,20 @@ def main():
     prim = torch.tensor([float(np.sum((z_local - Dl @ beta) ** 2))], dtype=torch.float64)
     dist.all_reduce(prim)
     assert abs(float(prim[0]) - np.sum((z_ref - D @ beta) ** 2)) < 1e-11 * float(prim[0])
+    # ---- test-set metrics of a row-sharded test set (rbl_b200.metrics.DeviceTestSet(sharded=True)): the 16 numbers
+    # are sums over rows -> one all-reduce; the host formulas (product code) then give the whole-set statistics
+    from rbl_b200.metrics import statistics_from_counts
+    grp = (rng.random(n) < 0.4).astype(int)
+    wm = rng.normal(size=d) * 0.5
+    cnt, sb, sbl = O.confusion_by_group(wm, X[lo:hi], y[lo:hi], grp[lo:hi], 0.45)
+    c16 = torch.zeros(16, dtype=torch.float64)
+    c16[0] = O.calculate_accuracy(wm, X[lo:hi], y[lo:hi], 0.45) * (hi - lo)
+    c16[1], c16[14], c16[15] = hi - lo, sb, sbl
+    c16[2:14] = torch.from_numpy(cnt.reshape(-1))
+    dist.all_reduce(c16)
+    assert c16[1] == n and abs(float(c16[0]) / n - O.calculate_accuracy(wm, X, y, 0.45)) < 1e-15
+    assert np.allclose(statistics_from_counts(c16.numpy()), O.calculate_statistics(wm, X, y, grp, 0.45),
+                       rtol=1e-12, atol=1e-13)
     dist.barrier()
     print("OK", rank)
     dist.destroy_process_group()

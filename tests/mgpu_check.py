@@ -55,6 +55,19 @@ def main():
         if rank == 0:
             print(f"[{world} GPUs] {wf}/{loss}/{kw} n={n} d={d}: worst rel err {worst:.2e}, objective {obj:.12f} "
                   f"vs oracle {o.objective():.12f} -> {'OK' if good else 'FAIL'}", flush=True)
+        if loss == "binary_cross_entropy":
+            # test-set metrics of the row-sharded set: per-rank pass + one all-reduce of the 16 numbers
+            from rbl_b200.metrics import DeviceTestSet
+            grp = (np.random.default_rng(n).random(n) < 0.4).astype(int)
+            ts = DeviceTestSet(X[lo:hi], y[lo:hi], group=grp[lo:hi], sharded=True)
+            wv = s.w.reshape(-1)
+            acc, st = ts.accuracy(wv), ts.statistics(wv)
+            good_m = (acc == O.calculate_accuracy(wv, X, y) and
+                      np.allclose(st, O.calculate_statistics(wv, X, y, grp), rtol=1e-12, atol=1e-13, equal_nan=True))
+            ok = ok and good_m
+            if rank == 0:
+                print(f"[{world} GPUs] sharded test-set metrics n={n}: accuracy {acc:.6f} -> {'OK' if good_m else 'FAIL'}",
+                      flush=True)
         s.engine.close()
     t = torch.tensor([1.0 if ok else 0.0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
