@@ -218,7 +218,54 @@ def metrics():
     print("metrics.npz", os.path.getsize(os.path.join(OUT, "metrics.npz")))
 
 
+def trajectories_extra():
+    """tests/golden/trajectory_extra.npz: more forty-iteration runs of the reference's ADMMmethod.main_loop on the
+    datasets already committed (`python -m oracle.gen_golden extra`; the other fixtures are not touched):
+    the spectra the first set does not cover in a full loop (esrm, aorr_dc) and extremile on the FISTA branch."""
+    import torch
+
+    from oracle import ref_shim
+
+    ns = ref_shim.load(fista_dtype=torch.float64)
+    d1 = np.load(os.path.join(OUT, "data_300x40.npz"))
+    d2 = np.load(os.path.join(OUT, "data_600x64.npz"))
+    runs = [
+        ("esrm_l2", "esrm", [1.5], "binary_cross_entropy", None, dict(l2_reg=0.01)),
+        ("aorr_dc_bce_l2", "aorr_dc", [150, 30], "binary_cross_entropy", None, dict(l2_reg=1e-4)),
+        ("sq05_l2", "superquantile", [0.5], "binary_cross_entropy", None, dict(l2_reg=0.01)),
+        ("extremile_l1_fista", "extremile", [2.0], "binary_cross_entropy", None, dict(l1_reg=0.01)),
+        ("esrm_l1_fista", "esrm", [1.5], "binary_cross_entropy", None, dict(l1_reg=0.01)),
+    ]
+    snaps = (1, 2, 3, 10, 40)
+    tr = {}
+    for tag, wf, args, loss, B, kw in runs:
+        dd = d2 if tag.endswith("_fista") else d1
+        s = ns.algorithms.ADMMmethod(dd["X"], dd["y"], wf, loss, B=B, args=args, max_iter=40, tol=1e-6, **kw)
+        t0 = time.time()
+        for i in range(40):
+            with ref_shim.quiet():
+                done = ns.algorithms.Optimizer.main_loop(s, i, t0, False)
+            if (i + 1) in snaps:
+                tr[f"{tag}_w_{i+1}"] = np.asarray(s.w, dtype=np.float64).reshape(-1)
+                tr[f"{tag}_z_{i+1}"] = s.z.reshape(-1)
+                tr[f"{tag}_lam_{i+1}"] = s.lagrangian.reshape(-1)
+                tr[f"{tag}_rho_{i+1}"] = np.array(float(s.rho))
+            if done:
+                break
+        tr[f"{tag}_obj"] = np.array(s.objective.get_arrogate_loss(torch.from_numpy(s.w).double()))
+        tr[f"{tag}_meta"] = np.array([wf, "" if args is None else ",".join(map(str, args)), loss,
+                                      "" if B is None else str(B), repr(kw)])
+        print(tag, "iters", i + 1, "obj", float(tr[f"{tag}_obj"]))
+    np.savez_compressed(os.path.join(OUT, "trajectory_extra.npz"), **tr)
+    print("trajectory_extra.npz", os.path.getsize(os.path.join(OUT, "trajectory_extra.npz")))
+
+
 if __name__ == "__main__":
     import sys as _sys
 
-    metrics() if "metrics" in _sys.argv[1:] else (main(), metrics())
+    if "metrics" in _sys.argv[1:]:
+        metrics()
+    elif "extra" in _sys.argv[1:]:
+        trajectories_extra()
+    else:
+        main(), metrics(), trajectories_extra()

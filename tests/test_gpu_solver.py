@@ -120,12 +120,13 @@ def test_objective_vs_reference_golden(golden_dir):
         ob.problem.close()
 
 
-def test_trajectories_vs_oracle_and_reference(golden_dir):
+@pytest.mark.parametrize("fname", ["trajectory.npz", "trajectory_extra.npz"])
+def test_trajectories_vs_oracle_and_reference(golden_dir, fname):
     """40 ADMM iterations through the drop-in class vs the oracle (free-running, same inputs) and the
-    reference's recorded iterates."""
+    reference's recorded iterates (oracle/gen_golden.py: main and trajectories_extra)."""
     from src.optim.algorithms import ADMMmethod, Optimizer
 
-    g = _load(golden_dir, "trajectory.npz")
+    g = _load(golden_dir, fname)
     d1 = _load(golden_dir, "data_300x40.npz")
     d2 = _load(golden_dir, "data_600x64.npz")
     tags = sorted({k[:-5] for k in g.files if k.endswith("_meta")})
@@ -148,6 +149,8 @@ def test_trajectories_vs_oracle_and_reference(golden_dir):
             if f"{tag}_w_{i+1}" in g.files:
                 # vs the reference's own iterates: bounded by ITS inexact inner solvers (test_oracle.py)
                 tol = 2e-8 if i + 1 <= 3 else 1e-5
+                if wf == "aorr_dc" and i + 1 <= 3:
+                    tol = 1e-7  # rho0 = 2e-7: the reference's own z is only ~1e-9 * sigma/rho accurate (test_oracle.py)
                 assert _rel(s.w, g[f"{tag}_w_{i+1}"]) < tol, (tag, i + 1)
         obj = s.objective.get_arrogate_loss(torch.from_numpy(s.w).double())
         assert abs(obj - o.objective()) < 1e-9 * abs(obj)

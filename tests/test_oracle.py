@@ -147,12 +147,15 @@ def test_objective_matches_reference(golden_dir):
         assert abs(v - float(g[f"ref_{wf}_{loss}"])) < 1e-13 * max(1, abs(v))
 
 
-def test_trajectories_track_reference(golden_dir):
-    g = _load(golden_dir, "trajectory.npz")
+@pytest.mark.parametrize("fname,ntags", [("trajectory.npz", 9), ("trajectory_extra.npz", 5)])
+def test_trajectories_track_reference(golden_dir, fname, ntags):
+    """forty iterations of the reference's own ADMMmethod.main_loop (oracle/gen_golden.py: main and
+    trajectories_extra — esrm, aorr_dc, superquantile 0.5, extremile / esrm on the FISTA branch) vs the oracle"""
+    g = _load(golden_dir, fname)
     d1 = _load(golden_dir, "data_300x40.npz")
     d2 = _load(golden_dir, "data_600x64.npz")
-    tags = sorted({k[:-5] for k in g.files if k.endswith("_meta")})
-    assert len(tags) == 9
+    tags = sorted({k[:-5] for k in g.files if k.endswith("_meta") and not k.startswith("sadmm")})
+    assert len(tags) == ntags
     for tag in tags:
         wf, args, loss, B, kw = g[f"{tag}_meta"]
         args, B, kw = _args(args), (None if B == "" else float(B)), eval(kw)
@@ -167,6 +170,10 @@ def test_trajectories_track_reference(golden_dir):
                 # the reference's inner solvers are inexact (Newton 1e-6/1e-4, FISTA 7e-5, L-BFGS
                 # pgtol 1e-5): early iterates agree to ~1e-9, later ones drift with branch flips
                 tol = 2e-8 if i + 1 <= 3 else 1e-5
+                if wf == "aorr_dc" and i + 1 <= 3:
+                    # rho starts at 2e-7 (algorithms.py:52-53): the reference's Newton stop ||delta|| < 1e-6 leaves
+                    # its own z accurate to ~1e-9 * sigma/rho only (SURVEY §8a v); measured 4e-8 at iteration 3
+                    tol = 1e-7
                 assert ew < tol and ez < tol, (tag, i + 1, ew, ez)
         assert abs(o.objective() - float(g[f"{tag}_obj"])) < 1e-7, tag
 
