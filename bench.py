@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--n", type=int, default=1_000_000)
     ap.add_argument("--d", type=int, default=1000)
     ap.add_argument("--no-solve", action="store_true", help="skip the run-to-tolerance tail")
-    ap.add_argument("--cpu-rows", type=int, default=0, help="rows of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg (development runs)")
     return ap.parse_args()
 
 
@@ -62,6 +62,29 @@ def gen_rows_numpy(lo, hi, d):
     y = np.sign(X @ planted_wstar(d) + 0.1 * rng.standard_normal(hi - lo))
     y[y == 0] = 1.0
     return X, y.reshape(-1, 1)
+
+
+def gen_rows_device(torch, dev, lo, hi, n, d, pin=True):
+    """Rows [lo, hi) of THE bench data set, generated on the device in fixed 125k-row blocks with a
+    per-block seed — every --gpus N and both --impl arms get bit-identical rows — and returned as host tensors
+    (pinned: the e2e leg uploads from them inside its timed region)."""
+    wstar = torch.from_numpy(planted_wstar(d)).to(dev)
+    X_host = torch.empty((hi - lo, d), dtype=torch.float64, pin_memory=pin)
+    y_host = torch.empty(hi - lo, dtype=torch.float64, pin_memory=pin)
+    for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
+        b_lo, b_hi = blk * BLOCK_ROWS, min(n, (blk + 1) * BLOCK_ROWS)
+        g = torch.Generator(device=dev)
+        g.manual_seed(17 + blk)
+        Xb = torch.randn(b_hi - b_lo, d, generator=g, dtype=torch.float64, device=dev)
+        eb = torch.randn(b_hi - b_lo, generator=g, dtype=torch.float64, device=dev)
+        yb = torch.sign(Xb @ wstar + 0.1 * eb)
+        yb[yb == 0] = 1.0
+        s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+        X_host[s_lo - lo: s_hi - lo].copy_(Xb[s_lo - b_lo: s_hi - b_lo])
+        y_host[s_lo - lo: s_hi - lo].copy_(yb[s_lo - b_lo: s_hi - b_lo])
+        del Xb, eb, yb
+    torch.cuda.synchronize(dev)
+    return X_host, y_host
 
 
 class ClockSampler:
@@ -107,13 +130,8 @@ def measured_peak_gbs():
         return 6650.0, "fallback"
 
 
-def cpu_iters_per_sec(n_full, d, rows, warmup, iters):
-    """The oracle port (numpy/BLAS matvecs with all host threads, C stack-PAV, numpy FISTA fp64, i.e. the
-    reference's algorithm with its O(n^2) Python PAV replaced by an exact O(n) one) timed on `rows` rows of
-    the same recipe; ADMM cost is linear in rows (matvec-bound), so iterations/s is scaled by rows/n_full."""
-    from oracle import rbl_oracle as O
-
-    # all host cores for BLAS, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 per rank)
+def use_all_host_threads():
+    """all host cores for BLAS, whatever the launcher exported (torchrun sets OMP_NUM_THREADS=1 per rank)"""
     cores = os.cpu_count() or 1
     try:
         import torch
@@ -122,42 +140,125 @@ def cpu_iters_per_sec(n_full, d, rows, warmup, iters):
         pass
     try:
         from threadpoolctl import threadpool_limits
-        cpu_iters_per_sec._limits = threadpool_limits(limits=cores)  # kept alive: applies process-wide
+        use_all_host_threads._limits = threadpool_limits(limits=cores)  # kept alive: applies process-wide
     except Exception:  # noqa: BLE001
         pass
-    X, y = gen_rows_numpy(0, rows, d)
-    o = O.OracleADMM(X, y, "superquantile", "binary_cross_entropy", l1_reg=L1_REG, args=[Q], max_iter=10_000,
+    return cores
+
+
+def cpu_reference_run(X, y, W, K, after_step=None):
+    """The oracle port (numpy/BLAS matvecs with all host threads, C stack-PAV, numpy FISTA fp64: the reference's
+    algorithm with its O(n^2) Python PAV replaced by an exact O(n) one) on the FULL data set the GPU arm solves:
+    iterations 0..W-1 untimed, W..W+K-1 timed one by one (host clock around each oracle step only, so a lockstep
+    GPU comparison in `after_step` is not charged).  Returns (iterations/s, seconds, oracle)."""
+    from oracle import rbl_oracle as O
+
+    o = O.OracleADMM(X, y, "superquantile", "binary_cross_entropy", l1_reg=L1_REG, args=[Q], max_iter=100_000,
                      tol=TOL)
-    for _ in range(warmup):
+    dt = 0.0
+    for i in range(W + K):
+        t0 = time.perf_counter()
         o.step()
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        o.step()
-    dt = time.perf_counter() - t0
-    return (iters / dt) * (rows / n_full), dt, o.passes
+        if i >= W:
+            dt += time.perf_counter() - t0
+        if after_step is not None:
+            after_step(i, o)
+    return K / dt, dt, o
+
+
+CPU_SAMPLE = ("oracle port (numpy/BLAS matvecs on all host threads, C stack-PAV, numpy FISTA fp64) on the SAME {n} x {d} "
+              "rows the GPU arm solves (device-generated blocks copied to the host), ADMM iterations {w}..{last} of "
+              "one solve from the reference's initial state ({dt:.1f} s of CPU work), no scaling")
 
 
 def run_reference(args, rank):
+    """--impl reference: the CPU implementation of the path on this box's host cores, same data / config / steps."""
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    rows = args.cpu_rows or 400_000
-    W, K = min(args.warmup, 3), min(args.steps, 12)
-    v, dt, passes = cpu_iters_per_sec(args.n, args.d, rows, W, K)
-    sample = (f"oracle port (numpy/BLAS matvecs on all host threads, C stack-PAV, numpy FISTA fp64) on {rows} rows x "
-              f"{args.d} of the same planted recipe: ADMM iterations {W}..{W + K - 1} of one solve ({dt:.1f} s of CPU "
-              f"work); iterations/s scaled by rows/n = {rows}/{args.n} (cost is linear in rows)")
+    cores = use_all_host_threads()
+    import torch
+
+    n, d, W, K = args.n, args.d, args.warmup, args.steps
+    if torch.cuda.is_available():
+        # data only: the same device-generated blocks as the GPU arm, copied to (pageable) host memory
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        Xh, yh = gen_rows_device(torch, dev, 0, n, n, d, pin=False)
+        X, y, same = Xh.numpy(), yh.numpy().reshape(-1, 1), True
+        torch.cuda.empty_cache()
+    else:
+        X, y = gen_rows_numpy(0, n, d)
+        same = False
+    v, dt, o = cpu_reference_run(X, y, W, K)
+    sample = CPU_SAMPLE.format(n=n, d=d, w=W, last=W + K - 1, dt=dt)
+    if not same:
+        sample += " [no CUDA device here: numpy twin of the recipe, NOT the same random stream]"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+        "warmup": W, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SRM superquantile(q={Q}) BCE l1_reg={L1_REG} ADMM, n={args.n} d={args.d} fp64 "
-                               f"(BASELINE configs[1])",
+        "config": {"workload": workload_name(n, d),
+                   "same_data_as_gpu_arm": same,
                    "note": "the reference is pure Python with an O(n^2) sweep-PAV and cannot run this n (days per "
                            "z-step); its restated CPU port (exact stack PAV, same FISTA) is timed instead"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+        "state_after_timed_steps": {"primal": o.primal, "dual": o.dual, "rho": float(o.rho),
+                                    "objective": o.objective(), "nnz_w": int(np.count_nonzero(o.w))},
+    }), flush=True)
+
+
+def cpu_baseline_with_parity(torch, ADMMmethod, Optimizer, X_host, y_host, kw, W, K, n, d, quiet, timed_solver):
+    """cpu_baseline (N = 1, rank 0): the oracle port on the same rows, same W / K, no scaling — and, from the same
+    run, full-size parity: a second GPU solver built from the same host arrays is stepped ONE iteration at a time
+    (the per-iteration path replays the same graph as the native loop, bit for bit) in lockstep with the free-running
+    oracle; rel |w|, rel |z| are recorded after every iteration, both solvers run on without any re-synchronisation.
+    north_star tolerance: 1e-9 relative on iterates and objective (fp64)."""
+    cores = use_all_host_threads()
+    Xn, yn = X_host.numpy(), y_host.numpy().reshape(-1, 1)
+    with quiet:
+        par = ADMMmethod(Xn, yn, **kw)
+    rows = []
+
+    def rel(a, b):
+        return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+
+    def after_step(i, o):
+        with quiet:
+            Optimizer.main_loop(par, i, 0.0, False)
+        z_gpu = par.engine.z.cpu().numpy()
+        fi = getattr(o, "last_fista_info", (None, None, None))
+        rows.append({"iteration": i, "timed": i >= W, "rel_w": rel(par.w.reshape(-1), o.w), "rel_z": rel(z_gpu, o.z),
+                     "rel_rho": abs(float(par.rho) - float(o.rho)) / float(o.rho),
+                     "rel_primal": abs(par.primal_feasibility - o.primal) / max(o.primal, 1e-300),
+                     "fista_iters_cpu": fi[0]})
+
+    v, dt, o = cpu_reference_run(Xn, yn, W, K, after_step)
+    with quiet:
+        obj_gpu = par.objective.get_arrogate_loss(torch.from_numpy(par.w).double())
+    obj_cpu = o.objective()
+    # the timed solver has moved on to the stop test; its state after W + K iterations was the lockstep solver's
+    # (same inputs, same kernels: test_native_loop_equals_per_iteration_loop) — checked here on the final objective
+    tol = 1e-9
+    timed = [r for r in rows if r["timed"]]
+    parity = {"tolerance": tol, "iterations_compared": len(rows),
+              "max_rel_w": max(r["rel_w"] for r in rows), "max_rel_z": max(r["rel_z"] for r in rows),
+              "max_rel_w_timed": max(r["rel_w"] for r in timed), "max_rel_z_timed": max(r["rel_z"] for r in timed),
+              "max_rel_rho": max(r["rel_rho"] for r in rows), "max_rel_primal": max(r["rel_primal"] for r in rows),
+              "objective_gpu": obj_gpu, "objective_cpu": obj_cpu,
+              "rel_objective": abs(obj_gpu - obj_cpu) / abs(obj_cpu),
+              "per_iteration": [{k: (float("%.3e" % v) if isinstance(v, float) else v) for k, v in r.items()}
+                                for r in rows],
+              "how": "free-running lockstep of a GPU solver (per-iteration path) and the CPU oracle on the same "
+                     "n x d rows, no re-synchronisation; every iteration compared"}
+    parity["ok"] = bool(parity["max_rel_w"] <= tol and parity["max_rel_z"] <= tol and parity["rel_objective"] <= tol)
+    par.engine.close()
+    cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": CPU_SAMPLE.format(n=n, d=d, w=W, last=W + K - 1, dt=dt)}
+    return cpu, parity
+
+
+def workload_name(n, d):
+    return f"SRM superquantile(q={Q}) BCE l1_reg={L1_REG} ADMM, n={n} d={d} fp64 (BASELINE configs[1])"
 
 
 def main():
@@ -185,30 +286,10 @@ def main():
     n, d, K, W = args.n, args.d, args.steps, args.warmup
     lo, hi = shard_bounds(n, world, rank)
 
-    # ---- synthetic planted data, generated on the device in fixed blocks -----------
-    wstar = torch.from_numpy(planted_wstar(d)).to(dev)
-    Xs, ys = [], []
-    for blk in range(lo // BLOCK_ROWS, (hi + BLOCK_ROWS - 1) // BLOCK_ROWS):
-        b_lo, b_hi = blk * BLOCK_ROWS, min(n, (blk + 1) * BLOCK_ROWS)
-        g = torch.Generator(device=dev)
-        g.manual_seed(17 + blk)
-        Xb = torch.randn(b_hi - b_lo, d, generator=g, dtype=torch.float64, device=dev)
-        eb = torch.randn(b_hi - b_lo, generator=g, dtype=torch.float64, device=dev)
-        yb = torch.sign(Xb @ wstar + 0.1 * eb)
-        yb[yb == 0] = 1.0
-        s_lo, s_hi = max(lo, b_lo) - b_lo, min(hi, b_hi) - b_lo
-        Xs.append(Xb[s_lo:s_hi])
-        ys.append(yb[s_lo:s_hi])
-    X_dev = torch.cat(Xs) if len(Xs) > 1 else Xs[0].contiguous()
-    y_dev = torch.cat(ys) if len(ys) > 1 else ys[0].contiguous()
-    del Xs, ys
-    # host copies in pinned memory: the e2e leg uploads from these inside its timed region
-    X_host = torch.empty(X_dev.shape, dtype=torch.float64, pin_memory=True)
-    y_host = torch.empty(y_dev.shape, dtype=torch.float64, pin_memory=True)
-    X_host.copy_(X_dev)
-    y_host.copy_(y_dev)
-    del X_dev, y_dev
-    torch.cuda.synchronize()
+    # ---- synthetic planted data, generated on the device in fixed blocks, parked in pinned host
+    # memory: the e2e leg uploads from there inside its timed region ------------------------------------------
+    X_host, y_host = gen_rows_device(torch, dev, lo, hi, n, d, pin=True)
+    torch.cuda.empty_cache()
 
     def barrier():
         if world > 1:
@@ -377,14 +458,10 @@ def main():
         shutdown()
         return
 
-    cpu = None
-    if world == 1:
-        rows = args.cpu_rows or 400_000
-        v, dt, _ = cpu_iters_per_sec(n, d, rows, min(W, 3), min(K, 12))
-        cpu = {"value": v, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
-               "sample": f"oracle port (numpy/BLAS on all host threads, C stack-PAV, numpy FISTA fp64) on {rows} rows "
-                         f"x {d} of the same recipe, ADMM iterations {min(W, 3)}..{min(W, 3) + min(K, 12) - 1} "
-                         f"({dt:.1f} s of CPU work), iterations/s scaled by {rows}/{n}"}
+    cpu, parity = None, None
+    if world == 1 and not args.no_cpu:
+        cpu, parity = cpu_baseline_with_parity(torch, ADMMmethod, Optimizer, X_host, y_host, kw, W, K, n, d, quiet,
+                                               solver)
 
     stream_pass = {"kernel": "rbl_pass_kernel (fused r = b - D x, ||r||^2, D^T r over ALL rows)",
                    "achieved": achieved, "frac": achieved / peak, "algorithmic_bytes_per_launch": alg_bytes,
@@ -421,8 +498,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
         "ms_per_step": 1e3 * t_steps / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"SRM superquantile(q={Q}) BCE l1_reg={L1_REG} ADMM, n={n} d={d} fp64 "
-                               f"(BASELINE configs[1])",
+        "config": {"workload": workload_name(n, d),
                    "rows_per_gpu": hi - lo, "parallelism": f"rows sharded x{world}" if world > 1 else "single GPU",
                    "timed_iterations": f"{W}..{W + K - 1} of one solve from the reference's initial state",
                    "l2_flush": "none needed: every D pass streams %.1f GB per GPU, far above the 126 MB L2"
@@ -456,6 +532,7 @@ def main():
         "zstep": {"ms": 1e3 * t_z, "keys_per_s": n / t_z, "algorithmic_bytes": 68 * n,
                   "frac_of_hbm_peak": 68 * n / t_z / 1e9 / peak},
         "cpu_baseline": cpu,
+        "parity": parity,
         "solve": solve,
     }
     print(json.dumps(out), flush=True)
