@@ -20,6 +20,8 @@ int rbl_k_dual(rbl_ctx* c, const double* z, double* Dw, const double* b, const d
                double* lam, double rho, const double* w, const double* w_prev, double* out4, cudaStream_t s);
 int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const int32_t* perm, int use_clip,
                          double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s);
+int rbl_k_ehrm_sums(rbl_ctx* c, const double* ms, const double* sa, const double* sb, double B, double rho,
+                    double* out2, cudaStream_t s);
 int rbl_k_objective(rbl_ctx* c, const double* u_sorted, const double* sigma, int loss, const double* w, double* out4,
                     cudaStream_t s);
 int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32_t* perm_out, cudaStream_t s,
@@ -54,6 +56,8 @@ int rbl_gram_persist_config(rbl_ctx* c);
 int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const double* red0, double lam, int thr_f32,
                          float L0, double tol, int max_iter, double* w_out, double* w_prev_out, int with_support,
                          cudaStream_t s);
+int rbl_k_lasso_cd_gram(rbl_ctx* c, const double* G, const double* w_ref, const double* red0, double l1, double tol,
+                        int max_iter, double* w_out, double* info, cudaStream_t s);
 int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate, double* G, double* scratch,
                      cudaStream_t s);
 int rbl_k_standardize_scratch_doubles(int num_sms, int64_t ld, int64_t* out);
@@ -400,10 +404,19 @@ int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const do
     return rbl_k_prox_elementwise(h, loss, sigma, m, n, rho, out, S(stream));
 }
 
+int rbl_ehrm_candidate_sums(rbl_handle_t h, const double* m_sorted, const double* sigma_a, const double* sigma_b,
+                            double B, double rho, double* out2, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(m_sorted && sigma_a && sigma_b && out2, "null argument");
+    RBL_REQUIRE(rho > 0.0, "rho must be positive");
+    return rbl_k_ehrm_sums(h, m_sorted, sigma_a, sigma_b, B, rho, out2, S(stream));
+}
+
 int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, int use_clip, double clip,
                   const double* lam, double rho, double* z, double* b, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(z_sorted && perm && z && (b == nullptr || lam != nullptr), "null argument");
+    RBL_REQUIRE(use_clip >= 0 && use_clip <= 2, "use_clip must be 0 (none), 1 (max(B, .)) or 2 (min(B, .))");
     return rbl_k_scatter(h, z_sorted, perm, use_clip, clip, lam, rho, z, b, S(stream));
 }
 
@@ -412,6 +425,7 @@ int rbl_scatter_active(rbl_handle_t h, const double* z_sorted, const double* m_s
                        rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(z_sorted && m_sorted && perm && z && (b == nullptr || lam != nullptr), "null argument");
+    RBL_REQUIRE(use_clip >= 0 && use_clip <= 2, "use_clip must be 0 (none), 1 (max(B, .)) or 2 (min(B, .))");
     return rbl_k_scatter_active(h, z_sorted, m_sorted, perm, use_clip, clip, lam, rho, z, b, S(stream));
 }
 
@@ -708,6 +722,16 @@ int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const doubl
     RBL_ENTER(h);
     RBL_REQUIRE(G && w0 && red0 && w && red_out, "null argument");
     return rbl_k_gram_eval(h, G, w0, red0, w, red_out, S(stream));
+}
+
+int rbl_lasso_cd_gram(rbl_handle_t h, const double* G, const double* w_ref, const double* red0, double l1, double tol,
+                      int max_iter, double* w_out, double* info3, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w_ref && red0 && w_out, "null argument");
+    RBL_REQUIRE(h->d <= 64, "rbl_lasso_cd_gram serves the reference's small-problem branch (d <= 60); d = %d", h->d);
+    RBL_REQUIRE(w_out != w_ref, "w_out and w_ref must not alias");
+    RBL_REQUIRE(l1 >= 0.0 && tol > 0.0 && max_iter > 0, "bad arguments");
+    return rbl_k_lasso_cd_gram(h, G, w_ref, red0, l1, tol, max_iter, w_out, info3, S(stream));
 }
 
 int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream) {

@@ -289,7 +289,7 @@ int rbl_k_pass_multi(rbl_ctx* c, const double* D, const double* x, int64_t xstri
     p.stages = c->batch_stages;
     p.ninst = ninst;
     const size_t smem = rbl_batch_smem(c->ld, c->batch_stages);
-    static size_t attr = 0;
+    RBL_PER_DEVICE(size_t, attr, c);
     if (smem > attr) {
         RBL_CUDA(cudaFuncSetAttribute(rbl_pass_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;

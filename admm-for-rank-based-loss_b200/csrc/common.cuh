@@ -48,6 +48,13 @@ inline cudaError_t rbl_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 #endif
+// cudaFuncSetAttribute is per device: "already raised" flags are kept per device ordinal, so a process that drives
+// several devices (handles on cuda:0 and cuda:1) opts every one of them in
+#define RBL_MAX_DEVICES 64
+#define RBL_PER_DEVICE(type, name, c) \
+    static type name##_dev[RBL_MAX_DEVICES] = {}; \
+    type& name = name##_dev[(c)->device & (RBL_MAX_DEVICES - 1)]
+
 #define RBL_LAUNCH_CHECK()             \
     do {                               \
         ++g_rbl_launches;              \

@@ -727,6 +727,107 @@ __global__ void gram_syrk_reduce_kernel(const double* __restrict__ part, int nsl
     }
 }
 
+
+// ---- small-problem l1 w-step: scikit-learn's Lasso coordinate descent on G (algorithms.py:194-197) ----------------
+// The reference solves n <= 500, d <= 60 problems with sklearn.linear_model.Lasso(alpha, tol=1e-8,
+// fit_intercept=False, max_iter=50000): cyclic coordinate descent from w = 0 on  1/2 ||b - D w||^2 + l1 ||w||_1
+// (l1 = alpha * n), residual kept up to date, and after every sweep whose largest coordinate change is below
+// tol * max|w_j| the duality gap against tol * b.b decides (scikit-learn 1.2.2, _cd_fast.pyx
+// enet_coordinate_descent; restated on the CPU in oracle/pav_oracle.c).  Here the same recursion runs on
+// q = D^T b and G = D^T D: the vector c = D^T (b - D w) = q - G w plays the residual's part (tmp_j = c_j + G_jj w_j,
+// c -= (w_j' - w_j) G_j), so a sweep costs d^2 flops and no pass over D.  ONE warp: lane l holds c_l and c_{l+32};
+// G sits in shared memory.  q and b.b come from the warm-start pass [g0 = D^T (b - D w_ref), ||b - D w_ref||^2].
+__global__ void __launch_bounds__(32) lasso_cd_gram_kernel(const double* __restrict__ G, int64_t ldg, int d,
+                                                           const double* __restrict__ w_ref,
+                                                           const double* __restrict__ red0, double l1, double tol,
+                                                           int max_iter, double* __restrict__ w_out,
+                                                           double* __restrict__ info) {
+    __shared__ double Gs[64 * 64];
+    __shared__ double ws[64], qs[64];
+    const int lane = threadIdx.x;
+    const unsigned full = 0xffffffffu;
+    for (int i = lane; i < 64 * 64; i += 32) {
+        const int r = i >> 6, k = i & 63;
+        Gs[i] = (r < d && k < d) ? G[(int64_t)r * ldg + k] : 0.0;
+    }
+    for (int k = lane; k < 64; k += 32) ws[k] = k < d ? w_ref[k] : 0.0;
+    __syncwarp();
+    // q = g0 + G w_ref,  yy = b.b = ss0 + 2 w_ref.g0 + w_ref.(G w_ref)
+    double yy_part = 0.0;
+    for (int j = lane; j < 64; j += 32) {
+        double gw = 0.0;
+        for (int k = 0; k < d; ++k) gw = fma(Gs[j * 64 + k], ws[k], gw);
+        const double g0 = j < d ? red0[j] : 0.0;
+        qs[j] = g0 + gw;
+        yy_part += ws[j] * (2.0 * g0 + gw);
+    }
+    for (int o = 16; o; o >>= 1) yy_part += __shfl_xor_sync(full, yy_part, o);
+    const double yy = red0[d] + yy_part;
+    __syncwarp();
+    double c0 = qs[lane], c1 = qs[lane + 32];  // c = q - G w with w = 0
+    double w0 = 0.0, w1 = 0.0;                 // lane l owns w_l and w_{l+32}
+    const double gap_tol = tol * yy;
+    double gap = tol + 1.0;
+    int it = 0;
+    for (it = 0; it < max_iter; ++it) {
+        double w_max = 0.0, d_w_max = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double gjj = Gs[j * 64 + j];
+            if (gjj == 0.0) continue;
+            const int src = j & 31;
+            const double cj = __shfl_sync(full, j < 32 ? c0 : c1, src);
+            const double wj = __shfl_sync(full, j < 32 ? w0 : w1, src);
+            const double tmp = cj + gjj * wj;
+            const double a = fabs(tmp) - l1;
+            const double wn = (tmp > 0.0 ? 1.0 : (tmp < 0.0 ? -1.0 : 0.0)) * (a > 0.0 ? a : 0.0) / gjj;
+            const double dl = wn - wj;
+            if (dl != 0.0) {
+                c0 = fma(-dl, Gs[j * 64 + lane], c0);
+                c1 = fma(-dl, Gs[j * 64 + lane + 32], c1);
+                if (lane == src) {
+                    if (j < 32) w0 = wn; else w1 = wn;
+                }
+            }
+            d_w_max = fmax(d_w_max, fabs(dl));
+            w_max = fmax(w_max, fabs(wn));
+        }
+        if (w_max == 0.0 || d_w_max / w_max < tol || it == max_iter - 1) {
+            // duality gap (formulation A): R.R = yy - w.q - w.c,  R.y = yy - w.q,  X^T R = c
+            double dn = fmax(fabs(c0), fabs(c1));
+            double wq = w0 * qs[lane] + w1 * qs[lane + 32];
+            double wc = w0 * c0 + w1 * c1;
+            double l1n = fabs(w0) + fabs(w1);
+            for (int o = 16; o; o >>= 1) {
+                dn = fmax(dn, __shfl_xor_sync(full, dn, o));
+                wq += __shfl_xor_sync(full, wq, o);
+                wc += __shfl_xor_sync(full, wc, o);
+                l1n += __shfl_xor_sync(full, l1n, o);
+            }
+            const double R2 = yy - wq - wc, Ry = yy - wq;
+            double cst;
+            if (dn > l1) {
+                cst = l1 / dn;
+                gap = 0.5 * (R2 + R2 * cst * cst);
+            } else {
+                cst = 1.0;
+                gap = R2;
+            }
+            gap += l1 * l1n - cst * Ry;
+            if (gap < gap_tol) {
+                ++it;
+                break;
+            }
+        }
+    }
+    if (lane < d) w_out[lane] = w0;
+    if (lane + 32 < d) w_out[lane + 32] = w1;
+    if (lane == 0 && info) {
+        info[0] = (double)it;
+        info[1] = gap;
+        info[2] = gap_tol;
+    }
+}
+
 }  // namespace
 
 // ---- host launchers ------------------------------------------------------------------------------------
@@ -753,8 +854,9 @@ static GramParams gram_params(rbl_ctx* c, const double* G, const double* w0, con
     return p;
 }
 
-static int gram_set_smem(size_t smem) {
-    static size_t attr2 = 0, attr1 = 0;
+static int gram_set_smem(rbl_ctx* c, size_t smem) {
+    RBL_PER_DEVICE(size_t, attr2, c);
+    RBL_PER_DEVICE(size_t, attr1, c);
     if (smem > 48 * 1024) {
         if (smem > attr2) {
             RBL_CUDA(cudaFuncSetAttribute(gram_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -780,7 +882,7 @@ int rbl_k_gram_fista_init(rbl_ctx* c, const double* G, const double* w0, const d
 int rbl_k_gram_fista_steps(rbl_ctx* c, const double* G, int nsteps, cudaStream_t s) {
     const GramParams p = gram_params(c, G, c->gram_w0, c->gram_red0);
     const size_t smem = 2 * (size_t)c->ld * sizeof(double);
-    int rc = gram_set_smem(smem);
+    int rc = gram_set_smem(c, smem);
     if (rc != RBL_OK) return rc;
     const int grid = (c->d + kGWarps - 1) / kGWarps;
     for (int i = 0; i < nsteps; ++i) {
@@ -802,7 +904,7 @@ int rbl_k_gram_eval(rbl_ctx* c, const double* G, const double* w0, const double*
     p.w = w;
     p.red_out = red_out;
     const size_t smem = (size_t)c->ld * sizeof(double);
-    int rc = gram_set_smem(2 * smem);
+    int rc = gram_set_smem(c, 2 * smem);
     if (rc != RBL_OK) return rc;
     const int grid = (c->d + kGWarps - 1) / kGWarps;
     gram_step_kernel<1><<<grid, kGThreads, smem, s>>>(p);
@@ -929,6 +1031,13 @@ int rbl_k_gram_fista_run(rbl_ctx* c, const double* G, const double* w0, const do
                      : c->gp_kc == 2 ? (const void*)gram_fista_persistent_kernel<2>
                                      : (const void*)gram_fista_persistent_kernel<1>;
     RBL_CUDA(cudaLaunchCooperativeKernel(fn, dim3(c->gp_grid), dim3(kGThreads), args, c->gp_smem, s));
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+int rbl_k_lasso_cd_gram(rbl_ctx* c, const double* G, const double* w_ref, const double* red0, double l1, double tol,
+                        int max_iter, double* w_out, double* info, cudaStream_t s) {
+    lasso_cd_gram_kernel<<<1, 32, 0, s>>>(G, c->ld, c->d, w_ref, red0, l1, tol, max_iter, w_out, info);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

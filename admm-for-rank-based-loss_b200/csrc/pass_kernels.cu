@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherPar
 
 template <int CJ>
 int launch_gather_t(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
-    static size_t attr_smem = 0;
+    RBL_PER_DEVICE(size_t, attr_smem, c);
     if (c->pass_smem > attr_smem) {
         RBL_CUDA(cudaFuncSetAttribute(rbl_gather_kernel<CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)c->pass_smem));
@@ -397,7 +397,7 @@ int launch_gather_t(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
 
 template <int XJ, int WPR, int CJ>
 int launch_t(rbl_ctx* c, const PassParams& p, cudaStream_t s) {
-    static size_t attr_smem = 0;  // per instantiation; one device per process (one rank per GPU)
+    RBL_PER_DEVICE(size_t, attr_smem, c);  // per instantiation and per device
     if (c->pass_smem > attr_smem) {
         RBL_CUDA(cudaFuncSetAttribute(rbl_pass_kernel<XJ, WPR, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)c->pass_smem));

@@ -653,7 +653,7 @@ int rbl_k_segments(rbl_ctx* c, cudaStream_t s) {
 int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* z_sorted, cudaStream_t s) {
     const int64_t n = c->n_global;
     const int64_t nch = c->nchunks;
-    static bool attr_set = false;
+    RBL_PER_DEVICE(bool, attr_set, c);
     if (!attr_set) {
         RBL_CUDA(cudaFuncSetAttribute(pav_chunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)sizeof(ChunkSmem)));

@@ -878,14 +878,14 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         int nb2 = 16;
         while (nb2 < q.nb) nb2 <<= 1;
         const size_t smem = (size_t)nb2 * sizeof(uint64_t) + (size_t)q.nb * sizeof(uint32_t);
-        static size_t attr = 0;
+        RBL_PER_DEVICE(size_t, attr, c);
         if (smem > 48 * 1024 && smem > attr) {
             RBL_CUDA(cudaFuncSetAttribute(ss_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
         RBL_CUDA(rbl_launch_pdl(ss_partition_kernel, dim3(tiles), dim3(kSSThreads), smem, s, q));
         RBL_LAUNCH_CHECK();
-        static bool battr = false;
+        RBL_PER_DEVICE(bool, battr, c);
         if (!battr) {
             RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSCap * 12));
             battr = true;

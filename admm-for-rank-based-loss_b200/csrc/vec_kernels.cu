@@ -271,18 +271,79 @@ __global__ void margins_kernel(const double* __restrict__ Dw, const double* __re
         m[i] = Dw[i] - lam[i] / rho;
 }
 
+// EHRM clip of the isotonic prox at B (PAV_cpt.py:203-226,268-288): use_clip 1 = candidate 2, max(B, prox with
+// sigma = b) (:213,271); use_clip 2 = candidate 1, min(B, prox with sigma = a) (:207,264); 0 = none.  With a bound
+// scalar block (captured graphs) the mode travels in scal[3] so one graph serves both candidates.
+__device__ __forceinline__ double apply_clip(double v, int use_clip, double clip) {
+    if (use_clip == 1) return v < clip ? clip : v;
+    if (use_clip == 2) return v > clip ? clip : v;
+    return v;
+}
+
+// ---- EHRM: the two scalars the reference compares to pick its candidate (PAV_cpt.py:203-226) -----------------
+// f1 = sum_i a_i log(1+e^{x1_i}) + rho/2 |x1 - m|^2 with x1 = min(prox_{sigma=a}(m), B),
+// f2 = sum_i b_i log(1+e^{x2_i}) + rho/2 |x2 - m|^2 with x2 = max(prox_{sigma=b}(m), B)   (element level, sorted m).
+// Fixed assignment of elements to threads and fixed-order reductions: bit-reproducible.
+__global__ void ehrm_sums_kernel(const double* __restrict__ ms, const double* __restrict__ sa,
+                                 const double* __restrict__ sb, double B, double rho, int64_t n,
+                                 double* __restrict__ part, int np, const double* __restrict__ scal) {
+    __shared__ double sh[33];
+    if (scal) rho = scal[0];
+    double l1 = 0.0, q1 = 0.0, l2 = 0.0, q2 = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double m = ms[i], a = sa[i], b = sb[i];
+        double x1 = rbl_block_prox(RBL_LOSS_BCE, a, m, rho);
+        double x2 = rbl_block_prox(RBL_LOSS_BCE, b, m, rho);
+        if (x1 > B) x1 = B;    // :207
+        if (x2 <= B) x2 = B;   // :213
+        l1 = fma(a, rbl_log1pexp(x1), l1);
+        q1 = fma(x1 - m, x1 - m, q1);
+        l2 = fma(b, rbl_log1pexp(x2), l2);
+        q2 = fma(x2 - m, x2 - m, q2);
+    }
+    l1 = block_sum(l1, sh);
+    q1 = block_sum(q1, sh);
+    l2 = block_sum(l2, sh);
+    q2 = block_sum(q2, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = l1;
+        part[np + blockIdx.x] = q1;
+        part[2 * np + blockIdx.x] = l2;
+        part[3 * np + blockIdx.x] = q2;
+    }
+}
+
+__global__ void __launch_bounds__(1024) ehrm_sums_finalize_kernel(const double* __restrict__ part, int np,
+                                                                  double rho, double* __restrict__ out2,
+                                                                  const double* __restrict__ scal) {
+    __shared__ double sh[33];
+    if (scal) rho = scal[0];
+    double v[4];
+    for (int q = 0; q < 4; ++q) {
+        double a = 0.0;
+        for (int k = threadIdx.x; k < np; k += blockDim.x) a += part[q * np + k];
+        v[q] = block_sum(a, sh);
+    }
+    if (threadIdx.x == 0) {
+        out2[0] = v[0] + rho / 2 * v[1];
+        out2[1] = v[2] + rho / 2 * v[3];
+    }
+}
+
 // ---- z[perm] = z_sorted (algorithms.py:103-104), only the rows this rank owns; b = z + lambda/rho
 __global__ void scatter_kernel(const double* __restrict__ zs, const int32_t* __restrict__ perm, int64_t n_global,
                                int64_t row_lo, int64_t n_local, int use_clip, double clip,
                                const double* __restrict__ lam, double rho, double* __restrict__ z,
                                double* __restrict__ b, const double* __restrict__ scal) {
-    if (scal) rho = scal[0];
+    if (scal) {
+        rho = scal[0];
+        if (use_clip) use_clip = (int)scal[3];
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_global;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t row = (int64_t)perm[i] - row_lo;
         if (row >= 0 && row < n_local) {
-            double v = zs[i];
-            if (use_clip && v < clip) v = clip;  // EHRM: max(B, isotonic prox) (PAV_cpt.py:213,271)
+            const double v = apply_clip(zs[i], use_clip, clip);
             z[row] = v;
             if (b) b[row] = v + lam[row] / rho;
         }
@@ -302,8 +363,7 @@ __device__ __forceinline__ bool active_item(const double* __restrict__ zs, const
                                             int64_t n_local, int use_clip, double clip, int64_t* row_out,
                                             double* v_out, double* delta_out) {
     const int64_t row = (int64_t)perm[i] - row_lo;
-    double v = zs[i];
-    if (use_clip && v < clip) v = clip;  // EHRM: max(B, isotonic prox) (PAV_cpt.py:213,271)
+    const double v = apply_clip(zs[i], use_clip, clip);
     *row_out = row;
     *v_out = v;
     const double dl = v - ms[i];
@@ -318,7 +378,10 @@ __global__ void __launch_bounds__(kActThreads) scatter_active_kernel(
     const double* __restrict__ scal) {
     rbl_pdl_wait();
     __shared__ int wcount[kActThreads / 32];
-    if (scal) rho = scal[0];
+    if (scal) {
+        rho = scal[0];
+        if (use_clip) use_clip = (int)scal[3];
+    }
     const int64_t r0 = (int64_t)blockIdx.x * chunk;
     const int64_t r1 = (r0 + chunk < n_global) ? r0 + chunk : n_global;
     int cnt = 0;
@@ -345,8 +408,10 @@ __global__ void __launch_bounds__(kActThreads) scatter_active_kernel(
 __global__ void __launch_bounds__(kActThreads) compact_active_kernel(
     const double* __restrict__ zs, const double* __restrict__ ms, const int32_t* __restrict__ perm, int64_t n_global,
     int64_t row_lo, int64_t n_local, int use_clip, double clip, int64_t chunk, const int* __restrict__ cta_count,
-    int32_t* __restrict__ act_row, double* __restrict__ act_delta, int* __restrict__ act_total) {
+    int32_t* __restrict__ act_row, double* __restrict__ act_delta, int* __restrict__ act_total,
+    const double* __restrict__ scal) {
     rbl_pdl_wait();
+    if (scal && use_clip) use_clip = (int)scal[3];
     __shared__ int sh[kActThreads / 32 + 1];
     __shared__ int s_base;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -756,6 +821,16 @@ int rbl_k_scatter(rbl_ctx* c, const double* zs, const int32_t* perm, int use_cli
     return RBL_OK;
 }
 
+int rbl_k_ehrm_sums(rbl_ctx* c, const double* ms, const double* sa, const double* sb, double B, double rho,
+                    double* out2, cudaStream_t s) {
+    ehrm_sums_kernel<<<c->vec_grid, kVecThreads, 0, s>>>(ms, sa, sb, B, rho, c->n_global, c->vpart, c->vec_grid,
+                                                        c->scal);
+    RBL_LAUNCH_CHECK();
+    ehrm_sums_finalize_kernel<<<1, 1024, 0, s>>>(c->vpart, c->vec_grid, rho, out2, c->scal);
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
 int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const int32_t* perm, int use_clip,
                          double clip, const double* lam, double rho, double* z, double* b, cudaStream_t s) {
     const int grid = c->vec_grid;
@@ -765,7 +840,7 @@ int rbl_k_scatter_active(rbl_ctx* c, const double* zs, const double* ms, const i
     RBL_LAUNCH_CHECK();
     RBL_CUDA(rbl_launch_pdl(compact_active_kernel, dim3(grid), dim3(kActThreads), 0, s, zs, ms, perm, c->n_global, c->row_lo, c->n_local, use_clip,
                                                       clip, chunk, c->act_cta_count, c->act_row, c->act_delta,
-                                                      c->act_total));
+                                                      c->act_total, c->scal));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rbl_sort_config": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "rbl_pav_config": (_c.c_int, [_c.c_void_p, _c.c_int, _c.POINTER(_c.c_int32)]),
     "rbl_prox_elementwise": (_c.c_int, [_c.c_void_p, _c.c_int, _dp, _dp, _c.c_int64, _c.c_double, _dp, _c.c_void_p]),
+    "rbl_ehrm_candidate_sums": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _dp, _c.c_void_p]),
     "rbl_scatter_z": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_int, _c.c_double, _dp, _c.c_double, _dp, _dp,
                                  _c.c_void_p]),
     "rbl_scatter_active": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_int, _c.c_double, _dp, _c.c_double, _dp, _dp,
@@ -69,6 +70,8 @@ _SIGNATURES = {
     "rbl_gram_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_result": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
+    "rbl_lasso_cd_gram": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _c.c_int, _dp, _dp,
+                                     _c.c_void_p]),
     "rbl_dual_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_int,
                                  _dp, _dp, _c.c_void_p]),
     "rbl_build_transpose": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),
@@ -93,6 +96,7 @@ _SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2  # RBL_ABI_VERSION in include/rbl_b200.h
 
 
 class RblError(RuntimeError):
@@ -104,7 +108,8 @@ def lib_path():
 
 
 def load():
-    """Load the shared library (building it first only if nvcc is at hand and the .so is absent)."""
+    """Load the shared library; it is (re)built first when it is absent, or older than its sources and nvcc is at
+    hand (a stale binary after editing csrc/ would otherwise be used silently)."""
     global _lib
     if _lib is not None:
         return _lib
@@ -115,13 +120,27 @@ def load():
         except Exception as e:  # noqa: BLE001
             raise RblError(f"librbl_b200.so is missing at {path} and could not be built ({e}); "
                            "run `python __graft_entry__.py build`. There is no CPU fallback.") from e
+    elif _build.stale() and _build.have_nvcc():
+        try:
+            _build.build()
+        except Exception as e:  # noqa: BLE001
+            raise RblError(f"librbl_b200.so is older than csrc/ and the rebuild failed ({e})") from e
     lib = ctypes.CDLL(path)
+    try:
+        got = lib.rbl_version()
+    except AttributeError as e:
+        raise RblError(f"{path} does not export rbl_version: not a librbl_b200 build") from e
+    if got != ABI_VERSION:
+        raise RblError(f"librbl_b200.so ABI version {got} != {ABI_VERSION} expected by this package; rebuild with "
+                       "`python __graft_entry__.py build`")
     for name, (res, args) in _SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError if the ABI drifted
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise RblError(f"librbl_b200.so does not export {name} (stale build?); rebuild with "
+                           "`python __graft_entry__.py build`") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.rbl_version() != 1:
-        raise RblError("librbl_b200.so ABI version mismatch")
     _lib = lib
     return lib
 

@@ -15,7 +15,13 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC"]
 
 
-def _stale():
+def have_nvcc():
+    import shutil
+
+    return shutil.which(os.environ.get("NVCC", "nvcc")) is not None
+
+
+def stale():
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
@@ -23,7 +29,7 @@ def _stale():
 
 
 def build(force=False, verbose=False):
-    if not force and not _stale():
+    if not force and not stale():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "nvcc")
     cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES

@@ -80,6 +80,12 @@ class DeviceProblem:
         else:               # X holds global rows [row_lo, row_lo + n_local) of an n_global-row problem
             self.world = torch.distributed.get_world_size(group)
             self.rank = torch.distributed.get_rank(group)
+            # the all-gather of the margins (gather_rows) assumes THIS partition on every rank
+            want = shard_bounds(int(n_global), self.world, self.rank)
+            if (int(row_lo), int(row_lo) + int(X.shape[0])) != want:
+                raise ValueError(f"rank {self.rank} of {self.world} must hold rows [{want[0]}, {want[1]}) of the "
+                                 f"{int(n_global)}-row problem (rbl_b200.engine.shard_bounds), got "
+                                 f"[{int(row_lo)}, {int(row_lo) + int(X.shape[0])})")
         self.n_local, self.d = int(X.shape[0]), int(X.shape[1])
         self.n_global, self.row_lo = int(n_global), int(row_lo)
         self.ld = self.d + (self.d & 1)
@@ -183,6 +189,7 @@ class DeviceProblem:
         if getattr(self, "_graph", None) is not None or getattr(self, "_graph_l2", None) is not None:
             torch.cuda.synchronize(self.device)
             self._graph = self._graph_l2 = None
+            self._graphs_l2_ehrm = {}
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.rbl_destroy(self.h)
             self.h = ctypes.c_void_p()
@@ -248,9 +255,13 @@ class AdmmEngine(DeviceProblem):
     @classmethod
     def child(cls, parent):
         """a further solver instance over the parent's design matrix (shares D, G = D^T D and D^T)"""
-        return cls(None, None, parent.loss, parent.sigma, clip=parent.clip, _share=parent)
+        return cls(None, None, parent.loss, parent.sigma, clip=parent.clip, ehrm=parent.ehrm, _share=parent)
 
-    def __init__(self, X, y, loss, sigma, clip=None, **kw):
+    def __init__(self, X, y, loss, sigma, clip=None, ehrm=None, **kw):
+        """sigma: the spectrum of the isotonic prox; clip: lower clip B applied after it (EHRM candidate 2 only —
+        kept for callers that fix the candidate); ehrm=(sigma_a, sigma_b, B): the reference's EHRM z-step with its
+        per-call choice between min(B, prox_{sigma_a}) and max(B, prox_{sigma_b}) (PAV_cpt.py:203-226); `sigma` and
+        `clip` are then ignored."""
         import time as _time
         _t0 = _time.perf_counter()
         if kw.get("_share") is None and X is not None:
@@ -263,12 +274,24 @@ class AdmmEngine(DeviceProblem):
         if loss not in LOSS_IDS:
             raise ValueError(f"Unrecognized loss '{loss}'! Options: ['binary_cross_entropy', 'hinge']")
         self.loss, self.loss_id = loss, LOSS_IDS[loss]
+        self.ehrm = ehrm
+        if ehrm is not None:
+            if loss != "binary_cross_entropy":
+                raise ValueError("ehrm only can be with binary_cross_entropy.")  # pav.py:60
+            sigma, clip = ehrm[1], float(ehrm[2])  # candidate 2 until the first z-step has compared the two sums
         self.clip = clip
+        self.clip_mode = 0 if clip is None else 1   # rbl_scatter_z use_clip: 1 = max(B, .), 2 = min(B, .)
+        self.ehrm_stats = {"cand1": 0, "cand2": 0, "switches": 0, "last": None}
         dev, f64 = self.device, torch.float64
         nl, ng, d = self.n_local, self.n_global, self.d
         with torch.cuda.device(dev):
             self.sigma = self.vec(sigma)
             assert self.sigma.numel() == ng
+            if ehrm is not None:
+                self.sig_a, self.sig_b = self.vec(ehrm[0]), self.sigma
+                assert self.sig_a.numel() == ng
+                self._ehrm_dev = torch.zeros(2, dtype=f64, device=dev)
+                self._ehrm_host = torch.zeros(2, dtype=f64).pin_memory()
             _cabi.check(self.lib.rbl_set_spectrum(self.h, self.sigma.data_ptr(), self._stream()))
             self.w = torch.zeros(d, dtype=f64, device=dev)
             self.w_prev = torch.zeros(d, dtype=f64, device=dev)
@@ -314,6 +337,7 @@ class AdmmEngine(DeviceProblem):
         self.graph_mgpu = os.environ.get("RBL_GRAPH_MGPU", "1") != "0"  # capture the NCCL collectives as well
         self._graph, self._graph_key, self._iters_eager = None, None, 0
         self._graph_l2, self._graph_l2_active, self._iters_eager_l2, self._pre_done = None, False, 0, False
+        self._graphs_l2_ehrm = {}  # EHRM: one graph of (PAV, scatter, gradient pass) per candidate
         # dual pass: D w reads only the touched sectors of D when nnz(w) <= sparse_cap (0 disables)
         self.sparse_cap = int(os.environ.get("RBL_SPARSE_CAP", str(max(1, d // 16))))
         self.dual_stats = {"sparse": 0, "dense": 0, "nnz_last": d}
@@ -413,6 +437,13 @@ class AdmmEngine(DeviceProblem):
 
     # ---- z-step: margins -> sort -> PAV prox -> scatter (algorithms.py:88-106) -----------------
     def z_step(self, rho):
+        self._z_pre(rho)
+        return self._z_post(rho)
+
+    def _z_pre(self, rho):
+        """margins, all-gather, sort; for EHRM also the reference's candidate choice (PAV_cpt.py:203-226): the two
+        scalar sums are formed on the device, read back (one 16-byte copy + stream synchronisation) and the
+        spectrum / clip direction of the isotonic prox that follows is switched when the winner changes"""
         lib, s = self.lib, self._stream()
         if not self.Dw_valid:
             self.refresh_Dw()
@@ -426,19 +457,43 @@ class AdmmEngine(DeviceProblem):
             _cabi.check(lib.rbl_sort_margins(self.h, self.m_glob.data_ptr(), self.m_sorted.data_ptr(),
                                              self.perm.data_ptr(), s))
             self._sorted_valid = True
+        if self.ehrm is not None:
+            self._ehrm_select(rho)
+
+    def _ehrm_select(self, rho):
+        lib, s = self.lib, self._stream()
+        _cabi.check(lib.rbl_ehrm_candidate_sums(self.h, self.m_sorted.data_ptr(), self.sig_a.data_ptr(),
+                                                self.sig_b.data_ptr(), float(self.ehrm[2]), float(rho),
+                                                self._ehrm_dev.data_ptr(), s))
+        self._ehrm_host.copy_(self._ehrm_dev, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        f1, f2 = float(self._ehrm_host[0]), float(self._ehrm_host[1])
+        mode = 2 if f1 <= f2 else 1   # :222-226: opt_array1 everywhere iff fval1 <= fval2, else opt_array2
+        st = self.ehrm_stats
+        st["cand1" if mode == 2 else "cand2"] += 1
+        st["last"] = (f1, f2)
+        if mode != self.clip_mode:
+            st["switches"] += 1
+            self.clip_mode = mode
+            self.sigma = self.sig_a if mode == 2 else self.sig_b
+            _cabi.check(lib.rbl_set_spectrum(self.h, self.sigma.data_ptr(), s))
+        if hasattr(self, "_scal_np"):
+            self._scal_np[3] = float(self.clip_mode)
+
+    def _z_post(self, rho):
+        lib, s = self.lib, self._stream()
+        clip = 0.0 if self.clip is None else float(self.clip)
         _cabi.check(lib.rbl_pav_prox(self.h, self.loss_id, self.m_sorted.data_ptr(), float(rho),
                                      self.z_sorted.data_ptr(), s))
         if self.w_mode == "gram" and self.active_dense_frac > 0:
             _cabi.check(lib.rbl_scatter_active(self.h, self.z_sorted.data_ptr(), self.m_sorted.data_ptr(),
-                                               self.perm.data_ptr(), 0 if self.clip is None else 1,
-                                               0.0 if self.clip is None else float(self.clip), self.lam.data_ptr(),
+                                               self.perm.data_ptr(), self.clip_mode, clip, self.lam.data_ptr(),
                                                float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
             self._delta_valid = True  # until w, z or lambda change
         else:
-            _cabi.check(lib.rbl_scatter_z(self.h, self.z_sorted.data_ptr(), self.perm.data_ptr(),
-                                          0 if self.clip is None else 1,
-                                          0.0 if self.clip is None else float(self.clip), self.lam.data_ptr(),
-                                          float(rho), self.z.data_ptr(), self.b.data_ptr(), s))
+            _cabi.check(lib.rbl_scatter_z(self.h, self.z_sorted.data_ptr(), self.perm.data_ptr(), self.clip_mode,
+                                          clip, self.lam.data_ptr(), float(rho), self.z.data_ptr(),
+                                          self.b.data_ptr(), s))
         return self.z
 
     # ---- w-step, l1: FISTA (fast_lasso.py:22-69 via algorithms.py:190-202) ---------------------
@@ -562,6 +617,29 @@ class AdmmEngine(DeviceProblem):
         self._r_matches_w = True
         return info
 
+    # ---- w-step, l1, small problems: scikit-learn's Lasso coordinate descent (algorithms.py:194-197) --------
+    def w_step_lasso_cd(self, l1, tol=1e-8, max_iter=50000):
+        """w = argmin 1/2 ||b - D w||^2 + l1 ||w||_1 by sklearn's cyclic coordinate descent (from w = 0, duality-gap
+        stop) on G = D^T D: one warm-start pass over D (active rows only right after a z-step) for D^T b and b.b,
+        then the whole solve in one single-warp kernel.  l1 = alpha * n with the reference's alpha = reg/(2 rho n)."""
+        self.gram()
+        if not hasattr(self, "_cd_info"):
+            self._cd_info = torch.zeros(4, dtype=torch.float64, device=self.device)
+        use_active, self._delta_valid = self._delta_valid, False
+        self.w_prev.copy_(self.w)
+        self._pass_at(self.w_prev, self.b, use_active)
+        _cabi.check(self.lib.rbl_lasso_cd_gram(self.h, self.G.data_ptr(), self.w_prev.data_ptr(),
+                                               self.red0.data_ptr(), float(l1), float(tol), int(max_iter),
+                                               self.w.data_ptr(), self._cd_info.data_ptr(), self._stream()))
+        self._r_matches_w = False
+        self._support_ready = False
+        return {"mode": "lasso_cd"}
+
+    def lasso_cd_info(self):
+        """(sweeps, duality gap, gap tolerance) of the last w_step_lasso_cd (synchronises)"""
+        v = self._cd_info.cpu().numpy()
+        return int(v[0]), float(v[1]), float(v[2])
+
     # ---- w-step, l2: host L-BFGS-B over fused device f/g (w_LBFGS.py:31-53) ---------------------
     def fg_smooth(self, w_np, rho, reg_fg):
         """f = rho/2 ||D w - b||^2 + R(w), g = rho D^T(D w - b) + R'(w) — the n x d part is ONE fused pass
@@ -606,10 +684,19 @@ class AdmmEngine(DeviceProblem):
         can_graph = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
                      and self._iters_eager_l2 >= 2 and self.Dw_valid and self.G is not None
                      and not getattr(self, "_r_matches_w", False))
+        if can_graph and self.ehrm is not None:
+            # the candidate choice needs the host (one 16-byte read-back): margins + sort + the two sums run eagerly,
+            # the rest (PAV, scatter, gradient pass) is the replayed graph of the chosen candidate
+            self._ensure_scalars()
+            self._z_pre(rho)
+            self._graph_l2 = self._graphs_l2_ehrm.get(self.clip_mode)
         if can_graph and self._graph_l2 is None:
             self._capture_l2()
+            if self.ehrm is not None and self._graph_l2 is not None:
+                self._graphs_l2_ehrm[self.clip_mode] = self._graph_l2
         if can_graph and self._graph_l2 is not None:
             self._scal_np[0] = float(rho)
+            self._scal_np[3] = float(self.clip_mode)
             self._graph_l2.replay()
             self._graph_l2_replays += 1
             self._delta_valid, self._pre_done = False, True
@@ -625,6 +712,7 @@ class AdmmEngine(DeviceProblem):
             self.scal = torch.zeros(4, dtype=torch.float64, device=self.device)
             self.scal_host = torch.zeros(4, dtype=torch.float64).pin_memory()
             self._scal_np = self.scal_host.numpy()
+            self._scal_np[3] = float(self.clip_mode)  # [rho, lam, thr_f32, clip mode]
 
     def _capture_l2(self):
         dev = self.device
@@ -643,14 +731,18 @@ class AdmmEngine(DeviceProblem):
                 g.capture_begin()
                 try:
                     self.scal.copy_(self.scal_host, non_blocking=True)
-                    self.z_step(1.0)                      # by-value scalars are ignored while bound
+                    if self.ehrm is not None:             # (margins, sort and the candidate choice ran eagerly)
+                        self._z_post(1.0)
+                    else:
+                        self.z_step(1.0)                  # by-value scalars are ignored while bound
                     self._graph_l2_active = bool(self._delta_valid)
                     self._warm_start_pass()
                 finally:
                     g.capture_end()
             cur.wait_stream(self._cap_stream)
             self._graph_l2 = g
-            self._graph_l2_launches, self._graph_l2_replays = int(self.lib.rbl_launch_count()) - n0, 0
+            self._graph_l2_launches = int(self.lib.rbl_launch_count()) - n0
+            self._graph_l2_replays = getattr(self, "_graph_l2_replays", 0) if self.ehrm is not None else 0
         except Exception as exc:  # noqa: BLE001 — capture unsupported here: stay on eager launches
             import warnings
             warnings.warn(f"rbl_b200: CUDA graph capture of the z-step + gradient pass failed ({exc!r}); "
@@ -762,7 +854,7 @@ class AdmmEngine(DeviceProblem):
         thr_f32 = 1.0 if type(lam) is float or isinstance(lam, (int, np.float32)) else 0.0
         key = (float(tol), int(max_iter))
         can_graph = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
-                     and self._persistent is True
+                     and self._persistent is True and self.ehrm is None
                      and self._iters_eager >= 2 and self.Dw_valid and (self.Dt is not None or not self.transpose_ok
                                                      or self.dual_stats["sparse"] < 1)
                      and not getattr(self, "_r_matches_w", False))
@@ -801,7 +893,7 @@ class AdmmEngine(DeviceProblem):
         """True once the iteration graph exists (capturing it now if the engine state allows it)"""
         key = (float(tol), int(max_iter))
         ok = (self.graph_ok and self.w_mode == "gram" and (self.world == 1 or self.graph_mgpu)
-              and self._persistent is True and self._iters_eager >= 2 and self.Dw_valid
+              and self._persistent is True and self.ehrm is None and self._iters_eager >= 2 and self.Dw_valid
               and (self.Dt is not None or not self.transpose_ok or self.dual_stats["sparse"] < 1)
               and not getattr(self, "_r_matches_w", False))
         if ok and (self._graph is None or self._graph_key != key):

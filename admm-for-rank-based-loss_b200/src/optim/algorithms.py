@@ -8,11 +8,14 @@ Per iteration (reference :119-164):
             l2: scipy L-BFGS-B on the host driving a fused device f/g pass        (:109-116, w_LBFGS.py)
     dual    lambda += rho (z - D w), residual norms, stop test, rho schedule     (device + host scalars)
 
+EHRM: the reference's all-or-nothing choice between its two clipped candidates (PAV_cpt.py:222-226) is made on
+the device from the same two sums at every z-step.
+
 Documented deviations from the shipped reference: exact PAV + machine-precision
 Newton in the z-step (the reference's sweep PAV / loose Newton converge to the same unique prox);
 closed-form hinge prox; stable sort; FISTA in float64 by default (`fista_dtype` is accepted for API
-compatibility; float32 is the shipped default there and is chaotic at its own tolerance); the
-tiny-problem sklearn-Lasso branch (:194-197) is served by the same FISTA kernels.
+compatibility; float32 is the shipped default there and is chaotic at its own tolerance).  The
+tiny-problem sklearn-Lasso branch (:194-197) runs scikit-learn's coordinate descent on the device.
 """
 import time
 
@@ -72,9 +75,14 @@ class Optimizer:
         self.store = False
         self.weight_function = weight_function
 
-        # EHRM as shipped == max(B, isotonic prox with sigma = betas) (PAV_cpt.py:203-293)
-        sigma_for_prox = self.sigma_b if weight_function == 'ehrm' else self.sigma_a
-        self.engine = AdmmEngine(X, y, loss, sigma_for_prox, clip=B if weight_function == 'ehrm' else None, **_shard)
+        # EHRM (PAV_cpt.py:203-293): every z-step compares the reference's two scalar sums on the device and runs
+        # the winner, min(B, isotonic prox with sigma = alphas) or max(B, isotonic prox with sigma = betas)
+        if weight_function == 'ehrm':
+            if B is None:
+                raise TypeError("weight_function 'ehrm' needs B (PAV_cpt.py:207 compares the prox with it)")
+            self.engine = AdmmEngine(X, y, loss, None, ehrm=(self.sigma_a, self.sigma_b, float(B)), **_shard)
+        else:
+            self.engine = AdmmEngine(X, y, loss, self.sigma_a, **_shard)
         self.objective._attach(self.engine)
         nl = self.engine.n_local
         self.engine.set_state(w=w_init, z=np.full(nl, lam0), lam=np.full(nl, lam0))
@@ -137,8 +145,18 @@ class Optimizer:
         self.engine.z_step(self.rho)
         return self.z
 
+    def _rebuild_b(self):
+        """b = z + lagrangian / rho from the CURRENT state, as the reference forms it at the top of every w-step
+        (:111, w_LBFGS.py:34, :191) — the engine's b is only the by-product of the last z-step's scatter"""
+        e = self.engine
+        e._delta_valid = False  # not the z-step's z - m any more: the gradient pass reads every row
+        e._pre_done = False
+        e.b.copy_(e.z + e.lam / float(self.rho))
+
     def w_subproblem(self):
+        """reference :109-116 — standalone l2 w-step on the current (z, lagrangian, rho); returns numpy d x 1"""
         if self.w_flag == 2:
+            self._rebuild_b()
             self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg)
         else:
             raise ValueError("w_flag can only be 0, 1 or 2.")
@@ -273,13 +291,21 @@ class ADMMmethod(Optimizer):
     def _z_subproblem(self):
         return super(ADMMmethod, self).z_subproblem()
 
+    def _small_lasso(self):
+        return self.num_row <= 500 and self.num_feature <= 60  # :194
+
     def _whole_iteration_on_device(self):
-        return self.w_flag == 1 and self.engine.w_mode == "gram"
+        return self.w_flag == 1 and self.engine.w_mode == "gram" and not self._small_lasso()
 
     def _w_subproblem_device(self):
         if self.w_flag == 1:
             # const_y = z + lambda/rho was written by the scatter kernel; lam = alpha*n = reg/(2 rho) (:192-193,200)
             alpha = self.reg / (2 * self.rho * self.num_row)
+            if self._small_lasso():
+                # :194-197 — sklearn.linear_model.Lasso(alpha, tol=1e-8, fit_intercept=False, max_iter=50000):
+                # its coordinate descent, on the device
+                self.last_info = self.engine.w_step_lasso_cd(alpha * self.num_row, tol=1e-8, max_iter=50000)
+                return
             self.last_info = self.engine.w_step_fista(alpha * self.num_row, tol=self.w_tol,
                                                       max_iter=self.fista_max_iter)
         elif self.w_flag == 0 or self.w_flag == 2:
@@ -289,11 +315,9 @@ class ADMMmethod(Optimizer):
 
     def _w_subproblem(self):
         """reference :190-207 — standalone w-step on the current (z, lambda, rho); returns numpy d x 1"""
-        e = self.engine
-        e._delta_valid = False  # b is rebuilt from the current (z, lambda, rho): not the z-step's z - m any more
-        e.b.copy_(e.z + e.lam / float(self.rho))
+        self._rebuild_b()
         self._w_subproblem_device()
-        return e.w.cpu().numpy().reshape(-1, 1)
+        return self.engine.w.cpu().numpy().reshape(-1, 1)
 
     def advance(self, i0, n_iters, verbose=False, t_start=0.0):
         """Iterations i0 .. i0 + n_iters - 1 of the reference loop (:209-216); returns (next i, converged).
@@ -360,6 +384,12 @@ class smoothADMMmethod(Optimizer):
 
     def _w_step_is_lbfgs(self):
         return self.w_flag in (1, 2)  # the Huber-smoothed l1 problem goes through L-BFGS-B as well (:247-251)
+
+    def _w_subproblem(self):
+        """reference :237-251 — standalone w-step on the current (z, lagrangian, rho, t); returns numpy d x 1"""
+        self._rebuild_b()
+        self._w_subproblem_device()
+        return self.engine.w.cpu().numpy().reshape(-1, 1)
 
     def _w_subproblem_device(self):
         if self.w_flag == 1:

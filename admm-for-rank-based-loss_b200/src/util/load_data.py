@@ -9,7 +9,7 @@ from sklearn import preprocessing
 from sklearn.datasets import make_classification
 
 
-def get_data(dataname, num_row=None, num_feature=None, seed=None, device=None):
+def get_data(dataname, num_row=None, num_feature=None, seed=17, device=None):
     if dataname == "synthetic":
         if num_row is None or num_feature is None:
             raise ValueError("Number of samples and features should be specified for synthetic data!")

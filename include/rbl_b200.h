@@ -31,7 +31,7 @@ extern "C" {
 typedef struct rbl_ctx* rbl_handle_t;
 typedef void* rbl_stream_t; /* cudaStream_t */
 
-#define RBL_ABI_VERSION 1
+#define RBL_ABI_VERSION 2
 
 /* loss ids (src/optim/objective.py:26-37 get_loss) */
 #define RBL_LOSS_BINARY_CROSS_ENTROPY 0
@@ -42,8 +42,8 @@ const char* rbl_last_error(void);
 /* kernels launched through the library by this process (instrumentation for bench.py) */
 int64_t rbl_launch_count(void);
 
-/* Per-iteration scalars from DEVICE memory: d_scal = [rho, lam of the FISTA call, thr_f32 (0/1)] (3 doubles, caller
- * owned).  While bound (non-NULL), rbl_margins, rbl_pav_prox, rbl_scatter_*, rbl_dual_pass and rbl_gram_fista_run read
+/* Per-iteration scalars from DEVICE memory: d_scal = [rho, lam of the FISTA call, thr_f32 (0/1), EHRM clip mode
+ * (1 or 2, see rbl_scatter_z)] (4 doubles, caller owned).  While bound (non-NULL), rbl_margins, rbl_pav_prox, rbl_scatter_*, rbl_dual_pass and rbl_gram_fista_run read
  * these instead of their by-value arguments, so the host layer can capture one ADMM iteration as a CUDA graph and
  * replay it after updating d_scal (the rho schedule of algorithms.py:147-157 changes rho every iteration).
  * NULL unbinds. */
@@ -108,8 +108,17 @@ int rbl_pav_config(rbl_handle_t h, int force_tree, int32_t* h_nseg);
 int rbl_prox_elementwise(rbl_handle_t h, int loss, const double* sigma, const double* m, int64_t n, double rho,
                          double* out, rbl_stream_t stream);
 
-/* z[perm] = max(clip, z_sorted) on the rows this rank owns; b = z + lambda/rho (may be NULL).
- * algorithms.py:103-104,192 */
+/* EHRM candidate selection, PAV_cpt.py:203-226: out2 (device) = [fval1, fval2] with
+ *   fval1 = func_value(sigma_a, min(prox_{sigma_a}(m), B)),  fval2 = func_value(sigma_b, max(prox_{sigma_b}(m), B))
+ * at element level on the sorted margins (func_value = sum sigma log(1+e^x) + rho/2 |x - m|^2, :41-43).  The
+ * reference takes candidate 1 everywhere when fval1 <= fval2 and candidate 2 otherwise (a scalar comparison); the
+ * caller then runs rbl_pav_prox on the chosen spectrum and scatters with use_clip = 2 or 1.  Fixed-order sums. */
+int rbl_ehrm_candidate_sums(rbl_handle_t h, const double* m_sorted, const double* sigma_a, const double* sigma_b,
+                            double B, double rho, double* out2, rbl_stream_t stream);
+
+/* z[perm] = clipped z_sorted on the rows this rank owns; b = z + lambda/rho (may be NULL).  use_clip: 0 none,
+ * 1 max(clip, .) (EHRM candidate 2, PAV_cpt.py:213,271), 2 min(clip, .) (candidate 1, :207,264).  While a scalar
+ * block is bound (rbl_bind_scalars) a non-zero use_clip is replaced by (int)scal[3].  algorithms.py:103-104,192 */
 int rbl_scatter_z(rbl_handle_t h, const double* z_sorted, const int32_t* perm, int use_clip, double clip,
                   const double* lam, double rho, double* z, double* b, rbl_stream_t stream);
 
@@ -205,6 +214,14 @@ int rbl_dual_pass(rbl_handle_t h, const double* D, const double* Dt, const doubl
  * rbl_dual_pass reads the nnz(w) touched columns as contiguous n-vectors (coalesced) instead of one 32-byte sector
  * per row and column (DRAM-activate bound).  Pass Dt = NULL to rbl_dual_pass when no copy is kept. */
 int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream);
+
+/* Small-problem l1 w-step (algorithms.py:194-197: n <= 500 and d <= 60 go to sklearn.linear_model.Lasso(alpha,
+ * tol=1e-8, fit_intercept=False, max_iter=50000)): scikit-learn's cyclic coordinate descent with its duality-gap
+ * stop, from w = 0, for  1/2 ||b - D w||^2 + l1 ||w||_1  (l1 = alpha * n), run on G = D^T D and
+ * red0 = [D^T (b - D w_ref) (d), ||b - D w_ref||^2] (the warm-start pass at any point w_ref) — no pass over D.
+ * d <= 64.  info3 (device, may be NULL) = [sweeps, duality gap, tol * b.b]. */
+int rbl_lasso_cd_gram(rbl_handle_t h, const double* G, const double* w_ref, const double* red0, double l1, double tol,
+                      int max_iter, double* w_out, double* info3, rbl_stream_t stream);
 
 /* ---- native outer loop.  The host layer captures ONE ADMM iteration (z-step, FISTA w-step, dual step, read-back of
  * out8/out9 into pinned memory) as a CUDA graph whose first node copies the pinned scalar block h_scal =

@@ -260,6 +260,106 @@ def trajectories_extra():
     print("trajectory_extra.npz", os.path.getsize(os.path.join(OUT, "trajectory_extra.npz")))
 
 
+def ehrm_select():
+    """tests/golden/zstep_ehrm.npz (`python -m oracle.gen_golden ehrm`): the reference's EHRM z-step where its
+    all-or-nothing candidate choice (PAV_cpt.py:222-226) goes either way.  (a) PAV_solver_CPT.get_opt on sorted
+    margins for a grid of (B, rho, margin scale); (b) 40-iteration ADMMmethod trajectories with B = 0.5 and B = -1
+    (candidate 1 wins at least part of the way) next to the shipped B = -5 of trajectory.npz."""
+    import torch
+
+    from oracle import ref_shim
+
+    ns = ref_shim.load(fista_dtype=torch.float64)
+    rng = np.random.default_rng(20261020)
+    n = 400
+    sa = ns.objective.get_weights("ehrm", None)[0](n).numpy().reshape(-1)
+    sb = ns.objective.get_weights("ehrm", None)[1](n).numpy().reshape(-1)
+    out = {"sigma_a": sa, "sigma_b": sb}
+    k = 0
+    for B in (-5.0, -1.0, 0.0, 0.5, 2.0, 5.0):
+        for rho in (1e-4, 1e-2, 1.0):
+            for scale in (0.01, 1.0, 5.0):
+                m = np.sort(rng.normal(size=n) * scale)
+                solver = ns.pav_cpt.PAV_solver_CPT(sa, sb, B, m, rho)
+                out[f"k{k}_m"] = m
+                out[f"k{k}_par"] = np.array([B, rho, scale])
+                out[f"k{k}_ref_z"] = np.asarray(solver._orig_get_opt(), dtype=np.float64)
+                k += 1
+    out["ncases"] = np.array(k)
+    d1 = np.load(os.path.join(OUT, "data_300x40.npz"))
+    snaps = (1, 2, 3, 10, 40)
+    for tag, B in (("ehrm_B05_l2", 0.5), ("ehrm_Bm1_l2", -1.0)):
+        s = ns.algorithms.ADMMmethod(d1["X"], d1["y"], "ehrm", "binary_cross_entropy", B=B, l2_reg=0.01, max_iter=40,
+                                     tol=1e-6)
+        t0 = time.time()
+        for i in range(40):
+            with ref_shim.quiet():
+                done = ns.algorithms.Optimizer.main_loop(s, i, t0, False)
+            if (i + 1) in snaps:
+                out[f"{tag}_w_{i+1}"] = np.asarray(s.w, dtype=np.float64).reshape(-1)
+                out[f"{tag}_z_{i+1}"] = s.z.reshape(-1)
+                out[f"{tag}_rho_{i+1}"] = np.array(float(s.rho))
+            if done:
+                break
+        out[f"{tag}_obj"] = np.array(s.objective.get_arrogate_loss(torch.from_numpy(s.w).double()))
+        out[f"{tag}_B"] = np.array(B)
+        print(tag, "iters", i + 1, "obj", float(out[f"{tag}_obj"]))
+    np.savez_compressed(os.path.join(OUT, "zstep_ehrm.npz"), **out)
+    print("zstep_ehrm.npz", os.path.getsize(os.path.join(OUT, "zstep_ehrm.npz")))
+
+
+def config1():
+    """tests/golden/c1_trajectory.npz (`python -m oracle.gen_golden c1`): BASELINE configs[0] exactly, run by the
+    reference itself — run_SRM.py:21-36: get_data("synthetic", 10000, 1000, seed=17), 60/40 split (random_state=17)
+    -> 6000 x 1000, ERM, BCE, l1_reg = 0.01, ADMMmethod(tol=1e-6), float64 FISTA.  Stored: w at selected iterations,
+    the residual norms and rho of EVERY iteration, the final objective, the reference's wall time here, and a
+    checksum of the data (the tests regenerate X with scikit-learn's seeded generator and verify the checksum; the
+    48 MB matrix itself is not committed)."""
+    import torch
+    from sklearn.model_selection import train_test_split
+
+    from oracle import ref_shim
+
+    ns = ref_shim.load(fista_dtype=torch.float64)
+    X, y = ns.load_data.get_data("synthetic", num_row=10000, num_feature=1000, seed=17)
+    Xtr, _, ytr, _ = train_test_split(X, y, test_size=0.4, random_state=17)
+    out = {"x_checksum": np.array([float(Xtr.sum()), float(np.abs(Xtr).sum()), float((Xtr * Xtr).sum()),
+                                   float(Xtr[::7, ::11].sum())]),
+           "y_sum": np.array(float(ytr.sum())), "shape": np.array(Xtr.shape)}
+    s = ns.algorithms.ADMMmethod(Xtr, ytr, "erm", "binary_cross_entropy", l1_reg=0.01, max_iter=200, tol=1e-6)
+    snaps = (1, 2, 3, 5, 10, 20, 40, 80, 120)
+    prim, dual, rhos = [], [], []
+    t0 = time.time()
+    for i in range(200):
+        rho_used = float(s.rho)
+        with ref_shim.quiet():
+            import contextlib
+            import io
+            buf = io.StringIO()
+            with contextlib.redirect_stdout(buf):
+                w_prev = s.w.copy()
+                done = ns.algorithms.Optimizer.main_loop(s, i, t0, False)
+        Dw = s.D @ s.w
+        # the multiplier was updated with the old rho: z - Dw = (lam_new - lam_old)/rho; recompute the norms directly
+        prim.append(float(np.linalg.norm(s.z - Dw)))
+        dual.append(float(np.linalg.norm(s.w - w_prev)))
+        rhos.append(rho_used)
+        if (i + 1) in snaps or done:
+            out[f"w_{i+1}"] = np.asarray(s.w, dtype=np.float64).reshape(-1)
+        if done:
+            break
+    wall = time.time() - t0
+    out["iterations"] = np.array(i + 1)
+    out["primal"], out["dual"], out["rho"] = np.array(prim), np.array(dual), np.array(rhos)
+    out["w_final"] = np.asarray(s.w, dtype=np.float64).reshape(-1)
+    out["objective"] = np.array(s.objective.get_arrogate_loss(torch.from_numpy(s.w).double()))
+    out["ref_wall_s"] = np.array(wall)
+    out["ref_cores"] = np.array(os.cpu_count() or 1)
+    print("c1: iterations", i + 1, "objective", float(out["objective"]), "wall", wall)
+    np.savez_compressed(os.path.join(OUT, "c1_trajectory.npz"), **out)
+    print("c1_trajectory.npz", os.path.getsize(os.path.join(OUT, "c1_trajectory.npz")))
+
+
 if __name__ == "__main__":
     import sys as _sys
 
@@ -267,5 +367,9 @@ if __name__ == "__main__":
         metrics()
     elif "extra" in _sys.argv[1:]:
         trajectories_extra()
+    elif "ehrm" in _sys.argv[1:]:
+        ehrm_select()
+    elif "c1" in _sys.argv[1:]:
+        config1()
     else:
-        main(), metrics(), trajectories_extra()
+        main(), metrics(), trajectories_extra(), ehrm_select(), config1()

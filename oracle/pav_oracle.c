@@ -16,8 +16,13 @@
  *     reference sweeps (merge every violating run, re-solve, repeat); the fixed point is
  *     the unique isotonic prox, which a classic stack PAV reaches in O(n).  Block value
  *     depends only on (sum sigma, sum m, count)  (pav.py:134-140: means of the block).
- *   - src/util/PAV_cpt.py:203-293  EHRM: as shipped this is max(B, isotonic prox with
- *     sigma = b); rbl_oracle_pav() takes an optional clip.
+ *   - src/util/PAV_cpt.py:203-293  EHRM: min(B, isotonic prox with sigma = a) or max(B, isotonic
+ *     prox with sigma = b), chosen by the scalar comparison of :222-226 (made in
+ *     rbl_oracle.py::ehrm_pav); rbl_oracle_pav() takes the optional lower clip.
+ *   - scikit-learn's Lasso coordinate descent (third-party, un-vendored: README.md pins
+ *     scikit-learn 1.2.2), called by the small-problem w-step at src/optim/algorithms.py:194-197:
+ *     rbl_oracle_lasso_cd() restates sklearn/linear_model/_cd_fast.pyx::enet_coordinate_descent
+ *     of that release (cyclic, no screening, duality-gap stop).
  *
  * Parity status: the reference holds no golden vectors for this path ("parity unpinned"
  * by the reference).  This file is pinned instead against outputs of the shimmed
@@ -111,4 +116,74 @@ int64_t rbl_oracle_pav(int loss, int64_t n, const double* sigma, const double* m
 void rbl_oracle_prox_vec(int loss, int64_t n, const double* sigma, const double* m, double rho,
                          double* out) {
     for (int64_t i = 0; i < n; ++i) out[i] = rbl_oracle_prox(loss, sigma[i], m[i], rho);
+}
+
+/*
+ * scikit-learn 1.2.2 `enet_coordinate_descent` (sklearn/linear_model/_cd_fast.pyx) for
+ *     min_w  1/2 ||y - X w||^2 + alpha ||w||_1            (beta = 0: Lasso, l1_ratio = 1)
+ * as reached from Lasso(alpha=a, tol=1e-8, fit_intercept=False, max_iter=50000).fit(X, y)
+ * (algorithms.py:195-196): alpha = a * n_samples, tol is scaled by y.y, w starts at 0 (a fresh
+ * estimator has no coef_ to warm-start from), cyclic coordinate order, residual R kept up to date by
+ * axpy, and after every sweep whose largest update is below tol relative to the largest |w_j| the
+ * duality gap decides.  X is column-major n x d.  Returns the number of sweeps.
+ */
+int rbl_oracle_lasso_cd(int n, int d, const double* X, const double* y, double alpha, double tol,
+                        int max_iter, double* w, double* gap_out) {
+    double* R = (double*)malloc(sizeof(double) * (size_t)n);
+    double* nrm = (double*)malloc(sizeof(double) * (size_t)d);
+    double yy = 0.0, gap = tol + 1.0;
+    const double d_w_tol = tol;
+    for (int i = 0; i < n; ++i) { R[i] = y[i]; yy += y[i] * y[i]; }
+    for (int j = 0; j < d; ++j) {
+        double a = 0.0;
+        const double* xj = X + (size_t)j * n;
+        for (int i = 0; i < n; ++i) a += xj[i] * xj[i];
+        nrm[j] = a;
+        w[j] = 0.0;
+    }
+    tol *= yy;
+    int it = 0;
+    for (it = 0; it < max_iter; ++it) {
+        double w_max = 0.0, d_w_max = 0.0;
+        for (int j = 0; j < d; ++j) {
+            if (nrm[j] == 0.0) continue;
+            const double* xj = X + (size_t)j * n;
+            const double w_j = w[j];
+            if (w_j != 0.0)
+                for (int i = 0; i < n; ++i) R[i] += w_j * xj[i];
+            double tmp = 0.0;
+            for (int i = 0; i < n; ++i) tmp += xj[i] * R[i];
+            const double a = fabs(tmp) - alpha;
+            w[j] = (tmp > 0 ? 1.0 : (tmp < 0 ? -1.0 : 0.0)) * (a > 0 ? a : 0.0) / nrm[j];
+            if (w[j] != 0.0)
+                for (int i = 0; i < n; ++i) R[i] -= w[j] * xj[i];
+            const double d_w_j = fabs(w[j] - w_j);
+            if (d_w_j > d_w_max) d_w_max = d_w_j;
+            if (fabs(w[j]) > w_max) w_max = fabs(w[j]);
+        }
+        if (w_max == 0.0 || d_w_max / w_max < d_w_tol || it == max_iter - 1) {
+            double dual_norm = 0.0, R2 = 0.0, Ry = 0.0, l1 = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double* xj = X + (size_t)j * n;
+                double a = 0.0;
+                for (int i = 0; i < n; ++i) a += xj[i] * R[i];
+                if (fabs(a) > dual_norm) dual_norm = fabs(a);
+                l1 += fabs(w[j]);
+            }
+            for (int i = 0; i < n; ++i) { R2 += R[i] * R[i]; Ry += R[i] * y[i]; }
+            double c;
+            if (dual_norm > alpha) {
+                c = alpha / dual_norm;
+                gap = 0.5 * (R2 + R2 * c * c);
+            } else {
+                c = 1.0;
+                gap = R2;
+            }
+            gap += alpha * l1 - c * Ry;
+            if (gap < tol) { ++it; break; }
+        }
+    }
+    if (gap_out) *gap_out = gap;
+    free(R); free(nrm);
+    return it;
 }

@@ -61,6 +61,9 @@ def _lib():
                                        ctypes.c_int, ctypes.c_double, dp]
         lib.rbl_oracle_prox_vec.restype = None
         lib.rbl_oracle_prox_vec.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, dp]
+        lib.rbl_oracle_lasso_cd.restype = ctypes.c_int
+        lib.rbl_oracle_lasso_cd.argtypes = [ctypes.c_int, ctypes.c_int, dp, dp, ctypes.c_double, ctypes.c_double,
+                                            ctypes.c_int, dp, ctypes.POINTER(ctypes.c_double)]
         _LIB = lib
     return _LIB
 
@@ -210,13 +213,69 @@ def ehrm_candidate_sums(sigma_a, sigma_b, B, m_sorted, rho):
     return f1, f2
 
 
+def ehrm_pav(sigma_a, sigma_b, B, m_sorted, rho, return_choice=False):
+    """PAV_solver_CPT(sigma_a, sigma_b, B, m_sorted, rho).get_opt() (PAV_cpt.py:169-293).  The reference picks
+    between its two clipped candidates by comparing two SCALARS (:222-226 — `fval1 <= fval2` indexes the whole
+    vector), so the start is candidate 1 = min(prox_a, B) everywhere or candidate 2 = max(prox_b, B) everywhere,
+    and the sweep that follows (:229-288) pools the winner: the result is min(B, isotonic prox with sigma_a) or
+    max(B, isotonic prox with sigma_b) (pinned against the reference's outputs in tests/golden/zstep_ehrm.npz)."""
+    f1, f2 = ehrm_candidate_sums(sigma_a, sigma_b, B, m_sorted, rho)
+    if f1 <= f2:
+        zs = np.minimum(pav_prox("binary_cross_entropy", sigma_a, m_sorted, rho), B)
+    else:
+        zs = pav_prox("binary_cross_entropy", sigma_b, m_sorted, rho, clip=B)
+    return (zs, 1 if f1 <= f2 else 2) if return_choice else zs
+
+
+def ehrm_sweep_literal(sigma_a, sigma_b, B, m_sorted, rho):
+    """Small-n literal restatement of PAV_solver_CPT (PAV_cpt.py:203-293): per pass, block values of BOTH
+    candidates from the unweighted block means (:122-123), the scalar choice between them re-made on the pooled
+    blocks (:262-288), adjacent violators merged in chains (:236-246).  Exact block solves instead of the
+    reference's tol-1e-4 Newton.  Returns (z, list of per-pass choices) — used to check that the choice made at
+    element level is the one every later pass makes too."""
+    blocks = [[i] for i in range(len(m_sorted))]
+    choices = []
+    while True:
+        s1 = np.array([np.mean(sigma_a[b]) for b in blocks])
+        s2 = np.array([np.mean(sigma_b[b]) for b in blocks])
+        mm = np.array([np.mean(m_sorted[b]) for b in blocks])
+        x1 = np.minimum(prox_vec("binary_cross_entropy", s1, mm, rho), B)
+        x2 = prox_vec("binary_cross_entropy", s2, mm, rho)
+        x2[x2 <= B] = B
+        f1 = float(np.sum(s1 * log1pexp(x1)) + rho / 2 * np.dot(x1 - mm, x1 - mm))
+        f2 = float(np.sum(s2 * log1pexp(x2)) + rho / 2 * np.dot(x2 - mm, x2 - mm))
+        x = x1 if f1 <= f2 else x2
+        choices.append(1 if f1 <= f2 else 2)
+        new, i, viol = [], 0, False
+        while i < len(blocks) - 1:
+            if x[i] <= x[i + 1]:
+                new.append(blocks[i])
+            else:
+                viol = True
+                cur = list(blocks[i])
+                while i < len(blocks) - 1 and x[i] > x[i + 1]:
+                    cur = cur + blocks[i + 1]
+                    i += 1
+                new.append(cur)
+            i += 1
+        if len(blocks) >= 2 and x[-1] >= x[-2]:
+            new.append(blocks[-1])
+        if not viol:
+            break
+        blocks = new
+    z = np.empty(len(m_sorted))
+    for b, v in zip(blocks, x):
+        z[b] = v
+    return z, choices
+
+
 def z_step(D, w, lam, rho, sigma, loss, B=None, sigma_b=None, return_all=False):
     """Optimizer.z_subproblem (algorithms.py:88-106)."""
     m = (D @ w.reshape(-1) - lam.reshape(-1) / rho)
     perm = np.argsort(m, kind="stable")
     ms = m[perm]
-    if B is not None:  # EHRM, PAV_cpt.py:169-293 == max(B, isotonic prox with sigma=b)
-        zs = pav_prox("binary_cross_entropy", sigma_b, ms, rho, clip=B)
+    if B is not None:  # EHRM, PAV_cpt.py:169-293
+        zs = ehrm_pav(sigma, sigma_b, B, ms, rho)
     else:
         zs = pav_prox(loss, sigma, ms, rho)
     z = np.zeros(m.shape[0])
@@ -282,6 +341,21 @@ def fista(beta, X, y, lam, L=np.float32(17), eta=np.float32(2.5), tol=7e-5, max_
     if return_info:
         return b, {"iters": k + 1, "passes": n_pass, "L": float(L_prev)}
     return b
+
+
+def lasso_cd(X, y, alpha, tol=1e-8, max_iter=50000, return_info=False):
+    """sklearn.linear_model.Lasso(alpha, tol, fit_intercept=False, max_iter).fit(X, y).coef_ as called at
+    algorithms.py:195-196 — scikit-learn is third-party and un-vendored (README.md pins 1.2.2): restated from that
+    release's published `enet_coordinate_descent` (cyclic coordinate descent, duality-gap stop; pav_oracle.c).
+    Minimises 1/(2n) ||y - X w||^2 + alpha ||w||_1; pinned against the installed scikit-learn in tests/test_oracle."""
+    X = np.asfortranarray(X, dtype=np.float64)
+    y = np.ascontiguousarray(y, dtype=np.float64).reshape(-1)
+    n, d = X.shape
+    w = np.zeros(d)
+    gap = ctypes.c_double(0.0)
+    sweeps = _lib().rbl_oracle_lasso_cd(n, d, _dptr(X), _dptr(y), float(alpha) * n, float(tol), int(max_iter),
+                                        _dptr(w), ctypes.byref(gap))
+    return (w, {"sweeps": sweeps, "gap": gap.value}) if return_info else w
 
 
 # ---------------------------------------------------------------------------------------
@@ -382,11 +456,15 @@ class OracleADMM:
             b = self.z + self.lam / self.rho
             alpha = self.reg / (2 * self.rho * self.n)
             if self.n <= 500 and self.d <= 60 and self.small_lasso:  # :194-197 tiny-problem branch
-                from sklearn.linear_model import Lasso
+                if self.small_lasso == "sklearn":  # the installed scikit-learn itself (cross-check only)
+                    from sklearn.linear_model import Lasso
 
-                mdl = Lasso(alpha=alpha, tol=1e-8, fit_intercept=False, max_iter=50000, warm_start=True)
-                mdl.fit(X=self.D, y=b)
-                return mdl.coef_.reshape(-1).astype(np.float64)
+                    mdl = Lasso(alpha=alpha, tol=1e-8, fit_intercept=False, max_iter=50000, warm_start=True)
+                    mdl.fit(X=self.D, y=b)
+                    return mdl.coef_.reshape(-1).astype(np.float64)
+                w, info = lasso_cd(self.D, b, alpha, tol=1e-8, max_iter=50000, return_info=True)
+                self.last_cd_sweeps = info["sweeps"]
+                return w
             w, info = fista(self.w, self.D, b, alpha * self.n, np.float32(17), np.float32(2.5), tol=7e-5,
                             max_iter=5000, dtype=self.fista_dtype, return_info=True)
             self.passes += info["passes"]

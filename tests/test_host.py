@@ -26,7 +26,7 @@ def test_cabi_library_loads_and_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in include/rbl_b200.h but not exported"
     assert sorted(_cabi.exported_symbols()) == declared      # the ctypes binding covers the whole header
-    assert _cabi.load().rbl_version() == 1
+    assert _cabi.load().rbl_version() == _cabi.ABI_VERSION == 2
 
 
 def test_product_fails_loudly_without_gpu():
