@@ -814,6 +814,25 @@ int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double*
     return rbl_k_objective(h, h->obj_tmp, sigma, loss, w, out4, S(stream));
 }
 
+// ---- CPT spectra of EHRM on the host (objective.py:148-164) ------------------------------------------------------
+// a_i = distort((i+1)/n, 0.69) - distort(i/n, 0.69), b_i = distort((n-i)/n, 0.61) - distort((n-i-1)/n, 0.61) with
+// distort(p, g) = p^g / (p^g + (1-p)^g)^(1/g).  The differences cancel ~log10(n) digits, so the LAST bit of every
+// pow matters: the reference evaluates them one Python float at a time (libm pow); the same scalar libm calls in
+// the same order are made here (a vectorised pow differs in the last ulp: 3e-9 relative in sigma at n = 4M).
+static double cpt_distort(double p, double g) { return pow(p, g) / pow(pow(p, g) + pow(1.0 - p, g), 1.0 / g); }
+
+int rbl_cpt_weights(int64_t n, int which, double* h_out) {
+    RBL_REQUIRE(n > 0 && h_out != nullptr && (which == 0 || which == 1), "bad arguments");
+    const double dn = (double)n;
+    if (which == 0)
+        for (int64_t i = 0; i < n; ++i)
+            h_out[i] = cpt_distort((double)(i + 1) / dn, 0.69) - cpt_distort((double)i / dn, 0.69);
+    else
+        for (int64_t i = 0; i < n; ++i)
+            h_out[i] = cpt_distort((double)(n - i) / dn, 0.61) - cpt_distort((double)(n - i - 1) / dn, 0.61);
+    return RBL_OK;
+}
+
 // ---- test-set metrics (no handle: a test set has its own row count) -------------------------------------------
 static int metrics_device(int device, int* num_sms) {
     int ndev = 0, cc_major = 0;

@@ -213,7 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
                 // lambda += rho (z - D w), partial ||z - D w||^2 (algorithms.py:132,135) in the matvec epilogue
                 const double res = bv - dot;
                 out[row0 + tid] = dot;
-                p.lam[row0 + tid] = lv + rho * res;
+                // product and sum rounded separately, like numpy's lam + rho * (z - Dw) (:132): an FMA here leaves
+                // 1-ulp residues where the reference cancels to exactly 0 (rows with z = m while w = 0)
+                p.lam[row0 + tid] = __dadd_rn(lv, __dmul_rn(rho, res));
                 ss = fma(res, res, ss);
             } else {
                 out[row0 + tid] = dot;

@@ -472,7 +472,7 @@ __global__ void dual_kernel(const double* __restrict__ z, double* __restrict__ D
             dw = Dw[i];
         }
         const double res = z[i] - dw;
-        lam[i] = lam[i] + rho * res;
+        lam[i] = __dadd_rn(lam[i], __dmul_rn(rho, res));  // two roundings, like numpy (:132)
         a = fma(res, res, a);
     }
     a = block_sum(a, sh);
@@ -593,7 +593,7 @@ __device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, i
             if (sub == 0 && i < n) {
                 const double res = zv[u] - a[u];
                 Dw[i] = a[u];
-                lam[i] = lv[u] + rho * res;
+                lam[i] = __dadd_rn(lv[u], __dmul_rn(rho, res));  // two roundings, like numpy (:132)
                 acc = fma(res, res, acc);
             }
         }
@@ -671,11 +671,11 @@ __global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __rest
             if (i + 1 < n) Dw[i + 1] = a1;
             if (last_chunk) {
                 const double r0 = z[i] - a0;
-                lam[i] = lam[i] + rho * r0;
+                lam[i] = __dadd_rn(lam[i], __dmul_rn(rho, r0));  // two roundings, like numpy (:132)
                 acc = fma(r0, r0, acc);
                 if (i + 1 < n) {
                     const double r1 = z[i + 1] - a1;
-                    lam[i + 1] = lam[i + 1] + rho * r1;
+                    lam[i + 1] = __dadd_rn(lam[i + 1], __dmul_rn(rho, r1));
                     acc = fma(r1, r1, acc);
                 }
             }

@@ -72,6 +72,7 @@ _SIGNATURES = {
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_lasso_cd_gram": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _c.c_int, _dp, _dp,
                                      _c.c_void_p]),
+    "rbl_cpt_weights": (_c.c_int, [_c.c_int64, _c.c_int, _c.POINTER(_c.c_double)]),
     "rbl_dual_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_int,
                                  _dp, _dp, _c.c_void_p]),
     "rbl_build_transpose": (_c.c_int, [_c.c_void_p, _dp, _dp, _c.c_void_p]),

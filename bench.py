@@ -40,11 +40,20 @@ def parse():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=1_000_000)
+    ap.add_argument("--config", default="c2", choices=["c1", "c2", "c3", "c4", "c5"],
+                    help="BASELINE.json configs[0..4]; c2 (the configuration the metric is quoted on) is the default "
+                         "and the line the driver records; the others are bench_configs.py")
+    ap.add_argument("--n", type=int, default=0, help="rows (0 = the configuration's own)")
     ap.add_argument("--d", type=int, default=1000)
+    ap.add_argument("--loss", default=None, help="c4: hinge (default, run_AoRR_ratio.py) or binary_cross_entropy")
+    ap.add_argument("--instances-per-gpu", type=int, default=32, help="c5")
+    ap.add_argument("--batch-mode", default=None, help="c5: gram | stream (default: auto)")
     ap.add_argument("--no-solve", action="store_true", help="skip the run-to-tolerance tail")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg (development runs)")
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.config == "c2" and not a.n:
+        a.n = 1_000_000
+    return a
 
 
 def planted_wstar(d):
@@ -266,6 +275,19 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.config != "c2":
+        import bench_configs
+
+        me = sys.modules[__name__]
+        if args.impl == "reference":
+            if args.config == "c5":
+                raise SystemExit("--impl reference --config c5: see the cpu_baseline block of the c5 line")
+            bench_configs.run_reference(args, me)
+        elif args.config == "c5":
+            bench_configs.run_c5(args, me)
+        else:
+            bench_configs.run(args, me)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

@@ -223,6 +223,12 @@ int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_
 int rbl_lasso_cd_gram(rbl_handle_t h, const double* G, const double* w_ref, const double* red0, double l1, double tol,
                       int max_iter, double* w_out, double* info3, rbl_stream_t stream);
 
+/* HOST function (no device work): the CPT spectra of EHRM, objective.py:148-164 — which = 0: a_i (gamma 0.69),
+ * which = 1: b_i (gamma 0.61), i = 0..n-1 in ascending rank, into the host array h_out.  Scalar libm pow in the
+ * reference's order, so the values equal the reference's Python-float loop bit for bit (the differences
+ * distort((i+1)/n) - distort(i/n) cancel ~log10(n) digits; a vectorised pow is 3e-9 off at n = 4M). */
+int rbl_cpt_weights(int64_t n, int which, double* h_out);
+
 /* ---- native outer loop.  The host layer captures ONE ADMM iteration (z-step, FISTA w-step, dual step, read-back of
  * out8/out9 into pinned memory) as a CUDA graph whose first node copies the pinned scalar block h_scal =
  * [rho, lam, thr_f32] to the block bound with rbl_bind_scalars.  rbl_admm_run then replays it up to max_iters

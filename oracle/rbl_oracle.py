@@ -473,6 +473,7 @@ class OracleADMM:
             return w.astype(np.float64) if self.fista_dtype == np.float64 else w
         w, info = w_step_l2(self.w, self.z, self.lam, self.rho, self.D, self.reg, self.DTD, return_info=True)
         self.passes += 2 * info["nfev"]
+        self.last_lbfgs_info = (int(info["nit"]), int(info["nfev"]))
         return w
 
     def step(self):

@@ -2,6 +2,7 @@
 produced by the reference itself (tests/golden, oracle/gen_golden.py) and (b) the CPU oracle run on
 the same inputs.  Tolerances stated per assert."""
 import contextlib
+import ctypes
 import io
 import os
 
@@ -309,7 +310,7 @@ def test_smooth_admm_vs_oracle_and_reference(golden_dir):
     ("AoRR fixed hinge", 800, 12, "aorr_dc", [500, 10], "hinge", None, dict(l2_reg=1e-4), True),
     ("AoRR fixed bce", 800, 12, "aorr_dc", [500, 10], "binary_cross_entropy", None, dict(l2_reg=1e-4), True),
 ])
-def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw, intercept):
+def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw, intercept, w_mode):
     """Reduced-n twins of BASELINE configs 2-4 on planted data, 30 ADMM iterations in lockstep
     with the oracle: every iteration starts from the device state and must land within 1e-9 (w, z) unless
     the inner solver took a different branch on a rounding-level near-tie (then ~ the inner tolerance)."""
@@ -324,7 +325,7 @@ def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw
         X = np.hstack([X, np.ones((n, 1))])
     s = ADMMmethod(X, y, wf, loss, B=B, args=args, max_iter=30, tol=1e-9, **kw)
     o = O.OracleADMM(X, y, wf, loss, B=B, args=args, max_iter=30, tol=1e-9, small_lasso=False, **kw)
-    flips = 0
+    flips = []
     for i in range(30):
         o.w, o.z, o.lam, o.rho = s.w.reshape(-1).copy(), s.z.reshape(-1).copy(), s.lagrangian.reshape(-1).copy(), s.rho
         with contextlib.redirect_stdout(io.StringIO()):
@@ -333,9 +334,27 @@ def test_reduced_size_twins_of_baseline_configs(tag, n, d, wf, args, loss, B, kw
         ew, ez = _rel(s.w, o.w), _rel(s.z, o.z)
         assert ez < 1e-9, (tag, i, ez)
         if ew >= 1e-9:
-            flips += 1
+            # allowed ONLY when the inner solver demonstrably took another branch on a rounding-level near-tie: the
+            # device's and the oracle's inner iteration / evaluation counts must differ, and the two answers must
+            # still agree to the inner solver's own tolerance
+            if "l1_reg" in kw:
+                hi, hd = (ctypes.c_int32 * 8)(), (ctypes.c_double * 4)()
+                s.engine.lib.rbl_fista_poll(s.engine.h, s.engine._stream(), hi, hd)
+                dev_info, cpu_info = (int(hi[1]), int(hi[3])), tuple(o.last_fista_info[:2])
+            else:
+                dev_info, cpu_info = (s.last_info["nit"], s.last_info["nfev"]), o.last_lbfgs_info
+            flips.append({"tag": tag, "w_mode": w_mode, "iteration": i, "rel_w": ew, "device": dev_info,
+                          "oracle": cpu_info})
+            assert dev_info != cpu_info, ("w differs without a recorded branch difference", flips[-1])
             assert ew < 5e-3, (tag, i, ew)
-    assert flips <= 2, (tag, flips)
+    # the escape hatch is counted and logged (gpurun_out/twin_flips.jsonl when the directory exists)
+    print(f"[twin] {tag} ({w_mode}): {len(flips)} inner-solver branch flips in 30 iterations {flips}")
+    out_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out_dir):
+        import json
+        with open(os.path.join(out_dir, "twin_flips.jsonl"), "a") as f:
+            f.write(json.dumps({"tag": tag, "w_mode": w_mode, "flips": flips}, default=str) + "\n")
+    assert len(flips) <= 2, (tag, flips)
     obj = s.objective.get_arrogate_loss(torch.from_numpy(s.w).double())
     o.w = s.w.reshape(-1).copy()
     assert abs(obj - o.objective()) < 1e-11 * abs(obj)
