@@ -274,6 +274,20 @@ int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global,
     return RBL_OK;
 }
 
+int rbl_set_storage(rbl_handle_t h, int elem_bytes) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(elem_bytes == 8 || elem_bytes == 4, "elem_bytes must be 8 (fp64) or 4 (fp32), got %d", elem_bytes);
+    RBL_REQUIRE(h->batch_cap == 0 || elem_bytes == 8, "the batched multi-RHS pass reads fp64 storage only");
+    const int old = h->esz;
+    h->esz = elem_bytes;
+    const int rc = rbl_pass_configure(h);  // row tiles are sized in bytes
+    if (rc != RBL_OK) {
+        h->esz = old;
+        rbl_pass_configure(h);
+    }
+    return rc;
+}
+
 int rbl_destroy(rbl_handle_t h) {
     if (!h) return RBL_OK;
     cudaSetDevice(h->device);
@@ -554,6 +568,7 @@ int rbl_fista_result(rbl_handle_t h, double* w_out, double* r_out, rbl_stream_t 
 int rbl_batch_create(rbl_handle_t h, int B) {
     RBL_ENTER(h);
     RBL_REQUIRE(B > 0 && B <= 4096, "bad batch size %d", B);
+    RBL_REQUIRE(h->esz != 4, "the batched multi-RHS pass reads fp64 storage only (rbl_set_storage)");
     RBL_REQUIRE(h->batch_cap == 0, "batched buffers already created for this handle");
     RBL_REQUIRE(h->ld <= 1024, "batched mode supports d <= 1024 (got %d)", h->d);
     int dev_max = 0;

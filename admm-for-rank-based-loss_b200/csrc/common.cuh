@@ -102,6 +102,7 @@ struct rbl_ctx {
     int64_t n_local, n_global, row_lo;
     int d;
     int64_t ld;
+    int esz;            // bytes per stored element of D / D^T: 8 (fp64, default) or 4 (optional fp32 storage)
     // ---- pass kernels
     int pass_grid;      // persistent CTAs
     int pass_rows;      // rows per tile

@@ -612,7 +612,7 @@ constexpr int kSK = 16;    // rows of D per stage
 constexpr int kSLd = 68;   // padded smem leading dimension (doubles): 4 mod 16 -> conflict-free fragment loads
 
 struct SyrkParams {
-    const double* D;
+    const void* D;
     int64_t ld;
     int64_t n;
     int d;
@@ -631,7 +631,9 @@ __device__ __forceinline__ void pair_to_tiles(int pair, int* ti, int* tj) {
     *tj = pair;
 }
 
+template <typename T>
 __global__ void __launch_bounds__(256) gram_syrk_kernel(const SyrkParams p) {
+    const T* __restrict__ Dp = reinterpret_cast<const T*>(p.D);
     __shared__ __align__(16) double As[2][kSK][kSLd];  // rows k, columns of tile ti
     __shared__ __align__(16) double Bs[2][kSK][kSLd];  // rows k, columns of tile tj
     int ti, tj;
@@ -660,8 +662,8 @@ __global__ void __launch_bounds__(256) gram_syrk_kernel(const SyrkParams p) {
             const int r = e >> 6, c = e & 63;
             const int64_t gr = r0 + r;
             const bool ok = gr < r_end;
-            ra[q] = (ok && ci0 + c < p.d) ? __ldg(&p.D[gr * p.ld + ci0 + c]) : 0.0;
-            rb[q] = (ok && cj0 + c < p.d) ? __ldg(&p.D[gr * p.ld + cj0 + c]) : 0.0;
+            ra[q] = (ok && ci0 + c < p.d) ? (double)__ldg(&Dp[gr * p.ld + ci0 + c]) : 0.0;
+            rb[q] = (ok && cj0 + c < p.d) ? (double)__ldg(&Dp[gr * p.ld + cj0 + c]) : 0.0;
         }
     };
     auto stash = [&](int buf) {
@@ -944,7 +946,8 @@ int rbl_k_gram_build(rbl_ctx* c, const double* D, int64_t nrows, int accumulate,
     p.part = scratch;
     if (!accumulate) RBL_CUDA(cudaMemsetAsync(G, 0, (size_t)c->d * c->ld * sizeof(double), s));
     dim3 grid(npairs, p.nslab);
-    gram_syrk_kernel<<<grid, 256, 0, s>>>(p);
+    if (c->esz == 4) gram_syrk_kernel<float><<<grid, 256, 0, s>>>(p);
+    else gram_syrk_kernel<double><<<grid, 256, 0, s>>>(p);
     RBL_LAUNCH_CHECK();
     gram_syrk_reduce_kernel<<<npairs, 256, 0, s>>>(scratch, p.nslab, npairs, c->d, c->ld, G, accumulate);
     RBL_LAUNCH_CHECK();

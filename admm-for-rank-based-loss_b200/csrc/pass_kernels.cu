@@ -65,8 +65,16 @@ __device__ __forceinline__ uint64_t l2_policy_evict_first() {
     return pol;
 }
 
+// storage type of the design matrix: fp64 (default) or fp32 (optional mode, rbl_set_storage: halves the HBM bytes of
+// every pass; products and sums stay fp64)
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+__device__ __forceinline__ double2 to_d2(double2 v) { return v; }
+__device__ __forceinline__ double2 to_d2(float2 v) { return make_double2((double)v.x, (double)v.y); }
+
 struct PassParams {
-    const double* D;
+    const void* D;
     int64_t ld;
     int64_t n;
     int d;
@@ -94,9 +102,11 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxRows = 64;
 
-// XJ : double2 of x held per lane;  WPR : warps cooperating on one row;  CJ : double2 columns per thread
-template <int XJ, int WPR, int CJ>
+// T : storage type of D;  XJ : double2 of x held per lane;  WPR : warps cooperating on one row;  CJ : column pairs
+// per thread
+template <typename T, int XJ, int WPR, int CJ>
 __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams p) {
+    using V2 = typename Vec2<T>::type;
     rbl_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -137,10 +147,10 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
         const int s = (int)(k % S);
         const int64_t row0 = (first + k * stride) * R;
         const int rows = (int)((p.n - row0 < R) ? (p.n - row0) : R);
-        const uint32_t bytes = (uint32_t)((size_t)rows * ld * sizeof(double));
+        const uint32_t bytes = (uint32_t)((size_t)rows * ld * sizeof(T));
         mbar_expect_tx(&bars[s], bytes);
         void* dst = stage_base + (size_t)s * p.stage_stride;
-        const void* src = p.D + row0 * ld;
+        const void* src = reinterpret_cast<const T*>(p.D) + row0 * ld;
         if (p.evict_first) tma_bulk_g2s_hint(dst, src, bytes, &bars[s], policy);
         else tma_bulk_g2s(dst, src, bytes, &bars[s]);
     };
@@ -176,17 +186,17 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
         if (dual && tid < rows) lv = p.lam[row0 + tid];
         while (!mbar_try_wait(&bars[s], parity)) {
         }
-        const double2* T2 = reinterpret_cast<const double2*>(stage_base + (size_t)s * p.stage_stride);
+        const V2* T2 = reinterpret_cast<const V2*>(stage_base + (size_t)s * p.stage_stride);
 
         // ---- phase A: row dots
         for (int i = grp; i < rows; i += G) {
-            const double2* row = T2 + (size_t)i * ld2;
+            const V2* row = T2 + (size_t)i * ld2;
             double a0 = 0.0, a1 = 0.0;
 #pragma unroll
             for (int j = 0; j < XJ; ++j) {
                 const int c2 = lane + 32 * (j * WPR + h);
                 if (c2 < ld2) {
-                    const double2 v = row[c2];
+                    const double2 v = to_d2(row[c2]);
                     a0 = fma(v.x, xr[j].x, a0);
                     a1 = fma(v.y, xr[j].y, a1);
                 }
@@ -226,12 +236,12 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
             // ---- phase B: g += D_tile^T r_tile, thread-owned columns
             for (int i = 0; i < rows; ++i) {
                 const double ri = rt[i];
-                const double2* row = T2 + (size_t)i * ld2;
+                const V2* row = T2 + (size_t)i * ld2;
 #pragma unroll
                 for (int j = 0; j < CJ; ++j) {
                     const int c2 = tid + kThreads * j;
                     if (c2 < ld2) {
-                        const double2 v = row[c2];
+                        const double2 v = to_d2(row[c2]);
                         acc[j].x = fma(v.x, ri, acc[j].x);
                         acc[j].y = fma(v.y, ri, acc[j].y);
                     }
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_pass_kernel(const PassParams 
 // HBM still sees multi-KB contiguous bursts.  Only the column accumulation runs (r = delta is known), and the
 // traffic is (#active rows / n) of a full pass: 0.2 for superquantile q = 0.8 once the pooled block is small.
 struct GatherParams {
-    const double* D;
+    const void* D;
     int64_t ld;
     const int32_t* rows;
     const double* delta;
@@ -287,8 +297,9 @@ struct GatherParams {
     uint32_t stage_stride;
 };
 
-template <int CJ>
+template <typename T, int CJ>
 __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherParams p) {
+    using V2 = typename Vec2<T>::type;
     rbl_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -311,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherPar
     }
     __syncthreads();
     const uint64_t policy = l2_policy_evict_first();
-    const uint32_t row_bytes = (uint32_t)(ld * sizeof(double));
+    const uint32_t row_bytes = (uint32_t)(ld * sizeof(T));
     double ss = 0.0;
     // warp 0 issues tile k: lane i < rows copies list entry k R + i
     auto issue = [&](int64_t k) {
@@ -328,7 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherPar
         __syncwarp();
         if (lane < rows) {
             tma_bulk_g2s_hint(stage_base + (size_t)s * p.stage_stride + (size_t)lane * row_bytes,
-                              p.D + (int64_t)row * ld, row_bytes, &bars[s], policy);
+                              reinterpret_cast<const T*>(p.D) + (int64_t)row * ld, row_bytes, &bars[s], policy);
             dl[s * kMaxRows + lane] = dv;
             ss = fma(dv, dv, ss);
         }
@@ -349,15 +360,15 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherPar
         const int rows = (int)((count - e0 < R) ? (count - e0) : R);
         while (!mbar_try_wait(&bars[s], parity)) {
         }
-        const double2* T2 = reinterpret_cast<const double2*>(stage_base + (size_t)s * p.stage_stride);
+        const V2* T2 = reinterpret_cast<const V2*>(stage_base + (size_t)s * p.stage_stride);
         for (int i = 0; i < rows; ++i) {
             const double ri = dl[s * kMaxRows + i];
-            const double2* row = T2 + (size_t)i * ld2;
+            const V2* row = T2 + (size_t)i * ld2;
 #pragma unroll
             for (int j = 0; j < CJ; ++j) {
                 const int c2 = tid + kThreads * j;
                 if (c2 < ld2) {
-                    const double2 v = row[c2];
+                    const double2 v = to_d2(row[c2]);
                     acc[j].x = fma(v.x, ri, acc[j].x);
                     acc[j].y = fma(v.y, ri, acc[j].y);
                 }
@@ -384,30 +395,40 @@ __global__ void __launch_bounds__(kThreads, 1) rbl_gather_kernel(const GatherPar
     }
 }
 
-template <int CJ>
-int launch_gather_t(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
+template <typename T, int CJ>
+int launch_gather_tt(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
     RBL_PER_DEVICE(size_t, attr_smem, c);
     if (c->pass_smem > attr_smem) {
-        RBL_CUDA(cudaFuncSetAttribute(rbl_gather_kernel<CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        RBL_CUDA(cudaFuncSetAttribute(rbl_gather_kernel<T, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)c->pass_smem));
         attr_smem = c->pass_smem;
     }
-    RBL_CUDA(rbl_launch_pdl(rbl_gather_kernel<CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
+    RBL_CUDA(rbl_launch_pdl(rbl_gather_kernel<T, CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
+    RBL_LAUNCH_CHECK();
+    return RBL_OK;
+}
+
+template <int CJ>
+int launch_gather_t(rbl_ctx* c, const GatherParams& p, cudaStream_t s) {
+    return c->esz == 4 ? launch_gather_tt<float, CJ>(c, p, s) : launch_gather_tt<double, CJ>(c, p, s);
+}
+
+template <typename T, int XJ, int WPR, int CJ>
+int launch_tt(rbl_ctx* c, const PassParams& p, cudaStream_t s) {
+    RBL_PER_DEVICE(size_t, attr_smem, c);  // per instantiation and per device
+    if (c->pass_smem > attr_smem) {
+        RBL_CUDA(cudaFuncSetAttribute(rbl_pass_kernel<T, XJ, WPR, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)c->pass_smem));
+        attr_smem = c->pass_smem;
+    }
+    RBL_CUDA(rbl_launch_pdl(rbl_pass_kernel<T, XJ, WPR, CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
 
 template <int XJ, int WPR, int CJ>
 int launch_t(rbl_ctx* c, const PassParams& p, cudaStream_t s) {
-    RBL_PER_DEVICE(size_t, attr_smem, c);  // per instantiation and per device
-    if (c->pass_smem > attr_smem) {
-        RBL_CUDA(cudaFuncSetAttribute(rbl_pass_kernel<XJ, WPR, CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)c->pass_smem));
-        attr_smem = c->pass_smem;
-    }
-    RBL_CUDA(rbl_launch_pdl(rbl_pass_kernel<XJ, WPR, CJ>, dim3(c->pass_grid), dim3(kThreads), c->pass_smem, s, p));
-    RBL_LAUNCH_CHECK();
-    return RBL_OK;
+    return c->esz == 4 ? launch_tt<float, XJ, WPR, CJ>(c, p, s) : launch_tt<double, XJ, WPR, CJ>(c, p, s);
 }
 
 int pick_wpr(int64_t ld2) { return ld2 <= 512 ? 1 : ld2 <= 1024 ? 2 : ld2 <= 2048 ? 4 : 8; }
@@ -416,8 +437,10 @@ int pick_wpr(int64_t ld2) { return ld2 <= 512 ? 1 : ld2 <= 1024 ? 2 : ld2 <= 204
 
 int rbl_pass_configure(rbl_ctx* c) {
     const int64_t ld2 = c->ld / 2;
-    if (c->ld % 2 != 0) {
-        rbl_set_error("leading dimension must be even (16-byte rows for TMA bulk copies), got %lld", (long long)c->ld);
+    if (c->esz != 4) c->esz = 8;
+    if ((c->ld * c->esz) % 16 != 0) {
+        rbl_set_error("rows must be a multiple of 16 bytes for the TMA bulk copies: leading dimension %lld must be a "
+                      "multiple of %d for %d-byte elements", (long long)c->ld, 16 / c->esz, c->esz);
         return RBL_ERR_ARG;
     }
     if (ld2 > 4096) {
@@ -426,7 +449,7 @@ int rbl_pass_configure(rbl_ctx* c) {
     }
     const int wpr = pick_wpr(ld2);
     const int G = kWarps / wpr;
-    const size_t row_bytes = (size_t)c->ld * sizeof(double);
+    const size_t row_bytes = (size_t)c->ld * c->esz;
     int R = (int)(65536 / row_bytes);
     R = (R / G) * G;
     if (R < G) R = G;
@@ -473,8 +496,8 @@ int rbl_launch_pass(rbl_ctx* c, int mode, const double* D, const double* x, cons
     p.stages = c->pass_stages;
     p.mode = mode;
     // stream D through L2 when it cannot stay resident (B200 L2 ~126 MB); keep it when it can
-    p.evict_first = ((size_t)c->n_local * c->ld * sizeof(double) > ((size_t)96 << 20)) ? 1 : 0;
-    const size_t row_bytes = (size_t)c->ld * sizeof(double);
+    p.evict_first = ((size_t)c->n_local * c->ld * c->esz > ((size_t)96 << 20)) ? 1 : 0;
+    const size_t row_bytes = (size_t)c->ld * c->esz;
     p.stage_stride = (uint32_t)(((size_t)c->pass_rows * row_bytes + 127) & ~(size_t)127);
     const int64_t ld2 = c->ld / 2;
     const int wpr = pick_wpr(ld2);
@@ -501,7 +524,7 @@ int rbl_launch_gather(rbl_ctx* c, const double* D, const int32_t* rows, const do
     p.sspart = c->sspart;
     p.R = c->pass_rows > 32 ? 32 : c->pass_rows;  // one issuing lane per row
     p.stages = c->pass_stages;
-    const size_t row_bytes = (size_t)c->ld * sizeof(double);
+    const size_t row_bytes = (size_t)c->ld * c->esz;
     p.stage_stride = (uint32_t)(((size_t)c->pass_rows * row_bytes + 127) & ~(size_t)127);
     const int64_t ld2 = c->ld / 2;
     if (ld2 <= 256) return launch_gather_t<1>(c, p, s);

@@ -5,6 +5,8 @@
 // Replaces: src/optim/algorithms.py:23 (D = -y*X), :89 (margins), :103-104 (scatter), :132-136 (dual
 // update + residual norms), src/util/fast_lasso.py:44-65 (FISTA line search / momentum / stop test —
 // here a device-resident state machine), src/optim/objective.py:71-87 (rank-weighted objective).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace {
@@ -37,14 +39,15 @@ __device__ __forceinline__ double block_sum(double v, double* sh) {
 }
 
 // ---- D = -y (.) X with zero-filled padding columns (algorithms.py:23) ---------------------------
+template <typename T>
 __global__ void build_design_kernel(const double* __restrict__ X, int64_t ldx, const double* __restrict__ y,
-                                    double* __restrict__ D, int64_t ld, int64_t n, int d) {
+                                    T* __restrict__ D, int64_t ld, int64_t n, int d) {
     const int64_t total = n * ld;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i = idx / ld;
         const int c = (int)(idx - i * ld);
-        D[idx] = (c < d) ? -(y[i] * X[i * ldx + c]) : 0.0;
+        D[idx] = (T)((c < d) ? -(y[i] * X[i * ldx + c]) : 0.0);  // fp32 storage: one rounding of the fp64 product
     }
 }
 
@@ -549,8 +552,8 @@ __global__ void __launch_bounds__(1024) support_kernel(const double* __restrict_
 // whole 8 d-byte row (HBM traffic down by d / (4 nnz)).  A group of GS lanes owns a row (GS = 8, 16 or 32,
 // the smallest that covers nnz), 4 rows in flight per group.  Runs only when nnz <= cap; the dense
 // pass (RBL_PASS_DUAL) is gated the other way.
-template <int GS>
-__device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, int64_t ld, int64_t n,
+template <int GS, typename T>
+__device__ __forceinline__ void sparse_dual_rows(const T* __restrict__ D, int64_t ld, int64_t n,
                                                  const int32_t* __restrict__ idx, const double* __restrict__ val,
                                                  int nnz, const double* __restrict__ z, double* __restrict__ Dw,
                                                  double* __restrict__ lam, double rho, double& acc) {
@@ -582,7 +585,7 @@ __device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, i
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int64_t i = i0 + u * gstride;
-                if (i < n) a[u] = fma(__ldg(&D[i * ld + j]), wv, a[u]);
+                if (i < n) a[u] = fma((double)__ldg(&D[i * ld + j]), wv, a[u]);
             }
         }
 #pragma unroll
@@ -600,7 +603,8 @@ __device__ __forceinline__ void sparse_dual_rows(const double* __restrict__ D, i
     }
 }
 
-__global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restrict__ D, int64_t ld, int64_t n,
+template <typename T>
+__global__ void __launch_bounds__(256) sparse_dual_kernel(const T* __restrict__ D, int64_t ld, int64_t n,
                                                           const int32_t* __restrict__ idx,
                                                           const double* __restrict__ val,
                                                           const int* __restrict__ nnz_ptr, int cap,
@@ -624,7 +628,8 @@ __global__ void __launch_bounds__(256) sparse_dual_kernel(const double* __restri
 // Same update from the TRANSPOSED copy Dt (d x n, row j = column j of D): the nnz touched columns are read as
 // contiguous n-vectors, so the traffic is nnz n 8 bytes of fully coalesced loads (80 MB at nnz = 10, n = 1M)
 // instead of one DRAM page activation per row of D (the sector gather above is activate-bound: ~2 TB/s).
-__global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __restrict__ Dt, int64_t n,
+template <typename T>
+__global__ void __launch_bounds__(256) sparse_dual_t_kernel(const T* __restrict__ Dt, int64_t n,
                                                             const int32_t* __restrict__ idx,
                                                             const double* __restrict__ val,
                                                             const int* __restrict__ nnz_ptr, int cap,
@@ -651,20 +656,22 @@ __global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __rest
         const bool first = (k0 == 0), last_chunk = (k0 + 256 >= nnz);
         for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < n;
              i += (int64_t)gridDim.x * blockDim.x * 2) {
-            const bool two = (i + 1 < n) && ((n & 1) == 0);  // double2 loads need 16-byte aligned columns
+            using V2 = typename std::conditional<sizeof(T) == 4, float2, double2>::type;
+            const bool two = (i + 1 < n) && ((n & 1) == 0);  // two-element loads need aligned columns
             double a0 = first ? 0.0 : Dw[i], a1 = (two && !first) ? Dw[i + 1] : 0.0;
             if (two) {
 #pragma unroll 4
                 for (int k = 0; k < kn; ++k) {
-                    const double2 v = __ldg(reinterpret_cast<const double2*>(Dt + (int64_t)s_idx[k] * n + i));
-                    a0 = fma(v.x, s_val[k], a0);
-                    a1 = fma(v.y, s_val[k], a1);
+                    const V2 v = __ldg(reinterpret_cast<const V2*>(Dt + (int64_t)s_idx[k] * n + i));
+                    a0 = fma((double)v.x, s_val[k], a0);
+                    a1 = fma((double)v.y, s_val[k], a1);
                 }
             } else {
-                for (int k = 0; k < kn; ++k) a0 = fma(__ldg(Dt + (int64_t)s_idx[k] * n + i), s_val[k], a0);
+                for (int k = 0; k < kn; ++k) a0 = fma((double)__ldg(Dt + (int64_t)s_idx[k] * n + i), s_val[k], a0);
                 if (i + 1 < n) {
                     a1 = first ? 0.0 : Dw[i + 1];
-                    for (int k = 0; k < kn; ++k) a1 = fma(__ldg(Dt + (int64_t)s_idx[k] * n + i + 1), s_val[k], a1);
+                    for (int k = 0; k < kn; ++k)
+                        a1 = fma((double)__ldg(Dt + (int64_t)s_idx[k] * n + i + 1), s_val[k], a1);
                 }
             }
             Dw[i] = a0;
@@ -686,9 +693,10 @@ __global__ void __launch_bounds__(256) sparse_dual_t_kernel(const double* __rest
 }
 
 // Dt = D^T (d x n) through a 32 x 33 shared-memory tile
-__global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict__ D, int64_t ld, int64_t n, int d,
-                                                        double* __restrict__ Dt) {
-    __shared__ double tile[32][33];
+template <typename T>
+__global__ void __launch_bounds__(256) transpose_kernel(const T* __restrict__ D, int64_t ld, int64_t n, int d,
+                                                        T* __restrict__ Dt) {
+    __shared__ T tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
     const int64_t ntr = (n + 31) / 32;
     const int ntc = (d + 31) / 32;
@@ -701,7 +709,7 @@ __global__ void __launch_bounds__(256) transpose_kernel(const double* __restrict
         for (int q = 0; q < 4; ++q) {
             const int64_t r = r0 + ty + 8 * q;
             const int c = c0 + tx;
-            tile[ty + 8 * q][tx] = (r < n && c < d) ? D[r * ld + c] : 0.0;
+            tile[ty + 8 * q][tx] = (r < n && c < d) ? D[r * ld + c] : (T)0;
         }
         __syncthreads();
 #pragma unroll
@@ -777,7 +785,11 @@ __global__ void objective_kernel(const double* __restrict__ u_sorted, const doub
 // ---- host launchers ----------------------------------------------------------------------------
 int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
                        cudaStream_t s) {
-    build_design_kernel<<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, D, c->ld, nrows, c->d);
+    if (c->esz == 4)
+        build_design_kernel<float><<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, reinterpret_cast<float*>(D), c->ld, nrows,
+                                                                c->d);
+    else
+        build_design_kernel<double><<<c->num_sms * 8, 256, 0, s>>>(X, ldx, y, D, c->ld, nrows, c->d);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
@@ -862,17 +874,32 @@ int rbl_k_dual_sparse(rbl_ctx* c, const double* D, const double* Dt, const doubl
         RBL_LAUNCH_CHECK();
     }
     if (Dt)
-        RBL_CUDA(rbl_launch_pdl(sparse_dual_t_kernel, dim3(c->vec_grid), dim3(kVecThreads), 0, s, Dt, c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
-                                                                cap, z, Dw, lam, rho, c->vpart, c->scal));
+        if (c->esz == 4)
+            RBL_CUDA(rbl_launch_pdl(sparse_dual_t_kernel<float>, dim3(c->vec_grid), dim3(kVecThreads), 0, s,
+                                    reinterpret_cast<const float*>(Dt), c->n_local, c->sup_idx, c->sup_val, c->sup_nnz,
+                                    cap, z, Dw, lam, rho, c->vpart, c->scal));
+        else
+            RBL_CUDA(rbl_launch_pdl(sparse_dual_t_kernel<double>, dim3(c->vec_grid), dim3(kVecThreads), 0, s, Dt,
+                                    c->n_local, c->sup_idx, c->sup_val, c->sup_nnz, cap, z, Dw, lam, rho, c->vpart,
+                                    c->scal));
+    else if (c->esz == 4)
+        RBL_CUDA(rbl_launch_pdl(sparse_dual_kernel<float>, dim3(c->vec_grid), dim3(kVecThreads), 0, s,
+                                reinterpret_cast<const float*>(D), c->ld, c->n_local, c->sup_idx, c->sup_val,
+                                c->sup_nnz, cap, z, Dw, lam, rho, c->vpart, c->scal));
     else
-        RBL_CUDA(rbl_launch_pdl(sparse_dual_kernel, dim3(c->vec_grid), dim3(kVecThreads), 0, s, D, c->ld, c->n_local, c->sup_idx, c->sup_val,
-                                                              c->sup_nnz, cap, z, Dw, lam, rho, c->vpart, c->scal));
+        RBL_CUDA(rbl_launch_pdl(sparse_dual_kernel<double>, dim3(c->vec_grid), dim3(kVecThreads), 0, s, D, c->ld,
+                                c->n_local, c->sup_idx, c->sup_val, c->sup_nnz, cap, z, Dw, lam, rho, c->vpart,
+                                c->scal));
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }
 
 int rbl_k_transpose(rbl_ctx* c, const double* D, double* Dt, cudaStream_t s) {
-    transpose_kernel<<<c->num_sms * 16, 256, 0, s>>>(D, c->ld, c->n_local, c->d, Dt);
+    if (c->esz == 4)
+        transpose_kernel<float><<<c->num_sms * 16, 256, 0, s>>>(reinterpret_cast<const float*>(D), c->ld, c->n_local,
+                                                                c->d, reinterpret_cast<float*>(Dt));
+    else
+        transpose_kernel<double><<<c->num_sms * 16, 256, 0, s>>>(D, c->ld, c->n_local, c->d, Dt);
     RBL_LAUNCH_CHECK();
     return RBL_OK;
 }

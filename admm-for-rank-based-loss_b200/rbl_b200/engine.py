@@ -49,9 +49,23 @@ class DeviceProblem:
     """D = -y (.) X resident in HBM (row-major, padded to an even leading dimension) plus the library
     handle that owns the scratch for passes, sort and PAV over it."""
 
-    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None, _share=None, _want_gram=False):
+    def __init__(self, X, y, device=None, group=None, row_lo=None, n_global=None, _share=None, _want_gram=False,
+                 storage=None):
+        """storage: "fp64" (default) or "fp32" — the OPTIONAL mode that keeps D (and D^T) in float32 in HBM: every
+        D-reading kernel moves half the bytes; all arithmetic (dots, column sums, G = D^T D, every vector) stays
+        fp64.  Results then differ from the fp64 run by the rounding of D's entries (~1e-7 relative)."""
         self.lib = _cabi.load()
         self._parent = _share
+        storage = (storage or os.environ.get("RBL_STORAGE", "fp64")).lower()
+        if storage in ("float32", "f32"):
+            storage = "fp32"
+        if storage in ("float64", "f64"):
+            storage = "fp64"
+        if storage not in ("fp64", "fp32"):
+            raise ValueError(f"storage must be 'fp64' or 'fp32' (got {storage!r})")
+        self.storage = storage if _share is None else _share.storage
+        self.esz = 4 if self.storage == "fp32" else 8
+        self.store_dtype = torch.float32 if self.esz == 4 else torch.float64
         if _share is not None:
             # another solver instance over the SAME design matrix (batched mode): own handle, scratch and state,
             # D / G / D^T borrowed from the parent
@@ -63,6 +77,8 @@ class DeviceProblem:
                 _cabi.check(self.lib.rbl_create(ctypes.byref(h), self.device.index or 0, self.n_local, self.n_global,
                                                 self.row_lo, self.d, self.ld))
                 self.h = h
+                if self.esz == 4:
+                    _cabi.check(self.lib.rbl_set_storage(self.h, 4))
                 self.D = p.D
                 self._out4 = torch.zeros(16, dtype=torch.float64, device=self.device)
                 self._out4_host = torch.zeros(16, dtype=torch.float64).pin_memory()
@@ -88,7 +104,7 @@ class DeviceProblem:
                                  f"[{int(row_lo)}, {int(row_lo) + int(X.shape[0])})")
         self.n_local, self.d = int(X.shape[0]), int(X.shape[1])
         self.n_global, self.row_lo = int(n_global), int(row_lo)
-        self.ld = self.d + (self.d & 1)
+        self.ld = self.d + (self.d & 1) if self.esz == 8 else (self.d + 3) // 4 * 4   # 16-byte rows
         import time as _time
         self.build_times = {}
         with torch.cuda.device(self.device):
@@ -97,11 +113,13 @@ class DeviceProblem:
             _cabi.check(self.lib.rbl_create(ctypes.byref(h), self.device.index or 0, self.n_local, self.n_global,
                                             self.row_lo, self.d, self.ld))
             self.h = h
+            if self.esz == 4:
+                _cabi.check(self.lib.rbl_set_storage(self.h, 4))
             t1 = _time.perf_counter()
             self.G = None
             yd = self._to_device(np.asarray(y, dtype=np.float64).reshape(-1) if not torch.is_tensor(y)
                                  else y.reshape(-1).to(torch.float64))
-            self.D = torch.empty((self.n_local, self.ld), dtype=torch.float64, device=self.device)
+            self.D = torch.empty((self.n_local, self.ld), dtype=self.store_dtype, device=self.device)
             chunk = int(os.environ.get("RBL_PIPELINE_ROWS", "0")) or max(4096, (256 << 20) // (8 * self.d))  # ~256 MB
             if (not torch.is_tensor(X)) and self.n_local >= 4 * chunk and os.environ.get("RBL_PIPELINE", "1") != "0":
                 # host array: upload X chunk by chunk on a copy stream while the previous chunk is turned into rows
@@ -410,12 +428,12 @@ class AdmmEngine(DeviceProblem):
             self.Dt, self.transpose_ok = self._parent.Dt, self._parent.transpose_ok
             return
         free, _ = torch.cuda.mem_get_info(self.device)
-        need = self.n_local * self.d * 8
+        need = self.n_local * self.d * self.esz
         if need + (2 << 30) > free:
             self.transpose_ok = False  # not enough HBM left: keep the sector-gather kernel
             return
         with torch.cuda.device(self.device):
-            Dt = torch.empty((self.d, self.n_local), dtype=torch.float64, device=self.device)
+            Dt = torch.empty((self.d, self.n_local), dtype=self.store_dtype, device=self.device)
             _cabi.check(self.lib.rbl_build_transpose(self.h, self.D.data_ptr(), Dt.data_ptr(), self._stream()))
             # one-off: finish before publishing it — child engines (batched mode) read it from other streams
             torch.cuda.current_stream(self.device).synchronize()

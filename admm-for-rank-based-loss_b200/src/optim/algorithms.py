@@ -28,14 +28,18 @@ from src.optim.objective import rankbasedObjective
 
 class Optimizer:
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
-                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None):
+                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None, _storage=None):
         # _shard (extension, not in the reference): dict(row_lo=, n_global=[, group=]) when X, y are this
         # rank's contiguous rows of a row-sharded problem (one process per GPU, torch.distributed/NCCL)
+        # _storage (extension): "fp32" keeps D in float32 in HBM (optional mode: half the bytes per pass, fp64
+        # arithmetic throughout; iterates within ~1e-6 of the fp64 run) — default "fp64" (env RBL_STORAGE)
         _t0 = time.perf_counter()
         if not torch.is_tensor(X):  # a (device) tensor is taken as it is: no copy back to the host
             X = np.asarray(X)
         y = y.detach().cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
-        _shard = _shard or {}
+        _shard = dict(_shard or {})
+        if _storage is not None:
+            _shard["storage"] = _storage
         self.num_row = int(_shard.get("n_global", X.shape[0]))
         self.num_feature = X.shape[1]
         # regularization (:30) — raises TypeError below when both are None, like the reference (:32)
@@ -120,7 +124,7 @@ class Optimizer:
 
     @property
     def D(self):
-        return self.engine.D[:, : self.num_feature].cpu().numpy()
+        return self.engine.D[:, : self.num_feature].cpu().numpy().astype(np.float64, copy=False)
 
     @property
     def DTD(self):
@@ -279,9 +283,9 @@ class _Deferred:
 class ADMMmethod(Optimizer):
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                  l2_reg=None, l1_reg=None, B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4,
-                 _shard=None):
+                 _shard=None, _storage=None):
         super(ADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
-                                         args, w0, max_iter, tol, _shard)
+                                         args, w0, max_iter, tol, _shard, _storage)
 
     def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                     B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):
@@ -369,9 +373,9 @@ class smoothADMMmethod(Optimizer):
 
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                  B=None, l2_reg=None, l1_reg=None, n_class=None, args=None, w0=None, t=1, max_iter=200, tol=1e-4,
-                 _shard=None):
+                 _shard=None, _storage=None):
         super(smoothADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
-                                               args, w0, max_iter, tol, _shard)
+                                               args, w0, max_iter, tol, _shard, _storage)
         self.t = t
 
     def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",

@@ -1,10 +1,12 @@
 """Drop-in for src/util/fast_lasso.py: FISTA(beta, X, y, lam, L, eta, tol, max_iter, dtype) on the B200.
 
 Same argument meaning as the reference (:22); the backtracking loop (:40-67) runs as a device-resident
-state machine with one fused pass over X per line-search trial (librbl_b200: rbl_fista_*).  The
-computation is float64; `dtype` is accepted for signature compatibility (the reference's float32 mode
-is chaotic at its own tolerance, SURVEY.md §8a vi-vii) and the global torch default dtype is NOT
-mutated (:23-26 side effect deliberately not reproduced)."""
+state machine with one fused pass over X per line-search trial (librbl_b200: rbl_fista_*).
+`dtype=torch.float64`: everything in float64.  `dtype=torch.float32` (the reference's default, :22): the
+OPTIONAL fp32 mode — X is kept in float32 in HBM (half the bytes per pass) while every product, sum and the
+FISTA state stay float64, and the result is returned as float32 like the reference's (:69).  That is tighter
+than the reference's all-float32 arithmetic (chaotic at its own tolerance, overflowing L_cur: SURVEY.md §8a
+vi-vii), by design.  The global torch default dtype is NOT mutated (:23-26 side effect not reproduced)."""
 import numpy as np
 import torch
 
@@ -19,12 +21,15 @@ def FISTA(beta, X, y, lam, L, eta, tol=1e-4, max_iter=5000, dtype=torch.float32,
     X = np.asarray(X, dtype=np.float64)
     n, d = X.shape
     # D = -(-1) * X = X exactly
-    eng = AdmmEngine(X, -np.ones(n), "binary_cross_entropy", np.ones(n) / n)
+    if dtype not in (torch.float32, torch.float64):
+        raise ValueError(f"dtype must be torch.float32 or torch.float64 (got {dtype})")
+    f32 = dtype == torch.float32
+    eng = AdmmEngine(X, -np.ones(n), "binary_cross_entropy", np.ones(n) / n, storage="fp32" if f32 else "fp64")
     try:
         b = eng.vec(np.asarray(y, dtype=np.float64))
         w0 = eng.vec(np.asarray(beta, dtype=np.float64))
         w, info = eng.fista(w0, b, lam, L=L, eta=eta, tol=tol, max_iter=max_iter)
-        out = w.cpu().numpy()
+        out = w.cpu().numpy().astype(np.float32) if f32 else w.cpu().numpy()
     finally:
         eng.close()
     return (out, info) if return_info else out

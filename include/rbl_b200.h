@@ -53,6 +53,14 @@ int rbl_bind_scalars(rbl_handle_t h, const double* d_scal);
 int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global, int64_t row_lo, int32_t d,
                int64_t ld);
 int rbl_destroy(rbl_handle_t h);
+
+/* OPTIONAL fp32 storage of the design matrix (north_star: "1e-5 in an optional fp32 mode"; the reference ships a
+ * float32 FISTA, algorithms.py:199-201, fast_lasso.py:22-26).  elem_bytes = 4: every `D` / `Dt` / `D_rows` pointer
+ * passed to this handle afterwards points to FLOAT rows (leading dimension a multiple of 4 elements = 16 bytes);
+ * rbl_build_design* round the fp64 product -y*x once to float.  All dots, column sums, G = D^T D and every vector
+ * stay fp64 — only the HBM bytes of the D-reading kernels halve.  elem_bytes = 8 (default) restores fp64.  Call it
+ * right after rbl_create, before D is built.  Not available together with rbl_batch_create. */
+int rbl_set_storage(rbl_handle_t h, int elem_bytes);
 /* h_out[0..8) = num_sms, pass_grid, rows_per_tile, pass_stages, pass_smem_bytes, scratch_bytes, vec_grid,
  * pav_chunk */
 int rbl_info(rbl_handle_t h, int64_t* h_out);
