@@ -459,10 +459,12 @@ __global__ void sigma_ascents_kernel(const double* __restrict__ sigma, int64_t n
     }
 }
 
+constexpr int kSegMergeThreads = 1024;  // all of them scan the chunk totals; warps 0 and 1 then run the searches
+
 // two warps: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1;
 // warp 0 searches the left end of the pooled block while warp 1 searches the right end (independent
 // dependent-load chains, ~50 us each at n = 1M)
-__global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
+__global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
                                                            int nseg, SegBlocks* __restrict__ out) {
     rbl_pdl_wait();
     __shared__ int s_nblk;
@@ -482,10 +484,12 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
     stamp();
     if (tid == 0) s_nblk = 0;
     {   // exclusive scan of the chunk totals of the margins (what chunk_offsets_kernel does for the tree route):
-        // 64 threads x contiguous slices, double-double throughout
-        __shared__ double s_wh[2], s_wl[2];
+        // the whole CTA takes part (one or a few chunks per thread — 64 threads walking 16 chunks each was a
+        // quarter of this kernel's time), double-double throughout, fixed order
+        __shared__ double s_wh[32], s_wl[32];
+        const int nt = blockDim.x, nw = nt >> 5;
         const int64_t nch = P.nchunks;
-        const int64_t per = (nch + 63) / 64;
+        const int64_t per = (nch + nt - 1) / nt;
         const int64_t c0 = (int64_t)tid * per;
         dd_t run = dd_make(0.0);
         for (int64_t c = c0; c < c0 + per && c < nch; ++c) {
@@ -505,15 +509,29 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
             s_wl[warp] = x.lo;
         }
         __syncthreads();
+        if (warp == 0) {  // exclusive scan of the warp totals
+            dd_t t = dd_make(0.0);
+            if (lane < nw) {
+                t.hi = s_wh[lane];
+                t.lo = s_wl[lane];
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                dd_t y = shfl_up_dd(t, o);
+                if (lane >= o) t = dd_add(y, t);
+            }
+            dd_t e = shfl_up_dd(t, 1);
+            if (lane == 0) e = dd_make(0.0);
+            s_wh[lane] = e.hi;
+            s_wl[lane] = e.lo;
+        }
+        __syncthreads();
         dd_t incl_prev = shfl_up_dd(x, 1);
         if (lane == 0) incl_prev = dd_make(0.0);
-        dd_t ex = incl_prev;
-        if (warp == 1) {
-            dd_t w0t;
-            w0t.hi = s_wh[0];
-            w0t.lo = s_wl[0];
-            ex = dd_add(w0t, ex);
-        }
+        dd_t wbase;
+        wbase.hi = s_wh[warp];
+        wbase.lo = s_wl[warp];
+        dd_t ex = dd_add(wbase, incl_prev);
         for (int64_t c = c0; c < c0 + per && c < nch; ++c) {
             P.pm_off_hi_w[c] = ex.hi;
             P.pm_off_lo_w[c] = ex.lo;
@@ -522,7 +540,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
             t.lo = P.pm_tot_lo[c];
             ex = dd_add(ex, t);
         }
-        if (tid == 63) {  // grand total closes the offsets (thread 63 owns the last slice, possibly empty)
+        if (tid == nt - 1) {  // grand total closes the offsets (the last thread owns the last slice, possibly empty)
             P.pm_off_hi_w[nch] = ex.hi;
             P.pm_off_lo_w[nch] = ex.lo;
         }
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(64) pav_seg_merge_kernel(const TreeParams P, c
     for (int j = 1; j < nseg; ++j) {
         const int64_t b = bounds[j], c = bounds[j + 1];
         const bool violated = val(b - 1) > val(b);  // block-uniform
-        if (violated) {
+        if (violated && warp < 2) {
             const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, gps, gpm, (int64_t)0, b, c)
                                         : merge_kary_right(P.loss, rho, val, gps, gpm, (int64_t)0, b, c);
             if (lane == 0) s_end[warp] = e;
@@ -690,7 +708,7 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.dbg = c->sort_dbg;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
-        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(64), 0, s, P, c->seg_bounds, c->nseg, blk));
+        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(kSegMergeThreads), 0, s, P, c->seg_bounds, c->nseg, blk));
         RBL_LAUNCH_CHECK();
         RBL_CUDA(rbl_launch_pdl(pav_seg_fill_kernel, dim3(c->vec_grid), dim3(256), 0, s, blk, z_sorted));
         RBL_LAUNCH_CHECK();

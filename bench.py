@@ -503,6 +503,8 @@ def main():
         g_launches = K  # one gradient pass per ADMM iteration
         traffic, traffic_note = None, "no ncu capture on file"
         try:
+            if args.storage != "fp64":
+                raise RuntimeError("the ncu capture on file is of the fp64 kernel")
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gather_traffic.json")))
             per_row = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["active_rows"]
             traffic = per_row * gather["active_rows"]
