@@ -1,6 +1,9 @@
 // api.cu — the C ABI declared in include/rbl_b200.h: handle, scratch, and thin launch wrappers.
 #include <math.h>
 #include <stdarg.h>
+
+#include <thread>
+#include <vector>
 #include <stdlib.h>
 #include <string.h>
 
@@ -195,6 +198,9 @@ void ctx_free(rbl_ctx* c) {
     for (int i = 0; i < c->n_extra; ++i)
         if (c->extra[i]) cudaFree(c->extra[i]);
     if (c->fista_host) cudaFreeHost(c->fista_host);
+    if (c->eval_stage) cudaFreeHost(c->eval_stage);
+    if (c->eval_w) cudaFree(c->eval_w);
+    if (c->eval_red) cudaFree(c->eval_red);
     if (c->bfista_host) cudaFreeHost(c->bfista_host);
 }
 
@@ -404,7 +410,8 @@ int rbl_sort_debug(rbl_handle_t h, uint64_t* d_stamps) {
 
 int rbl_pav_config(rbl_handle_t h, int force_tree, int32_t* h_nseg) {
     RBL_REQUIRE(h != nullptr, "null handle");
-    h->force_tree = force_tree ? 1 : 0;
+    h->force_tree = (force_tree & 1) ? 1 : 0;
+    h->pav_no_hints = (force_tree & 2) ? 1 : 0;
     if (h_nseg) *h_nseg = h->nseg;
     return RBL_OK;
 }
@@ -749,6 +756,27 @@ int rbl_lasso_cd_gram(rbl_handle_t h, const double* G, const double* w_ref, cons
     return rbl_k_lasso_cd_gram(h, G, w_ref, red0, l1, tol, max_iter, w_out, info3, S(stream));
 }
 
+int rbl_gram_eval_host(rbl_handle_t h, const double* G, const double* w0, const double* red0, const double* h_w,
+                       double* h_red_out, rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w0 && red0 && h_w && h_red_out, "null argument");
+    const size_t nw = (size_t)h->d, nr = (size_t)h->d + 2;
+    if (!h->eval_stage) {  // pinned staging [w (ld + 8) | red (ld + 8)], device copy of w: created on first use
+        RBL_CUDA(cudaMallocHost((void**)&h->eval_stage, 2 * ((size_t)h->ld + 8) * sizeof(double)));
+        RBL_CUDA(cudaMalloc((void**)&h->eval_w, ((size_t)h->ld + 8) * sizeof(double)));
+        RBL_CUDA(cudaMalloc((void**)&h->eval_red, ((size_t)h->ld + 8) * sizeof(double)));
+    }
+    double* st_w = h->eval_stage;
+    double* st_r = h->eval_stage + h->ld + 8;
+    memcpy(st_w, h_w, nw * sizeof(double));
+    RBL_CUDA(cudaMemcpyAsync(h->eval_w, st_w, nw * sizeof(double), cudaMemcpyHostToDevice, S(stream)));
+    RBL_TRY(rbl_k_gram_eval(h, G, w0, red0, h->eval_w, h->eval_red, S(stream)));
+    RBL_CUDA(cudaMemcpyAsync(st_r, h->eval_red, nr * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
+    RBL_CUDA(cudaStreamSynchronize(S(stream)));
+    memcpy(h_red_out, st_r, nr * sizeof(double));
+    return RBL_OK;
+}
+
 int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_t stream) {
     RBL_ENTER(h);
     RBL_REQUIRE(D && Dt, "null argument");
@@ -827,6 +855,84 @@ int rbl_objective(rbl_handle_t h, int loss, const double* margins, const double*
     RBL_REQUIRE(margins && sigma && out4, "null argument");
     RBL_TRY(rbl_k_sort(h, margins, h->n_global, h->obj_tmp, nullptr, S(stream)));
     return rbl_k_objective(h, h->obj_tmp, sigma, loss, w, out4, S(stream));
+}
+
+// ---- upload from PAGEABLE host memory (a user's numpy array) -----------------------------------------------------
+// cudaMemcpyAsync from pageable memory is staged by the driver through one small pinned buffer on the calling
+// thread (~10 GB/s).  Here `nthreads` host threads copy 8 MB chunks into their own pinned slots (2 per thread)
+// and each issues its DMA on its own stream, so the host-side memcpy runs at the memory system's multi-threaded
+// bandwidth and overlaps the transfers; `stream` then waits for every chunk.  The pinned slots are created once
+// per process and device.  Returns when all chunks are staged (the transfers may still be in flight on `stream`).
+namespace {
+constexpr size_t kUpChunk = (size_t)8 << 20;
+constexpr int kUpMaxThreads = 16;
+struct UploadLane {
+    void* pin[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    cudaStream_t s = nullptr;
+};
+struct UploadPool {
+    int device = -1;
+    UploadLane lane[kUpMaxThreads];
+    int nready = 0;
+};
+UploadPool g_up[RBL_MAX_DEVICES];
+
+int upload_prepare(UploadPool& up, int device, int nthreads) {
+    up.device = device;
+    for (int t = up.nready; t < nthreads; ++t) {
+        UploadLane& L = up.lane[t];
+        for (int k = 0; k < 2; ++k) {
+            RBL_CUDA(cudaMallocHost(&L.pin[k], kUpChunk));
+            RBL_CUDA(cudaEventCreateWithFlags(&L.done[k], cudaEventDisableTiming));
+        }
+        RBL_CUDA(cudaStreamCreateWithFlags(&L.s, cudaStreamNonBlocking));
+        up.nready = t + 1;
+    }
+    return RBL_OK;
+}
+}  // namespace
+
+int rbl_h2d_pageable(int device, void* d_dst, const void* h_src, int64_t bytes, int nthreads, rbl_stream_t stream) {
+    RBL_REQUIRE(d_dst && h_src && bytes >= 0, "bad arguments");
+    RBL_REQUIRE(device >= 0 && device < RBL_MAX_DEVICES, "bad device %d", device);
+    if (bytes == 0) return RBL_OK;
+    RBL_CUDA(cudaSetDevice(device));
+    if (nthreads < 1) nthreads = 1;
+    if (nthreads > kUpMaxThreads) nthreads = kUpMaxThreads;
+    const int64_t nchunks = (bytes + (int64_t)kUpChunk - 1) / (int64_t)kUpChunk;
+    if (nchunks < nthreads) nthreads = (int)nchunks;
+    UploadPool& up = g_up[device];
+    RBL_TRY(upload_prepare(up, device, nthreads));
+    // the destination may still be read by earlier work on `stream`: the lanes start after it
+    cudaEvent_t start;
+    RBL_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    RBL_CUDA(cudaEventRecord(start, S(stream)));
+    std::vector<int> rc(nthreads, 0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        th.emplace_back([&, t]() {
+            if (cudaSetDevice(device) != cudaSuccess) { rc[t] = 1; return; }
+            UploadLane& L = up.lane[t];
+            if (cudaStreamWaitEvent(L.s, start, 0) != cudaSuccess) { rc[t] = 1; return; }
+            int slot = 0;
+            for (int64_t k = t; k < nchunks; k += nthreads, slot ^= 1) {
+                const size_t off = (size_t)k * kUpChunk;
+                const size_t len = (size_t)bytes - off < kUpChunk ? (size_t)bytes - off : kUpChunk;
+                if (cudaEventSynchronize(L.done[slot]) != cudaSuccess) { rc[t] = 1; return; }  // slot free again
+                memcpy(L.pin[slot], (const char*)h_src + off, len);
+                if (cudaMemcpyAsync((char*)d_dst + off, L.pin[slot], len, cudaMemcpyHostToDevice, L.s) != cudaSuccess ||
+                    cudaEventRecord(L.done[slot], L.s) != cudaSuccess) { rc[t] = 1; return; }
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    RBL_CUDA(cudaEventDestroy(start));
+    for (int t = 0; t < nthreads; ++t) {
+        RBL_REQUIRE(rc[t] == 0, "upload lane %d failed: %s", t, cudaGetErrorString(cudaGetLastError()));
+        for (int k = 0; k < 2; ++k) RBL_CUDA(cudaStreamWaitEvent(S(stream), up.lane[t].done[k], 0));
+    }
+    return RBL_OK;
 }
 
 // ---- CPT spectra of EHRM on the host (objective.py:148-164) ------------------------------------------------------

@@ -165,6 +165,7 @@ struct rbl_ctx {
     int has_sigma;
     int nseg;               // runs of non-increasing sigma (0: too many, use the merge tree)
     int force_tree;         // testing: always take the merge tree
+    int pav_no_hints;       // testing: few-segment merge without the warm start from the previous call's blocks
     int* seg_count;
     int64_t* seg_bounds;    // [nseg + 1] device
     void* seg_blocks;       // SegBlocks (pooled blocks of the last few-segment call)
@@ -177,6 +178,8 @@ struct rbl_ctx {
     double* brbuf[2];       // [B][n_local]
     double* bred;           // [B][ld+8]
     double *bgpart, *bsspart, *bc0part;  // [grid][8][ld], [grid][8], [B][vec_grid]
+    // ---- host-driven f/g evaluations (rbl_gram_eval_host): pinned staging and device copies, created on first use
+    double *eval_stage, *eval_w, *eval_red;
     // ---- objective
     double* obj_tmp;        // n_global
     size_t bytes;           // total scratch allocated

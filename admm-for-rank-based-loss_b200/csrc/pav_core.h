@@ -125,6 +125,41 @@ RBL_HD int64_t pav_gallop_lower_from_hi(const V& val, int64_t lo, int64_t hi, do
     return pav_lower_bound(val, probe + 1, prev, u);
 }
 
+// upper_bound over [lo,hi) started at an arbitrary position h (a guess of the answer): gallops away from h in the
+// direction the value at h dictates — O(log |answer - h|) reads
+template <class V>
+RBL_HD int64_t pav_upper_bound_near(const V& val, int64_t lo, int64_t hi, double u, int64_t h) {
+    if (hi <= lo) return lo;
+    if (h < lo) h = lo;
+    if (h > hi - 1) h = hi - 1;
+    if (val(h) <= u) return pav_gallop_upper_from_lo(val, h, hi, u);  // everything before h is <= u as well
+    int64_t step = 1, prev = h, probe = h - 1;                        // invariant: val(prev) > u
+    while (probe >= lo && val(probe) > u) {
+        prev = probe;
+        step <<= 1;
+        probe = h - step;
+    }
+    if (probe < lo) probe = lo - 1;
+    return pav_upper_bound(val, probe + 1, prev, u);
+}
+
+// lower_bound over [lo,hi) started at an arbitrary position h
+template <class V>
+RBL_HD int64_t pav_lower_bound_near(const V& val, int64_t lo, int64_t hi, double u, int64_t h) {
+    if (hi <= lo) return lo;
+    if (h < lo) h = lo;
+    if (h > hi - 1) h = hi - 1;
+    if (val(h) >= u) return pav_gallop_lower_from_hi(val, lo, h + 1, u);  // everything from h on is >= u as well
+    int64_t step = 1, prev = h + 1, probe = h + 1;                        // invariant: everything before prev is < u
+    while (probe < hi && val(probe) < u) {
+        prev = probe + 1;
+        probe = h + 1 + step;
+        step <<= 1;
+    }
+    if (probe > hi) probe = hi;
+    return pav_lower_bound(val, prev, probe, u);
+}
+
 // sum_{i in [l,r)} f_i'(u) with the one-sided loss derivative
 template <class PS, class PM>
 RBL_HD double pav_phi(int loss, double rho, const PS& ps, const PM& pm, int64_t l, int64_t r, double u, int side) {
@@ -297,6 +332,41 @@ RBL_HD bool pav_probe_right(int loss, double rho, const V& val, const PS& ps, co
     return pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0;
 }
 
+// the same probes with the opposite-side bound searched outward from a guess h2 of it (warm start: the pooled
+// block of the previous z-step — ranks move little between ADMM iterations)
+template <class V, class PS, class PM>
+RBL_HD bool pav_probe_left_near(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
+                                int64_t c, int64_t p, int64_t h2, int64_t* r_out, int64_t* rs_out, int64_t* re_out) {
+    const double u = val(p);
+    const int64_t l = pav_run_end(val, p, b, u);
+    const int64_t r = pav_upper_bound_near(val, b, c, u, h2);
+    *r_out = r;
+    *re_out = l;
+    *rs_out = pav_run_start(val, p, a, u);
+    return pav_phi(loss, rho, ps, pm, l, r, u, +1) >= 0.0;
+}
+
+template <class V, class PS, class PM>
+RBL_HD bool pav_probe_right_near(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a, int64_t b,
+                                 int64_t c, int64_t p, int64_t h2, int64_t* l_out, int64_t* rs_out, int64_t* re_out) {
+    const double u = val(p);
+    const int64_t l = pav_lower_bound_near(val, a, b, u, h2);
+    const int64_t r = pav_run_start(val, p, b, u);
+    *l_out = l;
+    *rs_out = r;
+    *re_out = pav_run_end(val, p, c, u);
+    return pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0;
+}
+
+// probe position of lane j of a WARM-STARTED first round: 16 positions below the guess h at distances 2^15 .. 1 and
+// 16 at and above it at distances 0, 1, 3, .. 2^15 - 1, clamped to [lo, hi] (ascending in j; duplicates are harmless)
+RBL_HD int64_t pav_hint_pos(int64_t h, int64_t lo, int64_t hi, int j) {
+    int64_t p = j < 16 ? h - ((int64_t)1 << (15 - j)) : h + ((int64_t)1 << (j - 16)) - 1;
+    if (p < lo) p = lo;
+    if (p > hi) p = hi;
+    return p;
+}
+
 // probe position of lane j when the unknown candidates are [lo, lo+width); lanes j >= width idle if width <= 32
 RBL_HD int64_t pav_kary_pos(int64_t lo, int64_t width, int j) {
     if (width <= 32) return lo + j;
@@ -322,14 +392,39 @@ RBL_HD void pav_kary_finish(int loss, double rho, const V& val, const PS& ps, co
     *v_out = v;
 }
 
-// lane-loop version (host emulation); the CUDA kernel mirrors it with one lane per probe
+// lane-loop version (host emulation); the CUDA kernel mirrors it with one lane per probe.
+// hint_lo / hint_hi (-1: none): the pooled block [lo*, hi*) this merge produced at the previous z-step.  With hints
+// the first round of each side probes around the guess (pav_hint_pos) instead of at exponential distances from the
+// boundary, and its opposite-side bounds are searched outward from the other guess; the result never depends on them.
 template <class V, class PS, class PM>
 RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
-                                  int64_t b, int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out) {
+                                  int64_t b, int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out,
+                                  int64_t hint_lo = -1, int64_t hint_hi = -1) {
     if (!(val(b - 1) > val(b))) return false;
+    const bool hinted = hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c;
     // ---- left: first p in [a, b-1] whose probe is true (b-1 is): pattern over p is F..F T..T
     int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
     bool first = true;
+    if (hinted && lo < hi) {
+        int64_t rr[32], rs[32], re[32];
+        bool pr[32];
+        for (int j = 0; j < 32; ++j)
+            pr[j] = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, j), hint_hi,
+                                        &rr[j], &rs[j], &re[j]);
+        int f = -1;
+        for (int j = 0; j < 32; ++j)
+            if (pr[j]) { f = j; break; }
+        if (f >= 0) {
+            hi = rs[f] < hi ? rs[f] : hi;
+            xhi = rr[f];
+            if (f > 0) { lo = re[f - 1] > lo ? re[f - 1] : lo; xlo = rr[f - 1]; }
+        } else {
+            lo = re[31] > lo ? re[31] : lo;
+            xlo = rr[31];
+        }
+        if (hi < lo) hi = lo;
+        first = false;
+    }
     while (lo < hi) {
         const int64_t width = hi - lo;
         int active;
@@ -374,6 +469,26 @@ RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& 
     xlo = a;
     xhi = b;
     first = true;
+    if (hinted && lo < hi) {
+        int64_t ll[32], rs[32], re[32];
+        bool pr[32];
+        for (int j = 0; j < 32; ++j)
+            pr[j] = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, j), hint_lo,
+                                         &ll[j], &rs[j], &re[j]);
+        int f = -1;
+        for (int j = 0; j < 32; ++j)
+            if (pr[j]) { f = j; break; }
+        if (f >= 0) {
+            hi = rs[f] < hi ? rs[f] : hi;
+            xhi = ll[f];
+            if (f > 0) { lo = re[f - 1] > lo ? re[f - 1] : lo; xlo = ll[f - 1]; }
+        } else {
+            lo = re[31] > lo ? re[31] : lo;
+            xlo = ll[31];
+        }
+        if (hi < lo) hi = lo;
+        first = false;
+    }
     while (lo < hi) {
         const int64_t width = hi - lo;
         int active;

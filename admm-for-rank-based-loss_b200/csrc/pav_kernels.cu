@@ -178,11 +178,35 @@ struct TreeParams {
 // left half of the merge search: first p in [a, b-1] whose run joins the pooled block (full warp)
 template <class V, class PS, class PM>
 __device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
-                                   int64_t b, int64_t c) {
+                                   int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
     bool first = true;
+    if (hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c && lo < hi) {
+        // warm start (pav_core.h: pav_merge_search_kary): 32 probes around last z-step's block start
+        int64_t rr = 0, rs = 0, re = 0;
+        const bool pr = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, lane),
+                                            hint_hi, &rr, &rs, &re);
+        const unsigned ball = __ballot_sync(FULL, pr);
+        const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
+        const int fs = f >= 0 ? f : 31, fm = f > 0 ? f - 1 : 0;
+        const int64_t rs_f = __shfl_sync(FULL, rs, fs), rr_f = __shfl_sync(FULL, rr, fs), re_f = __shfl_sync(FULL, re, fs);
+        const int64_t re_m = __shfl_sync(FULL, re, fm), rr_m = __shfl_sync(FULL, rr, fm);
+        if (f >= 0) {
+            hi = rs_f < hi ? rs_f : hi;
+            xhi = rr_f;
+            if (f > 0) {
+                lo = re_m > lo ? re_m : lo;
+                xlo = rr_m;
+            }
+        } else {
+            lo = re_f > lo ? re_f : lo;
+            xlo = rr_f;
+        }
+        if (hi < lo) hi = lo;
+        first = false;
+    }
     while (lo < hi) {
         const int64_t width = hi - lo;
         int active;
@@ -239,11 +263,35 @@ __device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS&
 // right half: first p in [b+1, c) whose run stays out of the pooled block, else c (full warp)
 template <class V, class PS, class PM>
 __device__ int64_t merge_kary_right(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
-                                    int64_t b, int64_t c) {
+                                    int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     int64_t lo = b + 1, hi = c, xlo = a, xhi = b;
     bool first = true;
+    if (hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c && lo < hi) {
+        // warm start: 32 probes around last z-step's block end
+        int64_t ll = 0, rs = 0, re = 0;
+        const bool pr = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, lane),
+                                             hint_lo, &ll, &rs, &re);
+        const unsigned ball = __ballot_sync(FULL, pr);
+        const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
+        const int fs = f >= 0 ? f : 31, fm = f > 0 ? f - 1 : 0;
+        const int64_t rs_f = __shfl_sync(FULL, rs, fs), ll_f = __shfl_sync(FULL, ll, fs), re_f = __shfl_sync(FULL, re, fs);
+        const int64_t re_m = __shfl_sync(FULL, re, fm), ll_m = __shfl_sync(FULL, ll, fm);
+        if (f >= 0) {
+            hi = rs_f < hi ? rs_f : hi;
+            xhi = ll_f;
+            if (f > 0) {
+                lo = re_m > lo ? re_m : lo;
+                xlo = ll_m;
+            }
+        } else {
+            lo = re_f > lo ? re_f : lo;
+            xlo = ll_f;
+        }
+        if (hi < lo) hi = lo;
+        first = false;
+    }
     while (lo < hi) {
         const int64_t width = hi - lo;
         int active;
@@ -446,6 +494,9 @@ struct SegBlocks {
     int pad;
     int64_t lo[kMaxSeg], hi[kMaxSeg];
     double v[kMaxSeg];
+    // the pooled block merge j produced at the previous call on this handle (0, 0: none yet) — the warm start of
+    // the next call's searches; ranks move little between two ADMM iterations
+    int64_t hint_lo[kMaxSeg], hint_hi[kMaxSeg];
 };
 
 // positions i (1 <= i < n) where sigma steps up; count may exceed cap (then the list is truncated)
@@ -464,8 +515,9 @@ constexpr int kSegMergeThreads = 1024;  // all of them scan the chunk totals; wa
 // two warps: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1;
 // warp 0 searches the left end of the pooled block while warp 1 searches the right end (independent
 // dependent-load chains, ~50 us each at n = 1M)
-__global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const TreeParams P, const int64_t* __restrict__ bounds,
-                                                           int nseg, SegBlocks* __restrict__ out) {
+__global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const TreeParams P,
+                                                                         const int64_t* __restrict__ bounds, int nseg,
+                                                                         SegBlocks* __restrict__ out, int use_hints) {
     rbl_pdl_wait();
     __shared__ int s_nblk;
     __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
@@ -554,8 +606,9 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
         const int64_t b = bounds[j], c = bounds[j + 1];
         const bool violated = val(b - 1) > val(b);  // block-uniform
         if (violated && warp < 2) {
-            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, gps, gpm, (int64_t)0, b, c)
-                                        : merge_kary_right(P.loss, rho, val, gps, gpm, (int64_t)0, b, c);
+            const int64_t h_lo = use_hints ? out->hint_lo[j] : -1, h_hi = use_hints ? out->hint_hi[j] : -1;
+            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, gps, gpm, (int64_t)0, b, c, h_lo, h_hi)
+                                        : merge_kary_right(P.loss, rho, val, gps, gpm, (int64_t)0, b, c, h_lo, h_hi);
             if (lane == 0) s_end[warp] = e;
         }
         __syncthreads();
@@ -564,6 +617,8 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
             int64_t lo, hi;
             double v;
             pav_kary_finish(P.loss, rho, val, gps, gpm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            out->hint_lo[j] = s_end[0];   // (the searches' own answers: the finish only snaps them to whole runs)
+            out->hint_hi[j] = s_end[1];
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
             int k2 = 0;
             const int nb = s_nblk;
@@ -708,7 +763,8 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.dbg = c->sort_dbg;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
-        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(kSegMergeThreads), 0, s, P, c->seg_bounds, c->nseg, blk));
+        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(kSegMergeThreads), 0, s, P, c->seg_bounds, c->nseg, blk,
+                                c->pav_no_hints ? 0 : 1));
         RBL_LAUNCH_CHECK();
         RBL_CUDA(rbl_launch_pdl(pav_seg_fill_kernel, dim3(c->vec_grid), dim3(256), 0, s, blk, z_sorted));
         RBL_LAUNCH_CHECK();

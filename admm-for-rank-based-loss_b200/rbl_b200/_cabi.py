@@ -70,9 +70,11 @@ _SIGNATURES = {
                                       _c.c_int, _dp, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_result": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
+    "rbl_gram_eval_host": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_lasso_cd_gram": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _c.c_int, _dp, _dp,
                                      _c.c_void_p]),
+    "rbl_h2d_pageable": (_c.c_int, [_c.c_int, _dp, _c.c_void_p, _c.c_int64, _c.c_int, _c.c_void_p]),
     "rbl_cpt_weights": (_c.c_int, [_c.c_int64, _c.c_int, _c.POINTER(_c.c_double)]),
     "rbl_dual_pass": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _c.c_double, _c.c_int, _c.c_int,
                                  _dp, _dp, _c.c_void_p]),

@@ -160,12 +160,22 @@ class DeviceProblem:
             self.G = torch.empty((d, self.ld), dtype=torch.float64, device=dev)
         copy_stream.wait_stream(main)
         ms = ctypes.c_void_p(main.cuda_stream)
+        # a caller's numpy array is PAGEABLE: the driver would stage it through one small pinned buffer on this
+        # thread (~10 GB/s); librbl_b200 stages it with several host threads through pinned slots instead
+        pageable = not Xt.is_pinned()
+        threads = int(os.environ.get("RBL_UPLOAD_THREADS", "0")) or min(8, max(1, (os.cpu_count() or 2) // 2))
+        self.upload_path = f"pageable: {threads} staging threads (rbl_h2d_pageable)" if pageable else "pinned: direct DMA"
+        cs = ctypes.c_void_p(copy_stream.cuda_stream)
         for k, r0 in enumerate(range(0, n, chunk)):
             r1, b = min(n, r0 + chunk), k % 2
             with torch.cuda.stream(copy_stream):
                 if k >= 2:
                     copy_stream.wait_event(consumed[b])
-                stage[b][: r1 - r0].copy_(Xt[r0:r1], non_blocking=True)
+                if pageable:
+                    _cabi.check(self.lib.rbl_h2d_pageable(dev.index or 0, stage[b].data_ptr(),
+                                                          Xt[r0:r1].data_ptr(), (r1 - r0) * d * 8, threads, cs))
+                else:
+                    stage[b][: r1 - r0].copy_(Xt[r0:r1], non_blocking=True)
                 copied[b].record(copy_stream)
             main.wait_event(copied[b])
             Dk = self.D[r0:r1]
@@ -662,19 +672,26 @@ class AdmmEngine(DeviceProblem):
     def fg_smooth(self, w_np, rho, reg_fg):
         """f = rho/2 ||D w - b||^2 + R(w), g = rho D^T(D w - b) + R'(w) — the n x d part is ONE fused pass
         over D on the device; `reg_fg(w) -> (R, R')` is a d-vector formula evaluated on the host."""
-        self._wtmp.copy_(torch.from_numpy(w_np))
         if self.w_mode == "gram":
-            # one sweep over G: [D^T (b - D w), ||b - D w||^2] from the pass made at the warm start
-            _cabi.check(self.lib.rbl_gram_eval(self.h, self.G.data_ptr(), self.w_prev.data_ptr(),
-                                               self.red0.data_ptr(), self._wtmp.data_ptr(), self.red1.data_ptr(),
-                                               self._stream()))
-            self.red_host.copy_(self.red1, non_blocking=True)
-        else:
-            _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
-                                                self.r.data_ptr(), self.red.data_ptr(), self._stream()))
-            self.all_reduce(self.red)
-            self.fista_stats["d_passes"] += 1
-            self.red_host.copy_(self.red, non_blocking=True)
+            # one sweep over G: [D^T (b - D w), ||b - D w||^2] from the pass made at the warm start; host array in,
+            # host array out, one library call (staging, launch, read-back, synchronisation)
+            w_np = np.ascontiguousarray(w_np, dtype=np.float64)
+            red = self._fg_red
+            _cabi.check(self.lib.rbl_gram_eval_host(self.h, self.G.data_ptr(), self.w_prev.data_ptr(),
+                                                    self.red0.data_ptr(), w_np.ctypes.data, red.ctypes.data,
+                                                    self._stream()))
+            R, dR = reg_fg(w_np)
+            f = 0.5 * rho * float(red[self.d]) + R
+            g = -rho * red[: self.d] + dR
+            self._last_eval = w_np.copy()
+            self.lbfgs_evals += 1
+            return f, g
+        self._wtmp.copy_(torch.from_numpy(w_np))
+        _cabi.check(self.lib.rbl_fused_pass(self.h, self.D.data_ptr(), self._wtmp.data_ptr(), self.b.data_ptr(),
+                                            self.r.data_ptr(), self.red.data_ptr(), self._stream()))
+        self.all_reduce(self.red)
+        self.fista_stats["d_passes"] += 1
+        self.red_host.copy_(self.red, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         red = self.red_host.numpy()
         R, dR = reg_fg(w_np)
@@ -778,6 +795,7 @@ class AdmmEngine(DeviceProblem):
 
         if not hasattr(self, "_wtmp"):
             self._wtmp = torch.zeros(self.d, dtype=torch.float64, device=self.device)
+            self._fg_red = np.zeros(self.d + 2, dtype=np.float64)
             self.lbfgs_evals = 0
         pre_done, self._pre_done = getattr(self, "_pre_done", False), False
         if not pre_done:  # (z_and_grad has already made the warm-start pass, inside its graph)

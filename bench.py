@@ -52,6 +52,7 @@ def parse():
     ap.add_argument("--instances-per-gpu", type=int, default=32, help="c5")
     ap.add_argument("--batch-mode", default=None, help="c5: gram | stream (default: auto)")
     ap.add_argument("--no-solve", action="store_true", help="skip the run-to-tolerance tail")
+    ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-input e2e variant")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg (development runs)")
     a = ap.parse_args()
     if a.config == "c2" and not a.n:
@@ -338,9 +339,12 @@ def main():
     Xw = rng_w.standard_normal((4096, d))
     yw = np.sign(Xw @ planted_wstar(d) + 0.1 * rng_w.standard_normal(4096)).reshape(-1, 1)
     yw[yw == 0] = 1.0
+    t_cold0 = time.perf_counter()
     with contextlib.redirect_stdout(io.StringIO()):
         warm = ADMMmethod(Xw, yw, **{**kw, "max_iter": 8})
         warm.advance(0, 8)
+    torch.cuda.synchronize()
+    t_cold = time.perf_counter() - t_cold0   # the one-off cost a fresh process pays on its first solve
     warm.engine.close()
     del warm, Xw, yw
     torch.cuda.synchronize()
@@ -477,6 +481,32 @@ def main():
             t_e2e = float(tt[0])
         e2e_value, e2e_iters = it2 / t_e2e, it2
 
+    # ---- the same call on a PAGEABLE numpy array (what a user's array is; X_host above is pinned) ------------------
+    e2e_pageable = None
+    if solve is not None and not args.no_pageable:
+        X_page = np.array(X_host.numpy())          # ordinary (pageable) copy, made outside the timed region
+        y_page = np.array(y_host.numpy()).reshape(-1, 1)
+        barrier()
+        g0, g1, g2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        g0.record()
+        with quiet:
+            s2 = ADMMmethod(X_page, y_page, _shard=shard, **kw)
+            g1.record()
+            it_p, done_p = s2.advance(0, 1000)
+        g2.record()
+        barrier()
+        tp_build, tp_all = g0.elapsed_time(g1) / 1e3, g0.elapsed_time(g2) / 1e3
+        if world > 1:
+            tt = torch.tensor([tp_build, tp_all], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            tp_build, tp_all = float(tt[0]), float(tt[1])
+        e2e_pageable = {"value": it_p / tp_all, "unit": UNIT, "iterations": it_p, "converged": bool(done_p),
+                        "upload_and_build_s": tp_build, "total_s": tp_all,
+                        "upload_path": getattr(s2.engine, "upload_path", None),
+                        "same_result": bool(np.array_equal(s2.w, solver.w))}
+        s2.engine.close()
+        del s2, X_page, y_page
+
     def shutdown():
         # release the captured iteration graph (it holds NCCL work) before the process group goes away
         solver.engine.close()
@@ -561,7 +591,14 @@ def main():
                          "solve / (upload + build + solve) device time" % e2e_iters) if solve else
                         "K iterations through ADMMmethod plus the whole host -> HBM upload and build charged to "
                         "the K steps (--no-solve)",
-                "upload_and_build_s": t_upload},
+                "upload_and_build_s": t_upload,
+                "input": "pinned host memory (best case)",
+                "pageable_input": e2e_pageable,
+                "cold_first_call_s": {"value": t_cold,
+                                      "what": "wall time of the untimed warm-up solve (4096 x d, 8 iterations) that "
+                                              "a fresh process runs first: library load, lazy kernel loading, "
+                                              "function attributes, first allocations — paid once per process, "
+                                              "NOT included in the e2e figures"}},
         "gpu_launches": launches_timed,
         "clocks": clocks,
         "roofline": roofline,

@@ -108,7 +108,9 @@ int rbl_pav_prox(rbl_handle_t h, int loss, const double* m_sorted, double rho, d
 
 /* The element prox is already isotonic over every run of ranks where sigma does not increase, so a spectrum with
  * few such runs (ERM 1, superquantile / AoRR <= 3) needs (#runs - 1) merges instead of the merge tree; rbl_set_spectrum
- * finds the runs.  force_tree != 0 makes rbl_pav_prox take the general tree anyway (testing);
+ * finds the runs; the merge searches are warm-started from the pooled blocks the previous rbl_pav_prox call on this
+ * handle found (ranks move little between ADMM iterations; the result never depends on the guess).  force_tree
+ * bit 0 makes rbl_pav_prox take the general tree anyway, bit 1 switches the warm start off (both for testing);
  * *h_nseg (may be NULL) = number of runs, 0 if there are too many for the few-segment path. */
 int rbl_pav_config(rbl_handle_t h, int force_tree, int32_t* h_nseg);
 
@@ -202,6 +204,12 @@ int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const 
 int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream);
 /* red_out = [D^T (b - D w) (d), ||b - D w||^2, 0] at any w, from G, w0, red0 (same layout as rbl_fused_pass):
  * the f/g evaluation of w_LBFGS.py:31-45 */
+/* rbl_gram_eval for a host-side optimiser (scipy's L-BFGS-B, w_LBFGS.py:48-62): h_w (d doubles) and h_red_out
+ * (d + 2 doubles) are HOST arrays; the call stages w through pinned memory, runs the sweep over G, reads the
+ * result back and synchronises `stream` — one call per f/g evaluation instead of a copy, a launch, a copy and a
+ * synchronisation driven from the interpreter. */
+int rbl_gram_eval_host(rbl_handle_t h, const double* G, const double* w0, const double* red0, const double* h_w,
+                       double* h_red_out, rbl_stream_t stream);
 int rbl_gram_eval(rbl_handle_t h, const double* G, const double* w0, const double* red0, const double* w,
                   double* red_out, rbl_stream_t stream);
 
@@ -230,6 +238,12 @@ int rbl_build_transpose(rbl_handle_t h, const double* D, double* Dt, rbl_stream_
  * d <= 64.  info3 (device, may be NULL) = [sweeps, duality gap, tol * b.b]. */
 int rbl_lasso_cd_gram(rbl_handle_t h, const double* G, const double* w_ref, const double* red0, double l1, double tol,
                       int max_iter, double* w_out, double* info3, rbl_stream_t stream);
+
+/* Upload from PAGEABLE host memory (what a caller's numpy array is): nthreads (<= 16) host threads stage 8 MB chunks
+ * through per-thread pinned slots and issue the DMA of each chunk on their own streams; `stream` is made to wait
+ * for all of them.  Replaces the single-threaded staging copy the driver performs for a pageable cudaMemcpyAsync.
+ * The ingest side of Optimizer.__init__ (algorithms.py:21-23: X.copy(), -y * X). */
+int rbl_h2d_pageable(int device, void* d_dst, const void* h_src, int64_t bytes, int nthreads, rbl_stream_t stream);
 
 /* HOST function (no device work): the CPT spectra of EHRM, objective.py:148-164 — which = 0: a_i (gamma 0.69),
  * which = 1: b_i (gamma 0.61), i = 0..n-1 in ascending rank, into the host array h_out.  Scalar libm pow in the

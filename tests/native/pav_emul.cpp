@@ -78,8 +78,20 @@ struct ValOverlayHost {
     }
 };
 
+// hints_in (may be null): [2 (#runs - 1)] guesses (lo*, hi*) of the pooled block of every merge (-1: none), e.g. the
+// blocks of an earlier call on similar margins; hints_out (may be null) receives this call's blocks the same way
+extern "C" int emul_pav_fewseg_hinted(int loss, int64_t n, const double* sigma, const double* m, double rho,
+                                      int chunk_log2, double* val, int64_t* n_runs, const int64_t* hints_in,
+                                      int64_t* hints_out);
+
 extern "C" int emul_pav_fewseg(int loss, int64_t n, const double* sigma, const double* m, double rho, int chunk_log2,
                                double* val, int64_t* n_runs) {
+    return emul_pav_fewseg_hinted(loss, n, sigma, m, rho, chunk_log2, val, n_runs, nullptr, nullptr);
+}
+
+extern "C" int emul_pav_fewseg_hinted(int loss, int64_t n, const double* sigma, const double* m, double rho,
+                                      int chunk_log2, double* val, int64_t* n_runs, const int64_t* hints_in,
+                                      int64_t* hints_out) {
     const int64_t CH = int64_t(1) << chunk_log2;
     const int64_t nch = (n + CH - 1) / CH;
     for (int64_t i = 0; i < n; ++i) val[i] = rbl_block_prox(loss, sigma[i], m[i], rho);
@@ -115,7 +127,13 @@ extern "C" int emul_pav_fewseg(int loss, int64_t n, const double* sigma, const d
         const int64_t b = bounds[j], c = bounds[j + 1];
         int64_t lo, hi;
         double vv;
-        if (!pav_merge_search_kary(loss, rho, ov, ps, pm, (int64_t)0, b, c, &lo, &hi, &vv)) continue;
+        const int64_t h_lo = hints_in ? hints_in[2 * (j - 1)] : -1, h_hi = hints_in ? hints_in[2 * (j - 1) + 1] : -1;
+        if (hints_out) hints_out[2 * (j - 1)] = hints_out[2 * (j - 1) + 1] = -1;
+        if (!pav_merge_search_kary(loss, rho, ov, ps, pm, (int64_t)0, b, c, &lo, &hi, &vv, h_lo, h_hi)) continue;
+        if (hints_out) {
+            hints_out[2 * (j - 1)] = lo;
+            hints_out[2 * (j - 1) + 1] = hi;
+        }
         std::vector<int64_t> nlo, nhi;
         std::vector<double> nv;
         for (size_t k = 0; k < blo.size(); ++k) {

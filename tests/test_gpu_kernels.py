@@ -182,6 +182,38 @@ def test_pav_matches_oracle(E, loss, n):
             e.close()
 
 
+@pytest.mark.parametrize("loss", ["binary_cross_entropy", "hinge"])
+@pytest.mark.parametrize("wf,args", [("superquantile", [0.8]), ("aorr", [0.2, 0.8]), ("superquantile", [0.5])])
+def test_few_segment_merge_warm_start_is_only_a_guess(E, loss, wf, args):
+    """A sequence of related z-steps (margins drift and rescale as along a solve, then jump): the warm-started
+    few-segment merge (guesses = the previous call's pooled blocks) must return the bit-identical z_sorted of the
+    cold search every time, and both must equal the oracle's stack PAV."""
+    n = 300_000
+    rng = np.random.default_rng(len(wf) + n)
+    sig = O.spectrum(wf, n, args)
+    warm, cold = _mk(E, np.zeros((n, 2)), loss=loss, sigma=sig), _mk(E, np.zeros((n, 2)), loss=loss, sigma=sig)
+    E[1].check(cold.lib.rbl_pav_config(cold.h, 2, None))      # bit 1: no warm start
+    m = np.sort(rng.normal(size=n))
+    rho = 1e-5
+    for it in range(14):
+        if it == 10:
+            m = np.sort(rng.normal(size=n) * 5 + 3)            # a jump: the guesses are useless
+        else:
+            m = np.sort(m * (1.0 + 0.05 * rng.normal()) + 0.02 * rng.normal(size=n))
+        rho *= 1.3
+        zs = []
+        for e in (warm, cold):
+            e.m_sorted.copy_(e.vec(m))
+            E[1].check(e.lib.rbl_pav_prox(e.h, O.LOSS_IDS[loss], e.m_sorted.data_ptr(), rho, e.z_sorted.data_ptr(),
+                                          e._stream()))
+            zs.append(e.z_sorted.cpu().numpy())
+        np.testing.assert_array_equal(zs[0], zs[1], err_msg=str((wf, loss, it)))
+        zo = O.pav_prox(loss, sig, m, rho)
+        assert np.max(np.abs(zs[0] - zo)) <= 1e-12 * max(1.0, np.max(np.abs(zo))), (wf, loss, it)
+    warm.close()
+    cold.close()
+
+
 def test_prox_elementwise(E):
     rng = np.random.default_rng(3)
     n = 10000

@@ -93,6 +93,9 @@ def _emul_lib():
                              ctypes.POINTER(ctypes.c_int64)]
     lib.emul_pav_fewseg.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_int, dp,
                                     ctypes.POINTER(ctypes.c_int64)]
+    ip = ctypes.POINTER(ctypes.c_int64)
+    lib.emul_pav_fewseg_hinted.argtypes = [ctypes.c_int, ctypes.c_int64, dp, dp, ctypes.c_double, ctypes.c_int, dp, ip,
+                                           ip, ip]
     lib.emul_key.restype = ctypes.c_uint64
     lib.emul_key.argtypes = [ctypes.c_double]
     lib.emul_unkey.restype = ctypes.c_double
@@ -171,6 +174,64 @@ def test_few_segment_pav_route_matches_stack_pav_on_cpu():
         assert np.all(np.diff(z) >= 0)
         if kind in (0, 1, 2):
             assert runs.value <= 3, (kind, runs.value)
+        # warm-started searches (the pooled blocks of a previous z-step as guesses): exact, shifted, far-off and
+        # nonsense guesses must all give the bit-identical result — a guess only moves the first round of probes
+        nm = max(int(runs.value) - 1, 1)
+        ip = ctypes.POINTER(ctypes.c_int64)
+        blocks = np.full(2 * nm, -1, dtype=np.int64)
+        chunk = int(rng.integers(1, 8))
+        z1 = np.empty_like(m)
+        lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m.ctypes.data_as(dp), rho, chunk,
+                                   z1.ctypes.data_as(dp), None, None, blocks.ctypes.data_as(ip))
+        np.testing.assert_array_equal(z1, z)
+        for mode in range(4):
+            if mode == 0:
+                h = blocks.copy()
+            elif mode == 1:
+                h = blocks + rng.integers(-3, 4, size=blocks.size)
+            elif mode == 2:
+                h = blocks + rng.integers(-n, n + 1, size=blocks.size)
+            else:
+                h = rng.integers(-5, n + 5, size=blocks.size)
+            h = np.ascontiguousarray(h, dtype=np.int64)
+            z2 = np.empty_like(m)
+            lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m.ctypes.data_as(dp), rho, chunk,
+                                       z2.ctypes.data_as(dp), None, h.ctypes.data_as(ip), None)
+            np.testing.assert_array_equal(z2, z, err_msg=str((trial, n, loss, kind, mode)))
+
+
+def test_warm_started_merge_search_at_scale_on_cpu():
+    """the warm-started few-segment merge at n ~ 1e5 (probe offsets up to 2^15 around the guess really spread out):
+    guesses taken from a neighbouring problem (margins perturbed as between two ADMM iterations), shifted by up to
+    +-5000 ranks, or absent — bit-identical pooled blocks every time, equal to the oracle's stack PAV."""
+    lib = _emul_lib()
+    dp, ip = ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)
+    rng = np.random.default_rng(99)
+    for trial in range(12):
+        n = int(rng.integers(80_000, 250_000))
+        loss = ["binary_cross_entropy", "hinge"][trial % 2]
+        sig = (O.spectrum("superquantile", n, [rng.uniform(0.5, 0.95)]) if trial % 3 else
+               O.spectrum("aorr", n, [0.2, 0.8]))
+        sig = np.ascontiguousarray(sig, dtype=np.float64)
+        rho = 10 ** rng.uniform(-5, -1)
+        m0 = np.sort(rng.normal(size=n))
+        m1 = np.sort(m0 * 1.02 + 0.01 * rng.normal(size=n))      # the next iteration's margins
+        nm = 3
+        prev = np.full(2 * nm, -1, dtype=np.int64)
+        z0 = np.empty(n)
+        lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m0.ctypes.data_as(dp), rho, 10,
+                                   z0.ctypes.data_as(dp), None, None, prev.ctypes.data_as(ip))
+        zo = O.pav_prox(loss, sig, m1, rho)
+        ref = np.empty(n)
+        lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m1.ctypes.data_as(dp), rho, 10,
+                                   ref.ctypes.data_as(dp), None, None, None)
+        assert np.max(np.abs(ref - zo)) <= 1e-13 * max(1.0, np.max(np.abs(zo)))
+        for shift in (0, 7, -300, 5000, -5000):
+            h = np.ascontiguousarray(np.where(prev >= 0, prev + shift, -1), dtype=np.int64)
+            z = np.empty(n)
+            lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m1.ctypes.data_as(dp), rho, 10,
+                                       z.ctypes.data_as(dp), None, h.ctypes.data_as(ip), None)
+            np.testing.assert_array_equal(z, ref, err_msg=str((trial, n, loss, shift)))
 
 
 def test_radix_key_transform_is_order_preserving():
