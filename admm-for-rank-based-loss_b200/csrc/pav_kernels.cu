@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
     rbl_pdl_wait();
     __shared__ double sh[16];
     if (scal) rho = scal[0];
-    const int64_t base = (int64_t)blockIdx.x * kChunk;
+    // chunks are taken from the TOP ranks down: rank-based spectra put their weight (and so the Newton solves of the
+    // element prox) on the largest margins — those CTAs start first instead of forming the tail of the grid
+    const int64_t chunk = (int64_t)gridDim.x - 1 - blockIdx.x;
+    const int64_t base = chunk * kChunk;
     const int64_t i0 = base + (int64_t)threadIdx.x * kPer;
     double v[kPer];
     dd_t run = dd_make(0.0);
@@ -109,8 +112,8 @@ __global__ void __launch_bounds__(kPavThreads) chunk_prefix_kernel(const double*
         ex = dd_add_d(ex, v[q]);
     }
     if (threadIdx.x == 0) {
-        tot_hi[blockIdx.x] = total.hi;
-        tot_lo[blockIdx.x] = total.lo;
+        tot_hi[chunk] = total.hi;
+        tot_lo[chunk] = total.lo;
         if (n - base < kChunk) {  // entry n closes a partial last chunk
             loc_hi[n] = total.hi;
             loc_lo[n] = total.lo;
@@ -512,6 +515,50 @@ __global__ void sigma_ascents_kernel(const double* __restrict__ sigma, int64_t n
 
 constexpr int kSegMergeThreads = 1024;  // all of them scan the chunk totals; warps 0 and 1 then run the searches
 
+// Shared-memory windows around the two guessed block ends of a merge: the searches, the finish and the block value
+// read block values and prefix sums at ~20 dependent positions per round, all within a few hundred ranks of the
+// guesses when those are good — from shared memory (~30 cycles) instead of L2 (~600).  Outside the windows the
+// accessors fall through to global memory, so a bad guess costs time, never correctness; the cached entries are the
+// exact values the global accessors return (the prefix entries are combined with the same dd_add).
+constexpr int kWinHalf = 1024;
+constexpr int kWinLen = 2 * kWinHalf + 1;  // positions per window (prefix sums have an entry one past the end)
+struct SegWindows {
+    double val[2][kWinLen];
+    double psh[2][kWinLen], psl[2][kWinLen], pmh[2][kWinLen], pml[2][kWinLen];
+};
+
+template <class V>
+struct ValWin {
+    V base;
+    const double* w[2];
+    int64_t b[2], e[2];  // window k caches positions [b[k], e[k])
+    __device__ __forceinline__ double operator()(int64_t i) const {
+        if (i >= b[0] && i < e[0]) return w[0][i - b[0]];
+        if (i >= b[1] && i < e[1]) return w[1][i - b[1]];
+        return base(i);
+    }
+};
+
+struct PrefWin {
+    PrefixChunked base;
+    const double *h[2], *l[2];
+    int64_t b[2], e[2];  // window k caches entries [b[k], e[k]]  (inclusive end)
+    __device__ __forceinline__ dd_t get(int64_t i) const {
+        dd_t r;
+        if (i >= b[0] && i <= e[0]) {
+            r.hi = h[0][i - b[0]];
+            r.lo = l[0][i - b[0]];
+            return r;
+        }
+        if (i >= b[1] && i <= e[1]) {
+            r.hi = h[1][i - b[1]];
+            r.lo = l[1][i - b[1]];
+            return r;
+        }
+        return base.get(i);
+    }
+};
+
 // two warps: merge the solved prefix [0, bounds[j]) with the run [bounds[j], bounds[j+1]) for j = 1..nseg-1;
 // warp 0 searches the left end of the pooled block while warp 1 searches the right end (independent
 // dependent-load chains, ~50 us each at n = 1M)
@@ -519,6 +566,8 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
                                                                          const int64_t* __restrict__ bounds, int nseg,
                                                                          SegBlocks* __restrict__ out, int use_hints) {
     rbl_pdl_wait();
+    extern __shared__ __align__(16) unsigned char seg_smem[];
+    SegWindows& W = *reinterpret_cast<SegWindows*>(seg_smem);
     __shared__ int s_nblk;
     __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
     __shared__ double s_v[kMaxSeg];
@@ -601,14 +650,41 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
     stamp();
     PrefixChunked gps{P.ps_loc_hi, P.ps_loc_lo, P.ps_off_hi, P.ps_off_lo, kChunkLog2};
     PrefixChunked gpm{P.pm_loc_hi, P.pm_loc_lo, P.pm_off_hi, P.pm_off_lo, kChunkLog2};
-    ValOverlay val{P.val, &s_nblk, s_lo, s_hi, s_v};
+    ValOverlay gval{P.val, &s_nblk, s_lo, s_hi, s_v};
     for (int j = 1; j < nseg; ++j) {
         const int64_t b = bounds[j], c = bounds[j + 1];
-        const bool violated = val(b - 1) > val(b);  // block-uniform
+        const bool violated = gval(b - 1) > gval(b);  // block-uniform
+        const int64_t h_lo = use_hints ? out->hint_lo[j] : -1, h_hi = use_hints ? out->hint_hi[j] : -1;
+        const bool hinted = h_lo >= 0 && h_lo < b && h_hi > b && h_hi <= c;
+        // windows around the guessed block ends (empty without a usable guess): filled by the whole CTA
+        ValWin<ValOverlay> val{gval, {W.val[0], W.val[1]}, {0, 0}, {0, 0}};
+        PrefWin ps{gps, {W.psh[0], W.psh[1]}, {W.psl[0], W.psl[1]}, {0, 0}, {-1, -1}};
+        PrefWin pm{gpm, {W.pmh[0], W.pmh[1]}, {W.pml[0], W.pml[1]}, {0, 0}, {-1, -1}};
+        if (violated && hinted) {
+            for (int k = 0; k < 2; ++k) {
+                const int64_t ctr = k == 0 ? h_lo : h_hi;
+                int64_t w0 = ctr - kWinHalf, w1 = ctr + kWinHalf;  // entries [w0, w1] of the prefixes, [w0, w1) of val
+                if (w0 < 0) w0 = 0;
+                if (w1 > P.n) w1 = P.n;
+                if (k == 1 && w0 <= val.e[0] && val.e[0] > val.b[0]) w0 = val.e[0] < w1 ? val.e[0] : w1;  // disjoint
+                val.b[k] = w0;
+                val.e[k] = w1;
+                ps.b[k] = pm.b[k] = w0;
+                ps.e[k] = pm.e[k] = w1;
+                for (int64_t i = w0 + tid; i <= w1; i += kSegMergeThreads) {
+                    if (i < w1) W.val[k][i - w0] = gval(i);
+                    const dd_t a = gps.get(i), m2 = gpm.get(i);
+                    W.psh[k][i - w0] = a.hi;
+                    W.psl[k][i - w0] = a.lo;
+                    W.pmh[k][i - w0] = m2.hi;
+                    W.pml[k][i - w0] = m2.lo;
+                }
+            }
+        }
+        __syncthreads();
         if (violated && warp < 2) {
-            const int64_t h_lo = use_hints ? out->hint_lo[j] : -1, h_hi = use_hints ? out->hint_hi[j] : -1;
-            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, gps, gpm, (int64_t)0, b, c, h_lo, h_hi)
-                                        : merge_kary_right(P.loss, rho, val, gps, gpm, (int64_t)0, b, c, h_lo, h_hi);
+            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi)
+                                        : merge_kary_right(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi);
             if (lane == 0) s_end[warp] = e;
         }
         __syncthreads();
@@ -616,7 +692,7 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
         if (violated && tid == 0) {
             int64_t lo, hi;
             double v;
-            pav_kary_finish(P.loss, rho, val, gps, gpm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            pav_kary_finish(P.loss, rho, val, ps, pm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
             out->hint_lo[j] = s_end[0];   // (the searches' own answers: the finish only snaps them to whole runs)
             out->hint_hi[j] = s_end[1];
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
@@ -763,8 +839,14 @@ int rbl_k_pav(rbl_ctx* c, int loss, const double* m_sorted, double rho, double* 
     P.dbg = c->sort_dbg;
     if (few) {
         SegBlocks* blk = reinterpret_cast<SegBlocks*>(c->seg_blocks);
-        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(kSegMergeThreads), 0, s, P, c->seg_bounds, c->nseg, blk,
-                                c->pav_no_hints ? 0 : 1));
+        RBL_PER_DEVICE(bool, seg_attr, c);
+        if (!seg_attr) {
+            RBL_CUDA(cudaFuncSetAttribute(pav_seg_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)sizeof(SegWindows)));
+            seg_attr = true;
+        }
+        RBL_CUDA(rbl_launch_pdl(pav_seg_merge_kernel, dim3(1), dim3(kSegMergeThreads), sizeof(SegWindows), s, P,
+                                c->seg_bounds, c->nseg, blk, c->pav_no_hints ? 0 : 1));
         RBL_LAUNCH_CHECK();
         RBL_CUDA(rbl_launch_pdl(pav_seg_fill_kernel, dim3(c->vec_grid), dim3(256), 0, s, blk, z_sorted));
         RBL_LAUNCH_CHECK();

@@ -162,7 +162,7 @@ class DeviceProblem:
         ms = ctypes.c_void_p(main.cuda_stream)
         # a caller's numpy array is PAGEABLE: the driver would stage it through one small pinned buffer on this
         # thread (~10 GB/s); librbl_b200 stages it with several host threads through pinned slots instead
-        pageable = not Xt.is_pinned()
+        pageable = (not Xt.is_pinned()) and os.environ.get("RBL_PAGEABLE_STAGING", "1") != "0"
         threads = int(os.environ.get("RBL_UPLOAD_THREADS", "0")) or min(8, max(1, (os.cpu_count() or 2) // 2))
         self.upload_path = f"pageable: {threads} staging threads (rbl_h2d_pageable)" if pageable else "pinned: direct DMA"
         cs = ctypes.c_void_p(copy_stream.cuda_stream)

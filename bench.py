@@ -503,6 +503,7 @@ def main():
         e2e_pageable = {"value": it_p / tp_all, "unit": UNIT, "iterations": it_p, "converged": bool(done_p),
                         "upload_and_build_s": tp_build, "total_s": tp_all,
                         "upload_path": getattr(s2.engine, "upload_path", None),
+                        "build_times_s": {k: round(v, 4) for k, v in s2.engine.build_times.items()},
                         "same_result": bool(np.array_equal(s2.w, solver.w))}
         s2.engine.close()
         del s2, X_page, y_page

@@ -97,3 +97,52 @@ def test_split_group_on_device_rows_match_host_split():
     np.testing.assert_array_equal(dev[1].cpu().numpy(), host[1])
     for a, b in zip(dev[2:], host[2:]):
         np.testing.assert_array_equal(a, b)
+
+
+@pytest.mark.parametrize("nbytes,threads", [(8, 1), (1 << 20, 3), ((8 << 20) - 8, 4), ((8 << 20) + 8, 4), (100_000_008, 8),
+                                            (300_000_000, 16)])
+def test_pageable_upload_is_exact(nbytes, threads):
+    """rbl_h2d_pageable: a pageable host array staged by several host threads through pinned slots lands on the
+    device byte for byte, for sizes around the 8 MB chunking, more threads than chunks, and repeated calls that
+    reuse the slots while earlier transfers may still be in flight."""
+    import ctypes
+
+    from rbl_b200 import _cabi
+
+    lib = _cabi.load()
+    rng = np.random.default_rng(nbytes % 1000 + threads)
+    n = nbytes // 8
+    dst = torch.empty(n, dtype=torch.float64, device="cuda")
+    stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for rep in range(3):
+        src = rng.standard_normal(n)                      # ordinary numpy memory: pageable
+        _cabi.check(lib.rbl_h2d_pageable(0, dst.data_ptr(), src.ctypes.data, n * 8, threads, stream))
+        got = dst.cpu().numpy()                           # same stream: ordered after the upload
+        np.testing.assert_array_equal(got, src)
+
+
+def test_solver_from_pageable_equals_solver_from_pinned():
+    """the pipelined constructor (chunks of X staged, turned into rows of D and accumulated into G while the next
+    chunk travels) gives bit-identical D and G whether X is pageable (threaded staging) or pinned (direct DMA)."""
+    from rbl_b200.engine import AdmmEngine
+
+    rng = np.random.default_rng(8)
+    n, d = 70_000, 120
+    X = rng.standard_normal((n, d))
+    y = np.where(rng.random(n) > 0.5, 1.0, -1.0)
+    Xp = torch.empty((n, d), dtype=torch.float64, pin_memory=True)
+    Xp.copy_(torch.from_numpy(X))
+    import os
+    os.environ["RBL_PIPELINE_ROWS"] = "9000"              # force several chunks at this size
+    try:
+        a = AdmmEngine(X, y, "binary_cross_entropy", np.ones(n) / n)
+        b = AdmmEngine(Xp.numpy(), y, "binary_cross_entropy", np.ones(n) / n)
+    finally:
+        del os.environ["RBL_PIPELINE_ROWS"]
+    assert a.upload_path.startswith("pageable") and b.upload_path.startswith("pinned")
+    assert torch.equal(a.D, b.D)
+    if a.G is not None:
+        assert torch.equal(a.gram(), b.gram())
+    np.testing.assert_array_equal(a.D[:, :d].cpu().numpy(), -y[:, None] * X)
+    a.close()
+    b.close()
