@@ -358,10 +358,14 @@ RBL_HD bool pav_probe_right_near(int loss, double rho, const V& val, const PS& p
     return pav_phi(loss, rho, ps, pm, l, r, u, -1) > 0.0;
 }
 
-// probe position of lane j of a WARM-STARTED first round: 16 positions below the guess h at distances 2^15 .. 1 and
-// 16 at and above it at distances 0, 1, 3, .. 2^15 - 1, clamped to [lo, hi] (ascending in j; duplicates are harmless)
+// probe position of lane j of a WARM-STARTED first round: 32 positions spaced 32 ranks apart around the guess h
+// (h - 480 .. h + 512), clamped to [lo, hi] (ascending in j; duplicates are harmless).  A block end that moved by
+// fewer than ~500 ranks since the guess was taken is bracketed to 32 candidates, which the next round resolves
+// exactly; all these probes stay inside the shared-memory windows the device kernel keeps around the guesses.
+// Farther moves fall back to the even 32-ary subdivision of what is left.
+#define RBL_HINT_STRIDE 32
 RBL_HD int64_t pav_hint_pos(int64_t h, int64_t lo, int64_t hi, int j) {
-    int64_t p = j < 16 ? h - ((int64_t)1 << (15 - j)) : h + ((int64_t)1 << (j - 16)) - 1;
+    int64_t p = h + (int64_t)(j - 15) * RBL_HINT_STRIDE;
     if (p < lo) p = lo;
     if (p > hi) p = hi;
     return p;

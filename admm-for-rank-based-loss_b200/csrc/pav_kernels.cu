@@ -500,6 +500,10 @@ struct SegBlocks {
     // the pooled block merge j produced at the previous call on this handle (0, 0: none yet) — the warm start of
     // the next call's searches; ranks move little between two ADMM iterations
     int64_t hint_lo[kMaxSeg], hint_hi[kMaxSeg];
+    // ... and how far each end moved between the last two calls: along a solve the pooled block shrinks by a slowly
+    // decaying number of ranks per iteration (measured at n = 1M: 13 k ranks at iteration 10, 2.6 k at 20, 1 k at
+    // 30), so the guess is the last answer extrapolated by 7/8 of its last move
+    int64_t move_lo[kMaxSeg], move_hi[kMaxSeg];
 };
 
 // positions i (1 <= i < n) where sigma steps up; count may exceed cap (then the list is truncated)
@@ -520,7 +524,7 @@ constexpr int kSegMergeThreads = 1024;  // all of them scan the chunk totals; wa
 // guesses when those are good — from shared memory (~30 cycles) instead of L2 (~600).  Outside the windows the
 // accessors fall through to global memory, so a bad guess costs time, never correctness; the cached entries are the
 // exact values the global accessors return (the prefix entries are combined with the same dd_add).
-constexpr int kWinHalf = 1024;
+constexpr int kWinHalf = 640;  // the warm-started round probes h - 480 .. h + 512
 constexpr int kWinLen = 2 * kWinHalf + 1;  // positions per window (prefix sums have an entry one past the end)
 struct SegWindows {
     double val[2][kWinLen];
@@ -654,8 +658,16 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
     for (int j = 1; j < nseg; ++j) {
         const int64_t b = bounds[j], c = bounds[j + 1];
         const bool violated = gval(b - 1) > gval(b);  // block-uniform
-        const int64_t h_lo = use_hints ? out->hint_lo[j] : -1, h_hi = use_hints ? out->hint_hi[j] : -1;
-        const bool hinted = h_lo >= 0 && h_lo < b && h_hi > b && h_hi <= c;
+        const int64_t p_lo = use_hints ? out->hint_lo[j] : -1, p_hi = use_hints ? out->hint_hi[j] : -1;
+        const bool have_prev = p_lo >= 0 && p_lo < b && p_hi > b && p_hi <= c;
+        int64_t h_lo = -1, h_hi = -1;
+        if (have_prev) {  // last answer + 7/8 of its last move, kept inside the valid ranges
+            h_lo = p_lo + (out->move_lo[j] * 7) / 8;
+            h_hi = p_hi + (out->move_hi[j] * 7) / 8;
+            h_lo = h_lo < 0 ? 0 : (h_lo > b - 1 ? b - 1 : h_lo);
+            h_hi = h_hi < b + 1 ? b + 1 : (h_hi > c ? c : h_hi);
+        }
+        const bool hinted = have_prev;
         // windows around the guessed block ends (empty without a usable guess): filled by the whole CTA
         ValWin<ValOverlay> val{gval, {W.val[0], W.val[1]}, {0, 0}, {0, 0}};
         PrefWin ps{gps, {W.psh[0], W.psh[1]}, {W.psl[0], W.psl[1]}, {0, 0}, {-1, -1}};
@@ -672,8 +684,28 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
                 ps.b[k] = pm.b[k] = w0;
                 ps.e[k] = pm.e[k] = w1;
                 for (int64_t i = w0 + tid; i <= w1; i += kSegMergeThreads) {
-                    if (i < w1) W.val[k][i - w0] = gval(i);
-                    const dd_t a = gps.get(i), m2 = gpm.get(i);
+                    // all nine loads of a position are issued before any is used (PrefixChunked::get would make
+                    // the chunk-local entries wait for the offsets); same dd_add, same values
+                    const int64_t ch = i >> kChunkLog2;
+                    const bool inner = (i & (((int64_t)1 << kChunkLog2) - 1)) != 0;
+                    const double v0 = i < w1 ? __ldg(P.val + i) : 0.0;
+                    dd_t so, sl, mo, ml;
+                    so.hi = P.ps_off_hi[ch];
+                    so.lo = P.ps_off_lo[ch];
+                    mo.hi = P.pm_off_hi[ch];
+                    mo.lo = P.pm_off_lo[ch];
+                    sl.hi = P.ps_loc_hi[i];
+                    sl.lo = P.ps_loc_lo[i];
+                    ml.hi = P.pm_loc_hi[i];
+                    ml.lo = P.pm_loc_lo[i];
+                    if (i < w1) {
+                        double vv = v0;
+                        const int nb = s_nblk;
+                        for (int q = 0; q < nb; ++q)
+                            if (i >= s_lo[q] && i < s_hi[q]) vv = s_v[q];
+                        W.val[k][i - w0] = vv;
+                    }
+                    const dd_t a = inner ? dd_add(so, sl) : so, m2 = inner ? dd_add(mo, ml) : mo;
                     W.psh[k][i - w0] = a.hi;
                     W.psl[k][i - w0] = a.lo;
                     W.pmh[k][i - w0] = m2.hi;
@@ -682,6 +714,7 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
             }
         }
         __syncthreads();
+        stamp();
         if (violated && warp < 2) {
             const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi)
                                         : merge_kary_right(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi);
@@ -693,6 +726,14 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
             int64_t lo, hi;
             double v;
             pav_kary_finish(P.loss, rho, val, ps, pm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            if (P.dbg && j < 4) {  // dev tool: guesses and answers of this merge
+                P.dbg[40 + 4 * j] = (unsigned long long)h_lo;
+                P.dbg[41 + 4 * j] = (unsigned long long)h_hi;
+                P.dbg[42 + 4 * j] = (unsigned long long)s_end[0];
+                P.dbg[43 + 4 * j] = (unsigned long long)s_end[1];
+            }
+            out->move_lo[j] = have_prev ? s_end[0] - p_lo : 0;
+            out->move_hi[j] = have_prev ? s_end[1] - p_hi : 0;
             out->hint_lo[j] = s_end[0];   // (the searches' own answers: the finish only snaps them to whole runs)
             out->hint_hi[j] = s_end[1];
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)
