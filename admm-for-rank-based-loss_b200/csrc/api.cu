@@ -9,6 +9,7 @@
 
 #include "../../include/rbl_b200.h"
 #include "common.cuh"
+#include "lbfgs_core.h"
 
 // launchers defined in the kernel translation units
 int rbl_k_build_design(rbl_ctx* c, const double* X, int64_t ldx, const double* y, double* D, int64_t nrows,
@@ -774,6 +775,74 @@ int rbl_gram_eval_host(rbl_handle_t h, const double* G, const double* w0, const 
     RBL_CUDA(cudaMemcpyAsync(st_r, h->eval_red, nr * sizeof(double), cudaMemcpyDeviceToHost, S(stream)));
     RBL_CUDA(cudaStreamSynchronize(S(stream)));
     memcpy(h_red_out, st_r, nr * sizeof(double));
+    return RBL_OK;
+}
+
+// ---- the smooth w-steps in the library (w_LBFGS.py:48-62): L-BFGS-B on the host (csrc/lbfgs_core.h) over device
+// f/g evaluations on G.  f(w) = rho/2 ||D w - b||^2 + R(w), grad = rho D^T (D w - b) + R'(w) with
+//   reg_kind 0: R = reg/2 ||w||^2                                        (wl2_fun / wl2_fun_gradient, :31-45)
+//   reg_kind 1: R = reg/2 sum_j (w_j^2 / (2t) if |w_j| <= t else |w_j| - t/2)   (wl1_fun_smooth, :11-28)
+int rbl_lbfgs_gram(rbl_handle_t h, const double* G, const double* w0, const double* red0, double rho, double reg,
+                   int reg_kind, double t, int maxiter, double* h_w, double* d_w_out, int32_t* h_info,
+                   rbl_stream_t stream) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(G && w0 && red0 && h_w && h_info, "null argument");
+    RBL_REQUIRE(reg_kind == 0 || (reg_kind == 1 && t > 0.0), "reg_kind must be 0 (l2) or 1 (smoothed l1, t > 0)");
+    RBL_REQUIRE(rho > 0.0 && maxiter > 0, "bad arguments");
+    const int d = h->d;
+    if (!h->eval_stage) {
+        RBL_CUDA(cudaMallocHost((void**)&h->eval_stage, 2 * ((size_t)h->ld + 8) * sizeof(double)));
+        RBL_CUDA(cudaMalloc((void**)&h->eval_w, ((size_t)h->ld + 8) * sizeof(double)));
+        RBL_CUDA(cudaMalloc((void**)&h->eval_red, ((size_t)h->ld + 8) * sizeof(double)));
+    }
+    double* st_w = h->eval_stage;
+    double* st_r = h->eval_stage + h->ld + 8;
+    cudaStream_t s = S(stream);
+    int cuda_rc = RBL_OK;
+    auto fg = [&](const double* x, double* f, double* g) -> int {
+        memcpy(st_w, x, (size_t)d * sizeof(double));
+        if (cudaMemcpyAsync(h->eval_w, st_w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s) != cudaSuccess)
+            return cuda_rc = RBL_ERR_CUDA;
+        if ((cuda_rc = rbl_k_gram_eval(h, G, w0, red0, h->eval_w, h->eval_red, s)) != RBL_OK) return cuda_rc;
+        if (cudaMemcpyAsync(st_r, h->eval_red, ((size_t)d + 2) * sizeof(double), cudaMemcpyDeviceToHost, s) !=
+                cudaSuccess ||
+            cudaStreamSynchronize(s) != cudaSuccess)
+            return cuda_rc = RBL_ERR_CUDA;
+        double R = 0.0;
+        if (reg_kind == 0) {
+            double ww = 0.0;
+            for (int j = 0; j < d; ++j) ww += x[j] * x[j];
+            R = 0.5 * reg * ww;
+            for (int j = 0; j < d; ++j) g[j] = -rho * st_r[j] + reg * x[j];
+        } else {
+            double sq = 0.0, ab = 0.0;
+            for (int j = 0; j < d; ++j) {
+                const double a = fabs(x[j]);
+                if (a <= t) {
+                    sq += x[j] * x[j];
+                    g[j] = -rho * st_r[j] + 0.5 * reg * x[j] / t;
+                } else {
+                    ab += a - 0.5 * t;
+                    g[j] = -rho * st_r[j] + 0.5 * reg * (x[j] > 0.0 ? 1.0 : -1.0);
+                }
+            }
+            R = 0.5 * 0.5 * reg * sq / t + 0.5 * reg * ab;
+        }
+        *f = 0.5 * rho * st_r[d] + R;
+        return 0;
+    };
+    const rbl_lbfgs::Result res = rbl_lbfgs::minimize(d, h_w, fg, 10, maxiter);
+    if (cuda_rc != RBL_OK) {
+        rbl_set_error("rbl_lbfgs_gram: a device evaluation failed (%s)", cudaGetErrorString(cudaGetLastError()));
+        return cuda_rc;
+    }
+    h_info[0] = res.nit;
+    h_info[1] = res.nfev;
+    h_info[2] = res.status;
+    if (d_w_out) {
+        memcpy(st_w, h_w, (size_t)d * sizeof(double));
+        RBL_CUDA(cudaMemcpyAsync(d_w_out, st_w, (size_t)d * sizeof(double), cudaMemcpyHostToDevice, s));
+    }
     return RBL_OK;
 }
 

@@ -70,6 +70,8 @@ _SIGNATURES = {
                                       _c.c_int, _dp, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_steps": (_c.c_int, [_c.c_void_p, _dp, _c.c_int, _c.c_void_p]),
     "rbl_gram_fista_result": (_c.c_int, [_c.c_void_p, _dp, _c.c_void_p]),
+    "rbl_lbfgs_gram": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _c.c_int, _c.c_double, _c.c_int,
+                                  _c.c_void_p, _dp, _c.POINTER(_c.c_int32), _c.c_void_p]),
     "rbl_gram_eval_host": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "rbl_gram_eval": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_lasso_cd_gram": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _c.c_double, _c.c_double, _c.c_int, _dp, _dp,

@@ -9,7 +9,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "librbl_b200.so")
 SOURCES = ["api.cu", "pass_kernels.cu", "vec_kernels.cu", "sort_kernels.cu", "pav_kernels.cu", "batch_kernels.cu",
            "gram_kernels.cu", "metrics_kernels.cu", "ingest_kernels.cu"]
-HEADERS = ["common.cuh", "prox_core.h", "pav_core.h", os.path.join("..", "..", "include", "rbl_b200.h")]
+HEADERS = ["common.cuh", "prox_core.h", "pav_core.h", "lbfgs_core.h", os.path.join("..", "..", "include", "rbl_b200.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--shared",
               "-Xcompiler", "-fPIC"]

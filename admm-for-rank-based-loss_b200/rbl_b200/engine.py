@@ -788,21 +788,45 @@ class AdmmEngine(DeviceProblem):
             self.fista_stats, self.dual_stats, self.active_stats = stats
             self._active_pending = False
 
-    def w_step_lbfgs(self, rho, reg, maxiter=1000, reg_fg=None):
-        """scipy L-BFGS-B (host, d-vector control logic) over the fused device pass.
-        reg_fg=None: the l2 problem of w_LBFGS.py:31-53; otherwise a smooth regulariser (sADMM)."""
-        from scipy.optimize import minimize
-
+    def w_step_lbfgs(self, rho, reg, maxiter=1000, reg_fg=None, huber_t=None):
+        """The smooth w-step (w_LBFGS.py:48-62).  huber_t=None: the l2 problem (:31-53); huber_t=t: the smoothed-l1
+        problem of smoothADMMmethod (:11-28, 54-62).
+        Gram mode: ONE library call — librbl_b200's own L-BFGS-B (scipy's unconstrained control flow, pinned against
+        scipy in tests/test_host.py) over device f/g evaluations on G; no interpreter inside the w-step
+        (RBL_LBFGS=scipy keeps scipy's minimize over rbl_gram_eval_host for cross-checks).
+        Stream mode: scipy's L-BFGS-B over the fused pass; `reg_fg(w) -> (R, R')` may replace the regulariser."""
         if not hasattr(self, "_wtmp"):
             self._wtmp = torch.zeros(self.d, dtype=torch.float64, device=self.device)
             self._fg_red = np.zeros(self.d + 2, dtype=np.float64)
+            self._lb_info = (ctypes.c_int32 * 4)()
             self.lbfgs_evals = 0
         pre_done, self._pre_done = getattr(self, "_pre_done", False), False
         if not pre_done:  # (z_and_grad has already made the warm-start pass, inside its graph)
             self._warm_start_pass()
+        rho, reg = float(rho), float(reg)
+        native = (self.w_mode == "gram" and reg_fg is None and os.environ.get("RBL_LBFGS", "native") != "scipy")
+        if native:
+            torch.cuda.current_stream(self.device).synchronize()
+            wh = self.w_host.numpy()          # pinned copy of the warm start, overwritten with the solution
+            _cabi.check(self.lib.rbl_lbfgs_gram(self.h, self.G.data_ptr(), self.w_prev.data_ptr(),
+                                                self.red0.data_ptr(), rho, reg, 0 if huber_t is None else 1,
+                                                0.0 if huber_t is None else float(huber_t), int(maxiter),
+                                                wh.ctypes.data, self.w.data_ptr(), self._lb_info, self._stream()))
+            self.lbfgs_evals += int(self._lb_info[1])
+            self._r_matches_w = False
+            return {"nit": int(self._lb_info[0]), "nfev": int(self._lb_info[1]), "solver": "librbl_b200"}
+        from scipy.optimize import minimize
+
         torch.cuda.current_stream(self.device).synchronize()
         w0 = self.w_host.numpy().copy()
-        rho, reg = float(rho), float(reg)
+        if reg_fg is None and huber_t is not None:
+            t = float(huber_t)
+
+            def reg_fg(w):  # wl1_fun_smooth / wl1_fun_smooth_gradient, w_LBFGS.py:11-28
+                small = np.abs(w) <= t
+                R = 0.5 * 0.5 * reg * float(np.sum(np.square(w[small]))) / t
+                R += 0.5 * reg * float(np.sum(np.abs(w[~small]) - 0.5 * t))
+                return R, np.where(small, 0.5 * reg * w / t, 0.5 * reg * np.sign(w))
         if reg_fg is None:
             def reg_fg(w):  # wl2_fun / wl2_fun_gradient regulariser, w_LBFGS.py:36,44
                 return 0.5 * reg * float(w @ w), reg * w
@@ -811,7 +835,7 @@ class AdmmEngine(DeviceProblem):
         self.w.copy_(torch.from_numpy(res.x))
         # L-BFGS-B normally returns the last point it evaluated; then r = b - D w is already there
         self._r_matches_w = self.w_mode != "gram" and bool(np.array_equal(res.x, self._last_eval))
-        return {"nit": int(res.nit), "nfev": int(res.nfev)}
+        return {"nit": int(res.nit), "nfev": int(res.nfev), "solver": "scipy"}
 
     # ---- dual update + residuals (algorithms.py:132-136) -----------------------------------------
     def _dual_launch(self, rho):

@@ -397,16 +397,8 @@ class smoothADMMmethod(Optimizer):
 
     def _w_subproblem_device(self):
         if self.w_flag == 1:
-            reg, t = float(self.reg), float(self.t)
-
-            def huber(w):  # wl1_fun_smooth / wl1_fun_smooth_gradient, w_LBFGS.py:11-28
-                small = np.abs(w) <= t
-                R = 0.5 * 0.5 * reg * float(np.sum(np.square(w[small]))) / t
-                R += 0.5 * reg * float(np.sum(np.abs(w[~small]) - 0.5 * t))
-                g = np.where(small, 0.5 * reg * w / t, 0.5 * reg * np.sign(w))
-                return R, g
-
-            self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg, reg_fg=huber)
+            # wl1_fun_smooth / wl1_fun_smooth_gradient (w_LBFGS.py:11-28) minimised by L-BFGS-B (:54-62)
+            self.last_info = self.engine.w_step_lbfgs(self.rho, self.reg, huber_t=float(self.t))
         elif self.w_flag == 0 or self.w_flag == 2:
             super(smoothADMMmethod, self)._w_subproblem_device()
         else:

@@ -1,6 +1,7 @@
-"""Drop-in for src/util/w_LBFGS.py (l2 branch w_flag == 2, smoothed-l1 branch w_flag == 1): scipy L-BFGS-B on the host, the objective
-and gradient  f = rho/2 ||D w - b||^2 + reg/2 ||w||^2,  g = rho D^T (D w - b) + reg w  come from ONE
-fused pass over D on the B200 (rbl_fused_pass) instead of D@w plus DTD@w - D.T@b (:31-45)."""
+"""Drop-in for src/util/w_LBFGS.py (l2 branch w_flag == 2, smoothed-l1 branch w_flag == 1): L-BFGS-B with scipy's
+control flow (:48-62) — the library's own (rbl_lbfgs_gram) over f/g evaluations on G = D^T D when the engine runs
+in Gram mode, scipy's over one fused pass over D per evaluation (rbl_fused_pass) otherwise — for
+f = rho/2 ||D w - b||^2 + R(w),  g = rho D^T (D w - b) + R'(w)  (:11-45)."""
 import numpy as np
 
 from rbl_b200.engine import AdmmEngine
@@ -20,11 +21,7 @@ def w_solver(w_flag, w0, z, lagrangian, rho, DTD, D, reg, t=None):
         if w_flag == 2:
             eng.w_step_lbfgs(rho, reg)
         else:
-            def huber(w):  # wl1_fun_smooth / wl1_fun_smooth_gradient (:11-28)
-                small = np.abs(w) <= t
-                R = 0.25 * reg * float(np.sum(np.square(w[small]))) / t + 0.5 * reg * float(np.sum(np.abs(w[~small]) - 0.5 * t))
-                return R, np.where(small, 0.5 * reg * w / t, 0.5 * reg * np.sign(w))
-            eng.w_step_lbfgs(rho, reg, reg_fg=huber)
+            eng.w_step_lbfgs(rho, reg, huber_t=float(t))  # wl1_fun_smooth / wl1_fun_smooth_gradient (:11-28)
         w = eng.w.cpu().numpy().reshape(-1, 1)
     finally:
         eng.close()

@@ -204,6 +204,17 @@ int rbl_gram_fista_run(rbl_handle_t h, const double* G, const double* w0, const 
 int rbl_gram_fista_result(rbl_handle_t h, double* w_out, rbl_stream_t stream);
 /* red_out = [D^T (b - D w) (d), ||b - D w||^2, 0] at any w, from G, w0, red0 (same layout as rbl_fused_pass):
  * the f/g evaluation of w_LBFGS.py:31-45 */
+/* The smooth w-step as ONE call (w_LBFGS.py:48-62: scipy.optimize.minimize(method='L-BFGS-B', maxiter)): the
+ * library's own L-BFGS-B (csrc/lbfgs_core.h: scipy's unconstrained control flow — maxcor 10, ftol 2.2e-9, gtol 1e-5,
+ * maxls 20, More'-Thuente line search — pinned against scipy in tests/test_host.py) over f/g evaluations on G.
+ * reg_kind 0: R(w) = reg/2 ||w||^2 (wl2_fun, :31-45); 1: the Huber-type smoothing of reg/2 ||w||_1 with parameter t
+ * (wl1_fun_smooth, :11-28).  h_w (host, d doubles): start on entry, solution on exit, also copied to d_w_out (device,
+ * may be NULL) on `stream`; h_info = [iterations, evaluations, status (0 converged, 1 limit, 2 abnormal)].
+ * w0 / red0 as in rbl_gram_eval.  Synchronises `stream` once per evaluation. */
+int rbl_lbfgs_gram(rbl_handle_t h, const double* G, const double* w0, const double* red0, double rho, double reg,
+                   int reg_kind, double t, int maxiter, double* h_w, double* d_w_out, int32_t* h_info,
+                   rbl_stream_t stream);
+
 /* rbl_gram_eval for a host-side optimiser (scipy's L-BFGS-B, w_LBFGS.py:48-62): h_w (d doubles) and h_red_out
  * (d + 2 doubles) are HOST arrays; the call stages w through pinned memory, runs the sweep over G, reads the
  * result back and synchronises `stream` — one call per f/g evaluation instead of a copy, a launch, a copy and a

@@ -150,3 +150,15 @@ extern "C" int emul_pav_fewseg_hinted(int loss, int64_t n, const double* sigma, 
 extern "C" uint64_t emul_key(double x) { uint64_t b; memcpy(&b, &x, 8); return rbl_key_from_bits(b); }
 extern "C" double emul_unkey(uint64_t k) { uint64_t b = rbl_bits_from_key(k); double x; memcpy(&x, &b, 8); return x; }
 extern "C" double emul_prox(int loss, double s, double m, double rho) { return rbl_block_prox(loss, s, m, rho); }
+
+// ---- the library's L-BFGS-B (csrc/lbfgs_core.h) driven by a host callback, for comparison with scipy -----------
+#include "lbfgs_core.h"
+typedef int (*emul_fg_t)(const double* x, double* f, double* g);
+extern "C" int emul_lbfgs(int n, double* x, emul_fg_t fg, int m, int maxiter, int* nit, int* nfev, double* f_out) {
+    rbl_lbfgs::Result r = rbl_lbfgs::minimize(n, x, [&](const double* xx, double* f, double* g) { return fg(xx, f, g); },
+                                              m, maxiter);
+    *nit = r.nit;
+    *nfev = r.nfev;
+    *f_out = r.f;
+    return r.status;
+}
