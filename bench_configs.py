@@ -450,7 +450,10 @@ def run_c5(args, B):
                          f"grid (l1_reg {[float('%.3g' % regs[j]) for j in picks]}) x iterations 0..{kc - 1} "
                          f"({dt:.1f} s of CPU work)"}
         parity = {"tolerance": 1e-9, "instances_compared": len(os_), "iterations_compared": kc,
-                  "max_rel_w": worst_w, "max_rel_z": worst_z, "ok": bool(worst_w <= 1e-9 and worst_z <= 1e-9),
+                  "max_rel_w": worst_w, "max_rel_z": worst_z,
+                  # an instance whose regulariser kills w has z ~ 1e-7 in norm: its z is judged on the absolute error
+                  "ok": bool(all(pi["max_rel_w"] <= 1e-9 and (pi["max_rel_z"] <= 1e-9 or pi["max_abs_z"] <= 1e-12)
+                                 for pi in per_inst)),
                   "per_instance": per_inst,
                   "how": "free-running lockstep of batched GPU instances and per-instance CPU oracles"}
         bb.close()

@@ -18,10 +18,18 @@ d = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 first = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 20
 storage = sys.argv[5] if len(sys.argv) > 5 else "fp64"
+cfg = sys.argv[6] if len(sys.argv) > 6 else "c2"      # c2 | c3 | c4 (problem family; n and d as given)
 dev = torch.device("cuda", 0)
 Xh, yh = B.gen_rows_device(torch, dev, 0, n, n, d, pin=True)
-s = ADMMmethod(Xh.numpy(), yh.numpy().reshape(-1, 1), "superquantile", "binary_cross_entropy", l1_reg=0.01, args=[0.8],
-               max_iter=100000, tol=1e-12, _storage=storage)
+Xn = Xh.numpy()
+if cfg == "c3":
+    kw = dict(weight_function="ehrm", loss="binary_cross_entropy", B=-5, l2_reg=0.01)
+elif cfg == "c4":
+    kw = dict(weight_function="aorr", loss="hinge", args=[0.2, 0.8], l2_reg=1e-4)
+    Xn = np.hstack((Xn, np.ones((n, 1))))
+else:
+    kw = dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.01, args=[0.8])
+s = ADMMmethod(Xn, yh.numpy().reshape(-1, 1), max_iter=100000, tol=1e-12, _storage=storage, **kw)
 quiet = contextlib.redirect_stdout(io.StringIO())
 with quiet:
     s.advance(0, first)
@@ -46,7 +54,7 @@ for ev in prof.events():
         a[0] += 1
         a[1] += ev.device_time
 tot = sum(v[1] for v in agg.values())
-print(f"# n={n} d={d} storage={storage}: iterations {first}..{first + iters - 1}, {ms / iters * 1e3:.1f} us per iteration under the "
+print(f"# {cfg} n={n} d={d} storage={storage}: iterations {first}..{first + iters - 1}, {ms / iters * 1e3:.1f} us per iteration under the "
       f"profiler, kernels sum {tot / iters:.1f} us per iteration")
 print(f"{'kernel':70s} {'per it':>7s} {'mean us':>9s} {'us / it':>9s} {'share':>7s}")
 for name, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
