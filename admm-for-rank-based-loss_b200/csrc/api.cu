@@ -909,6 +909,52 @@ int rbl_admm_run(rbl_handle_t h, void* graph_exec, rbl_stream_t stream, double* 
     return RBL_OK;
 }
 
+// ---- native outer loop for the smooth (l2) problems: [graph: z-step + warm-start gradient pass] -> L-BFGS-B in the
+// library -> [graph: dual pass + read-back], with the reference's stop test and rho schedule in between
+int rbl_admm_run_l2(rbl_handle_t h, void* graph_pre, void* graph_dual, rbl_stream_t stream, double* h_scal,
+                    const double* h_out, const double* G, const double* w0, const double* red0, double* h_w,
+                    double* d_w, double reg, int32_t lbfgs_maxiter, int32_t max_iters, double tol, int32_t num_feature,
+                    int64_t dense_above, double rho, rbl_run_stats* out) {
+    RBL_ENTER(h);
+    RBL_REQUIRE(graph_pre && graph_dual && h_scal && h_out && G && w0 && red0 && h_w && d_w && out && max_iters >= 0,
+                "bad arguments");
+    memset(out, 0, sizeof(*out));
+    const double rho_cap = 217.0 * (double)num_feature;  // algorithms.py:153-157
+    int32_t info[4];
+    for (int it = 0; it < max_iters; ++it) {
+        h_scal[0] = rho;
+        RBL_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_pre, S(stream)));
+        RBL_CUDA(cudaStreamSynchronize(S(stream)));  // h_w (pinned) now holds the warm start, red0 the gradient pass
+        RBL_TRY(rbl_lbfgs_gram(h, G, w0, red0, rho, reg, 0, 0.0, lbfgs_maxiter, h_w, d_w, info, stream));
+        RBL_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_dual, S(stream)));
+        RBL_CUDA(cudaStreamSynchronize(S(stream)));
+        const double primal = sqrt(h_out[0]), dual = sqrt(h_out[1]);
+        out->iters = it + 1;
+        out->primal = primal;
+        out->dual = dual;
+        out->nnz_last = (int32_t)h_out[4];
+        if (h_out[5] != 0.0) ++out->sparse_dual; else ++out->dense_dual;
+        out->fista_iters += info[0];   // L-BFGS iterations
+        out->fista_sweeps += info[1];  // f/g evaluations (one sweep over G each)
+        out->last_sweeps = info[1];
+        const int64_t rows = (int64_t)h_out[8];
+        if (rows <= dense_above) {
+            ++out->gathered;
+            out->rows_read += rows;
+        } else {
+            out->rows_read += h->n_local;
+        }
+        if (primal < tol && dual < tol) {
+            out->converged = 1;
+            break;
+        }
+        rho = fmin(rho * (primal > 1e-2 ? 1.02 : 1.07), rho_cap);
+    }
+    out->rho = rho;
+    out->rho_is_pyfloat = 0;
+    return RBL_OK;
+}
+
 int rbl_dual_update(rbl_handle_t h, const double* z, double* Dw, const double* b, const double* r,
                     int from_residual, double* lam, double rho, const double* w, const double* w_prev, double* out4,
                     rbl_stream_t stream) {

@@ -36,6 +36,9 @@ _SIGNATURES = {
     "rbl_admm_run": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_int32,
                                 _c.c_double, _c.c_double, _c.c_int64, _c.c_int32, _c.c_int64, _c.c_double,
                                 _c.c_int32, _c.POINTER(RunStats)]),
+    "rbl_admm_run_l2": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _dp,
+                                   _dp, _dp, _c.c_void_p, _dp, _c.c_double, _c.c_int32, _c.c_int32, _c.c_double,
+                                   _c.c_int32, _c.c_int64, _c.c_double, _c.POINTER(RunStats)]),
     "rbl_bind_scalars": (_c.c_int, [_c.c_void_p, _dp]),
     "rbl_sort_margins_near": (_c.c_int, [_c.c_void_p, _dp, _dp, _dp, _dp, _c.c_void_p]),
     "rbl_sort_stats": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.POINTER(_c.c_int32)]),

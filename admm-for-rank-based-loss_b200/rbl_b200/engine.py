@@ -209,14 +209,16 @@ class DeviceProblem:
         """kernels launched through librbl_b200 by this process (bench.py's gpu_launches)"""
         return (int(self.lib.rbl_launch_count())
                 + getattr(self, "_graph_replays", 0) * getattr(self, "_graph_launches", 0)
-                + getattr(self, "_graph_l2_replays", 0) * getattr(self, "_graph_l2_launches", 0))
+                + getattr(self, "_graph_l2_replays", 0) * getattr(self, "_graph_l2_launches", 0)
+                + getattr(self, "_graph_dual_replays", 0) * getattr(self, "_graph_dual_launches", 0))
 
     def close(self):
         # a captured iteration graph holds NCCL work in a row-sharded job: drop it before the handle (and before
         # the caller destroys the process group)
-        if getattr(self, "_graph", None) is not None or getattr(self, "_graph_l2", None) is not None:
+        if (getattr(self, "_graph", None) is not None or getattr(self, "_graph_l2", None) is not None
+                or getattr(self, "_graph_dual", None) is not None):
             torch.cuda.synchronize(self.device)
-            self._graph = self._graph_l2 = None
+            self._graph = self._graph_l2 = self._graph_dual = None
             self._graphs_l2_ehrm = {}
         if getattr(self, "h", None) is not None and self.h.value:
             self.lib.rbl_destroy(self.h)
@@ -787,6 +789,85 @@ class AdmmEngine(DeviceProblem):
             _cabi.check(self.lib.rbl_bind_scalars(self.h, 0))
             self.fista_stats, self.dual_stats, self.active_stats = stats
             self._active_pending = False
+
+    # ---- native loop of l2 iterations (rbl_admm_run_l2) ------------------------------------------------------------
+    def _capture_dual(self):
+        """the dual step (dual pass, [all-reduce of the primal partial], read-back of the residuals and of w into
+        pinned memory) as a CUDA graph whose first node refreshes the bound scalar block"""
+        dev = self.device
+        self._ensure_scalars()
+        torch.cuda.current_stream(dev).synchronize()
+        stats = (dict(self.fista_stats), dict(self.dual_stats), dict(self.active_stats))
+        g = torch.cuda.CUDAGraph()
+        n0 = int(self.lib.rbl_launch_count())
+        _cabi.check(self.lib.rbl_bind_scalars(self.h, self.scal.data_ptr()))
+        cur = torch.cuda.current_stream(dev)
+        if not hasattr(self, "_cap_stream"):
+            self._cap_stream = torch.cuda.Stream(device=dev)
+        try:
+            self._cap_stream.wait_stream(cur)
+            with torch.cuda.stream(self._cap_stream):
+                g.capture_begin()
+                try:
+                    self.scal.copy_(self.scal_host, non_blocking=True)
+                    self._r_matches_w = False
+                    self._dual_launch(1.0)                # by-value rho is ignored while the block is bound
+                finally:
+                    g.capture_end()
+            cur.wait_stream(self._cap_stream)
+            self._graph_dual = g
+            self._graph_dual_launches = int(self.lib.rbl_launch_count()) - n0
+        except Exception as exc:  # noqa: BLE001
+            import warnings
+            warnings.warn(f"rbl_b200: CUDA graph capture of the dual step failed ({exc!r}); continuing with the "
+                          "per-iteration loop", RuntimeWarning, stacklevel=2)
+            self._graph_dual, self.graph_ok = None, False
+        finally:
+            _cabi.check(self.lib.rbl_bind_scalars(self.h, 0))
+            self.fista_stats, self.dual_stats, self.active_stats = stats
+            self._active_pending = False
+
+    def run_lbfgs_iterations(self, n_iters, rho, reg, num_feature, tol, lbfgs_maxiter=1000):
+        """up to n_iters ADMM iterations of an l2 problem (stopping at the reference's stop test) in the library's
+        native loop: graph (z-step + gradient pass) -> L-BFGS-B in the library -> graph (dual step); returns the
+        rbl_run_stats, or None while the graphs are not available (first iterations, EHRM, stream mode)"""
+        ok = (n_iters > 0 and self.graph_ok and self.w_mode == "gram" and self.ehrm is None
+              and (self.world == 1 or self.graph_mgpu) and self._iters_eager_l2 >= 2 and self.Dw_valid
+              and self.G is not None and not getattr(self, "_r_matches_w", False)
+              and os.environ.get("RBL_LBFGS", "native") != "scipy")
+        if not ok:
+            return None
+        if self._graph_l2 is None:
+            self._capture_l2()
+        if self._graph_l2 is not None and getattr(self, "_graph_dual", None) is None:
+            self._capture_dual()
+        if self._graph_l2 is None or getattr(self, "_graph_dual", None) is None:
+            return None
+        if not hasattr(self, "_lb_info"):
+            self._lb_info = (ctypes.c_int32 * 4)()
+            self.lbfgs_evals = 0
+        st = _cabi.RunStats()
+        self._pre_done = False
+        _cabi.check(self.lib.rbl_admm_run_l2(
+            self.h, ctypes.c_void_p(self._graph_l2.raw_cuda_graph_exec()),
+            ctypes.c_void_p(self._graph_dual.raw_cuda_graph_exec()), self._stream(),
+            ctypes.c_void_p(self.scal_host.data_ptr()), ctypes.c_void_p(self._out4_host.data_ptr()),
+            self.G.data_ptr(), self.w_prev.data_ptr(), self.red0.data_ptr(), ctypes.c_void_p(self.w_host.data_ptr()),
+            self.w.data_ptr(), float(reg), int(lbfgs_maxiter), int(n_iters), float(tol), int(num_feature),
+            int(self.active_dense_frac * self.n_local), float(rho), ctypes.byref(st)))
+        self._graph_l2_replays += st.iters
+        self._graph_dual_replays = getattr(self, "_graph_dual_replays", 0) + st.iters
+        self.Dw_valid, self._delta_valid, self._r_matches_w = True, False, False
+        self.lbfgs_evals += st.fista_sweeps
+        ds, a = self.dual_stats, self.active_stats
+        ds["sparse"] += st.sparse_dual
+        ds["dense"] += st.dense_dual
+        ds["nnz_last"] = st.nnz_last
+        a["calls"] += st.iters
+        a["rows"] += st.rows_read
+        a["gathered"] += st.gathered
+        self.fista_stats["d_passes"] += (st.iters - st.gathered) + st.dense_dual
+        return st
 
     def w_step_lbfgs(self, rho, reg, maxiter=1000, reg_fg=None, huber_t=None):
         """The smooth w-step (w_LBFGS.py:48-62).  huber_t=None: the l2 problem (:31-53); huber_t=t: the smoothed-l1

@@ -336,6 +336,13 @@ class ADMMmethod(Optimizer):
                 stop = end if not verbose else min(end, i + 1 if i % 10 == 0 else (i // 10 + 1) * 10 + 1)
                 st = self.engine.run_fista_iterations(stop - i, self.rho, self.reg, self.num_row, self.num_feature,
                                                       self.tol, self.w_tol, self.fista_max_iter)
+            elif (not self.store and self.w_flag == 2 and self.engine.w_mode == "gram"
+                  and self.engine.ehrm is None):
+                # l2 problems: graph (z-step + gradient pass) -> the library's L-BFGS-B -> graph (dual step), natively
+                stop = end if not verbose else min(end, i + 1 if i % 10 == 0 else (i // 10 + 1) * 10 + 1)
+                st = self.engine.run_lbfgs_iterations(stop - i, self.rho, self.reg, self.num_feature, self.tol)
+                if st is not None:
+                    self.last_info = {"nit": None, "nfev": int(st.last_sweeps), "solver": "librbl_b200 (native loop)"}
             if st is None:
                 if super(ADMMmethod, self).main_loop(i, t_start, verbose):
                     return i + 1, True

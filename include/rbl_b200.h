@@ -285,6 +285,17 @@ int rbl_admm_run(rbl_handle_t h, void* graph_exec /* cudaGraphExec_t */, rbl_str
                  const double* h_out, int32_t max_iters, double tol, double reg, int64_t num_row,
                  int32_t num_feature, int64_t dense_above, double rho, int32_t rho_is_pyfloat, rbl_run_stats* out);
 
+/* The same loop for the l2 problems (w_flag == 2, algorithms.py:109-116 inside :119-157): graph_pre replays the z-step
+ * and the warm-start gradient pass (h_w, pinned, receives the warm start; red0 the pass result), the library's
+ * L-BFGS-B (rbl_lbfgs_gram, reg_kind 0) solves the w-step, graph_dual replays the dual pass and the read-back into
+ * h_out; both graphs start by copying h_scal to the bound scalar block.  In `out`, fista_iters / fista_sweeps count
+ * L-BFGS iterations / evaluations.  No interpreter in the loop; not for EHRM (its candidate choice needs the host
+ * between the sort and the prox). */
+int rbl_admm_run_l2(rbl_handle_t h, void* graph_pre, void* graph_dual, rbl_stream_t stream, double* h_scal,
+                    const double* h_out, const double* G, const double* w0, const double* red0, double* h_w,
+                    double* d_w, double reg, int32_t lbfgs_maxiter, int32_t max_iters, double tol, int32_t num_feature,
+                    int64_t dense_above, double rho, rbl_run_stats* out);
+
 /* ---- batched mode: B independent instances (lambda grid, seeds) sharing one D.  No reference counterpart
  * (the reference runs one ADMMmethod object per instance); SURVEY.md K10.  Buffers are laid out [B][...].
  * One pass over D serves 8 instances at a time (multi-RHS fused pass on the FP64 tensor-core path). */

@@ -399,6 +399,54 @@ def test_native_loop_equals_per_iteration_loop(w_mode):
     b.engine.close()
 
 
+@pytest.mark.parametrize("wf,args,loss,kw,n,d", [
+    ("superquantile", [0.8], "binary_cross_entropy", dict(l2_reg=0.01), 5000, 80),
+    ("aorr", [0.2, 0.8], "hinge", dict(l2_reg=1e-4), 2400, 201),
+    ("erm", None, "binary_cross_entropy", dict(l2_reg=1e-4), 3000, 33),
+])
+def test_native_l2_loop_equals_per_iteration_loop(w_mode, wf, args, loss, kw, n, d):
+    """l2 problems: ADMMmethod.main_loop runs [graph: z-step + gradient pass] -> the library's L-BFGS-B -> [graph:
+    dual step] in rbl_admm_run_l2; stepping Optimizer.main_loop one iteration at a time (same kernels, same L-BFGS-B,
+    interpreter in between) must give the same iterates bit for bit, the same rho and the same stopping iteration —
+    and both must track the oracle (scipy's L-BFGS-B) at 1e-9 per step."""
+    from src.optim.algorithms import ADMMmethod, Optimizer
+
+    if w_mode != "gram":
+        pytest.skip("the native l2 loop is a Gram-mode feature")
+    rng = np.random.default_rng(n + d)
+    X = rng.normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:5] = rng.normal(size=5)
+    y = np.sign(X @ ws + 0.1 * rng.normal(size=n)).reshape(-1, 1)
+    a = ADMMmethod(X, y, wf, loss, args=args, max_iter=45, tol=1e-3, **kw)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        wa = a.main_loop(verbose=True)
+    b = ADMMmethod(X, y, wf, loss, args=args, max_iter=45, tol=1e-3, **kw)
+    o = O.OracleADMM(X, y, wf, loss, args=args, max_iter=45, tol=1e-3, **kw)
+    it_b = None
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(45):
+            o.w, o.z, o.lam, o.rho = b.w.reshape(-1).copy(), b.z.reshape(-1).copy(), b.lagrangian.reshape(-1).copy(), b.rho
+            done = Optimizer.main_loop(b, i, 0.0, False)
+            o.step()
+            assert _rel(b.w, o.w) < 1e-9 and _rel(b.z, o.z) < 1e-9, (i, _rel(b.w, o.w), _rel(b.z, o.z))
+            if done:
+                it_b = i
+                break
+    np.testing.assert_array_equal(wa, b.w)
+    np.testing.assert_array_equal(a.z, b.z)
+    assert float(a.rho) == float(b.rho)
+    assert a.engine._graph_l2 is not None and getattr(a.engine, "_graph_dual", None) is not None
+    assert a.engine._graph_dual_replays > 0 and a.last_info["solver"].startswith("librbl_b200")
+    out = buf.getvalue()
+    assert "iter_num= 0 " in out and "iter_num= 10 " in out
+    if it_b is not None:
+        assert f"iter_num= {it_b} " in out and "algorithm converges within tolerance" in out
+    a.engine.close()
+    b.engine.close()
+
+
 def test_full_size_gram_route_equals_stream_route(w_mode, monkeypatch):
     """BASELINE config-2 row count (n = 1M; d = 32 keeps it small): eight ADMM iterations with the w-step on
     G = D^T D, the active-row gradient gather, the sparse dual pass and the replayed iteration graph must give the
