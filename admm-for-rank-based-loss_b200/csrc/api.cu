@@ -169,6 +169,7 @@ int ctx_alloc(rbl_ctx* c) {
     RBL_TRY(dev_alloc(c, &c->ss_bkey, rbl_ss_slots(c->n_global)));
     RBL_TRY(dev_alloc(c, &c->ss_bval, rbl_ss_slots(c->n_global)));
     RBL_TRY(dev_alloc(c, &c->ss_count, (size_t)4096 + 8));
+    RBL_TRY(dev_alloc(c, &c->ss_spl, (size_t)4096 + 8));
     RBL_TRY(dev_alloc(c, &c->ss_flag, 16));
     c->chunk_log2 = rbl_pav_chunk_log2();
     c->nchunks = (c->n_global + ((int64_t)1 << c->chunk_log2) - 1) >> c->chunk_log2;

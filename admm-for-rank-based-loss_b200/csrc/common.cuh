@@ -147,7 +147,7 @@ struct rbl_ctx {
     int psort_checked, psort_ok, sort_legacy;
     // splitter sort (sort_kernels.cu): bucket slots, counts, overflow flag; ss_nb = 0: not used for this n
     int ss_nb, ss_off;
-    uint64_t* ss_bkey;
+    uint64_t *ss_bkey, *ss_spl;
     uint32_t *ss_bval, *ss_count;
     int* ss_flag;
     unsigned long long* sort_dbg;  // dev tool: phase timestamps of the persistent sort (null: off)

@@ -517,6 +517,7 @@ struct SSParams {
     const int32_t* prev_perm;   // permutation of an earlier call (splitters: today's keys of the rows that sat at
                                 // evenly spaced ranks then)
     int nb;                     // buckets (power of two, <= 4096)
+    uint64_t* spl;              // [nb2] sorted splitters of this call
     uint64_t* bkey;             // [nb][kSSCap]
     uint32_t* bval;
     uint32_t* count;            // [nb], zero on entry
@@ -527,18 +528,17 @@ struct SSParams {
     int32_t* perm_out;
 };
 
-__global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams p) {
+// the splitters, once per call (ONE CTA): today's keys of the rows that sat at nb - 1 evenly spaced ranks in the
+// previous order, put in exact order by a bitonic network in shared memory, written to p.spl for the partition CTAs
+// (each of them used to sort its own copy: fine for 1024 splitters, not for the 4096 that 4 M keys need)
+__global__ void __launch_bounds__(kSSThreads) ss_splitters_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char ssm[];
-    int nb2 = 16;  // the splitter array is sorted by a power-of-two network: pad with maximal keys
+    int nb2 = 16;  // power-of-two network: pad with maximal keys
     while (nb2 < p.nb) nb2 <<= 1;
-    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);          // [nb2] spl[j] = first key of bucket j (spl[0] = 0)
-    uint32_t* hist = reinterpret_cast<uint32_t*>(spl + nb2);   // [nb] tile counts, then tile bases
+    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);  // [nb2] spl[j] = first key of bucket j (spl[0] = 0)
     const int tid = threadIdx.x, nb = p.nb;
-    if (p.flag[1] > 0) {  // pausing after a recent overflow: straight to the LSD kernel
-        if (blockIdx.x == 0 && tid == 0) p.flag[0] = 1;
-        return;
-    }
+    if (p.flag[1] > 0) return;  // pausing after a recent overflow (the partition kernel raises the flag)
     for (int j = tid; j < nb2; j += kSSThreads) {
         uint64_t k = 0ull;
         if (j >= nb) {
@@ -550,11 +550,8 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
             k = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[row]);
         }
         spl[j] = k;
-        if (j < nb) hist[j] = 0u;
     }
     __syncthreads();
-    // the sampled rows kept their order almost everywhere: a bitonic network puts the splitters in exact order
-    // (every CTA sorts its own copy; nb2 <= 4096, warp-local stages for distances <= 32)
     {
         const int warp = tid >> 5, lane = tid & 31, npair = nb2 >> 1;
         auto cx = [&](int t, int j, int k) {
@@ -579,9 +576,27 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
             }
             __syncthreads();
         }
-        if (tid == 0) spl[0] = 0ull;  // bucket 0 starts at the smallest key (the 0 placed there sorted to the front)
-        __syncthreads();
     }
+    for (int j = tid; j < nb2; j += kSSThreads) p.spl[j] = j == 0 ? 0ull : spl[j];  // bucket 0 starts at the smallest key
+}
+
+__global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams p) {
+    rbl_pdl_wait();
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int nb2 = 16;
+    while (nb2 < p.nb) nb2 <<= 1;
+    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);          // [nb2] sorted splitters (ss_splitters_kernel)
+    uint32_t* hist = reinterpret_cast<uint32_t*>(spl + nb2);   // [nb] tile counts, then tile bases
+    const int tid = threadIdx.x, nb = p.nb;
+    if (p.flag[1] > 0) {  // pausing after a recent overflow: straight to the LSD kernel
+        if (blockIdx.x == 0 && tid == 0) p.flag[0] = 1;
+        return;
+    }
+    for (int j = tid; j < nb2; j += kSSThreads) {
+        spl[j] = p.spl[j];
+        if (j < nb) hist[j] = 0u;
+    }
+    __syncthreads();
     const int64_t base = (int64_t)blockIdx.x * (kSSThreads * kSSItems);
     uint64_t key[kSSItems];
     int bkt[kSSItems];
@@ -843,10 +858,11 @@ int rbl_sort_tiles(int64_t n) { return (int)((n + kTile - 1) / kTile); }
 int rbl_ss_buckets(int64_t n) {
     if (n < 65536) return 0;
     // mean load n / nb in (512, 1024]: >= 4x headroom to the 4096-slot cap for buckets that grow because the rank
-    // order moved.  Measured on B200 (us, LSD vs this): n = 100k 114 / 34, 1M 144 / 128, 2M 322 / 340, 4M 603 / 683 —
-    // above ~1M keys the LSD sort wins, so this route is for n <= 2^20.
+    // order moved.  Up to 4096 buckets (n <= 2^22): the splitters are sorted once per call by ss_splitters_kernel.
+    // (With at most 1024 buckets, each partition CTA sorting its own splitter copy, 2 M / 4 M keys meant buckets of
+    // 2 k / 4 k keys and the route lost to the LSD sort: 340 / 683 us vs 322 / 603 us.)
     int nb = 16;
-    while ((int64_t)nb * 1024 < n && nb < 1024) nb <<= 1;
+    while ((int64_t)nb * 1024 < n && nb < 4096) nb <<= 1;
     if ((int64_t)nb * 1024 < n) return 0;
     return nb;
 }
@@ -866,6 +882,7 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         q.n = n;
         q.prev_perm = prev_perm;
         q.nb = c->ss_nb;
+        q.spl = c->ss_spl;
         q.bkey = c->ss_bkey;
         q.bval = c->ss_bval;
         q.count = c->ss_count;
@@ -883,6 +900,8 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
             RBL_CUDA(cudaFuncSetAttribute(ss_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
+        RBL_CUDA(rbl_launch_pdl(ss_splitters_kernel, dim3(1), dim3(kSSThreads), (size_t)nb2 * sizeof(uint64_t), s, q));
+        RBL_LAUNCH_CHECK();
         RBL_CUDA(rbl_launch_pdl(ss_partition_kernel, dim3(tiles), dim3(kSSThreads), smem, s, q));
         RBL_LAUNCH_CHECK();
         RBL_PER_DEVICE(bool, battr, c);

@@ -29,6 +29,9 @@ def run(tag, arr, env):
     for k in env:
         del os.environ[k]
 run("pinned", Xp.numpy(), {})
+X2 = np.array(Xp.numpy())      # what bench.py times: a fresh pageable copy of the pinned array
+run("pageable copy of pinned, 8 thr", X2, {"RBL_UPLOAD_THREADS": "8"})
+del X2
 for th in ("4", "8", "16"):
     run(f"pageable, staging {th} threads", X, {"RBL_UPLOAD_THREADS": th})
 run("pageable, driver path", X, {"RBL_PAGEABLE_STAGING": "0"})

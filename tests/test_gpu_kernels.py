@@ -118,7 +118,7 @@ def test_splitter_sort_bit_exact_and_falls_back(E, n):
         np.testing.assert_array_equal(e.m_sorted.cpu().numpy(), m[ref] + 0.0)
         cabi.check(e.lib.rbl_sort_stats(e.h, e._stream(), st))
         assert st[3] == 0
-        assert (st[0] > 0) == (n <= (1 << 20))     # larger sorts always take the LSD route
+        assert (st[0] > 0) == (n <= (1 << 22))     # larger sorts always take the LSD route
         if route is not None and st[0] > 0:
             assert st[1] == route, (route, list(st))
 
