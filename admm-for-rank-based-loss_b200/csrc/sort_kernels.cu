@@ -503,7 +503,10 @@ __global__ void __launch_bounds__(kPT, 1) radix_sort_persistent_kernel(const PSo
 // its slice of the output at the prefix of the bucket counts.  No grid barrier and two launches instead of the
 // 16 barriers of the LSD sort.  If any bucket would overflow (first call, margins all equal, a jump in the data)
 // the partition raises a device flag: the bucket kernel exits and the gated LSD kernel runs instead.
-constexpr int kSSCap = 4096;       // slots per bucket
+constexpr int kSSCap = 4096;       // slots per bucket up to 2^20 keys
+constexpr int kSSCapBig = 8192;    // ... above (where the alternative, the LSD sort, costs 0.3-0.6 ms): the rank order
+                                   // of the AoRR / EHRM problems at 2-4 M keys keeps moving by 6-7 bucket loads
+static inline int ss_cap_for(int64_t n) { return n > ((int64_t)1 << 20) ? kSSCapBig : kSSCap; }
 constexpr int kSSThreads = 1024;
 constexpr int kSSItems = 4;        // keys per thread in the partition kernel
 #ifndef RBL_SB_THREADS
@@ -518,7 +521,8 @@ struct SSParams {
                                 // evenly spaced ranks then)
     int nb;                     // buckets (power of two, <= 4096)
     uint64_t* spl;              // [nb2] sorted splitters of this call
-    uint64_t* bkey;             // [nb][kSSCap]
+    int cap;                    // slots per bucket (kSSCap or kSSCapBig)
+    uint64_t* bkey;             // [nb][cap]
     uint32_t* bval;
     uint32_t* count;            // [nb], zero on entry
     int* flag;                  // [0] overflow flag, zero on entry; [1] calls left to pause after an overflow
@@ -626,8 +630,8 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
     for (int q = 0; q < kSSItems; ++q) {
         if (bkt[q] >= 0) {
             const uint32_t slot = hist[bkt[q]] + rnk[q];
-            if (slot < (uint32_t)kSSCap) {
-                const size_t at = (size_t)bkt[q] * kSSCap + slot;
+            if (slot < (uint32_t)p.cap) {
+                const size_t at = (size_t)bkt[q] * p.cap + slot;
                 p.bkey[at] = key[q];
                 p.bval[at] = (uint32_t)(base + q * kSSThreads + tid);
             } else {
@@ -640,8 +644,8 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
 __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char bsm[];
-    uint64_t* sk = reinterpret_cast<uint64_t*>(bsm);         // [kSSCap]
-    uint32_t* sv = reinterpret_cast<uint32_t*>(sk + kSSCap);  // [kSSCap]
+    uint64_t* sk = reinterpret_cast<uint64_t*>(bsm);         // [cap]
+    uint32_t* sv = reinterpret_cast<uint32_t*>(sk + p.cap);   // [cap]
     __shared__ uint32_t s_part[32];
     __shared__ uint32_t s_off;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.x, nb = p.nb;
@@ -677,8 +681,8 @@ __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p)
     const int N2 = Na + Nb;
     for (int i = tid; i < N2; i += kSBThreads) {
         const bool ok = i < (int)cnt;
-        sk[i] = ok ? p.bkey[(size_t)b * kSSCap + i] : 0xffffffffffffffffull;  // sentinels sort last
-        sv[i] = ok ? p.bval[(size_t)b * kSSCap + i] : 0xffffffffu;
+        sk[i] = ok ? p.bkey[(size_t)b * p.cap + i] : 0xffffffffffffffffull;  // sentinels sort last
+        sv[i] = ok ? p.bval[(size_t)b * p.cap + i] : 0xffffffffu;
     }
     __syncthreads();
     // bitonic network on (key, index): a total order, identical to the stable order of the keys.  Stages with
@@ -867,7 +871,7 @@ int rbl_ss_buckets(int64_t n) {
     return nb;
 }
 
-size_t rbl_ss_slots(int64_t n) { return (size_t)rbl_ss_buckets(n) * kSSCap; }
+size_t rbl_ss_slots(int64_t n) { return (size_t)rbl_ss_buckets(n) * ss_cap_for(n); }
 
 // sorted_out / perm_out may be null when only one of them is wanted (objective: keys only).
 // prev_perm (may be null): permutation of an earlier, similar call — enables the splitter sort with the LSD sort
@@ -882,6 +886,7 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         q.n = n;
         q.prev_perm = prev_perm;
         q.nb = c->ss_nb;
+        q.cap = ss_cap_for(n);
         q.spl = c->ss_spl;
         q.bkey = c->ss_bkey;
         q.bval = c->ss_bval;
@@ -906,10 +911,11 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         RBL_LAUNCH_CHECK();
         RBL_PER_DEVICE(bool, battr, c);
         if (!battr) {
-            RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSSCap * 12));
+            RBL_CUDA(cudaFuncSetAttribute(ss_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSSCapBig * 12));
             battr = true;
         }
-        RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSBThreads), kSSCap * 12, s, q));
+        RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSBThreads), (size_t)q.cap * 12, s, q));
         RBL_LAUNCH_CHECK();
         return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 1);  // runs only if the flag was raised
     }

@@ -8,15 +8,20 @@ from rbl_b200 import _cabi
 from src.optim.algorithms import ADMMmethod, Optimizer
 
 os.environ["RBL_GRAPH"] = sys.argv[1] if len(sys.argv) > 1 else "0"
-n, d = 1_000_000, 64
+cfg = sys.argv[2] if len(sys.argv) > 2 else "c2"
+n = int(sys.argv[3]) if len(sys.argv) > 3 else 1_000_000
+d = 64
 rng = np.random.default_rng(0)
 X = rng.standard_normal((n, d)); ws = np.zeros(d); ws[:10] = rng.normal(size=10)
 y = np.sign(X @ ws + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
-s = ADMMmethod(X, y, "superquantile", "binary_cross_entropy", l1_reg=0.01, args=[0.8], max_iter=100, tol=1e-9)
+kw = {"c2": dict(weight_function="superquantile", loss="binary_cross_entropy", l1_reg=0.01, args=[0.8]),
+      "c3": dict(weight_function="ehrm", loss="binary_cross_entropy", B=-5, l2_reg=0.01),
+      "c4": dict(weight_function="aorr", loss="hinge", args=[0.2, 0.8], l2_reg=1e-4)}[cfg]
+s = ADMMmethod(X, y, max_iter=100, tol=1e-9, **kw)
 e = s.engine
 st = (ctypes.c_int32 * 4)()
 with contextlib.redirect_stdout(io.StringIO()):
-    for i in range(40):
+    for i in range(60):
         Optimizer.main_loop(s, i, 0.0, False)
         _cabi.check(e.lib.rbl_sort_stats(e.h, e._stream(), st))
         if i < 15 or i % 5 == 0:
