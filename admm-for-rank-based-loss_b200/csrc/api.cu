@@ -296,6 +296,13 @@ int rbl_set_storage(rbl_handle_t h, int elem_bytes) {
     return rc;
 }
 
+int rbl_set_pass_grid(rbl_handle_t h, int grid) {
+    RBL_REQUIRE(h != nullptr, "null handle");
+    RBL_REQUIRE(grid >= 1, "grid must be positive");
+    h->pass_grid = grid > h->num_sms ? h->num_sms : grid;  // the partial buffers were sized for num_sms CTAs
+    return RBL_OK;
+}
+
 int rbl_destroy(rbl_handle_t h) {
     if (!h) return RBL_OK;
     cudaSetDevice(h->device);

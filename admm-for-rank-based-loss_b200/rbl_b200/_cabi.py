@@ -25,6 +25,7 @@ _SIGNATURES = {
                               _c.c_int64]),
     "rbl_destroy": (_c.c_int, [_c.c_void_p]),
     "rbl_set_storage": (_c.c_int, [_c.c_void_p, _c.c_int]),
+    "rbl_set_pass_grid": (_c.c_int, [_c.c_void_p, _c.c_int]),
     "rbl_info": (_c.c_int, [_c.c_void_p, _c.POINTER(_c.c_int64)]),
     "rbl_build_design": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _dp, _dp, _c.c_void_p]),
     "rbl_build_design_rows": (_c.c_int, [_c.c_void_p, _dp, _c.c_int64, _dp, _dp, _c.c_int64, _c.c_void_p]),

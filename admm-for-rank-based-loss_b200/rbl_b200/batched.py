@@ -156,8 +156,15 @@ class BatchedADMM:
         # the big per-slot matrices of the stream formulation are not needed
         self.Z = self.LAM = self.DW = self.Bv = self.R = None
         self.inst = []
+        # RBL_BATCH_PASS_GRID: persistent CTAs of every instance's D-reading kernels (default: one per SM).  Giving
+        # each instance a quarter of the SMs so that gathers overlap other instances' latency-bound kernels was
+        # measured and does not help (32 instances x 100k x 1000: 7.99 ms per batched step at 148 CTAs, 8.15 at 37,
+        # 9.0 at 24 / 16): the per-instance graphs do not overlap for another reason
+        share = int(os.environ.get("RBL_BATCH_PASS_GRID", "0")) or int(e.info["num_sms"])
+        self.pass_grid_per_instance = share
         for j in range(self.B):
             c = AdmmEngine.child(e)
+            _cabi.check(c.lib.rbl_set_pass_grid(c.h, share))
             reg = float(self.regs[j])
             lam0 = 0.1 * reg / n
             w_init = (np.asarray(w0s)[self.i_lo + j] if w0s is not None else np.full(d, 0.001 * reg / d / n))

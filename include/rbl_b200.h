@@ -54,6 +54,11 @@ int rbl_create(rbl_handle_t* out, int device, int64_t n_local, int64_t n_global,
                int64_t ld);
 int rbl_destroy(rbl_handle_t h);
 
+/* Persistent CTAs of the D-reading kernels of this handle (default and maximum: one per SM).  Batched mode gives every
+ * instance a fraction of the machine so that one instance's HBM-bound gather overlaps the latency-bound sort / PAV /
+ * FISTA kernels of the others.  Changes the number of per-CTA partials, i.e. the summation order (rounding only). */
+int rbl_set_pass_grid(rbl_handle_t h, int grid);
+
 /* OPTIONAL fp32 storage of the design matrix (north_star: "1e-5 in an optional fp32 mode"; the reference ships a
  * float32 FISTA, algorithms.py:199-201, fast_lasso.py:22-26).  elem_bytes = 4: every `D` / `Dt` / `D_rows` pointer
  * passed to this handle afterwards points to FLOAT rows (leading dimension a multiple of 4 elements = 16 bytes);
