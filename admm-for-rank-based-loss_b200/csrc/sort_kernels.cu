@@ -860,7 +860,9 @@ int rbl_sort_tiles(int64_t n) { return (int)((n + kTile - 1) / kTile); }
 
 // buckets of the splitter sort for n keys (0: n too small to bother)
 int rbl_ss_buckets(int64_t n) {
-    if (n < 65536) return 0;
+    // (a one-CTA shared-memory network over all n <= 8192 keys was tried for the reference's own 6000-row problem:
+    // 114 us, shared-memory-throughput bound on a single SM — no better than the LSD kernel; 16 buckets are)
+    if (n < 2048) return 0;
     // mean load n / nb in (512, 1024]: >= 4x headroom to the 4096-slot cap for buckets that grow because the rank
     // order moved.  Up to 4096 buckets (n <= 2^22): the splitters are sorted once per call by ss_splitters_kernel.
     // (With at most 1024 buckets, each partition CTA sorting its own splitter copy, 2 M / 4 M keys meant buckets of
