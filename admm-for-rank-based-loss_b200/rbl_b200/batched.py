@@ -97,10 +97,19 @@ class BatchedADMM:
         wf = _sp.get_weights(weight_function, args)
         sig_a, sig_b = (wf[0](self.n), wf[1](self.n)) if isinstance(wf, tuple) else (wf(self.n), None)
         self.sigma_a = sig_a
-        sigma_prox = sig_b if weight_function == "ehrm" else sig_a
         self.loss = loss
-        self.eng = AdmmEngine(X, y, loss, sigma_prox, clip=B_clip if weight_function == "ehrm" else None,
-                              device=device)
+        if weight_function == "ehrm":
+            # the reference's per-z-step choice between its two clipped candidates (PAV_cpt.py:203-226) needs the host
+            # between the sort and the prox of every instance: served by the per-instance engines of the gram mode
+            # (their iterations then run eagerly, not as replayed graphs); the multi-RHS stream mode has no such hook
+            if B_clip is None:
+                raise TypeError("weight_function 'ehrm' needs B_clip (PAV_cpt.py:207 compares the prox with it)")
+            if (mode or os.environ.get("RBL_BATCH_MODE", "auto")).lower() == "stream":
+                raise ValueError("batched EHRM runs in mode='gram' (the candidate choice is made per instance)")
+            mode = "gram"
+            self.eng = AdmmEngine(X, y, loss, None, ehrm=(sig_a, sig_b, float(B_clip)), device=device)
+        else:
+            self.eng = AdmmEngine(X, y, loss, sig_a, device=device)
         e = self.eng
         self.tol, self.max_iter = tol, max_iter
         self.rho0 = 1e-4 if weight_function == "ehrm" else (2e-7 if weight_function in ("aorr", "aorr_dc") else 1e-5)

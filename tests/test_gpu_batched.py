@@ -123,3 +123,34 @@ def test_batched_admm_ragged_convergence(mode):
         assert _rel(W[:, j], wo) < 1e-4, (j, _rel(W[:, j], wo))
         assert abs(b.objective(j) - o.objective()) < 1e-7 * abs(o.objective())
     b.close()
+
+
+@pytest.mark.parametrize("B_clip", [-5.0, 0.5])
+def test_batched_ehrm_makes_the_candidate_choice_per_instance(golden_dir, B_clip):
+    """EHRM in batched mode: every instance makes the reference's choice between min(B, prox_a) and max(B, prox_b)
+    (PAV_cpt.py:203-226) at each of its z-steps — B = -5: candidate 2, B = 0.5: candidate 1 — in lockstep with
+    per-instance oracles at 1e-9; the multi-RHS stream mode refuses EHRM."""
+    from rbl_b200.batched import BatchedADMM
+
+    d2 = np.load(os.path.join(golden_dir, "data_600x64.npz"))
+    X, y = d2["X"], d2["y"]
+    regs = [0.05, 0.01, 0.002]
+    b = BatchedADMM(X, y, "ehrm", "binary_cross_entropy", l1_regs=regs, B_clip=B_clip, max_iter=15, tol=1e-7)
+    assert b.mode == "gram"
+    orc = [O.OracleADMM(X, y, "ehrm", "binary_cross_entropy", l1_reg=r, B=B_clip, max_iter=15, tol=1e-7,
+                        small_lasso=False) for r in regs]
+    for it in range(15):
+        for j, o in enumerate(orc):
+            w, z, lam, rho = b.state(j)
+            o.w, o.z, o.lam, o.rho = w.copy(), z.copy(), lam.copy(), rho
+        b.step()
+        for j, o in enumerate(orc):
+            o.step()
+            w, z, lam, rho = b.state(j)
+            assert _rel(z, o.z) < 1e-9, (it, j, _rel(z, o.z))
+            assert _rel(w, o.w) < 1e-9 or np.linalg.norm(w - o.w) < 1e-9, (it, j, _rel(w, o.w))
+    picked = [c.ehrm_stats for c in b.inst]
+    assert all((s["cand1"] > 0) == (B_clip > -1) for s in picked), picked
+    b.close()
+    with pytest.raises(ValueError):
+        BatchedADMM(X, y, "ehrm", "binary_cross_entropy", l1_regs=regs, B_clip=B_clip, mode="stream")
