@@ -345,7 +345,7 @@ __device__ __forceinline__ void block_sum_vec(double (&v)[KC], double* sh) {
 template <int KC>
 __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(const GramPersist p) {
     extern __shared__ __align__(16) double psm[];
-    __shared__ double sh[(KC + 1) * kGWarps];
+    __shared__ double sh[KC * kGWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nt = kGThreads;
     const int d = p.d;
     const int64_t ld = p.ldg;
@@ -464,31 +464,14 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         grid_barrier(p.bar, target);
         stamp();
         // ---- line search, identical in every CTA: first i with NOT (Delta_i.G Delta_i > L_i ||Delta_i||^2)
-        // ... and, in the same pass and the same block reduction, the stop criterion of candidate 0 — the one that
-        // is accepted in almost every sweep once L has adapted: ||beta_0 - beta_prev||^2 with beta_0 recomputed by
-        // the very expression of the trial point (bit-identical to the accepted-candidate pass below, which then
-        // only runs when another candidate wins).  BETA receives beta_0 speculatively; it is only read after an
-        // acceptance, and a different winner overwrites it first.
-        double lhs[KC + 1];
+        double lhs[KC];
 #pragma unroll
-        for (int q = 0; q <= KC; ++q) lhs[q] = 0.0;
-        {
-            const double Ld0 = Ld[0], thr0 = thr[0];
-            for (int c = tid; c < d; c += nt) {
+        for (int q = 0; q < KC; ++q) lhs[q] = 0.0;
+        for (int c = tid; c < d; c += nt) {
 #pragma unroll
-                for (int q = 0; q < KC; ++q)
-                    lhs[q] = fma(DEL[(size_t)q * ld + c], __ldcg(&vu[(size_t)q * ld + c]), lhs[q]);
-                const double bp = BETA_P[c], g = G_P[c];
-                const double bs = bp + g / Ld0;
-                const double mag = fmax(fabs(bs) - thr0, 0.0);
-                const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
-                const double bn = mag * sgn;
-                BETA[c] = bn;
-                const double df = bn - BETA_PREV[c];
-                lhs[KC] = fma(df, df, lhs[KC]);
-            }
+            for (int q = 0; q < KC; ++q) lhs[q] = fma(DEL[(size_t)q * ld + c], __ldcg(&vu[(size_t)q * ld + c]), lhs[q]);
         }
-        block_sum_vec<KC + 1>(lhs, sh);
+        block_sum_vec<KC>(lhs, sh);
         stamp();
         int acc_q = -1;
 #pragma unroll
@@ -511,21 +494,18 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
         L_prev = L_acc;                                              // :58
         const double tnext = (1.0 + sqrt(1.0 + 4.0 * t * t)) / 2.0;  // :59
         t1 = (t - 1.0) / tnext;                                      // :61
-        double a2[1] = {lhs[KC]};
-        if (acc_q != 0) {  // (block-uniform) another candidate won: its iterate and stop criterion
-            a2[0] = 0.0;
-            for (int c = tid; c < d; c += nt) {
-                const double bp = BETA_P[c], g = G_P[c];
-                const double bs = bp + g / Lda;  // the accepted trial point, same expression as above
-                const double mag = fmax(fabs(bs) - thra, 0.0);
-                const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
-                const double bn = mag * sgn;
-                BETA[c] = bn;
-                const double df = bn - BETA_PREV[c];  // :60
-                a2[0] = fma(df, df, a2[0]);
-            }
-            block_sum_vec<1>(a2, sh);
+        double a2[1] = {0.0};
+        for (int c = tid; c < d; c += nt) {
+            const double bp = BETA_P[c], g = G_P[c];
+            const double bs = bp + g / Lda;  // the accepted trial point, same expression as above
+            const double mag = fmax(fabs(bs) - thra, 0.0);
+            const double sgn = (bs > 0.0) ? 1.0 : ((bs < 0.0) ? -1.0 : 0.0);
+            const double bn = mag * sgn;
+            BETA[c] = bn;
+            const double df = bn - BETA_PREV[c];  // :60
+            a2[0] = fma(df, df, a2[0]);
         }
+        block_sum_vec<1>(a2, sh);
         crit = sqrt(a2[0]);  // :63
         ++k;
         if (crit < p.tol || k >= p.max_iter) break;
