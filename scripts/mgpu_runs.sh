@@ -13,8 +13,6 @@ run() {  # nproc port out args...
 }
 run 8 29601 n8_c2 --steps 20 --warmup 5
 run 8 29602 n8_c3 --config c3 --steps 20 --warmup 5 --no-cpu
-run 4 29603 n4_c3 --config c3 --steps 20 --warmup 5 --no-cpu
 run 2 29604 n2_c3 --config c3 --steps 20 --warmup 5 --no-cpu
 run 8 29605 n8_c5 --config c5 --steps 20 --warmup 5 --no-cpu
 run 8 29606 n8_c4 --config c4 --steps 20 --warmup 5 --no-cpu
-run 8 29607 n8_c2_fp32 --steps 20 --warmup 5 --storage fp32 --no-pageable
