@@ -94,7 +94,7 @@ def test_sort_bit_exact_vs_stable_argsort(E, n):
     e.close()
 
 
-@pytest.mark.parametrize("n", [70001, 1 << 20, 3_000_017])
+@pytest.mark.parametrize("n", [3000, 70001, 1 << 20, 3_000_017, 1 << 22, (1 << 22) + 5])
 def test_splitter_sort_bit_exact_and_falls_back(E, n):
     """rbl_sort_margins_near: buckets from the previous rank order + per-bucket shared-memory sort must give the
     same bit-exact stable permutation as the LSD sort — with a good hint (same data, moved / shifted / scaled data),
@@ -131,8 +131,9 @@ def test_splitter_sort_bit_exact_and_falls_back(E, n):
     sort_near(base + 1e-2 * rng.normal(size=n), hint)                  # moved a lot: either route, same answer
     sort_near(np.round(base, 2), hint)                                 # ~600 distinct values: long runs of ties
     sort_near(base, np.arange(n))                                      # useless hint (identity)
-    sort_near(base, np.zeros(n, dtype=np.int32), 2)                    # degenerate hint (all row 0) -> LSD
-    sort_near(np.full(n, 0.25), hint, 2)                               # all keys equal -> LSD
+    overflow = 2 if n > 8192 else None                                 # (a few thousand keys fit in ONE bucket)
+    sort_near(base, np.zeros(n, dtype=np.int32), overflow)             # degenerate hint (all row 0) -> LSD
+    sort_near(np.full(n, 0.25), hint, overflow)                        # all keys equal -> LSD
     for _ in range(5):                                                 # after an overflow the bucket route pauses
         sort_near(base, hint)                                          # for 4 calls (still exact, via LSD) ...
     sort_near(base, hint, 1)                                           # ... and then works again
