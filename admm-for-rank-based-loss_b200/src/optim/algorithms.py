@@ -28,19 +28,31 @@ from src.optim.objective import rankbasedObjective
 
 class Optimizer:
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy", l2_reg=None, l1_reg=None,
-                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None, _storage=None):
+                 B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4, _shard=None, _storage=None,
+                 _share=None):
+        # _share (extension): another solver (or its engine) built on the SAME X, y — this one then borrows its
+        # device-resident D, G = D^T D and D^T (no second upload, no second SYRK) and only owns its state, spectrum
+        # and scratch: the ratio / spectrum / regulariser sweeps of run_AoRR_ratio.py:32-46 and run_SRM.py on one
+        # design matrix.  X and y may be None then.  The first solver must outlive the ones sharing with it.
         # _shard (extension, not in the reference): dict(row_lo=, n_global=[, group=]) when X, y are this
         # rank's contiguous rows of a row-sharded problem (one process per GPU, torch.distributed/NCCL)
         # _storage (extension): "fp32" keeps D in float32 in HBM (optional mode: half the bytes per pass, fp64
         # arithmetic throughout; iterates within ~1e-6 of the fp64 run) — default "fp64" (env RBL_STORAGE)
         _t0 = time.perf_counter()
-        if not torch.is_tensor(X):  # a (device) tensor is taken as it is: no copy back to the host
-            X = np.asarray(X)
-        y = y.detach().cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
         _shard = dict(_shard or {})
+        if _share is not None:
+            parent = getattr(_share, "engine", _share)
+            X, y = _ShapeOnly((parent.n_local, parent.d)), None
+            _shard = {"_share": parent}
+            if parent.world > 1:
+                _shard["n_global_hint"] = parent.n_global
+        elif not torch.is_tensor(X):  # a (device) tensor is taken as it is: no copy back to the host
+            X = np.asarray(X)
+        if _share is None:
+            y = y.detach().cpu().numpy() if torch.is_tensor(y) else np.asarray(y)
         if _storage is not None:
             _shard["storage"] = _storage
-        self.num_row = int(_shard.get("n_global", X.shape[0]))
+        self.num_row = int(_shard.pop("n_global_hint", _shard.get("n_global", X.shape[0])))
         self.num_feature = X.shape[1]
         # regularization (:30) — raises TypeError below when both are None, like the reference (:32)
         self.reg = l1_reg or l2_reg
@@ -81,12 +93,13 @@ class Optimizer:
 
         # EHRM (PAV_cpt.py:203-293): every z-step compares the reference's two scalar sums on the device and runs
         # the winner, min(B, isotonic prox with sigma = alphas) or max(B, isotonic prox with sigma = betas)
+        eX, ey = (None, None) if _share is not None else (X, y)
         if weight_function == 'ehrm':
             if B is None:
                 raise TypeError("weight_function 'ehrm' needs B (PAV_cpt.py:207 compares the prox with it)")
-            self.engine = AdmmEngine(X, y, loss, None, ehrm=(self.sigma_a, self.sigma_b, float(B)), **_shard)
+            self.engine = AdmmEngine(eX, ey, loss, None, ehrm=(self.sigma_a, self.sigma_b, float(B)), **_shard)
         else:
-            self.engine = AdmmEngine(X, y, loss, self.sigma_a, **_shard)
+            self.engine = AdmmEngine(eX, ey, loss, self.sigma_a, **_shard)
         self.objective._attach(self.engine)
         nl = self.engine.n_local
         self.engine.set_state(w=w_init, z=np.full(nl, lam0), lam=np.full(nl, lam0))
@@ -280,12 +293,19 @@ class _Deferred:
         return None
 
 
+class _ShapeOnly:
+    """stands in for X when the design matrix is borrowed from another solver (_share)"""
+
+    def __init__(self, shape):
+        self.shape = shape
+
+
 class ADMMmethod(Optimizer):
     def __init__(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                  l2_reg=None, l1_reg=None, B=None, n_class=None, args=None, w0=None, max_iter=200, tol=1e-4,
-                 _shard=None, _storage=None):
+                 _shard=None, _storage=None, _share=None):
         super(ADMMmethod, self).__init__(X, y, weight_function, loss, l2_reg, l1_reg, B, n_class,
-                                         args, w0, max_iter, tol, _shard, _storage)
+                                         args, w0, max_iter, tol, _shard, _storage, _share)
 
     def start_store(self, X, y, weight_function="erm", loss="binary_cross_entropy",
                     B=None, l2_reg=None, l1_reg=None, n_class=None, args=None):

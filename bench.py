@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--loss", default=None, help="c4: hinge (default, run_AoRR_ratio.py) or binary_cross_entropy")
     ap.add_argument("--instances-per-gpu", type=int, default=32, help="c5")
     ap.add_argument("--batch-mode", default=None, help="c5: gram | stream (default: auto)")
+    ap.add_argument("--share-design", action="store_true",
+                    help="c4: the solves of the sweep share one device-resident D / G (ADMMmethod(_share=first))")
     ap.add_argument("--no-solve", action="store_true", help="skip the run-to-tolerance tail")
     ap.add_argument("--no-pageable", action="store_true", help="skip the pageable-input e2e variant")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / parity leg (development runs)")

@@ -114,12 +114,17 @@ def run(args, B):
     roofline = None
     if rank == 0:
         sampler.start()
+    share = bool(getattr(args, "share_design", False)) and world == 1 and len(cfg["sweeps"]) > 1
+    first = None
     for sweep_args in cfg["sweeps"]:
         barrier()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
         ev[0].record()
         with quiet:
-            s = make(sweep_args, X, y, _shard=shard)
+            if share and first is not None:   # --share-design: solves 2.. borrow the first solver's D, G and D^T
+                s = make(sweep_args, None, None, _share=first)
+            else:
+                s = make(sweep_args, X, y, _shard=shard)
         ev[1].record()
         with quiet:
             it, done = s.advance(0, W)
@@ -196,9 +201,15 @@ def run(args, B):
                                    else "streams from HBM every pass"),
                         "zstep": {"ms": 1e3 * t_z, "keys_per_s": n / t_z, "algorithmic_bytes": 68 * n,
                                   "frac_of_hbm_peak": 68 * n / t_z / 1e9 / peak}}
+        if share and first is None:
+            first = s
+            continue
         s.engine.close()
         del s
-        torch.cuda.empty_cache()
+        if not share:
+            torch.cuda.empty_cache()
+    if first is not None:
+        first.engine.close()
     clocks = sampler.stop() if rank == 0 else None
     if rank != 0:
         if world > 1:
@@ -279,7 +290,10 @@ def run(args, B):
                                      if (hi - lo) * d_eff * 8 < 126e6 else "far larger than the 126 MB L2"),
                       "solves": sweeps_out},
            "e2e": {"value": tot_iters / tot_e2e_s, "unit": UNIT,
-                   "h2d_bytes_per_step": len(cfg["sweeps"]) * (X.size + y.size) * 8 / max(tot_iters, 1),
+                   "h2d_bytes_per_step": (1 if share else len(cfg["sweeps"])) * (X.size + y.size) * 8 / max(tot_iters, 1),
+                   "design_matrix": ("uploaded once, shared by the solves of the sweep (ADMMmethod(_share=first))"
+                                     if share else "uploaded by every solve (one ADMMmethod(X, y, ...) per solve, "
+                                                   "like the reference's drivers)"),
                    "d2h_bytes_per_step": (d_eff + 16) * 8,
                    "note": "ADMMmethod(X, y, ...) on host numpy arrays (upload, D = -y*X, G = D^T D) + the loop to the "
                            "stop test or the iteration cap, w and the residuals read back every iteration; all "

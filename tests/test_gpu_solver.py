@@ -645,3 +645,59 @@ def test_config1_lockstep_with_oracle(golden_dir, w_mode):
         assert _rel(s.w, o.w) < 1e-9 and _rel(s.z, o.z) < 1e-9, (i + 1, _rel(s.w, o.w), _rel(s.z, o.z))
         assert float(s.rho) == float(o.rho)
     s.engine.close()
+
+
+@pytest.mark.parametrize("kind", ["aorr_ratio_l2", "srm_spectra_l1", "ehrm_B_l2"])
+def test_sweep_over_a_shared_design_matrix(w_mode, kind):
+    """ADMMmethod(_share=first): the sweeps of run_AoRR_ratio.py:32-46 (four (k, m) ratios, hinge, l2), of the SRM
+    drivers (spectra x l1) and an EHRM B grid, all over ONE device-resident D, G = D^T D and D^T.  Every shared
+    solver must give, bit for bit, what a solver built from (X, y) on its own gives, hold the same D / G storage as
+    the first, and track the oracle; the solvers are advanced interleaved to show they do not share state."""
+    from src.optim.algorithms import ADMMmethod
+
+    if w_mode != "gram":
+        pytest.skip("sharing G is a Gram-mode feature")
+    rng = np.random.default_rng(7)
+    n, d = 2600, 61
+    X = rng.normal(size=(n, d))
+    ws = np.zeros(d)
+    ws[:6] = rng.normal(size=6)
+    y = np.sign(X @ ws + 0.2 * rng.normal(size=n)).reshape(-1, 1)
+    if kind == "aorr_ratio_l2":
+        X = np.hstack([X, np.ones((n, 1))])  # the driver's intercept column (run_AoRR_ratio.py:26)
+        cfgs = [dict(weight_function="aorr", loss="hinge", args=a, l2_reg=1e-4)
+                for a in ([0.1, 0.9], [0.2, 0.8], [0.3, 0.7], [0.05, 0.6])]
+    elif kind == "srm_spectra_l1":
+        cfgs = [dict(weight_function="superquantile", loss="binary_cross_entropy", args=[0.8], l1_reg=0.01),
+                dict(weight_function="extremile", loss="binary_cross_entropy", args=[2.5], l1_reg=0.003),
+                dict(weight_function="esrm", loss="hinge", args=[2.0], l1_reg=0.02),
+                dict(weight_function="erm", loss="binary_cross_entropy", l2_reg=1e-3)]
+    else:
+        cfgs = [dict(weight_function="ehrm", loss="binary_cross_entropy", B=b, l2_reg=0.01) for b in (-5, -1, 0.5)]
+    iters = 24
+    first = ADMMmethod(X, y, max_iter=iters, tol=1e-12, **cfgs[0])
+    shared = [first] + [ADMMmethod(None, None, max_iter=iters, tol=1e-12, _share=first, **c) for c in cfgs[1:]]
+    for s in shared[1:]:
+        assert s.engine.D.data_ptr() == first.engine.D.data_ptr()
+        assert s.engine.gram().data_ptr() == first.engine.gram().data_ptr()
+        assert s.num_row == n and s.num_feature == X.shape[1]
+    with contextlib.redirect_stdout(io.StringIO()):
+        for lo in range(0, iters, 8):           # interleaved: 8 iterations of each solver in turn
+            for s in shared:
+                s.advance(lo, 8)
+    for c, s in zip(cfgs, shared):
+        own = ADMMmethod(X, y, max_iter=iters, tol=1e-12, **c)
+        with contextlib.redirect_stdout(io.StringIO()):
+            for lo in range(0, iters, 8):
+                own.advance(lo, 8)
+        np.testing.assert_array_equal(s.w, own.w)
+        np.testing.assert_array_equal(s.z, own.z)
+        np.testing.assert_array_equal(s.lagrangian, own.lagrangian)
+        assert float(s.rho) == float(own.rho)
+        o = O.OracleADMM(X, y, max_iter=iters, tol=1e-12, **c)
+        for _ in range(iters):
+            o.step()
+        assert _rel(s.w, o.w) < 1e-7 and _rel(s.z, o.z) < 1e-7, (c, _rel(s.w, o.w), _rel(s.z, o.z))
+        own.engine.close()
+    for s in reversed(shared):
+        s.engine.close()
