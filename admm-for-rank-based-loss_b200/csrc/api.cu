@@ -395,6 +395,7 @@ int rbl_sort_config(rbl_handle_t h, int legacy) {
     RBL_REQUIRE(h != nullptr, "null handle");
     h->sort_legacy = (legacy & 1) ? 1 : 0;
     h->ss_off = (legacy & 2) ? 1 : 0;
+    h->ss_row_order = (legacy & 4) ? 1 : 0;
     return RBL_OK;
 }
 

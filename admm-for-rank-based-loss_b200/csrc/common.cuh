@@ -146,7 +146,9 @@ struct rbl_ctx {
     uint32_t* sort_counts;  // [num_sms][256] per-CTA digit counts of the persistent sort
     int psort_checked, psort_ok, sort_legacy;
     // splitter sort (sort_kernels.cu): bucket slots, counts, overflow flag; ss_nb = 0: not used for this n
-    int ss_nb, ss_off;
+    int ss_nb, ss_off, ss_row_order;
+    const int32_t* last_perm;  // the permutation buffer the last sort on this handle wrote (and its length):
+    int64_t last_perm_n;       // a hint equal to it is known to be a permutation (rank-order partition)
     uint64_t *ss_bkey, *ss_spl;
     uint32_t *ss_bval, *ss_count;
     int* ss_flag;

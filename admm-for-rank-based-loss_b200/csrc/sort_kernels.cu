@@ -641,6 +641,170 @@ __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams
     }
 }
 
+// The partition when the hint is known to be a permutation (the handle's own last output): walk the keys in the
+// PREVIOUS rank order.  The row that sat at rank i then is expected in bucket i * nb / n now — two loads of the
+// splitter table verify it (a gallop + bisection from there when the row has moved further), so the 10..12-step
+// search through a shared-memory table (4.8 M of its 7.1 M wavefronts were bank conflicts) is gone; a warp's 32
+// consecutive ranks fall into one or two buckets, so slots are reserved with one global atomic per (warp, bucket)
+// (no per-CTA histogram, no nb atomics per CTA) and the (key, row) stores of a warp are contiguous in the bucket.
+__global__ void __launch_bounds__(kSSThreads) ss_partition_ranked_kernel(const SSParams p) {
+    rbl_pdl_wait();
+    const int tid = threadIdx.x, lane = tid & 31, nb = p.nb;
+    if (p.flag[1] > 0) {  // pausing after a recent overflow: straight to the LSD kernel
+        if (blockIdx.x == 0 && tid == 0) p.flag[0] = 1;
+        return;
+    }
+    const uint64_t* __restrict__ spl = p.spl;
+    const int64_t base = (int64_t)blockIdx.x * (kSSThreads * kSSItems);
+    uint64_t key[kSSItems];
+    int64_t row[kSSItems];
+    int bkt[kSSItems];
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q) {
+        const int64_t i = base + q * kSSThreads + tid;
+        row[q] = -1;
+        if (i < p.n) {
+            int64_t r = p.prev_perm[i];
+            row[q] = r < 0 ? 0 : (r >= p.n ? p.n - 1 : r);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q)
+        if (row[q] >= 0) key[q] = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[row[q]]);
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q) {
+        bkt[q] = -1;
+        if (row[q] < 0) continue;
+        const int64_t i = base + q * kSSThreads + tid;
+        // rank i lay between the ranks floor(j n / nb) the splitters were taken from: j = the largest with that <= i
+        int g = (int)(((i + 1) * nb - 1) / p.n);  // i < 2^22, nb <= 2^12
+        g = g < 0 ? 0 : (g >= nb ? nb - 1 : g);
+        const uint64_t k = key[q];
+        int lo, hi;  // largest j with spl[j] <= k lies in [lo, hi)
+        if (spl[g] <= k) {
+            lo = g;
+            hi = g + 1;
+            for (int step = 1; hi < nb && spl[hi] <= k; step <<= 1) {
+                lo = hi;
+                hi = lo + step > nb ? nb : lo + step;
+            }
+        } else {  // spl[0] = 0 <= every key
+            hi = g;
+            lo = g - 1;
+            for (int step = 1; lo > 0 && spl[lo] > k; step <<= 1) {
+                hi = lo;
+                lo = hi - step < 0 ? 0 : hi - step;
+            }
+        }
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (spl[mid] <= k) lo = mid; else hi = mid;
+        }
+        bkt[q] = lo;
+    }
+#pragma unroll
+    for (int q = 0; q < kSSItems; ++q) {
+        const unsigned live = __ballot_sync(0xffffffffu, bkt[q] >= 0);
+        if (bkt[q] < 0) continue;
+        const unsigned peers = __match_any_sync(live, bkt[q]);
+        const int leader = __ffs(peers) - 1;
+        uint32_t slot0 = 0;
+        if (lane == leader) slot0 = atomicAdd(&p.count[bkt[q]], (uint32_t)__popc(peers));
+        slot0 = __shfl_sync(peers, slot0, leader);
+        const uint32_t slot = slot0 + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (slot < (uint32_t)p.cap) {
+            const size_t at = (size_t)bkt[q] * p.cap + slot;
+            p.bkey[at] = key[q];
+            p.bval[at] = (uint32_t)row[q];
+        } else {
+            *p.flag = 1;  // overflow: the LSD sort takes this call
+        }
+    }
+}
+
+// bitonic network of the bucket kernel over sk / sv [N2 = Na + Nb] in shared memory (see ss_bucket_kernel for the
+// A / B split).  kFull: compare (key, index) pairs — a total order, identical to the stable order of the keys;
+// otherwise the keys alone (enough when no two keys of the bucket are equal).
+template <bool kFull>
+__device__ __forceinline__ void ss_bucket_network(uint64_t* __restrict__ sk, uint32_t* __restrict__ sv, const int N2,
+                                                  const int Na, const int Nb) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // bitonic network on (key, index): a total order, identical to the stable order of the keys.  Stages with
+    // distance j > 32 run in shared memory across the block.  The stages with j <= 32 of every phase k stay inside
+    // blocks of 64 consecutive elements: a warp takes such a block into registers (2 elements per lane: x and
+    // x + 32), runs them with shuffles, and writes the block back once — one shared-memory round trip per phase
+    // instead of one per stage (the all-shared-memory version moved 72 x 24 B per key and was bound by it).
+    auto cmpx = [&](int t, int j, int k) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+        const int l = i | j;
+        const bool up = ((i & k) == 0);
+        const uint64_t ka = sk[i], kb = sk[l];
+        const uint32_t va = sv[i], vb = sv[l];
+        const bool gt = kFull ? ((ka > kb) || (ka == kb && va > vb)) : (ka > kb);
+        if (gt == up) {
+            sk[i] = kb; sk[l] = ka;
+            sv[i] = vb; sv[l] = va;
+        }
+    };
+    // register stages of phase k from distance j0 (<= 32) down to 1 on the 64 keys a warp holds
+    auto warp_stages = [&](int g0, int g1, int k, int j0, uint64_t& k0, uint64_t& k1, uint32_t& v0, uint32_t& v1) {
+        const bool upa = ((g0 & k) == 0), upb = ((g1 & k) == 0);
+        int jj = j0;
+        if (jj == 32) {  // partner of x is x + 32: both in this lane (k >= 64: one direction for the pair)
+            const bool gt = kFull ? ((k0 > k1) || (k0 == k1 && v0 > v1)) : (k0 > k1);
+            if (gt == upa) {
+                const uint64_t tk = k0; k0 = k1; k1 = tk;
+                const uint32_t tv = v0; v0 = v1; v1 = tv;
+            }
+            jj = 16;
+        }
+        for (; jj > 0; jj >>= 1) {
+            // element g (g0 or g1): direction from bit k of g, lower of its pair iff bit jj of g is clear
+            const uint64_t ok0 = __shfl_xor_sync(0xffffffffu, k0, jj), ok1 = __shfl_xor_sync(0xffffffffu, k1, jj);
+            const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
+            const bool lower = (lane & jj) == 0;
+            {
+                const bool mine_gt = kFull ? ((k0 > ok0) || (k0 == ok0 && v0 > ov0)) : (k0 > ok0);
+                const bool keep_min = (lower == upa);
+                if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
+            }
+            {
+                const bool mine_gt = kFull ? ((k1 > ok1) || (k1 == ok1 && v1 > ov1)) : (k1 > ok1);
+                const bool keep_min = (lower == upb);
+                if (mine_gt == keep_min) { k1 = ok1; v1 = ov1; }
+            }
+        }
+    };
+    // phases k = 2 .. 64 never leave a block of 64 keys: one load, 21 stages in registers, one store
+    for (int blk = warp; blk < (N2 >> 6); blk += kSBThreads / 32) {
+        const int g0 = (blk << 6) + lane, g1 = g0 + 32;
+        uint64_t k0 = sk[g0], k1 = sk[g1];
+        uint32_t v0 = sv[g0], v1 = sv[g1];
+#pragma unroll
+        for (int k = 2; k <= 64; k <<= 1) warp_stages(g0, g1, k, k >> 1, k0, k1, v0, v1);
+        sk[g0] = k0; sk[g1] = k1;
+        sv[g0] = v0; sv[g1] = v1;
+    }
+    __syncthreads();
+    for (int k = 128; k <= Na; k <<= 1) {
+        // B starts at a multiple of 2 Nb, so (i & k) gives it the same directions as a network of its own
+        const int lim = (k <= Nb) ? N2 : Na, npair = lim >> 1;
+        for (int j = k >> 1; j > 32; j >>= 1) {  // pairs span warps: block-wide stages
+            for (int t = tid; t < npair; t += kSBThreads) cmpx(t, j, k);
+            __syncthreads();
+        }
+        for (int blk = warp; blk < (lim >> 6); blk += kSBThreads / 32) {
+            const int g0 = (blk << 6) + lane, g1 = g0 + 32;
+            uint64_t k0 = sk[g0], k1 = sk[g1];
+            uint32_t v0 = sv[g0], v1 = sv[g1];
+            warp_stages(g0, g1, k, 32, k0, k1, v0, v1);
+            sk[g0] = k0; sk[g1] = k1;
+            sv[g0] = v0; sv[g1] = v1;
+        }
+        __syncthreads();
+    }
+}
+
 __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char bsm[];
@@ -685,79 +849,17 @@ __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p)
         sv[i] = ok ? p.bval[(size_t)b * p.cap + i] : 0xffffffffu;
     }
     __syncthreads();
-    // bitonic network on (key, index): a total order, identical to the stable order of the keys.  Stages with
-    // distance j > 32 run in shared memory across the block.  The stages with j <= 32 of every phase k stay inside
-    // blocks of 64 consecutive elements: a warp takes such a block into registers (2 elements per lane: x and
-    // x + 32), runs them with shuffles, and writes the block back once — one shared-memory round trip per phase
-    // instead of one per stage (the all-shared-memory version moved 72 x 24 B per key and was bound by it).
-    auto cmpx = [&](int t, int j, int k) {
-        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
-        const int l = i | j;
-        const bool up = ((i & k) == 0);
-        const uint64_t ka = sk[i], kb = sk[l];
-        const uint32_t va = sv[i], vb = sv[l];
-        const bool gt = (ka > kb) || (ka == kb && va > vb);
-        if (gt == up) {
-            sk[i] = kb; sk[l] = ka;
-            sv[i] = vb; sv[l] = va;
-        }
-    };
-    // register stages of phase k from distance j0 (<= 32) down to 1 on the 64 keys a warp holds
-    auto warp_stages = [&](int g0, int g1, int k, int j0, uint64_t& k0, uint64_t& k1, uint32_t& v0, uint32_t& v1) {
-        const bool upa = ((g0 & k) == 0), upb = ((g1 & k) == 0);
-        int jj = j0;
-        if (jj == 32) {  // partner of x is x + 32: both in this lane (k >= 64: one direction for the pair)
-            const bool gt = (k0 > k1) || (k0 == k1 && v0 > v1);
-            if (gt == upa) {
-                const uint64_t tk = k0; k0 = k1; k1 = tk;
-                const uint32_t tv = v0; v0 = v1; v1 = tv;
-            }
-            jj = 16;
-        }
-        for (; jj > 0; jj >>= 1) {
-            // element g (g0 or g1): direction from bit k of g, lower of its pair iff bit jj of g is clear
-            const uint64_t ok0 = __shfl_xor_sync(0xffffffffu, k0, jj), ok1 = __shfl_xor_sync(0xffffffffu, k1, jj);
-            const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
-            const bool lower = (lane & jj) == 0;
-            {
-                const bool mine_gt = (k0 > ok0) || (k0 == ok0 && v0 > ov0);
-                const bool keep_min = (lower == upa);
-                if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
-            }
-            {
-                const bool mine_gt = (k1 > ok1) || (k1 == ok1 && v1 > ov1);
-                const bool keep_min = (lower == upb);
-                if (mine_gt == keep_min) { k1 = ok1; v1 = ov1; }
-            }
-        }
-    };
-    // phases k = 2 .. 64 never leave a block of 64 keys: one load, 21 stages in registers, one store
-    for (int blk = warp; blk < (N2 >> 6); blk += kSBThreads / 32) {
-        const int g0 = (blk << 6) + lane, g1 = g0 + 32;
-        uint64_t k0 = sk[g0], k1 = sk[g1];
-        uint32_t v0 = sv[g0], v1 = sv[g1];
-#pragma unroll
-        for (int k = 2; k <= 64; k <<= 1) warp_stages(g0, g1, k, k >> 1, k0, k1, v0, v1);
-        sk[g0] = k0; sk[g1] = k1;
-        sv[g0] = v0; sv[g1] = v1;
-    }
-    __syncthreads();
-    for (int k = 128; k <= Na; k <<= 1) {
-        // B starts at a multiple of 2 Nb, so (i & k) gives it the same directions as a network of its own
-        const int lim = (k <= Nb) ? N2 : Na, npair = lim >> 1;
-        for (int j = k >> 1; j > 32; j >>= 1) {  // pairs span warps: block-wide stages
-            for (int t = tid; t < npair; t += kSBThreads) cmpx(t, j, k);
-            __syncthreads();
-        }
-        for (int blk = warp; blk < (lim >> 6); blk += kSBThreads / 32) {
-            const int g0 = (blk << 6) + lane, g1 = g0 + 32;
-            uint64_t k0 = sk[g0], k1 = sk[g1];
-            uint32_t v0 = sv[g0], v1 = sv[g1];
-            warp_stages(g0, g1, k, 32, k0, k1, v0, v1);
-            sk[g0] = k0; sk[g1] = k1;
-            sv[g0] = v0; sv[g1] = v1;
-        }
-        __syncthreads();
+    // The network on the keys alone first: exact ties between margins are rare, and a comparator that does not look
+    // at the row index is 2 instead of 7 instructions in an instruction-bound kernel.  If any two keys of this bucket
+    // turn out equal (or a real key equals the padding key) the bucket is sorted again with the full (key, index)
+    // comparator — the stable order either way.
+    ss_bucket_network<false>(sk, sv, N2, Na, Nb);
+    {
+        int tie = 0;
+        // (equal keys ACROSS the two parts are put in order by the (key, index) search below)
+        for (int i = tid; i < (int)cnt; i += kSBThreads)
+            tie |= (i > 0 && i != Na && sk[i] == sk[i - 1]) || sv[i] == 0xffffffffu;
+        if (__syncthreads_or(tie)) ss_bucket_network<true>(sk, sv, N2, Na, Nb);
     }
     const uint32_t off = s_off;
     for (int i = tid; i < (int)cnt; i += kSBThreads) {
@@ -909,7 +1011,12 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         }
         RBL_CUDA(rbl_launch_pdl(ss_splitters_kernel, dim3(1), dim3(kSSThreads), (size_t)nb2 * sizeof(uint64_t), s, q));
         RBL_LAUNCH_CHECK();
-        RBL_CUDA(rbl_launch_pdl(ss_partition_kernel, dim3(tiles), dim3(kSSThreads), smem, s, q));
+        // a hint that is the buffer this handle's last sort wrote is a permutation: partition in previous-rank order
+        const bool ranked = !c->ss_row_order && prev_perm == c->last_perm && n == c->last_perm_n;
+        if (ranked)
+            RBL_CUDA(rbl_launch_pdl(ss_partition_ranked_kernel, dim3(tiles), dim3(kSSThreads), 0, s, q));
+        else
+            RBL_CUDA(rbl_launch_pdl(ss_partition_kernel, dim3(tiles), dim3(kSSThreads), smem, s, q));
         RBL_LAUNCH_CHECK();
         RBL_PER_DEVICE(bool, battr, c);
         if (!battr) {
@@ -919,8 +1026,10 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
         }
         RBL_CUDA(rbl_launch_pdl(ss_bucket_kernel, dim3(q.nb), dim3(kSBThreads), (size_t)q.cap * 12, s, q));
         RBL_LAUNCH_CHECK();
+        if (perm_out) c->last_perm = perm_out, c->last_perm_n = n;
         return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 1);  // runs only if the flag was raised
     }
+    if (perm_out) c->last_perm = perm_out, c->last_perm_n = n;
     if (persistent) return rbl_k_sort_persistent(c, m, n, sorted_out, perm_out, s, 0);
     const int ntiles = rbl_sort_tiles(n);
     if (ntiles > c->sort_tiles) {

@@ -100,7 +100,9 @@ int rbl_sort_margins_near(rbl_handle_t h, const double* m, const int32_t* prev_p
  * rbl_sort_margins_near call took (1 buckets, 2 LSD fallback, 0 none yet), its largest bucket, overflow flag now */
 int rbl_sort_stats(rbl_handle_t h, rbl_stream_t stream, int32_t* h_out);
 /* bit 0: three launches per radix pass instead of the single persistent cooperative kernel; bit 1: never use the
- * splitter sort (testing) */
+ * splitter sort (testing); bit 2: the splitter sort always partitions in row order with the full splitter search
+ * (otherwise, when the hint is the permutation the handle's own last sort wrote, it walks the keys in the previous
+ * RANK order: the bucket of a key is then guessed from its previous rank and verified with two loads) */
 int rbl_sort_config(rbl_handle_t h, int legacy);
 /* dev tool: d_stamps (64 x u64, device) receives %globaltimer stamps of CTA 0 — the persistent sort writes 6 phase
  * boundaries for each of its 8 passes ([pass][6]), the persistent Gram-FISTA kernel a count in [0] followed by its

@@ -143,6 +143,40 @@ def test_splitter_sort_bit_exact_and_falls_back(E, n):
                                            e.perm.data_ptr(), e._stream()))
     mm = md.cpu().numpy()
     np.testing.assert_array_equal(e.perm.cpu().numpy(), np.argsort(mm, kind="stable"))
+    # ... which is the case where the partition walks the keys in the PREVIOUS RANK ORDER (bucket guessed from the
+    # rank, verified against the splitters, gallop + bisection when the row moved further): a chain of in-place
+    # calls over drifting, jumping, reversed, tied and constant data, each checked bit for bit; rbl_sort_config
+    # bit 2 (row-order partition) must give the same
+    for cfg in (0, 4):
+        cabi.check(e.lib.rbl_sort_config(e.h, cfg))
+        cur = base.copy()
+        amp = 50.0 / n   # a few per cent of a bucket's width: the regime of consecutive ADMM iterations
+        drift = ("drift", lambda c: c + amp * rng.normal(size=n))
+        chain = [drift] * 7     # (the first calls may still sit in the pause an earlier overflow started)
+        chain += [("jump", lambda c: c + 0.5 * rng.normal(size=n)), ("reverse", lambda c: -c),
+                  ("ties", lambda c: np.round(c, 2)), drift,
+                  ("scale", lambda c: 1e-30 * c), ("signs", lambda c: np.where(rng.random(n) < 0.5, 0.0, -0.0)),
+                  ("constant", lambda c: np.full(n, -3.5)), ("back", lambda c: base + 0.0)]
+        chain += [drift] * 11
+        if cfg == 4:            # the row-order partition has had its cases above: a short chain
+            chain = [drift] * 6 + chain[8:11] + [drift]
+        routes = []
+        for name, f in chain:
+            cur = f(cur)
+            md = e.vec(cur)
+            cabi.check(e.lib.rbl_sort_margins_near(e.h, md.data_ptr(), e.perm.data_ptr(), e.m_sorted.data_ptr(),
+                                                   e.perm.data_ptr(), e._stream()))
+            ref = np.argsort(cur, kind="stable")
+            np.testing.assert_array_equal(e.perm.cpu().numpy(), ref, err_msg=f"{name} cfg={cfg}")
+            np.testing.assert_array_equal(e.m_sorted.cpu().numpy(), cur[ref] + 0.0, err_msg=f"{name} cfg={cfg}")
+            cabi.check(e.lib.rbl_sort_stats(e.h, e._stream(), st))
+            assert st[3] == 0
+            routes.append(int(st[1]))
+        if st[0] > 0:
+            assert routes[5] == 1 and routes[6] == 1 and routes[-1] == 1, routes   # bucket route on drifting data
+            if n > 8192 and cfg == 0:
+                assert routes[13] == 2, routes                                      # constant keys: LSD fallback
+    cabi.check(e.lib.rbl_sort_config(e.h, 0))
     e.close()
 
 
