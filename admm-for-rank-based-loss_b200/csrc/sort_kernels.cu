@@ -764,6 +764,11 @@ __device__ __forceinline__ void ss_bucket_network(uint64_t* __restrict__ sk, uin
             const uint32_t ov0 = __shfl_xor_sync(0xffffffffu, v0, jj), ov1 = __shfl_xor_sync(0xffffffffu, v1, jj);
             const bool lower = (lane & jj) == 0;
             {
+                // (key, index) pairs are distinct, so "not greater" is "less".  Keys alone: two EQUAL keys make the
+                // upper lane take the lower lane's element while that one keeps it — the row index of the other is
+                // lost, the keys are not; the caller finds the equal keys side by side afterwards and starts over
+                // from the bucket's slots with kFull (a symmetric keys-only rule costs two more compares per
+                // element and stage: 49.6 instead of 38.7 us for the kernel at 1 M keys)
                 const bool mine_gt = kFull ? ((k0 > ok0) || (k0 == ok0 && v0 > ov0)) : (k0 > ok0);
                 const bool keep_min = (lower == upa);
                 if (mine_gt == keep_min) { k0 = ok0; v0 = ov0; }
@@ -843,23 +848,30 @@ __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p)
         }
     }
     const int N2 = Na + Nb;
-    for (int i = tid; i < N2; i += kSBThreads) {
-        const bool ok = i < (int)cnt;
-        sk[i] = ok ? p.bkey[(size_t)b * p.cap + i] : 0xffffffffffffffffull;  // sentinels sort last
-        sv[i] = ok ? p.bval[(size_t)b * p.cap + i] : 0xffffffffu;
-    }
-    __syncthreads();
+    auto load_bucket = [&]() {
+        for (int i = tid; i < N2; i += kSBThreads) {
+            const bool ok = i < (int)cnt;
+            sk[i] = ok ? p.bkey[(size_t)b * p.cap + i] : 0xffffffffffffffffull;  // sentinels sort last
+            sv[i] = ok ? p.bval[(size_t)b * p.cap + i] : 0xffffffffu;
+        }
+        __syncthreads();
+    };
+    load_bucket();
     // The network on the keys alone first: exact ties between margins are rare, and a comparator that does not look
-    // at the row index is 2 instead of 7 instructions in an instruction-bound kernel.  If any two keys of this bucket
-    // turn out equal (or a real key equals the padding key) the bucket is sorted again with the full (key, index)
-    // comparator — the stable order either way.
+    // at the row index is 2 instead of 7 instructions in an instruction-bound kernel.  The keys come out sorted either
+    // way (the key multiset survives, see ss_bucket_network); if any two of them turn out equal (or a padding entry
+    // sits among the real ones) the row indices cannot be trusted: the bucket is loaded again and sorted with the
+    // full (key, index) comparator — the stable order either way.
     ss_bucket_network<false>(sk, sv, N2, Na, Nb);
     {
         int tie = 0;
         // (equal keys ACROSS the two parts are put in order by the (key, index) search below)
         for (int i = tid; i < (int)cnt; i += kSBThreads)
             tie |= (i > 0 && i != Na && sk[i] == sk[i - 1]) || sv[i] == 0xffffffffu;
-        if (__syncthreads_or(tie)) ss_bucket_network<true>(sk, sv, N2, Na, Nb);
+        if (__syncthreads_or(tie)) {
+            load_bucket();
+            ss_bucket_network<true>(sk, sv, N2, Na, Nb);
+        }
     }
     const uint32_t off = s_off;
     for (int i = tid; i < (int)cnt; i += kSBThreads) {

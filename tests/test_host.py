@@ -394,3 +394,15 @@ def test_library_lbfgsb_tracks_scipy():
         # differences of the two (mathematically identical) direction formulas, the control flow stays identical
         tol = 1e-9 if k < 18 else 1e-6
         assert np.linalg.norm(x - ref.x) <= tol * max(1.0, np.linalg.norm(ref.x)), (k, np.linalg.norm(x - ref.x))
+
+
+def test_bucket_network_key_only_with_tie_fallback():
+    """the hinted sort's per-bucket network (restated in tests/emul/bucket_network.py): keys-only comparator, re-sort
+    with (key, index) when the bucket holds equal keys, A / B merge positions — stable order for distinct keys,
+    heavy ties, constant keys and a single tie, over the bucket loads that exercise every A / B split"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "bucket_network", os.path.join(os.path.dirname(__file__), "emul", "bucket_network.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.run_cases()
