@@ -93,7 +93,11 @@ int rbl_sort_margins(rbl_handle_t h, const double* m, double* m_sorted, int32_t*
  * ADMM iteration; may alias perm, may be NULL; n_global entries).  The rows that sat at B - 1 evenly spaced ranks
  * then, read at their new values and sorted, split the new keys into B ~ n/2048 buckets, each sorted by (key,
  * index) in shared memory by one CTA — two launches, no grid barrier, the same bit-exact stable permutation.  If a
- * bucket would overflow its 4096 slots (stale or useless hint) the LSD sort runs instead, chosen on the device. */
+ * bucket would overflow its 4096 slots (stale or useless hint) the LSD sort runs instead, chosen on the device.
+ * A hint in a buffer of the caller's own may hold anything (only speed depends on it).  When prev_perm is the very
+ * buffer the handle's LAST sort wrote its permutation to (the in-place call of the ADMM loop: prev_perm == perm), it is
+ * taken to still hold that permutation untouched, and the keys are partitioned in that rank order (see
+ * rbl_sort_config bit 2). */
 int rbl_sort_margins_near(rbl_handle_t h, const double* m, const int32_t* prev_perm, double* m_sorted,
                           int32_t* perm, rbl_stream_t stream);
 /* synchronises `stream`; h_out[0..4) = buckets B of the splitter sort for this n (0: not used), route the last
