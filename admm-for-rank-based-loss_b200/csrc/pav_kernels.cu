@@ -725,7 +725,32 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
         if (violated && tid == 0) {
             int64_t lo, hi;
             double v;
-            pav_kary_finish(P.loss, rho, val, ps, pm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            if (P.dbg) {  // dev tool: the steps of pav_kary_finish with a stamp after each
+                const double u0 = val(s_end[0]);
+                stamp();
+                lo = pav_run_start(val, s_end[0], (int64_t)0, u0);
+                stamp();
+                const double u1 = val(s_end[1] - 1);
+                stamp();
+                hi = pav_run_end(val, s_end[1] - 1, c, u1);
+                if (j < 4) {  // how far the snaps moved the searches' answers
+                    P.dbg[56 + 2 * j] = (unsigned long long)(s_end[0] - lo);
+                    P.dbg[57 + 2 * j] = (unsigned long long)(hi - s_end[1]);
+                }
+                stamp();
+                v = pav_block_value(P.loss, rho, ps, pm, lo, hi);
+                stamp();
+                if (lo > 0) {
+                    const double vl = val(lo - 1);
+                    if (v < vl) v = vl;
+                }
+                if (hi < c) {
+                    const double vr = val(hi);
+                    if (v > vr) v = vr;
+                }
+            } else {
+                pav_kary_finish(P.loss, rho, val, ps, pm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            }
             if (P.dbg && j < 4) {  // dev tool: guesses and answers of this merge
                 P.dbg[40 + 4 * j] = (unsigned long long)h_lo;
                 P.dbg[41 + 4 * j] = (unsigned long long)h_hi;
