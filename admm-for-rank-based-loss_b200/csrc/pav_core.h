@@ -364,8 +364,11 @@ RBL_HD bool pav_probe_right_near(int loss, double rho, const V& val, const PS& p
 // exactly; all these probes stay inside the shared-memory windows the device kernel keeps around the guesses.
 // Farther moves fall back to the even 32-ary subdivision of what is left.
 #define RBL_HINT_STRIDE 32
-RBL_HD int64_t pav_hint_pos(int64_t h, int64_t lo, int64_t hi, int j) {
-    int64_t p = h + (int64_t)(j - 15) * RBL_HINT_STRIDE;
+// stride: RBL_HINT_STRIDE, or a finer spacing when the last guesses were close (RBL_HINT_STRIDE_NEAR: the 32 probes
+// then cover h - 120 .. h + 128, whose lookups on the OPPOSITE side also stay inside that side's window).
+#define RBL_HINT_STRIDE_NEAR 8
+RBL_HD int64_t pav_hint_pos(int64_t h, int64_t lo, int64_t hi, int j, int stride = RBL_HINT_STRIDE) {
+    int64_t p = h + (int64_t)(j - 15) * stride;
     if (p < lo) p = lo;
     if (p > hi) p = hi;
     return p;
@@ -403,7 +406,7 @@ RBL_HD void pav_kary_finish(int loss, double rho, const V& val, const PS& ps, co
 template <class V, class PS, class PM>
 RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
                                   int64_t b, int64_t c, int64_t* lo_out, int64_t* hi_out, double* v_out,
-                                  int64_t hint_lo = -1, int64_t hint_hi = -1) {
+                                  int64_t hint_lo = -1, int64_t hint_hi = -1, int hint_stride = RBL_HINT_STRIDE) {
     if (!(val(b - 1) > val(b))) return false;
     const bool hinted = hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c;
     // ---- left: first p in [a, b-1] whose probe is true (b-1 is): pattern over p is F..F T..T
@@ -413,7 +416,7 @@ RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& 
         int64_t rr[32], rs[32], re[32];
         bool pr[32];
         for (int j = 0; j < 32; ++j)
-            pr[j] = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, j), hint_hi,
+            pr[j] = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, j, hint_stride), hint_hi,
                                         &rr[j], &rs[j], &re[j]);
         int f = -1;
         for (int j = 0; j < 32; ++j)
@@ -477,7 +480,7 @@ RBL_HD bool pav_merge_search_kary(int loss, double rho, const V& val, const PS& 
         int64_t ll[32], rs[32], re[32];
         bool pr[32];
         for (int j = 0; j < 32; ++j)
-            pr[j] = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, j), hint_lo,
+            pr[j] = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, j, hint_stride), hint_lo,
                                          &ll[j], &rs[j], &re[j]);
         int f = -1;
         for (int j = 0; j < 32; ++j)

@@ -181,7 +181,8 @@ struct TreeParams {
 // left half of the merge search: first p in [a, b-1] whose run joins the pooled block (full warp)
 template <class V, class PS, class PM>
 __device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
-                                   int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1) {
+                                   int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1,
+                                   int hint_stride = RBL_HINT_STRIDE) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     int64_t lo = a, hi = b - 1, xlo = b, xhi = c;
@@ -189,7 +190,7 @@ __device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS&
     if (hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c && lo < hi) {
         // warm start (pav_core.h: pav_merge_search_kary): 32 probes around last z-step's block start
         int64_t rr = 0, rs = 0, re = 0;
-        const bool pr = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, lane),
+        const bool pr = pav_probe_left_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_lo, lo, hi, lane, hint_stride),
                                             hint_hi, &rr, &rs, &re);
         const unsigned ball = __ballot_sync(FULL, pr);
         const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
@@ -266,7 +267,8 @@ __device__ int64_t merge_kary_left(int loss, double rho, const V& val, const PS&
 // right half: first p in [b+1, c) whose run stays out of the pooled block, else c (full warp)
 template <class V, class PS, class PM>
 __device__ int64_t merge_kary_right(int loss, double rho, const V& val, const PS& ps, const PM& pm, int64_t a,
-                                    int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1) {
+                                    int64_t b, int64_t c, int64_t hint_lo = -1, int64_t hint_hi = -1,
+                                    int hint_stride = RBL_HINT_STRIDE) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     int64_t lo = b + 1, hi = c, xlo = a, xhi = b;
@@ -274,7 +276,7 @@ __device__ int64_t merge_kary_right(int loss, double rho, const V& val, const PS
     if (hint_lo >= a && hint_lo < b && hint_hi > b && hint_hi <= c && lo < hi) {
         // warm start: 32 probes around last z-step's block end
         int64_t ll = 0, rs = 0, re = 0;
-        const bool pr = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, lane),
+        const bool pr = pav_probe_right_near(loss, rho, val, ps, pm, a, b, c, pav_hint_pos(hint_hi, lo, hi - 1, lane, hint_stride),
                                              hint_lo, &ll, &rs, &re);
         const unsigned ball = __ballot_sync(FULL, pr);
         const int f = ball ? (__ffs(ball) - 1) : -1;  // first true lane
@@ -504,6 +506,9 @@ struct SegBlocks {
     // decaying number of ranks per iteration (measured at n = 1M: 13 k ranks at iteration 10, 2.6 k at 20, 1 k at
     // 30), so the guess is the last answer extrapolated by 7/8 of its last move
     int64_t move_lo[kMaxSeg], move_hi[kMaxSeg];
+    // 1 + |answer - guess| of the last warm-started call (0: not known): while both ends keep landing within 64 ranks
+    // of their guesses the first round probes at RBL_HINT_STRIDE_NEAR instead of RBL_HINT_STRIDE
+    int64_t err_lo[kMaxSeg], err_hi[kMaxSeg];
 };
 
 // positions i (1 <= i < n) where sigma steps up; count may exceed cap (then the list is truncated)
@@ -575,7 +580,7 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
     __shared__ int s_nblk;
     __shared__ int64_t s_lo[kMaxSeg], s_hi[kMaxSeg];
     __shared__ double s_v[kMaxSeg];
-    __shared__ int64_t s_end[2];
+    __shared__ int64_t s_end[2], s_snap[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double rho = P.scal ? P.scal[0] : P.rho;
     int dbg_n = 0;
@@ -668,6 +673,11 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
             h_hi = h_hi < b + 1 ? b + 1 : (h_hi > c ? c : h_hi);
         }
         const bool hinted = have_prev;
+        int stride = RBL_HINT_STRIDE;
+        if (have_prev) {
+            const int64_t el = out->err_lo[j], eh = out->err_hi[j];
+            if (el > 0 && el <= 65 && eh > 0 && eh <= 65) stride = RBL_HINT_STRIDE_NEAR;
+        }
         // windows around the guessed block ends (empty without a usable guess): filled by the whole CTA
         ValWin<ValOverlay> val{gval, {W.val[0], W.val[1]}, {0, 0}, {0, 0}};
         PrefWin ps{gps, {W.psh[0], W.psh[1]}, {W.psl[0], W.psl[1]}, {0, 0}, {-1, -1}};
@@ -716,40 +726,33 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
         __syncthreads();
         stamp();
         if (violated && warp < 2) {
-            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi)
-                                        : merge_kary_right(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi);
-            if (lane == 0) s_end[warp] = e;
+            const int64_t e = warp == 0 ? merge_kary_left(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi, stride)
+                                        : merge_kary_right(P.loss, rho, val, ps, pm, (int64_t)0, b, c, h_lo, h_hi, stride);
+            if (lane == 0) {
+                // each side snaps its own answer to a whole run of equal values (what pav_kary_finish does first),
+                // the two sides side by side instead of one after the other on thread 0
+                s_end[warp] = e;
+                s_snap[warp] = warp == 0 ? pav_run_start(val, e, (int64_t)0, val(e))
+                                         : pav_run_end(val, e - 1, c, val(e - 1));
+            }
         }
         __syncthreads();
         stamp();
         if (violated && tid == 0) {
-            int64_t lo, hi;
-            double v;
-            if (P.dbg) {  // dev tool: the steps of pav_kary_finish with a stamp after each
-                const double u0 = val(s_end[0]);
-                stamp();
-                lo = pav_run_start(val, s_end[0], (int64_t)0, u0);
-                stamp();
-                const double u1 = val(s_end[1] - 1);
-                stamp();
-                hi = pav_run_end(val, s_end[1] - 1, c, u1);
-                if (j < 4) {  // how far the snaps moved the searches' answers
-                    P.dbg[56 + 2 * j] = (unsigned long long)(s_end[0] - lo);
-                    P.dbg[57 + 2 * j] = (unsigned long long)(hi - s_end[1]);
-                }
-                stamp();
-                v = pav_block_value(P.loss, rho, ps, pm, lo, hi);
-                stamp();
-                if (lo > 0) {
-                    const double vl = val(lo - 1);
-                    if (v < vl) v = vl;
-                }
-                if (hi < c) {
-                    const double vr = val(hi);
-                    if (v > vr) v = vr;
-                }
-            } else {
-                pav_kary_finish(P.loss, rho, val, ps, pm, (int64_t)0, c, s_end[0], s_end[1], &lo, &hi, &v);
+            const int64_t lo = s_snap[0], hi = s_snap[1];
+            double v = pav_block_value(P.loss, rho, ps, pm, lo, hi);  // the rest of pav_kary_finish
+            stamp();
+            if (lo > 0) {
+                const double vl = val(lo - 1);
+                if (v < vl) v = vl;
+            }
+            if (hi < c) {
+                const double vr = val(hi);
+                if (v > vr) v = vr;
+            }
+            if (P.dbg && j < 4) {  // how far the snaps moved the searches' answers
+                P.dbg[56 + 2 * j] = (unsigned long long)(s_end[0] - lo);
+                P.dbg[57 + 2 * j] = (unsigned long long)(hi - s_end[1]);
             }
             if (P.dbg && j < 4) {  // dev tool: guesses and answers of this merge
                 P.dbg[40 + 4 * j] = (unsigned long long)h_lo;
@@ -759,6 +762,8 @@ __global__ void __launch_bounds__(kSegMergeThreads) pav_seg_merge_kernel(const T
             }
             out->move_lo[j] = have_prev ? s_end[0] - p_lo : 0;
             out->move_hi[j] = have_prev ? s_end[1] - p_hi : 0;
+            out->err_lo[j] = have_prev ? 1 + (s_end[0] > h_lo ? s_end[0] - h_lo : h_lo - s_end[0]) : 0;
+            out->err_hi[j] = have_prev ? 1 + (s_end[1] > h_hi ? s_end[1] - h_hi : h_hi - s_end[1]) : 0;
             out->hint_lo[j] = s_end[0];   // (the searches' own answers: the finish only snaps them to whole runs)
             out->hint_hi[j] = s_end[1];
             // blocks are swallowed whole (a probe decides for the whole run of equal values around it)

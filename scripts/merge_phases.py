@@ -27,7 +27,7 @@ with contextlib.redirect_stdout(io.StringIO()):
             _cabi.check(e.lib.rbl_sort_debug(e.h, 0))
             _cabi.check(e.lib.rbl_sort_config(e.h, 0))
             t = st.cpu().numpy(); k = int(t[0]); ts = t[1:1 + k].astype(np.float64)
-            sys.stderr.write("it %d: %d stamps, total %.1f us; [offsets scan | (windows | search | first value read | run start | value read | run end | block value | rest of finish) per merge] = %s\n"
+            sys.stderr.write("it %d: %d stamps, total %.1f us; [offsets scan | (windows | search + run snaps | block value | rest of finish) per merge] = %s\n"
                              % (i, k, (ts[-1] - ts[0]) / 1e3, " ".join("%.1f" % x for x in np.diff(ts) / 1e3)))
             for j in (1, 2):
                 hl, hh, al, ah = (int(v) for v in t[40 + 4 * j: 44 + 4 * j])

@@ -84,6 +84,11 @@ extern "C" int emul_pav_fewseg_hinted(int loss, int64_t n, const double* sigma, 
                                       int chunk_log2, double* val, int64_t* n_runs, const int64_t* hints_in,
                                       int64_t* hints_out);
 
+// probe spacing of the warm-started first round (pav_hint_pos): RBL_HINT_STRIDE, or RBL_HINT_STRIDE_NEAR as the device
+// kernel uses while its guesses keep landing close — the pooled blocks never depend on it
+static int g_hint_stride = RBL_HINT_STRIDE;
+extern "C" void emul_set_hint_stride(int stride) { g_hint_stride = stride; }
+
 extern "C" int emul_pav_fewseg(int loss, int64_t n, const double* sigma, const double* m, double rho, int chunk_log2,
                                double* val, int64_t* n_runs) {
     return emul_pav_fewseg_hinted(loss, n, sigma, m, rho, chunk_log2, val, n_runs, nullptr, nullptr);
@@ -129,7 +134,7 @@ extern "C" int emul_pav_fewseg_hinted(int loss, int64_t n, const double* sigma, 
         double vv;
         const int64_t h_lo = hints_in ? hints_in[2 * (j - 1)] : -1, h_hi = hints_in ? hints_in[2 * (j - 1) + 1] : -1;
         if (hints_out) hints_out[2 * (j - 1)] = hints_out[2 * (j - 1) + 1] = -1;
-        if (!pav_merge_search_kary(loss, rho, ov, ps, pm, (int64_t)0, b, c, &lo, &hi, &vv, h_lo, h_hi)) continue;
+        if (!pav_merge_search_kary(loss, rho, ov, ps, pm, (int64_t)0, b, c, &lo, &hi, &vv, h_lo, h_hi, g_hint_stride)) continue;
         if (hints_out) {
             hints_out[2 * (j - 1)] = lo;
             hints_out[2 * (j - 1) + 1] = hi;

@@ -195,9 +195,11 @@ def test_few_segment_pav_route_matches_stack_pav_on_cpu():
                 h = rng.integers(-5, n + 5, size=blocks.size)
             h = np.ascontiguousarray(h, dtype=np.int64)
             z2 = np.empty_like(m)
+            lib.emul_set_hint_stride(8 if (trial + mode) % 2 else 32)   # both probe spacings of the device kernel
             lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m.ctypes.data_as(dp), rho, chunk,
                                        z2.ctypes.data_as(dp), None, h.ctypes.data_as(ip), None)
             np.testing.assert_array_equal(z2, z, err_msg=str((trial, n, loss, kind, mode)))
+        lib.emul_set_hint_stride(32)
 
 
 def test_warm_started_merge_search_at_scale_on_cpu():
@@ -226,12 +228,15 @@ def test_warm_started_merge_search_at_scale_on_cpu():
         lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m1.ctypes.data_as(dp), rho, 10,
                                    ref.ctypes.data_as(dp), None, None, None)
         assert np.max(np.abs(ref - zo)) <= 1e-13 * max(1.0, np.max(np.abs(zo)))
-        for shift in (0, 7, -300, 5000, -5000):
-            h = np.ascontiguousarray(np.where(prev >= 0, prev + shift, -1), dtype=np.int64)
-            z = np.empty(n)
-            lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m1.ctypes.data_as(dp), rho, 10,
-                                       z.ctypes.data_as(dp), None, h.ctypes.data_as(ip), None)
-            np.testing.assert_array_equal(z, ref, err_msg=str((trial, n, loss, shift)))
+        for stride in (32, 8):                # the device kernel's two probe spacings (pav_hint_pos)
+            lib.emul_set_hint_stride(stride)
+            for shift in (0, 7, -60, -300, 5000, -5000):
+                h = np.ascontiguousarray(np.where(prev >= 0, prev + shift, -1), dtype=np.int64)
+                z = np.empty(n)
+                lib.emul_pav_fewseg_hinted(O.LOSS_IDS[loss], n, sig.ctypes.data_as(dp), m1.ctypes.data_as(dp), rho,
+                                           10, z.ctypes.data_as(dp), None, h.ctypes.data_as(ip), None)
+                np.testing.assert_array_equal(z, ref, err_msg=str((trial, n, loss, shift, stride)))
+        lib.emul_set_hint_stride(32)
 
 
 def test_radix_key_transform_is_order_preserving():
