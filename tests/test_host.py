@@ -401,6 +401,18 @@ def test_library_lbfgsb_tracks_scipy():
         assert np.linalg.norm(x - ref.x) <= tol * max(1.0, np.linalg.norm(ref.x)), (k, np.linalg.norm(x - ref.x))
 
 
+def test_rank_order_partition_bucket_search():
+    """the bucket search of ss_partition_ranked_kernel (restated in tests/emul/partition_ranked.py): guess from the
+    previous rank, gallop + bisection from the guess — equal to the full bisection for any guess, with duplicated
+    splitters and keys equal to splitters"""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "partition_ranked", os.path.join(os.path.dirname(__file__), "emul", "partition_ranked.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    mod.run_cases()
+
+
 def test_bucket_network_key_only_with_tie_fallback():
     """the hinted sort's per-bucket network (restated in tests/emul/bucket_network.py): keys-only comparator, re-sort
     with (key, index) when the bucket holds equal keys, A / B merge positions — stable order for distinct keys,
