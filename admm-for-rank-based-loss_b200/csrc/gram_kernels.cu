@@ -388,9 +388,9 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     for (int i = tid; i < 128; i += nt) s_pow[i] = p.pow_tab[i];
     float L_prev = p.L0, L_acc = p.L0;
     int i_k0 = 0, i_k = 0, k = 0, sweeps = 0, trials = 0, par = 0;
-    // candidates evaluated per sweep: all KC while L climbs from L0 (the first iteration of a call rejects ~12
-    // candidates), 2 once an iteration has been accepted (L_prev is then right and i = 0 passes almost always);
-    // a sweep whose candidates are all rejected widens the next one again
+    // candidates evaluated per sweep: all KC, always.  (While L climbs from L0 the first iteration of a call rejects
+    // ~12 candidates; once one has been accepted L_prev is right and i = 0 passes almost always — narrowing the later
+    // sweeps to 2 candidates was measured and made no difference: a sweep is barrier latency, not arithmetic.)
     int kc = KC;
     double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
     unsigned int target = 0;
