@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(kGThreads, 1) gram_fista_persistent_kernel(con
     float L_prev = p.L0, L_acc = p.L0;
     int i_k0 = 0, i_k = 0, k = 0, sweeps = 0, trials = 0, par = 0;
     // candidates evaluated per sweep: all KC, always.  (While L climbs from L0 the first iteration of a call rejects
-    // ~12 candidates; once one has been accepted L_prev is right and i = 0 passes almost always — narrowing the later
-    // sweeps to 2 candidates was measured and made no difference: a sweep is barrier latency, not arithmetic.)
+    // ~12 candidates; once one has been accepted L_prev is right and i = 0 passes almost always — the later sweeps could
+    // be narrowed, but a sweep's cost is its barrier and reduction latency, not the arithmetic of the candidates.)
     int kc = KC;
     double t = 1.0, t1 = 0.0, crit = 0.0, lhs_acc = 0.0, rhs_acc = 0.0;
     unsigned int target = 0;
