@@ -701,3 +701,29 @@ def test_sweep_over_a_shared_design_matrix(w_mode, kind):
         own.engine.close()
     for s in reversed(shared):
         s.engine.close()
+
+
+def test_fista_session_reuses_the_uploaded_matrix(golden_dir, w_mode):
+    """FistaSession (extension of the fast_lasso seam for callers that loop over one X): same results as FISTA(),
+    bit for bit, for several (beta, y, lam) on the same matrix, with one engine / one upload behind them."""
+    from src.util.fast_lasso import FISTA, FistaSession
+
+    g = _load(golden_dir, "fista.npz")
+    d = _load(golden_dir, "data_300x40.npz")
+    D = -d["y"] * d["X"]
+    rng = np.random.default_rng(4)
+    cases = [(g["w0"], g["b"], np.float64(0.5)), (g["w0"] * 0.0, g["b"] + 0.1 * rng.normal(size=g["b"].shape), 20.0),
+             (rng.normal(size=g["w0"].shape) * 0.01, g["b"], np.float64(300.0))]
+    for dtype in (torch.float64, torch.float32):
+        with FistaSession(D, dtype=dtype) as sess:
+            eng = sess.engine
+            for beta, b, lam in cases:
+                w1, i1 = sess(beta, b, lam, np.float32(17), np.float32(2.5), tol=7e-5, max_iter=5000, return_info=True)
+                w2, i2 = FISTA(beta, D, b, lam, np.float32(17), np.float32(2.5), tol=7e-5, max_iter=5000, dtype=dtype,
+                               return_info=True)
+                np.testing.assert_array_equal(w1, w2)
+                assert w1.dtype == (np.float32 if dtype == torch.float32 else np.float64)
+                assert i1["iters"] == i2["iters"] and i1["L"] == i2["L"]
+                assert sess.engine is eng
+        with pytest.raises(RuntimeError):
+            sess(cases[0][0], cases[0][1], cases[0][2], np.float32(17), np.float32(2.5))
