@@ -532,58 +532,6 @@ struct SSParams {
     int32_t* perm_out;
 };
 
-// the splitters, once per call (ONE CTA): today's keys of the rows that sat at nb - 1 evenly spaced ranks in the
-// previous order, put in exact order by a bitonic network in shared memory, written to p.spl for the partition CTAs
-// (each of them used to sort its own copy: fine for 1024 splitters, not for the 4096 that 4 M keys need)
-__global__ void __launch_bounds__(kSSThreads) ss_splitters_kernel(const SSParams p) {
-    rbl_pdl_wait();
-    extern __shared__ __align__(16) unsigned char ssm[];
-    int nb2 = 16;  // power-of-two network: pad with maximal keys
-    while (nb2 < p.nb) nb2 <<= 1;
-    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);  // [nb2] spl[j] = first key of bucket j (spl[0] = 0)
-    const int tid = threadIdx.x, nb = p.nb;
-    if (p.flag[1] > 0) return;  // pausing after a recent overflow (the partition kernel raises the flag)
-    for (int j = tid; j < nb2; j += kSSThreads) {
-        uint64_t k = 0ull;
-        if (j >= nb) {
-            k = 0xffffffffffffffffull;
-        } else if (j > 0) {
-            const int64_t pos = (int64_t)(((__int128)j * p.n) / nb);
-            int64_t row = p.prev_perm[pos];
-            row = row < 0 ? 0 : (row >= p.n ? p.n - 1 : row);
-            k = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[row]);
-        }
-        spl[j] = k;
-    }
-    __syncthreads();
-    {
-        const int warp = tid >> 5, lane = tid & 31, npair = nb2 >> 1;
-        auto cx = [&](int t, int j, int k) {
-            const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), l = i | j;
-            const uint64_t a = spl[i], b2 = spl[l];
-            if ((a > b2) == ((i & k) == 0)) {
-                spl[i] = b2;
-                spl[l] = a;
-            }
-        };
-        for (int k = 2; k <= nb2; k <<= 1) {
-            int j = k >> 1;
-            for (; j > 32; j >>= 1) {
-                for (int t = tid; t < npair; t += kSSThreads) cx(t, j, k);
-                __syncthreads();
-            }
-            for (int t0 = warp * 32; t0 < npair; t0 += kSSThreads) {
-                for (int jj = j; jj > 0; jj >>= 1) {
-                    if (t0 + lane < npair) cx(t0 + lane, jj, k);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-        }
-    }
-    for (int j = tid; j < nb2; j += kSSThreads) p.spl[j] = j == 0 ? 0ull : spl[j];  // bucket 0 starts at the smallest key
-}
-
 __global__ void __launch_bounds__(kSSThreads) ss_partition_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char ssm[];
@@ -810,6 +758,38 @@ __device__ __forceinline__ void ss_bucket_network(uint64_t* __restrict__ sk, uin
     }
 }
 
+// the splitters, once per call (ONE CTA): today's keys of the rows that sat at nb - 1 evenly spaced ranks in the
+// previous order, put in exact order and written to p.spl for the partition CTAs (each of them used to sort its own
+// copy: fine for 1024 splitters, not for the 4096 that 4 M keys need).  Sorted by the bucket kernel's network on the
+// keys alone (register stages with shuffles: 12.6 us for 1024 splitters with an all-shared-memory network before).
+__global__ void __launch_bounds__(kSBThreads) ss_splitters_kernel(const SSParams p) {
+    rbl_pdl_wait();
+    extern __shared__ __align__(16) unsigned char ssm[];
+    int nb2 = 16;  // power-of-two network: pad with maximal keys
+    while (nb2 < p.nb) nb2 <<= 1;
+    const int N2 = nb2 < 64 ? 64 : nb2;                        // the network's smallest size
+    uint64_t* spl = reinterpret_cast<uint64_t*>(ssm);          // [N2] spl[j] = first key of bucket j (spl[0] = 0)
+    uint32_t* tag = reinterpret_cast<uint32_t*>(spl + N2);     // [N2] rides along (the network moves pairs)
+    const int tid = threadIdx.x, nb = p.nb;
+    if (p.flag[1] > 0) return;  // pausing after a recent overflow (the partition kernel raises the flag)
+    for (int j = tid; j < N2; j += kSBThreads) {
+        uint64_t k = 0ull;
+        if (j >= nb) {
+            k = 0xffffffffffffffffull;
+        } else if (j > 0) {
+            const int64_t pos = (int64_t)(((__int128)j * p.n) / nb);
+            int64_t row = p.prev_perm[pos];
+            row = row < 0 ? 0 : (row >= p.n ? p.n - 1 : row);
+            k = rbl_key_from_bits(reinterpret_cast<const uint64_t*>(p.m)[row]);
+        }
+        spl[j] = k;
+        tag[j] = (uint32_t)j;
+    }
+    __syncthreads();
+    ss_bucket_network<false>(spl, tag, N2, N2, 0);
+    for (int j = tid; j < nb2; j += kSBThreads) p.spl[j] = j == 0 ? 0ull : spl[j];  // bucket 0 starts at the smallest key
+}
+
 __global__ void __launch_bounds__(kSBThreads) ss_bucket_kernel(const SSParams p) {
     rbl_pdl_wait();
     extern __shared__ __align__(16) unsigned char bsm[];
@@ -1021,7 +1001,12 @@ int rbl_k_sort(rbl_ctx* c, const double* m, int64_t n, double* sorted_out, int32
             RBL_CUDA(cudaFuncSetAttribute(ss_partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             attr = smem;
         }
-        RBL_CUDA(rbl_launch_pdl(ss_splitters_kernel, dim3(1), dim3(kSSThreads), (size_t)nb2 * sizeof(uint64_t), s, q));
+        RBL_PER_DEVICE(bool, sattr, c);
+        if (!sattr) {  // 4096 splitters: 48 KB of dynamic shared memory next to the kernel's static words
+            RBL_CUDA(cudaFuncSetAttribute(ss_splitters_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4096 * 12));
+            sattr = true;
+        }
+        RBL_CUDA(rbl_launch_pdl(ss_splitters_kernel, dim3(1), dim3(kSBThreads), (size_t)(nb2 < 64 ? 64 : nb2) * 12, s, q));
         RBL_LAUNCH_CHECK();
         // a hint that is the buffer this handle's last sort wrote is a permutation: partition in previous-rank order
         const bool ranked = !c->ss_row_order && prev_perm == c->last_perm && n == c->last_perm_n;
